@@ -41,20 +41,6 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
-_lib = None
-
-
-def lib():
-    global _lib
-    if _lib is None:
-        build()
-        _lib = C.CDLL(_LIB_PATH)
-        _lib.oracle_ray_cells.restype = C.c_int64
-        _lib.oracle_outline_cells.restype = C.c_int64
-        _lib.oracle_area_cells.restype = C.c_int64
-    return _lib
-
-
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -132,53 +118,8 @@ def polygon_xy(poly) -> np.ndarray:
 
 
 def hardware_threads() -> int:
-    return int(lib().oracle_hardware_threads())
+    return int(default()._lib.oracle_hardware_threads())
 
-
-# ---- generators ------------------------------------------------------------------------------
-
-def to_discrete(res, poly) -> np.ndarray:
-    xy = polygon_xy(poly)
-    n = xy.size // 2
-    out = np.empty((n, 2), dtype=np.int32)
-    rc = lib().oracle_to_discrete(C.c_double(res), _p(xy), C.c_int64(n), _p(out))
-    if rc != 0:
-        raise ValueError("The resolution must be positive")
-    return out
-
-
-def ray_cells(b, e) -> np.ndarray:
-    cap = max(abs(e[0] - b[0]), abs(e[1] - b[1])) + 1
-    out = np.empty((cap, 2), dtype=np.int32)
-    n = lib().oracle_ray_cells(int(b[0]), int(b[1]), int(e[0]), int(e[1]), _p(out), C.c_int64(cap))
-    return out[:n]
-
-
-def outline_cells(sparse) -> np.ndarray:
-    s = np.ascontiguousarray(sparse, dtype=np.int32).reshape(-1, 2)
-    n = lib().oracle_outline_cells(_p(s), C.c_int64(len(s)), None, C.c_int64(0))
-    out = np.empty((max(n, 1), 2), dtype=np.int32)
-    lib().oracle_outline_cells(_p(s), C.c_int64(len(s)), _p(out), C.c_int64(n))
-    return out[:n]
-
-
-def area_cells(dense_outlines, return_max_ranges=False):
-    """dense_outlines: list of [n_i, 2] int arrays (each a dense closed outline). Raises RuntimeError for
-    the reference's std::logic_error."""
-    outs = [np.ascontiguousarray(o, dtype=np.int32).reshape(-1, 2) for o in dense_outlines]
-    sizes = np.array([len(o) for o in outs], dtype=np.int64)
-    cat = np.concatenate(outs) if outs else np.empty((0, 2), dtype=np.int32)
-    cat = np.ascontiguousarray(cat)
-    mr = C.c_int32(0)
-    n = lib().oracle_area_cells(_p(cat), _p(sizes), C.c_int32(len(outs)), None, C.c_int64(0), C.byref(mr))
-    if n < 0:
-        raise RuntimeError("Even number of line-pairs expected")
-    out = np.empty((max(n, 1), 2), dtype=np.int32)
-    lib().oracle_area_cells(_p(cat), _p(sizes), C.c_int32(len(outs)), _p(out), C.c_int64(n), C.byref(mr))
-    return (out[:n], mr.value) if return_max_ranges else out[:n]
-
-
-# ---- batches ---------------------------------------------------------------------------------
 
 def _outputs(n, want_cost=True):
     return (np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.float64) if want_cost else None, np.zeros(n, dtype=np.uint8))
@@ -194,43 +135,6 @@ def _pose_args(poses):
     return POSE_CS, arr, None, len(arr), arr
 
 
-def polygon_batch(cmap: Costmap, poly, poses, shape=SHAPE_AREA, op=OP_IS_FREE, first=0, count=None, threads=1) -> Result:
-    xy = polygon_xy(poly)
-    fmt, arr, lat, total, _keep = _pose_args(poses)
-    n = total - first if count is None else count
-    free, cost, status = _outputs(n)
-    read = C.c_int64(0)
-    m = cmap.c()
-    rc = lib().oracle_polygon_batch(C.byref(m), _p(xy), C.c_int32(xy.size // 2), C.c_int32(shape), C.c_int32(op),
-                                    C.c_int32(fmt), _p(arr), lat, C.c_int64(first), C.c_int64(n), _p(free), _p(cost),
-                                    _p(status), C.byref(read), C.c_int32(threads))
-    if rc != 0:
-        raise ValueError("oracle_polygon_batch failed (resolution must be positive)")
-    return Result(free, cost, status, read.value)
-
-
-def rays_batch(cmap: Costmap, segments, offset=None, op=OP_IS_FREE, threads=1) -> Result:
-    seg = np.ascontiguousarray(segments, dtype=np.int32).reshape(-1, 4)
-    off = None if offset is None else np.ascontiguousarray(offset, dtype=np.int32)
-    free, cost, status = _outputs(len(seg))
-    read = C.c_int64(0)
-    m = cmap.c()
-    lib().oracle_rays_batch(C.byref(m), _p(seg), C.c_int64(len(seg)), _p(off), C.c_int32(op), _p(free), _p(cost),
-                            _p(status), C.byref(read), C.c_int32(threads))
-    return Result(free, cost, status, read.value)
-
-
-def cells_batch(cmap: Costmap, cells, offsets, op=OP_IS_FREE, threads=1) -> Result:
-    cl = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 2)
-    off = np.ascontiguousarray(offsets, dtype=np.int32).reshape(-1, 2)
-    free, cost, status = _outputs(len(off))
-    read = C.c_int64(0)
-    m = cmap.c()
-    lib().oracle_cells_batch(C.byref(m), _p(cl), C.c_int64(len(cl)), _p(off), C.c_int64(len(off)), C.c_int32(op),
-                             _p(free), _p(cost), _p(status), C.byref(read), C.c_int32(threads))
-    return Result(free, cost, status, read.value)
-
-
 def pack_polygons(polys):
     """list of [2, V_k] -> (flat column-major xy, starts[int32, K+1])."""
     starts = np.zeros(len(polys) + 1, dtype=np.int32)
@@ -243,54 +147,187 @@ def pack_polygons(polys):
     return np.ascontiguousarray(xy, dtype=np.float64), starts
 
 
-def make_discrete_footprint(res, outlines, areas):
-    """generator_footprint::init + discrete_footprint::init: returns (outline_cells[No,2], area_cells[Na,2])."""
-    oxy, ost = pack_polygons(outlines)
-    axy, ast = pack_polygons(areas)
-    no, na = C.c_int64(0), C.c_int64(0)
-    args = (C.c_double(res), _p(oxy), _p(ost), C.c_int32(len(outlines)), _p(axy), _p(ast), C.c_int32(len(areas)))
-    rc = lib().oracle_make_discrete_footprint(*args, None, C.byref(no), None, C.byref(na))
-    if rc == -2:
-        raise RuntimeError("Even number of line-pairs expected")
-    if rc != 0:
-        raise ValueError("The resolution must be positive")
-    oc = np.empty((max(no.value, 1), 2), dtype=np.int32)
-    ac = np.empty((max(na.value, 1), 2), dtype=np.int32)
-    lib().oracle_make_discrete_footprint(*args, _p(oc), C.byref(no), _p(ac), C.byref(na))
-    return oc[:no.value], ac[:na.value]
 
 
-def discrete_footprint_batch(cmap: Costmap, bank, offsets, which=None, threads=1) -> Result:
-    """bank: list of (outline_cells[No,2], area_cells[Na,2]); which[i] selects the footprint of pose i."""
-    o_starts = np.zeros(len(bank) + 1, dtype=np.int64)
-    a_starts = np.zeros(len(bank) + 1, dtype=np.int64)
-    for k, (o, a) in enumerate(bank):
-        o_starts[k + 1] = o_starts[k] + len(o)
-        a_starts[k + 1] = a_starts[k] + len(a)
-    oc = np.ascontiguousarray(np.concatenate([np.asarray(o, dtype=np.int32).reshape(-1, 2) for o, _ in bank]))
-    ac = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.int32).reshape(-1, 2) for _, a in bank]))
-    off = np.ascontiguousarray(offsets, dtype=np.int32).reshape(-1, 2)
-    wh = None if which is None else np.ascontiguousarray(which, dtype=np.int32)
-    free, _, status = _outputs(len(off), want_cost=False)
-    read = C.c_int64(0)
-    m = cmap.c()
-    lib().oracle_discrete_footprint_batch(C.byref(m), _p(oc), _p(o_starts), _p(ac), _p(a_starts), C.c_int32(len(bank)),
-                                          _p(off), _p(wh), C.c_int64(len(off)), _p(free), _p(status), C.byref(read),
-                                          C.c_int32(threads))
-    return Result(free, None, status, read.value)
+class Backend:
+    """One loaded checker library: the restatement (liboracle.so) or the reference itself (oracle/_ref)."""
+
+    def __init__(self, path, name):
+        self.path, self.name = path, name
+        self._lib = C.CDLL(path)
+        self._lib.oracle_ray_cells.restype = C.c_int64
+        self._lib.oracle_outline_cells.restype = C.c_int64
+        self._lib.oracle_area_cells.restype = C.c_int64
+
+    def to_discrete(self, res, poly) -> np.ndarray:
+        xy = polygon_xy(poly)
+        n = xy.size // 2
+        out = np.empty((n, 2), dtype=np.int32)
+        rc = self._lib.oracle_to_discrete(C.c_double(res), _p(xy), C.c_int64(n), _p(out))
+        if rc != 0:
+            raise ValueError("The resolution must be positive")
+        return out
 
 
-def continuous_footprint_batch(cmap: Costmap, outlines, areas, poses, first=0, count=None, threads=1) -> Result:
-    oxy, ost = pack_polygons(outlines)
-    axy, ast = pack_polygons(areas)
-    fmt, arr, lat, total, _keep = _pose_args(poses)
-    n = total - first if count is None else count
-    free, _, status = _outputs(n, want_cost=False)
-    read = C.c_int64(0)
-    m = cmap.c()
-    rc = lib().oracle_continuous_footprint_batch(C.byref(m), _p(oxy), _p(ost), C.c_int32(len(outlines)), _p(axy), _p(ast),
-                                                 C.c_int32(len(areas)), C.c_int32(fmt), _p(arr), lat, C.c_int64(first),
-                                                 C.c_int64(n), _p(free), _p(status), C.byref(read), C.c_int32(threads))
-    if rc != 0:
-        raise ValueError("oracle_continuous_footprint_batch failed")
-    return Result(free, None, status, read.value)
+
+    def ray_cells(self, b, e) -> np.ndarray:
+        cap = max(abs(e[0] - b[0]), abs(e[1] - b[1])) + 1
+        out = np.empty((cap, 2), dtype=np.int32)
+        n = self._lib.oracle_ray_cells(int(b[0]), int(b[1]), int(e[0]), int(e[1]), _p(out), C.c_int64(cap))
+        return out[:n]
+
+
+
+    def outline_cells(self, sparse) -> np.ndarray:
+        s = np.ascontiguousarray(sparse, dtype=np.int32).reshape(-1, 2)
+        n = self._lib.oracle_outline_cells(_p(s), C.c_int64(len(s)), None, C.c_int64(0))
+        out = np.empty((max(n, 1), 2), dtype=np.int32)
+        self._lib.oracle_outline_cells(_p(s), C.c_int64(len(s)), _p(out), C.c_int64(n))
+        return out[:n]
+
+
+
+    def area_cells(self, dense_outlines, return_max_ranges=False):
+        """dense_outlines: list of [n_i, 2] int arrays (each a dense closed outline). Raises RuntimeError for
+        the reference's std::logic_error."""
+        outs = [np.ascontiguousarray(o, dtype=np.int32).reshape(-1, 2) for o in dense_outlines]
+        sizes = np.array([len(o) for o in outs], dtype=np.int64)
+        cat = np.concatenate(outs) if outs else np.empty((0, 2), dtype=np.int32)
+        cat = np.ascontiguousarray(cat)
+        mr = C.c_int32(0)
+        n = self._lib.oracle_area_cells(_p(cat), _p(sizes), C.c_int32(len(outs)), None, C.c_int64(0), C.byref(mr))
+        if n < 0:
+            raise RuntimeError("Even number of line-pairs expected")
+        out = np.empty((max(n, 1), 2), dtype=np.int32)
+        self._lib.oracle_area_cells(_p(cat), _p(sizes), C.c_int32(len(outs)), _p(out), C.c_int64(n), C.byref(mr))
+        return (out[:n], mr.value) if return_max_ranges else out[:n]
+
+
+
+    def polygon_batch(self, cmap: Costmap, poly, poses, shape=SHAPE_AREA, op=OP_IS_FREE, first=0, count=None, threads=1) -> Result:
+        xy = polygon_xy(poly)
+        fmt, arr, lat, total, _keep = _pose_args(poses)
+        n = total - first if count is None else count
+        free, cost, status = _outputs(n)
+        read = C.c_int64(0)
+        m = cmap.c()
+        rc = self._lib.oracle_polygon_batch(C.byref(m), _p(xy), C.c_int32(xy.size // 2), C.c_int32(shape), C.c_int32(op),
+                                        C.c_int32(fmt), _p(arr), lat, C.c_int64(first), C.c_int64(n), _p(free), _p(cost),
+                                        _p(status), C.byref(read), C.c_int32(threads))
+        if rc != 0:
+            raise ValueError("oracle_polygon_batch failed (resolution must be positive)")
+        return Result(free, cost, status, read.value)
+
+
+
+    def rays_batch(self, cmap: Costmap, segments, offset=None, op=OP_IS_FREE, threads=1) -> Result:
+        seg = np.ascontiguousarray(segments, dtype=np.int32).reshape(-1, 4)
+        off = None if offset is None else np.ascontiguousarray(offset, dtype=np.int32)
+        free, cost, status = _outputs(len(seg))
+        read = C.c_int64(0)
+        m = cmap.c()
+        self._lib.oracle_rays_batch(C.byref(m), _p(seg), C.c_int64(len(seg)), _p(off), C.c_int32(op), _p(free), _p(cost),
+                                _p(status), C.byref(read), C.c_int32(threads))
+        return Result(free, cost, status, read.value)
+
+
+
+    def cells_batch(self, cmap: Costmap, cells, offsets, op=OP_IS_FREE, threads=1) -> Result:
+        cl = np.ascontiguousarray(cells, dtype=np.int32).reshape(-1, 2)
+        off = np.ascontiguousarray(offsets, dtype=np.int32).reshape(-1, 2)
+        free, cost, status = _outputs(len(off))
+        read = C.c_int64(0)
+        m = cmap.c()
+        self._lib.oracle_cells_batch(C.byref(m), _p(cl), C.c_int64(len(cl)), _p(off), C.c_int64(len(off)), C.c_int32(op),
+                                 _p(free), _p(cost), _p(status), C.byref(read), C.c_int32(threads))
+        return Result(free, cost, status, read.value)
+
+
+
+    def make_discrete_footprint(self, res, outlines, areas):
+        """generator_footprint::init + discrete_footprint::init: returns (outline_cells[No,2], area_cells[Na,2])."""
+        oxy, ost = pack_polygons(outlines)
+        axy, ast = pack_polygons(areas)
+        no, na = C.c_int64(0), C.c_int64(0)
+        args = (C.c_double(res), _p(oxy), _p(ost), C.c_int32(len(outlines)), _p(axy), _p(ast), C.c_int32(len(areas)))
+        rc = self._lib.oracle_make_discrete_footprint(*args, None, C.byref(no), None, C.byref(na))
+        if rc == -2:
+            raise RuntimeError("Even number of line-pairs expected")
+        if rc != 0:
+            raise ValueError("The resolution must be positive")
+        oc = np.empty((max(no.value, 1), 2), dtype=np.int32)
+        ac = np.empty((max(na.value, 1), 2), dtype=np.int32)
+        self._lib.oracle_make_discrete_footprint(*args, _p(oc), C.byref(no), _p(ac), C.byref(na))
+        return oc[:no.value], ac[:na.value]
+
+
+
+    def discrete_footprint_batch(self, cmap: Costmap, bank, offsets, which=None, threads=1) -> Result:
+        """bank: list of (outline_cells[No,2], area_cells[Na,2]); which[i] selects the footprint of pose i."""
+        o_starts = np.zeros(len(bank) + 1, dtype=np.int64)
+        a_starts = np.zeros(len(bank) + 1, dtype=np.int64)
+        for k, (o, a) in enumerate(bank):
+            o_starts[k + 1] = o_starts[k] + len(o)
+            a_starts[k + 1] = a_starts[k] + len(a)
+        oc = np.ascontiguousarray(np.concatenate([np.asarray(o, dtype=np.int32).reshape(-1, 2) for o, _ in bank]))
+        ac = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.int32).reshape(-1, 2) for _, a in bank]))
+        off = np.ascontiguousarray(offsets, dtype=np.int32).reshape(-1, 2)
+        wh = None if which is None else np.ascontiguousarray(which, dtype=np.int32)
+        free, _, status = _outputs(len(off), want_cost=False)
+        read = C.c_int64(0)
+        m = cmap.c()
+        self._lib.oracle_discrete_footprint_batch(C.byref(m), _p(oc), _p(o_starts), _p(ac), _p(a_starts), C.c_int32(len(bank)),
+                                              _p(off), _p(wh), C.c_int64(len(off)), _p(free), _p(status), C.byref(read),
+                                              C.c_int32(threads))
+        return Result(free, None, status, read.value)
+
+
+
+    def continuous_footprint_batch(self, cmap: Costmap, outlines, areas, poses, first=0, count=None, threads=1) -> Result:
+        oxy, ost = pack_polygons(outlines)
+        axy, ast = pack_polygons(areas)
+        fmt, arr, lat, total, _keep = _pose_args(poses)
+        n = total - first if count is None else count
+        free, _, status = _outputs(n, want_cost=False)
+        read = C.c_int64(0)
+        m = cmap.c()
+        rc = self._lib.oracle_continuous_footprint_batch(C.byref(m), _p(oxy), _p(ost), C.c_int32(len(outlines)), _p(axy), _p(ast),
+                                                     C.c_int32(len(areas)), C.c_int32(fmt), _p(arr), lat, C.c_int64(first),
+                                                     C.c_int64(n), _p(free), _p(status), C.byref(read), C.c_int32(threads))
+        if rc != 0:
+            raise ValueError("oracle_continuous_footprint_batch failed")
+        return Result(free, None, status, read.value)
+
+
+
+_default = None
+_reference = None
+REF_LIB_PATH = os.path.join(_HERE, "_ref", "libcover_ref.so")
+
+
+def default() -> Backend:
+    """The CPU restatement (always available: built on demand with g++)."""
+    global _default
+    if _default is None:
+        _default = Backend(build(), "port")
+    return _default
+
+
+def reference():
+    """The reference's own sources compiled over shim headers, or None when oracle/_ref was not built
+    (it is built in the authoring container where /root/reference exists and travels with gpurun)."""
+    global _reference
+    if _reference is None and os.path.exists(REF_LIB_PATH):
+        _reference = Backend(REF_LIB_PATH, "reference")
+    return _reference
+
+
+def _delegate(name):
+    def f(*a, **k):
+        return getattr(default(), name)(*a, **k)
+    f.__name__ = name
+    return f
+
+
+for _n in ['to_discrete', 'ray_cells', 'outline_cells', 'area_cells', 'polygon_batch', 'rays_batch', 'cells_batch', 'make_discrete_footprint', 'discrete_footprint_batch', 'continuous_footprint_batch']:
+    globals()[_n] = _delegate(_n)

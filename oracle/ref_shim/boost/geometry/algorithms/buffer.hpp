@@ -1,0 +1,2 @@
+#pragma once
+#include <boost/geometry/geometry.hpp>
