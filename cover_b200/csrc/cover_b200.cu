@@ -1,0 +1,1026 @@
+// cover_b200.cu — kernels and the C ABI (include/cover_b200.h) of the batched footprint checker.
+//
+// One THREAD per pose.  Adjacent threads take adjacent poses, so on a pose lattice (x fastest) a warp
+// walks 32 copies of the same outline shifted by one cell: control flow is uniform and every load of the
+// warp falls into one or two 32-byte sectors of the costmap.  The costmap (<= 64 MB) lives in the 126 MB
+// L2; HBM only sees the first touch.  Kernels:
+//   k_outline<OP>       outline_generator checks   (a5 + a10/a13)
+//   k_area_packed<OP>   area checks, rows with <= 2 ranges: packed shared-memory row table
+//   k_area_list<OP>     area checks, any polygon: sorted per-row lists in global scratch (persistent grid);
+//                       also drains the poses k_area_packed could not finish
+//   k_rays<OP>          ray_generator checks       (a4)
+//   k_cells<OP>         cached discrete_polygon x offsets (a11)
+//   k_footprints        discrete/generator footprint bank x offsets (a15/a16)
+//   k_split             continuous_footprint::is_free (a14)
+// There is no CPU path in this file: without a CUDA device every entry returns COVER_E_CUDA.
+#include "../../include/cover_b200.h"
+#include "device_core.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace cvr;
+
+namespace {
+
+constexpr int kBlock = 128;
+constexpr int kPackedMaxRows = 96;      // 96 rows x 128 threads x 4 B = 48 KB of shared memory
+constexpr int kPackedMaxWidth = 32000;  // 15-bit relative x
+
+// ===================================================================================================
+// Kernels
+// ===================================================================================================
+
+/// Copies the polygon (column-major xy) into shared memory; returns the pointer.
+__device__ __forceinline__ double* stage_polygon(const double* __restrict__ poly, int nv, double* smem) {
+  for (int i = threadIdx.x; i < 2 * nv; i += blockDim.x) smem[i] = poly[i];
+  __syncthreads();
+  return smem;
+}
+
+template <int OP>
+struct CellSink {
+  Fold<OP> fold;
+  const MapView& m;
+  int ox, oy;
+  __device__ __forceinline__ CellSink(const MapView& mv, int offx = 0, int offy = 0) : m(mv), ox(offx), oy(offy) {}
+  __device__ __forceinline__ bool cell(int x, int y) { return fold.cell(m, x + ox, y + oy); }
+};
+
+template <int OP>
+__global__ void __launch_bounds__(kBlock) k_outline(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
+                                                   long long count, OutView out) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv, smem_d);
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const Pose T = load_pose(src, i);
+  int x0, y0, x1, y1;
+  bool ok;
+  CellSink<OP> sink(m);
+  if (src.format == POSE_NONE) {
+    ok = polygon_bbox<XF_NONE>(poly, nv, T, m, x0, y0, x1, y1);
+    if (ok) walk_outline<XF_NONE>(poly, nv, T, m, sink);
+  } else {
+    ok = polygon_bbox<XF_PATH_A>(poly, nv, T, m, x0, y0, x1, y1);
+    if (ok) walk_outline<XF_PATH_A>(poly, nv, T, m, sink);
+  }
+  if (!ok) {
+    store_failure(out, i, ST_COORD_RANGE);
+    return;
+  }
+  sink.fold.store(out, i);
+  if (out.status) out.status[i] = ST_OK;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kBlock) k_area_packed(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
+                                                       long long count, OutView out, int rows_cap, unsigned int* __restrict__ todo,
+                                                       unsigned int* __restrict__ todo_count) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv, smem_d);
+  uint32_t* table = reinterpret_cast<uint32_t*>(smem_d + 2 * nv);
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const Pose T = load_pose(src, i);
+  const bool none = src.format == POSE_NONE;
+  int x0, y0, x1, y1;
+  const bool ok = none ? polygon_bbox<XF_NONE>(poly, nv, T, m, x0, y0, x1, y1) : polygon_bbox<XF_PATH_A>(poly, nv, T, m, x0, y0, x1, y1);
+  if (!ok) {
+    store_failure(out, i, ST_COORD_RANGE);
+    return;
+  }
+  if (nv == 0) {  // empty generator: nothing is lethal, the sum is 0
+    Fold<OP> fold;
+    fold.store(out, i);
+    if (out.status) out.status[i] = ST_OK;
+    return;
+  }
+  const int rows = y1 - y0 + 1;
+  bool defer = rows > rows_cap || (x1 - x0) > kPackedMaxWidth;
+  PackedStore store{table + threadIdx.x, static_cast<int>(blockDim.x), x0, y0};
+  if (!defer) {
+    store.clear(rows);
+    RunDetector<PackedStore> runs(store, 0, x0, x1);
+    if (none) walk_outline<XF_NONE>(poly, nv, T, m, runs);
+    else walk_outline<XF_PATH_A>(poly, nv, T, m, runs);
+    runs.finish();
+    defer = store.overflow;
+  }
+  if (defer) {  // more than two ranges on some row: the list kernel finishes this pose
+    todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i);
+    return;
+  }
+  bool odd = false;
+  for (int r = 0; r < rows; ++r) odd |= (store.tab[r * store.stride] >> 30) == 1u;
+  if (odd) {  // std::logic_error("Even number of line-pairs expected")
+    store_failure(out, i, ST_LOGIC_ERROR);
+    return;
+  }
+  Fold<OP> fold;
+  for (int r = 0; r < rows; ++r) {
+    const uint32_t w = store.tab[r * store.stride];
+    if ((w >> 30) != 2u) continue;
+    if (!fold.span(m, y0 + r, x0 + static_cast<int>(w & 0x7FFFu), x0 + static_cast<int>((w >> 15) & 0x7FFFu))) break;
+  }
+  fold.store(out, i);
+  if (out.status) out.status[i] = ST_OK;
+}
+
+struct ListScratch {
+  int* cnt;
+  int2* rng;
+  int* seq;
+  int rows_cap;
+};
+
+/// Validates the per-row lists and folds the merged pairs in generator order (rows ascending, pairs in
+/// sorted order).  Returns the status.
+template <class FoldT>
+__device__ __forceinline__ int fold_list_rows(const ListStore& store, int rows, const MapView& m, FoldT& fold) {
+  if (store.out_of_rows) return ST_COORD_RANGE;
+  bool odd = false;
+  for (int r = 0; r < rows; ++r) odd |= (store.cnt[static_cast<long long>(r) * store.nthreads + store.me] & 1) != 0;
+  if (odd) return ST_LOGIC_ERROR;
+  if (store.overflow) return ST_ROW_COMPLEXITY;
+  for (int r = 0; r < rows; ++r) {
+    const int n = store.cnt[static_cast<long long>(r) * store.nthreads + store.me];
+    for (int k = 0; k < n; k += 2) {
+      const int lo = store.rng[store.at(r, k)].x, hi = store.rng[store.at(r, k + 1)].y;
+      if (!fold.span(m, store.yb + r, lo, hi)) return ST_OK;
+    }
+  }
+  return ST_OK;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kBlock) k_area_list(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
+                                                     long long count, OutView out, ListScratch scratch,
+                                                     const unsigned int* __restrict__ todo,
+                                                     const unsigned int* __restrict__ todo_count) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv, smem_d);
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long me = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n_items = todo ? static_cast<long long>(*todo_count) : count;
+  const bool none = src.format == POSE_NONE;
+  for (long long item = me; item < n_items; item += nthreads) {
+    const long long i = todo ? static_cast<long long>(todo[item]) : item;
+    const Pose T = load_pose(src, i);
+    int x0, y0, x1, y1;
+    const bool ok = none ? polygon_bbox<XF_NONE>(poly, nv, T, m, x0, y0, x1, y1) : polygon_bbox<XF_PATH_A>(poly, nv, T, m, x0, y0, x1, y1);
+    if (!ok) {
+      store_failure(out, i, ST_COORD_RANGE);
+      continue;
+    }
+    Fold<OP> fold;
+    int status = ST_OK;
+    if (nv > 0) {
+      const int rows = y1 - y0 + 1;
+      if (rows > scratch.rows_cap) {
+        status = ST_COORD_RANGE;
+      } else {
+        ListStore store{scratch.cnt, scratch.rng, scratch.seq, nthreads, me, y0, scratch.rows_cap};
+        store.clear(rows);
+        RunDetector<ListStore> runs(store, 0, x0, x1);
+        if (none) walk_outline<XF_NONE>(poly, nv, T, m, runs);
+        else walk_outline<XF_PATH_A>(poly, nv, T, m, runs);
+        runs.finish();
+        status = fold_list_rows(store, rows, m, fold);
+      }
+    }
+    if (status != ST_OK) {
+      store_failure(out, i, status);
+    } else {
+      fold.store(out, i);
+      if (out.status) out.status[i] = ST_OK;
+    }
+  }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kBlock) k_rays(MapView m, const int4* __restrict__ segments, long long count, int offx, int offy,
+                                                OutView out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int4 s = __ldg(segments + i);
+  CellSink<OP> sink(m, offx, offy);
+  walk_ray(s.x, s.y, s.z, s.w, sink);
+  sink.fold.store(out, i);
+  if (out.status) out.status[i] = ST_OK;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kBlock) k_cells(MapView m, const int2* __restrict__ cells, long long n_cells,
+                                                 const int2* __restrict__ offsets, long long count, OutView out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int2 off = __ldg(offsets + i);
+  Fold<OP> fold;
+  for (long long j = 0; j < n_cells; ++j) {
+    const int2 c = __ldg(cells + j);
+    if (!fold.cell(m, c.x + off.x, c.y + off.y)) break;
+  }
+  fold.store(out, i);
+  if (out.status) out.status[i] = ST_OK;
+}
+
+/// discrete_footprint::is_free(offset, map): outline cells collide on 253/254/outside, area cells on
+/// 254/outside (footprints.cpp:240-247).
+__global__ void __launch_bounds__(kBlock) k_footprints(MapView m, const int2* __restrict__ ocells, const long long* __restrict__ ostarts,
+                                                      const int2* __restrict__ acells, const long long* __restrict__ astarts,
+                                                      const int2* __restrict__ offsets, const int* __restrict__ which, long long count,
+                                                      OutView out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int2 off = __ldg(offsets + i);
+  const int k = which ? __ldg(which + i) : 0;
+  bool hit = false;
+  for (long long j = __ldg(ostarts + k), e = __ldg(ostarts + k + 1); j < e && !hit; ++j) {
+    const int2 c = __ldg(ocells + j);
+    const int x = c.x + off.x, y = c.y + off.y;
+    if (static_cast<unsigned>(x) >= static_cast<unsigned>(m.size_x) || static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y)) {
+      hit = true;
+    } else {
+      const int v = __ldg(m.data + static_cast<size_t>(y) * m.pitch + x);
+      hit = v == kInscribed || v == kLethal;
+    }
+  }
+  for (long long j = __ldg(astarts + k), e = __ldg(astarts + k + 1); j < e && !hit; ++j) {
+    const int2 c = __ldg(acells + j);
+    const int x = c.x + off.x, y = c.y + off.y;
+    hit = static_cast<unsigned>(x) >= static_cast<unsigned>(m.size_x) || static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) ||
+          __ldg(m.data + static_cast<size_t>(y) * m.pitch + x) == kLethal;
+  }
+  if (out.is_free) out.is_free[i] = hit ? 0 : 1;
+  if (out.status) out.status[i] = ST_OK;
+}
+
+/// Sink of continuous_footprint's outline loop: raw getCost, collide on 253 or 254 (footprints.cpp:166-173).
+struct InflatedSink {
+  const MapView& m;
+  bool hit = false;
+  __device__ __forceinline__ explicit InflatedSink(const MapView& mv) : m(mv) {}
+  __device__ __forceinline__ bool cell(int x, int y) {
+    const int v = __ldg(m.data + static_cast<size_t>(y) * m.pitch + x);
+    hit = v == kInscribed || v == kLethal;
+    return !hit;
+  }
+};
+
+struct SplitView {
+  const double* xy;     // all vertices, outlines first, then areas (column-major)
+  const int* starts;    // n_outlines + n_areas + 1 vertex offsets
+  int n_outlines, n_areas;
+};
+
+/// continuous_footprint::is_free(pose, map) — footprints.cpp:130-196.
+__global__ void __launch_bounds__(kBlock) k_split(MapView m, SplitView fp, int n_vertices_total, PoseSource src, long long count,
+                                                 OutView out, ListScratch scratch) {
+  extern __shared__ double smem_d[];
+  const double* xy = stage_polygon(fp.xy, n_vertices_total, smem_d);
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long me = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (long long i = me; i < count; i += nthreads) {
+    Pose T = load_pose(src, i);
+    T.tx = __dadd_rn(T.tx, -m.origin_x);  // Translation2d(-origin) * pose: translation += (-origin)
+    T.ty = __dadd_rn(T.ty, -m.origin_y);
+    const int n_polys = fp.n_outlines + fp.n_areas;
+    bool in_range = true;
+    for (int k = 0; k < n_polys; ++k) {
+      int a, b, c, d;
+      in_range &= polygon_bbox<XF_PATH_B>(xy + 2 * fp.starts[k], fp.starts[k + 1] - fp.starts[k], T, m, a, b, c, d);
+    }
+    if (!in_range) {
+      store_failure(out, i, ST_COORD_RANGE);
+      continue;
+    }
+    bool free_ = true;
+    int status = ST_OK;
+    for (int k = 0; k < n_polys && free_ && status == ST_OK; ++k) {
+      const double* poly = xy + 2 * fp.starts[k];
+      const int nv = fp.starts[k + 1] - fp.starts[k];
+      if (nv == 0) continue;
+      int x0, y0, x1, y1;
+      polygon_bbox<XF_PATH_B>(poly, nv, T, m, x0, y0, x1, y1);
+      if (x0 < 0 || y0 < 0 || x1 >= m.size_x || y1 >= m.size_y) {  // footprints.cpp:139-155
+        free_ = false;
+        break;
+      }
+      if (k < fp.n_outlines) {
+        InflatedSink sink(m);
+        walk_outline<XF_PATH_B>(poly, nv, T, m, sink);
+        free_ = !sink.hit;
+      } else {
+        const int rows = y1 - y0 + 1;
+        if (rows > scratch.rows_cap) {
+          status = ST_COORD_RANGE;
+          break;
+        }
+        ListStore store{scratch.cnt, scratch.rng, scratch.seq, nthreads, me, y0, scratch.rows_cap};
+        store.clear(rows);
+        RunDetector<ListStore> runs(store, 0, x0, x1);
+        walk_outline<XF_PATH_B>(poly, nv, T, m, runs);
+        runs.finish();
+        Fold<OP_IS_FREE> fold;
+        status = fold_list_rows(store, rows, m, fold);
+        free_ = !fold.hit;
+      }
+    }
+    if (status != ST_OK) {
+      store_failure(out, i, status);
+    } else {
+      if (out.is_free) out.is_free[i] = free_ ? 1 : 0;
+      if (out.status) out.status[i] = ST_OK;
+    }
+  }
+}
+
+// ===================================================================================================
+// Host side
+// ===================================================================================================
+
+struct DeviceBuffer {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    const cudaError_t e = cudaMalloc(&ptr, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return static_cast<T*>(ptr);
+  }
+};
+
+}  // namespace
+
+struct cover_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  int64_t launches = 0;
+  DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, todo, todo_count, list_cnt, list_rng, list_seq;
+};
+
+struct cover_map {
+  cover_ctx* ctx;
+  MapView view;
+  uint8_t* dev;
+  double resolution;
+};
+
+struct cover_cells {
+  cover_ctx* ctx;
+  int2* dev;
+  int64_t n;
+};
+
+struct cover_footprints {
+  cover_ctx* ctx;
+  int2 *ocells, *acells;
+  long long *ostarts, *astarts;
+  int32_t n;
+};
+
+struct cover_split {
+  cover_ctx* ctx;
+  double* xy;
+  int* starts;
+  int32_t n_outlines, n_areas, n_vertices;
+  double max_area_diameter;
+};
+
+namespace {
+
+int fail(cover_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->error = msg;
+  return code;
+}
+
+int cuda_fail(cover_ctx* ctx, cudaError_t e, const char* what) {
+  return fail(ctx, e == cudaErrorMemoryAllocation ? COVER_E_NOMEM : COVER_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(call)                                                 \
+  do {                                                           \
+    const cudaError_t e_ = (call);                               \
+    if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);     \
+  } while (0)
+
+struct Bind {  // makes `device` current for the duration of a call
+  int prev = -1;
+  explicit Bind(int device) {
+    cudaGetDevice(&prev);
+    if (prev != device) cudaSetDevice(device);
+    else prev = -1;
+  }
+  ~Bind() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+/// Results staged on the device when the caller's arrays are host memory.
+struct OutStage {
+  OutView dev{nullptr, nullptr, nullptr};
+  const cover_results* user = nullptr;
+  bool host = false;
+};
+
+int stage_out(cover_ctx* ctx, const cover_results* out, int64_t count, OutStage& st) {
+  st.user = out;
+  if (!out) return fail(ctx, COVER_E_INVALID_ARG, "results must not be NULL");
+  st.host = out->mem == COVER_MEM_HOST;
+  if (!st.host) {
+    st.dev = OutView{out->is_free, out->cost, out->status};
+    return COVER_OK;
+  }
+  const size_t n = static_cast<size_t>(std::max<int64_t>(count, 1));
+  if (out->is_free) {
+    CU(ctx->out_free.ensure(n));
+    st.dev.is_free = ctx->out_free.as<uint8_t>();
+  }
+  if (out->cost) {
+    CU(ctx->out_cost.ensure(n * sizeof(double)));
+    st.dev.cost = ctx->out_cost.as<double>();
+  }
+  if (out->status) {
+    CU(ctx->out_status.ensure(n));
+    st.dev.status = ctx->out_status.as<uint8_t>();
+  }
+  return COVER_OK;
+}
+
+int finish_out(cover_ctx* ctx, const OutStage& st, int64_t count) {
+  CU(cudaGetLastError());
+  if (!st.host) return COVER_OK;
+  const size_t n = static_cast<size_t>(count);
+  if (n) {
+    if (st.user->is_free) CU(cudaMemcpyAsync(st.user->is_free, st.dev.is_free, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (st.user->cost) CU(cudaMemcpyAsync(st.user->cost, st.dev.cost, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (st.user->status) CU(cudaMemcpyAsync(st.user->status, st.dev.status, n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return COVER_OK;
+}
+
+int stage_poses(cover_ctx* ctx, const cover_poses* poses, PoseSource& src) {
+  if (!poses) return fail(ctx, COVER_E_INVALID_ARG, "poses must not be NULL");
+  if (poses->count < 0) return fail(ctx, COVER_E_INVALID_ARG, "negative pose count");
+  std::memset(&src, 0, sizeof(src));
+  src.format = poses->format;
+  switch (poses->format) {
+    case COVER_POSE_CS: {
+      if (poses->count && !poses->data) return fail(ctx, COVER_E_INVALID_ARG, "POSE_CS needs data");
+      if (poses->mem == COVER_MEM_DEVICE) {
+        src.cs = static_cast<const double*>(poses->data);
+      } else {
+        const size_t bytes = static_cast<size_t>(poses->count) * 4 * sizeof(double);
+        CU(ctx->poses.ensure(std::max<size_t>(bytes, 32)));
+        if (bytes) CU(cudaMemcpyAsync(ctx->poses.ptr, poses->data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        src.cs = ctx->poses.as<double>();
+      }
+      return COVER_OK;
+    }
+    case COVER_POSE_LATTICE: {
+      const cover_lattice& L = poses->lattice;
+      if (L.nx <= 0 || L.ny <= 0 || L.ntheta <= 0 || !L.cs) return fail(ctx, COVER_E_INVALID_ARG, "bad lattice descriptor");
+      const int64_t total = static_cast<int64_t>(L.nx) * L.ny * L.ntheta;
+      if (poses->first < 0 || poses->first + poses->count > total) return fail(ctx, COVER_E_INVALID_ARG, "lattice range out of bounds");
+      const size_t bytes = static_cast<size_t>(L.ntheta) * 2 * sizeof(double);
+      CU(ctx->theta.ensure(bytes));
+      CU(cudaMemcpyAsync(ctx->theta.ptr, L.cs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+      src.theta_cs = ctx->theta.as<double>();
+      src.first = poses->first;
+      src.x0 = L.x0, src.dx = L.dx, src.y0 = L.y0, src.dy = L.dy;
+      src.nx = L.nx, src.ny = L.ny;
+      return COVER_OK;
+    }
+    case COVER_POSE_NONE:
+      if (poses->count != 1) return fail(ctx, COVER_E_INVALID_ARG, "POSE_NONE is a single check (count must be 1)");
+      return COVER_OK;
+    default:
+      return fail(ctx, COVER_E_INVALID_ARG, "unknown pose format");
+  }
+}
+
+double polygon_diameter(const double* xy, int n) {
+  double best = 0;
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j) best = std::max(best, std::hypot(xy[2 * i] - xy[2 * j], xy[2 * i + 1] - xy[2 * j + 1]));
+  return best;
+}
+
+/// Upper bound of the number of scan rows any rigid pose of a polygon with this diameter can touch.
+int rows_bound(double diameter, double inv_res) { return static_cast<int>(std::ceil(diameter * inv_res * 1.0001)) + 4; }
+
+bool is_convex(const double* xy, int n) {
+  if (n < 3) return true;
+  int sign = 0;
+  for (int i = 0; i < n; ++i) {
+    const double ax = xy[2 * ((i + 1) % n)] - xy[2 * i], ay = xy[2 * ((i + 1) % n) + 1] - xy[2 * i + 1];
+    const double bx = xy[2 * ((i + 2) % n)] - xy[2 * ((i + 1) % n)], by = xy[2 * ((i + 2) % n) + 1] - xy[2 * ((i + 1) % n) + 1];
+    const double cr = ax * by - ay * bx;
+    if (cr > 0) {
+      if (sign < 0) return false;
+      sign = 1;
+    } else if (cr < 0) {
+      if (sign > 0) return false;
+      sign = -1;
+    }
+  }
+  return true;
+}
+
+unsigned int grid_for(int64_t count) { return static_cast<unsigned int>((count + kBlock - 1) / kBlock); }
+
+/// Global scratch of the list store for `nthreads` resident threads.
+int ensure_list_scratch(cover_ctx* ctx, int rows_cap, long long nthreads, ListScratch& s) {
+  const size_t rows = static_cast<size_t>(rows_cap), nt = static_cast<size_t>(nthreads);
+  CU(ctx->list_cnt.ensure(rows * nt * sizeof(int)));
+  CU(ctx->list_rng.ensure(rows * kMaxRanges * nt * sizeof(int2)));
+  CU(ctx->list_seq.ensure(rows * kMaxRanges * nt * sizeof(int)));
+  s = ListScratch{ctx->list_cnt.as<int>(), ctx->list_rng.as<int2>(), ctx->list_seq.as<int>(), rows_cap};
+  return COVER_OK;
+}
+
+/// Persistent grid for the list kernels: at most `blocks_per_sm` blocks per SM, capped so that the
+/// scratch stays below ~2 GB.
+unsigned int list_grid(const cover_ctx* ctx, int64_t items, int rows_cap, int blocks_per_sm) {
+  const size_t per_thread = static_cast<size_t>(rows_cap) * (kMaxRanges * 12 + 4);
+  int64_t blocks = static_cast<int64_t>(ctx->sm_count) * blocks_per_sm;
+  const int64_t cap = std::max<int64_t>(1, static_cast<int64_t>((2ull << 30) / (per_thread * kBlock)));
+  blocks = std::min(blocks, cap);
+  blocks = std::min<int64_t>(blocks, std::max<int64_t>(1, (items + kBlock - 1) / kBlock));
+  return static_cast<unsigned int>(blocks);
+}
+
+enum Shape { SHAPE_OUTLINE = 1, SHAPE_AREA = 2 };
+
+constexpr int kMaxVertices = 4096;                                          // 64 KB of staged polygon
+constexpr int kMaxDynamicSmem = kMaxVertices * 16 + kPackedMaxRows * kBlock * 4;  // 112 KB
+
+/// Opt every kernel that stages a polygon into its dynamic shared-memory budget (once per device).
+cudaError_t configure_kernels() {
+  cudaError_t e = cudaSuccess;
+  auto set = [&e](const void* f) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem);
+  };
+  set(reinterpret_cast<const void*>(&k_outline<OP_IS_FREE>));
+  set(reinterpret_cast<const void*>(&k_outline<OP_ACCUMULATE>));
+  set(reinterpret_cast<const void*>(&k_outline<OP_MAX>));
+  set(reinterpret_cast<const void*>(&k_area_packed<OP_IS_FREE>));
+  set(reinterpret_cast<const void*>(&k_area_packed<OP_ACCUMULATE>));
+  set(reinterpret_cast<const void*>(&k_area_packed<OP_MAX>));
+  set(reinterpret_cast<const void*>(&k_area_list<OP_IS_FREE>));
+  set(reinterpret_cast<const void*>(&k_area_list<OP_ACCUMULATE>));
+  set(reinterpret_cast<const void*>(&k_area_list<OP_MAX>));
+  set(reinterpret_cast<const void*>(&k_split));
+  return e;
+}
+
+template <int OP>
+int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev, const double* poly_host, int nv, int shape,
+                   const PoseSource& src, int64_t count, const OutView& out) {
+  const size_t poly_bytes = static_cast<size_t>(nv) * 2 * sizeof(double);
+  if (count == 0) return COVER_OK;
+  if (shape == SHAPE_OUTLINE) {
+    k_outline<OP><<<grid_for(count), kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out);
+    ++ctx->launches;
+    return COVER_OK;
+  }
+  const int rows_cap = rows_bound(polygon_diameter(poly_host, nv), map->view.inv_res);
+  const bool packed = is_convex(poly_host, nv) && rows_cap <= kPackedMaxRows;
+  ListScratch scratch{};
+  if (packed) {
+    CU(ctx->todo.ensure(static_cast<size_t>(count) * sizeof(unsigned int)));
+    CU(ctx->todo_count.ensure(sizeof(unsigned int)));
+    CU(cudaMemsetAsync(ctx->todo_count.ptr, 0, sizeof(unsigned int), ctx->stream));
+    const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint32_t);
+    k_area_packed<OP><<<grid_for(count), kBlock, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
+                                                                      ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
+    ++ctx->launches;
+    // Drain whatever the packed kernel deferred (usually nothing) with a small persistent grid.
+    const unsigned int grid = list_grid(ctx, count, rows_cap, 1);
+    const int rc = ensure_list_scratch(ctx, rows_cap, static_cast<long long>(grid) * kBlock, scratch);
+    if (rc) return rc;
+    k_area_list<OP><<<grid, kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, scratch,
+                                                             ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
+    ++ctx->launches;
+  } else {
+    const unsigned int grid = list_grid(ctx, count, rows_cap, 4);
+    const int rc = ensure_list_scratch(ctx, rows_cap, static_cast<long long>(grid) * kBlock, scratch);
+    if (rc) return rc;
+    k_area_list<OP><<<grid, kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, scratch, nullptr, nullptr);
+    ++ctx->launches;
+  }
+  return COVER_OK;
+}
+
+int polygon_check(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t nv, int shape, int op,
+                  const cover_poses* poses, const cover_results* out) {
+  if (!ctx) return COVER_E_INVALID_ARG;
+  if (!map || map->ctx != ctx) return fail(ctx, COVER_E_INVALID_ARG, "map does not belong to this context");
+  if (nv < 0 || (nv > 0 && !polygon_xy)) return fail(ctx, COVER_E_INVALID_ARG, "bad polygon");
+  if (nv > kMaxVertices) return fail(ctx, COVER_E_UNSUPPORTED, "polygons with more than 4096 vertices are not supported");
+  Bind bind(ctx->device);
+  PoseSource src;
+  int rc = stage_poses(ctx, poses, src);
+  if (rc) return rc;
+  OutStage st;
+  rc = stage_out(ctx, out, poses->count, st);
+  if (rc) return rc;
+  const size_t poly_bytes = static_cast<size_t>(nv) * 2 * sizeof(double);
+  CU(ctx->poly.ensure(std::max<size_t>(poly_bytes, 16)));
+  if (poly_bytes) CU(cudaMemcpyAsync(ctx->poly.ptr, polygon_xy, poly_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const double* pd = ctx->poly.as<double>();
+  switch (op) {
+    case OP_IS_FREE: rc = launch_polygon<OP_IS_FREE>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev); break;
+    case OP_ACCUMULATE: rc = launch_polygon<OP_ACCUMULATE>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev); break;
+    default: rc = launch_polygon<OP_MAX>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev); break;
+  }
+  if (rc) return rc;
+  return finish_out(ctx, st, poses->count);
+}
+
+/// Copies a host or device int array into a context buffer when needed; returns the device pointer.
+template <class T>
+int stage_array(cover_ctx* ctx, DeviceBuffer& buf, const T* data, size_t n, int mem, const T** dev) {
+  if (mem == COVER_MEM_DEVICE) {
+    *dev = data;
+    return COVER_OK;
+  }
+  CU(buf.ensure(std::max<size_t>(n * sizeof(T), 16)));
+  if (n) CU(cudaMemcpyAsync(buf.ptr, data, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *dev = buf.as<T>();
+  return COVER_OK;
+}
+
+int rays_check(cover_ctx* ctx, const cover_map* map, const int32_t* segments, int32_t mem, int64_t count, const int32_t* offset,
+               int op, const cover_results* out) {
+  if (!ctx) return COVER_E_INVALID_ARG;
+  if (!map || map->ctx != ctx) return fail(ctx, COVER_E_INVALID_ARG, "map does not belong to this context");
+  if (count < 0 || (count && !segments)) return fail(ctx, COVER_E_INVALID_ARG, "bad segments");
+  Bind bind(ctx->device);
+  OutStage st;
+  int rc = stage_out(ctx, out, count, st);
+  if (rc) return rc;
+  const int32_t* dev = nullptr;
+  rc = stage_array(ctx, ctx->in_a, segments, static_cast<size_t>(count) * 4, mem, &dev);
+  if (rc) return rc;
+  const int ox = offset ? offset[0] : 0, oy = offset ? offset[1] : 0;
+  if (count) {
+    const int4* seg = reinterpret_cast<const int4*>(dev);
+    if (op == OP_IS_FREE) k_rays<OP_IS_FREE><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, seg, count, ox, oy, st.dev);
+    else if (op == OP_ACCUMULATE) k_rays<OP_ACCUMULATE><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, seg, count, ox, oy, st.dev);
+    else k_rays<OP_MAX><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, seg, count, ox, oy, st.dev);
+    ++ctx->launches;
+  }
+  return finish_out(ctx, st, count);
+}
+
+int cells_check(cover_ctx* ctx, const cover_map* map, const cover_cells* cells, const int32_t* offsets, int32_t mem, int64_t count,
+                int op, const cover_results* out) {
+  if (!ctx) return COVER_E_INVALID_ARG;
+  if (!map || map->ctx != ctx || !cells || cells->ctx != ctx) return fail(ctx, COVER_E_INVALID_ARG, "handle does not belong to this context");
+  if (count < 0 || (count && !offsets)) return fail(ctx, COVER_E_INVALID_ARG, "bad offsets");
+  Bind bind(ctx->device);
+  OutStage st;
+  int rc = stage_out(ctx, out, count, st);
+  if (rc) return rc;
+  const int32_t* dev = nullptr;
+  rc = stage_array(ctx, ctx->in_a, offsets, static_cast<size_t>(count) * 2, mem, &dev);
+  if (rc) return rc;
+  if (count) {
+    const int2* off = reinterpret_cast<const int2*>(dev);
+    if (op == OP_IS_FREE) k_cells<OP_IS_FREE><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->dev, cells->n, off, count, st.dev);
+    else if (op == OP_ACCUMULATE) k_cells<OP_ACCUMULATE><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->dev, cells->n, off, count, st.dev);
+    else k_cells<OP_MAX><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->dev, cells->n, off, count, st.dev);
+    ++ctx->launches;
+  }
+  return finish_out(ctx, st, count);
+}
+
+template <class T>
+int upload_new(cover_ctx* ctx, const T* host, size_t n, T** dev) {
+  *dev = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void**>(dev), std::max<size_t>(n * sizeof(T), 16)));
+  if (n) CU(cudaMemcpyAsync(*dev, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return COVER_OK;
+}
+
+}  // namespace
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+
+extern "C" {
+
+int cover_abi_version(void) { return COVER_B200_ABI_VERSION; }
+
+int cover_ctx_create(int device, cover_ctx** out) {
+  if (!out) return COVER_E_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return COVER_E_CUDA;  // no CPU fallback
+  cover_ctx* ctx = new (std::nothrow) cover_ctx();
+  if (!ctx) return COVER_E_NOMEM;
+  ctx->device = device;
+  Bind bind(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || configure_kernels() != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return COVER_E_CUDA;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return COVER_OK;
+}
+
+void cover_ctx_destroy(cover_ctx* ctx) {
+  if (!ctx) return;
+  Bind bind(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (DeviceBuffer* b : {&ctx->poses, &ctx->theta, &ctx->poly, &ctx->in_a, &ctx->in_b, &ctx->out_free, &ctx->out_cost, &ctx->out_status,
+                          &ctx->todo, &ctx->todo_count, &ctx->list_cnt, &ctx->list_rng, &ctx->list_seq})
+    b->release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* cover_last_error(const cover_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+void* cover_ctx_stream(cover_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+int64_t cover_ctx_launch_count(const cover_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cover_ctx_synchronize(cover_ctx* ctx) {
+  if (!ctx) return COVER_E_INVALID_ARG;
+  Bind bind(ctx->device);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return COVER_OK;
+}
+
+int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double resolution, double origin_x, double origin_y,
+                     cover_map** out) {
+  if (!ctx || !out) return COVER_E_INVALID_ARG;
+  *out = nullptr;
+  if (!(resolution > 0)) return fail(ctx, COVER_E_INVALID_ARG, "The resolution must be positive");
+  if (size_x <= 0 || size_y <= 0) return fail(ctx, COVER_E_INVALID_ARG, "map size must be positive");
+  Bind bind(ctx->device);
+  const int pitch = (size_x + 15) & ~15;
+  uint8_t* dev = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void**>(&dev), static_cast<size_t>(pitch) * size_y));
+  CU(cudaMemsetAsync(dev, 0, static_cast<size_t>(pitch) * size_y, ctx->stream));
+  cover_map* m = new (std::nothrow) cover_map();
+  if (!m) {
+    cudaFree(dev);
+    return fail(ctx, COVER_E_NOMEM, "out of host memory");
+  }
+  m->ctx = ctx;
+  m->dev = dev;
+  m->resolution = resolution;
+  m->view = MapView{dev, size_x, size_y, pitch, 1. / resolution, origin_x, origin_y};  // base.hpp:56: x * (1./res)
+  *out = m;
+  return COVER_OK;
+}
+
+int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem) {
+  if (!map || !data) return COVER_E_INVALID_ARG;
+  cover_ctx* ctx = map->ctx;
+  Bind bind(ctx->device);
+  const MapView& v = map->view;
+  CU(cudaMemcpy2DAsync(map->dev, v.pitch, data, v.size_x, v.size_x, v.size_y,
+                       mem == COVER_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  if (mem == COVER_MEM_HOST) CU(cudaStreamSynchronize(ctx->stream));
+  return COVER_OK;
+}
+
+int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x0, int32_t y0, int32_t w, int32_t h) {
+  if (!map || !full_image) return COVER_E_INVALID_ARG;
+  cover_ctx* ctx = map->ctx;
+  const MapView& v = map->view;
+  if (x0 < 0 || y0 < 0 || w < 0 || h < 0 || x0 + w > v.size_x || y0 + h > v.size_y) return fail(ctx, COVER_E_INVALID_ARG, "window outside the map");
+  if (w == 0 || h == 0) return COVER_OK;
+  Bind bind(ctx->device);
+  CU(cudaMemcpy2DAsync(map->dev + static_cast<size_t>(y0) * v.pitch + x0, v.pitch, full_image + static_cast<size_t>(y0) * v.size_x + x0,
+                       v.size_x, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return COVER_OK;
+}
+
+void cover_map_destroy(cover_map* map) {
+  if (!map) return;
+  Bind bind(map->ctx->device);
+  cudaStreamSynchronize(map->ctx->stream);
+  cudaFree(map->dev);
+  delete map;
+}
+
+int cover_area_is_free(cover_ctx* ctx, const cover_map* map, const double* xy, int32_t nv, const cover_poses* poses, const cover_results* out) {
+  return polygon_check(ctx, map, xy, nv, SHAPE_AREA, OP_IS_FREE, poses, out);
+}
+int cover_area_accumulate_cost(cover_ctx* ctx, const cover_map* map, const double* xy, int32_t nv, const cover_poses* poses, const cover_results* out) {
+  return polygon_check(ctx, map, xy, nv, SHAPE_AREA, OP_ACCUMULATE, poses, out);
+}
+int cover_area_max_cost(cover_ctx* ctx, const cover_map* map, const double* xy, int32_t nv, const cover_poses* poses, const cover_results* out) {
+  return polygon_check(ctx, map, xy, nv, SHAPE_AREA, OP_MAX, poses, out);
+}
+int cover_outline_is_free(cover_ctx* ctx, const cover_map* map, const double* xy, int32_t nv, const cover_poses* poses, const cover_results* out) {
+  return polygon_check(ctx, map, xy, nv, SHAPE_OUTLINE, OP_IS_FREE, poses, out);
+}
+int cover_outline_accumulate_cost(cover_ctx* ctx, const cover_map* map, const double* xy, int32_t nv, const cover_poses* poses, const cover_results* out) {
+  return polygon_check(ctx, map, xy, nv, SHAPE_OUTLINE, OP_ACCUMULATE, poses, out);
+}
+int cover_outline_max_cost(cover_ctx* ctx, const cover_map* map, const double* xy, int32_t nv, const cover_poses* poses, const cover_results* out) {
+  return polygon_check(ctx, map, xy, nv, SHAPE_OUTLINE, OP_MAX, poses, out);
+}
+
+int cover_ray_is_free(cover_ctx* ctx, const cover_map* map, const int32_t* seg, int32_t mem, int64_t count, const int32_t* offset, const cover_results* out) {
+  return rays_check(ctx, map, seg, mem, count, offset, OP_IS_FREE, out);
+}
+int cover_ray_accumulate_cost(cover_ctx* ctx, const cover_map* map, const int32_t* seg, int32_t mem, int64_t count, const int32_t* offset, const cover_results* out) {
+  return rays_check(ctx, map, seg, mem, count, offset, OP_ACCUMULATE, out);
+}
+int cover_ray_max_cost(cover_ctx* ctx, const cover_map* map, const int32_t* seg, int32_t mem, int64_t count, const int32_t* offset, const cover_results* out) {
+  return rays_check(ctx, map, seg, mem, count, offset, OP_MAX, out);
+}
+
+int cover_cells_create(cover_ctx* ctx, const int32_t* cells, int64_t n_cells, cover_cells** out) {
+  if (!ctx || !out) return COVER_E_INVALID_ARG;
+  *out = nullptr;
+  if (n_cells < 0 || (n_cells && !cells)) return fail(ctx, COVER_E_INVALID_ARG, "bad cell list");
+  Bind bind(ctx->device);
+  int2* dev = nullptr;
+  const int rc = upload_new(ctx, reinterpret_cast<const int2*>(cells), static_cast<size_t>(n_cells), &dev);
+  if (rc) return rc;
+  *out = new cover_cells{ctx, dev, n_cells};
+  return COVER_OK;
+}
+
+void cover_cells_destroy(cover_cells* cells) {
+  if (!cells) return;
+  Bind bind(cells->ctx->device);
+  cudaStreamSynchronize(cells->ctx->stream);
+  cudaFree(cells->dev);
+  delete cells;
+}
+
+int cover_cells_is_free(cover_ctx* ctx, const cover_map* map, const cover_cells* cells, const int32_t* offsets, int32_t mem, int64_t count, const cover_results* out) {
+  return cells_check(ctx, map, cells, offsets, mem, count, OP_IS_FREE, out);
+}
+int cover_cells_accumulate_cost(cover_ctx* ctx, const cover_map* map, const cover_cells* cells, const int32_t* offsets, int32_t mem, int64_t count, const cover_results* out) {
+  return cells_check(ctx, map, cells, offsets, mem, count, OP_ACCUMULATE, out);
+}
+int cover_cells_max_cost(cover_ctx* ctx, const cover_map* map, const cover_cells* cells, const int32_t* offsets, int32_t mem, int64_t count, const cover_results* out) {
+  return cells_check(ctx, map, cells, offsets, mem, count, OP_MAX, out);
+}
+
+int cover_footprints_create(cover_ctx* ctx, const int32_t* outline_cells, const int64_t* o_starts, const int32_t* area_cells,
+                            const int64_t* a_starts, int32_t n, cover_footprints** out) {
+  if (!ctx || !out) return COVER_E_INVALID_ARG;
+  *out = nullptr;
+  if (n <= 0 || !o_starts || !a_starts) return fail(ctx, COVER_E_INVALID_ARG, "bad footprint bank");
+  if (o_starts[0] != 0 || a_starts[0] != 0) return fail(ctx, COVER_E_INVALID_ARG, "starts must begin at 0");
+  for (int k = 0; k < n; ++k)
+    if (o_starts[k + 1] < o_starts[k] || a_starts[k + 1] < a_starts[k]) return fail(ctx, COVER_E_INVALID_ARG, "starts must be non-decreasing");
+  if ((o_starts[n] && !outline_cells) || (a_starts[n] && !area_cells)) return fail(ctx, COVER_E_INVALID_ARG, "missing cells");
+  Bind bind(ctx->device);
+  cover_footprints* f = new cover_footprints{ctx, nullptr, nullptr, nullptr, nullptr, n};
+  std::vector<long long> os(o_starts, o_starts + n + 1), as(a_starts, a_starts + n + 1);
+  int rc = upload_new(ctx, reinterpret_cast<const int2*>(outline_cells), static_cast<size_t>(o_starts[n]), &f->ocells);
+  if (!rc) rc = upload_new(ctx, reinterpret_cast<const int2*>(area_cells), static_cast<size_t>(a_starts[n]), &f->acells);
+  if (!rc) rc = upload_new(ctx, os.data(), os.size(), &f->ostarts);
+  if (!rc) rc = upload_new(ctx, as.data(), as.size(), &f->astarts);
+  if (rc) {
+    cover_footprints_destroy(f);
+    return rc;
+  }
+  *out = f;
+  return COVER_OK;
+}
+
+void cover_footprints_destroy(cover_footprints* f) {
+  if (!f) return;
+  Bind bind(f->ctx->device);
+  cudaStreamSynchronize(f->ctx->stream);
+  cudaFree(f->ocells);
+  cudaFree(f->acells);
+  cudaFree(f->ostarts);
+  cudaFree(f->astarts);
+  delete f;
+}
+
+int cover_footprints_is_free(cover_ctx* ctx, const cover_map* map, const cover_footprints* fps, const int32_t* offsets,
+                             const int32_t* which, int32_t mem, int64_t count, const cover_results* out) {
+  if (!ctx) return COVER_E_INVALID_ARG;
+  if (!map || map->ctx != ctx || !fps || fps->ctx != ctx) return fail(ctx, COVER_E_INVALID_ARG, "handle does not belong to this context");
+  if (count < 0 || (count && !offsets)) return fail(ctx, COVER_E_INVALID_ARG, "bad offsets");
+  if (mem == COVER_MEM_HOST && which)
+    for (int64_t i = 0; i < count; ++i)
+      if (which[i] < 0 || which[i] >= fps->n) return fail(ctx, COVER_E_INVALID_ARG, "footprint index out of range");
+  Bind bind(ctx->device);
+  OutStage st;
+  int rc = stage_out(ctx, out, count, st);
+  if (rc) return rc;
+  const int32_t *off_dev = nullptr, *which_dev = nullptr;
+  rc = stage_array(ctx, ctx->in_a, offsets, static_cast<size_t>(count) * 2, mem, &off_dev);
+  if (rc) return rc;
+  if (which) {
+    rc = stage_array(ctx, ctx->in_b, which, static_cast<size_t>(count), mem, &which_dev);
+    if (rc) return rc;
+  }
+  if (count) {
+    k_footprints<<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, fps->ocells, fps->ostarts, fps->acells, fps->astarts,
+                                                             reinterpret_cast<const int2*>(off_dev), which_dev, count, st.dev);
+    ++ctx->launches;
+  }
+  return finish_out(ctx, st, count);
+}
+
+int cover_split_create(cover_ctx* ctx, const double* outline_xy, const int32_t* outline_starts, int32_t n_outlines,
+                       const double* area_xy, const int32_t* area_starts, int32_t n_areas, cover_split** out) {
+  if (!ctx || !out) return COVER_E_INVALID_ARG;
+  *out = nullptr;
+  if (n_outlines < 0 || n_areas < 0 || (n_outlines && !outline_starts) || (n_areas && !area_starts)) return fail(ctx, COVER_E_INVALID_ARG, "bad split");
+  std::vector<double> xy;
+  std::vector<int> starts{0};
+  double diam = 0;
+  for (int k = 0; k < n_outlines; ++k) {
+    const int b = outline_starts[k], e = outline_starts[k + 1];
+    if (e < b) return fail(ctx, COVER_E_INVALID_ARG, "starts must be non-decreasing");
+    xy.insert(xy.end(), outline_xy + 2 * b, outline_xy + 2 * e);
+    starts.push_back(starts.back() + (e - b));
+  }
+  for (int k = 0; k < n_areas; ++k) {
+    const int b = area_starts[k], e = area_starts[k + 1];
+    if (e < b) return fail(ctx, COVER_E_INVALID_ARG, "starts must be non-decreasing");
+    diam = std::max(diam, polygon_diameter(area_xy + 2 * b, e - b));
+    xy.insert(xy.end(), area_xy + 2 * b, area_xy + 2 * e);
+    starts.push_back(starts.back() + (e - b));
+  }
+  if (starts.back() > kMaxVertices) return fail(ctx, COVER_E_UNSUPPORTED, "split footprints with more than 4096 vertices are not supported");
+  Bind bind(ctx->device);
+  cover_split* s = new cover_split{ctx, nullptr, nullptr, n_outlines, n_areas, starts.back(), diam};
+  int rc = upload_new(ctx, xy.data(), xy.size(), &s->xy);
+  if (!rc) rc = upload_new(ctx, starts.data(), starts.size(), &s->starts);
+  if (rc) {
+    cover_split_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return COVER_OK;
+}
+
+void cover_split_destroy(cover_split* s) {
+  if (!s) return;
+  Bind bind(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->xy);
+  cudaFree(s->starts);
+  delete s;
+}
+
+int cover_split_is_free(cover_ctx* ctx, const cover_map* map, const cover_split* split, const cover_poses* poses, const cover_results* out) {
+  if (!ctx) return COVER_E_INVALID_ARG;
+  if (!map || map->ctx != ctx || !split || split->ctx != ctx) return fail(ctx, COVER_E_INVALID_ARG, "handle does not belong to this context");
+  if (poses && poses->format == COVER_POSE_NONE) return fail(ctx, COVER_E_INVALID_ARG, "continuous_footprint::is_free needs a pose");
+  Bind bind(ctx->device);
+  PoseSource src;
+  int rc = stage_poses(ctx, poses, src);
+  if (rc) return rc;
+  OutStage st;
+  rc = stage_out(ctx, out, poses->count, st);
+  if (rc) return rc;
+  if (poses->count) {
+    const int rows_cap = rows_bound(split->max_area_diameter, map->view.inv_res);
+    const unsigned int grid = list_grid(ctx, poses->count, rows_cap, 4);
+    ListScratch scratch{};
+    rc = ensure_list_scratch(ctx, rows_cap, static_cast<long long>(grid) * kBlock, scratch);
+    if (rc) return rc;
+    const SplitView view{split->xy, split->starts, split->n_outlines, split->n_areas};
+    k_split<<<grid, kBlock, static_cast<size_t>(split->n_vertices) * 2 * sizeof(double), ctx->stream>>>(map->view, view, split->n_vertices,
+                                                                                                      src, poses->count, st.dev, scratch);
+    ++ctx->launches;
+  }
+  return finish_out(ctx, st, poses->count);
+}
+
+}  // extern "C"

@@ -1,0 +1,508 @@
+// device_core.cuh — device-side building blocks of the batched footprint checker (sm_100a).
+//
+// Everything here is integer/byte work plus a handful of FP64 operations per vertex; there is no
+// contraction, so no tensor cores.  The pieces mirror the reference's FUNCTIONS (not its code
+// structure): a pose transform + discretisation, a Bresenham outline walker that calls a sink per cell,
+// a run detector that turns the cell stream into the reference's scan-line ranges, two row stores
+// (a packed 2-range table in shared memory for y-monotone outlines, sorted lists in global scratch for
+// everything else) and byte-parallel row scans (4 cells per 32-bit word).
+//
+// Reference semantics restated (paths relative to the reference tree):
+//   to_cell            src/cover/base.hpp:50-57 + costmap.cpp:71-85 (path A) / footprints.cpp:134-135 (path B)
+//   walk_ray           src/cover/generators.cpp:30-52, generators.hpp:117-128
+//   walk_outline       src/cover/generators.cpp:54-93
+//   RunDetector        src/cover/generators.cpp:189-232 (runs, cusps, wrap-around)
+//   *Store::finalize   src/cover/generators.cpp:236-255 (sort by min, pair, merge)
+//   Fold<OP>           src/cover/costmap.hpp:81-133, costmap.cpp:35-46, impl/costmap.hpp:23-63
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace cvr {
+
+constexpr int kLethal = 254;
+constexpr int kNoInformation = 255;
+constexpr int kInscribed = 253;
+constexpr double kCoordLimit = 4194304.0;  // 2^22
+constexpr int kMaxRanges = 16;             // std::sort is insertion-stable up to 16 elements (libstdc++)
+
+enum Op : int { OP_IS_FREE = 0, OP_ACCUMULATE = 1, OP_MAX = 2 };
+enum Status : int { ST_OK = 0, ST_LOGIC_ERROR = 1, ST_ROW_COMPLEXITY = 2, ST_COORD_RANGE = 3 };
+enum PoseFormat : int { POSE_CS = 0, POSE_LATTICE = 1, POSE_NONE = 2 };
+enum XformKind : int { XF_NONE = 0, XF_PATH_A = 1, XF_PATH_B = 2 };
+
+/// Device copy of the costmap: rows padded to a multiple of 16 bytes so that any aligned word of a row
+/// may be read; the allocation is 256-byte aligned.
+struct MapView {
+  const uint8_t* __restrict__ data;
+  int size_x, size_y, pitch;
+  double inv_res, origin_x, origin_y;
+};
+
+struct Pose {
+  double c, s, tx, ty;  // linear part [c -s; s c] (Eigen::Rotation2D::toRotationMatrix)
+};
+
+struct PoseSource {
+  int format;
+  long long first;         // lattice: global index of this batch's first pose
+  const double* cs;        // POSE_CS: count x 4
+  const double* theta_cs;  // POSE_LATTICE: ntheta x 2 (device copy)
+  double x0, dx, y0, dy;
+  int nx, ny;
+};
+
+struct OutView {
+  uint8_t* is_free;
+  double* cost;
+  uint8_t* status;
+};
+
+__device__ __forceinline__ Pose load_pose(const PoseSource& src, long long i) {
+  Pose T;
+  if (src.format == POSE_CS) {
+    const double2* q = reinterpret_cast<const double2*>(src.cs) + 2 * i;
+    const double2 a = __ldg(q), b = __ldg(q + 1);
+    T.c = a.x, T.s = a.y, T.tx = b.x, T.ty = b.y;
+  } else if (src.format == POSE_LATTICE) {
+    const long long p = src.first + i;
+    const long long plane = static_cast<long long>(src.nx) * src.ny;
+    const int it = static_cast<int>(p / plane);
+    const int r = static_cast<int>(p - it * plane);
+    const int iy = r / src.nx, ix = r - iy * src.nx;
+    // t = x0 + ix*dx: multiply, then add, each rounded (no FMA) — the ABI's stated rule.
+    T.tx = __dadd_rn(src.x0, __dmul_rn(static_cast<double>(ix), src.dx));
+    T.ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(iy), src.dy));
+    const double2 cs = __ldg(reinterpret_cast<const double2*>(src.theta_cs) + it);
+    T.c = cs.x, T.s = cs.y;
+  } else {
+    T.c = 1, T.s = 0, T.tx = 0, T.ty = 0;
+  }
+  return T;
+}
+
+/// World vertex -> map cell.  Every FP operation is an explicitly rounded intrinsic so that nvcc can
+/// never contract a multiply-add: the CPU reference (x86-64 SSE2, no FMA) rounds after each step.
+template <int XF>
+__device__ __forceinline__ bool to_cell(const Pose& T, double px, double py, const MapView& m, int& cx, int& cy) {
+  double qx, qy;
+  if (XF == XF_NONE) {  // costmap.cpp:73-74
+    qx = __dsub_rn(px, m.origin_x);
+    qy = __dsub_rn(py, m.origin_y);
+  } else {
+    // Eigen Transform * Matrix: res = t; res += (l_i0*p_x) + (l_i1*p_y)
+    const double lx = __dadd_rn(__dmul_rn(T.c, px), __dmul_rn(-T.s, py));
+    const double ly = __dadd_rn(__dmul_rn(T.s, px), __dmul_rn(T.c, py));
+    qx = __dadd_rn(T.tx, lx);
+    qy = __dadd_rn(T.ty, ly);
+    if (XF == XF_PATH_A) {  // costmap.cpp:81-83: origin subtracted AFTER the transform
+      qx = __dsub_rn(qx, m.origin_x);
+      qy = __dsub_rn(qy, m.origin_y);
+    }  // XF_PATH_B: the caller folded (-origin) into T.tx/T.ty (footprints.cpp:134-135)
+  }
+  const double sx = __dmul_rn(qx, m.inv_res), sy = __dmul_rn(qy, m.inv_res);
+  cx = __double2int_rz(sx);  // base.hpp:56: cast<int>() truncates toward zero
+  cy = __double2int_rz(sy);
+  return (fabs(sx) < kCoordLimit) && (fabs(sy) < kCoordLimit);  // false also for NaN
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Byte-parallel row scans.  A row pointer is 16-byte aligned; x indexes bytes of the row.
+// ---------------------------------------------------------------------------------------------------
+
+/// Non-zero iff some byte of v is zero (exact as an existence test).
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; }
+
+/// Bytes of word `w` (covering x = 4w..4w+3) that lie inside [lo, hi], as a 0xFF-per-byte mask.
+__device__ __forceinline__ uint32_t keep_mask(int w, int lo, int hi) {
+  uint32_t k = 0xFFFFFFFFu;
+  const int a = lo - 4 * w, b = 4 * w + 3 - hi;
+  if (a > 0) k &= 0xFFFFFFFFu << (8 * a);
+  if (b > 0) k &= 0xFFFFFFFFu >> (8 * b);
+  return k;
+}
+
+/// true iff some cell of [lo,hi] equals the byte replicated in pat4.
+__device__ __forceinline__ bool row_any_eq(const uint8_t* __restrict__ row, int lo, int hi, uint32_t pat4) {
+  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(row);
+  const int w0 = lo >> 2, w1 = hi >> 2;
+  uint32_t acc;
+  {
+    const uint32_t v = (__ldg(p + w0) ^ pat4) | ~keep_mask(w0, lo, hi);
+    acc = zero_bytes(v);
+  }
+  for (int w = w0 + 1; w < w1; ++w) acc |= zero_bytes(__ldg(p + w) ^ pat4);
+  if (w1 > w0) {
+    const uint32_t v = (__ldg(p + w1) ^ pat4) | ~keep_mask(w1, lo, hi);
+    acc |= zero_bytes(v);
+  }
+  return acc != 0;
+}
+
+/// accumulate_cost over [lo,hi] in x order: adds costs to `sum`; returns 0, or -1 / -2 for the first
+/// LETHAL / NO_INFORMATION cell (costmap.cpp:35-46).
+__device__ __forceinline__ int row_accumulate(const uint8_t* __restrict__ row, int lo, int hi, unsigned long long& sum) {
+  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(row);
+  const int w0 = lo >> 2, w1 = hi >> 2;
+  unsigned int part = 0;
+  for (int w = w0; w <= w1; ++w) {
+    uint32_t u = __ldg(p + w);
+    if (w == w0 || w == w1) u &= keep_mask(w, lo, hi);
+    if (zero_bytes(~(u | 0x01010101u))) {  // some byte is 254 or 255
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t v = (u >> (8 * b)) & 0xFFu;
+        if (v == kLethal) return -1;
+        if (v == kNoInformation) return -2;
+        part += v;  // excluded bytes are zero
+      }
+    } else {
+      part = __dp4a(u, 0x01010101u, part);
+    }
+    if (part > 0x7FFFFFFFu) {
+      sum += part;
+      part = 0;
+    }
+  }
+  sum += part;
+  return 0;
+}
+
+__device__ __forceinline__ uint32_t row_max(const uint8_t* __restrict__ row, int lo, int hi, uint32_t best4) {
+  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(row);
+  const int w0 = lo >> 2, w1 = hi >> 2;
+  for (int w = w0; w <= w1; ++w) {
+    uint32_t u = __ldg(p + w);
+    if (w == w0 || w == w1) u &= keep_mask(w, lo, hi);
+    best4 = __vmaxu4(best4, u);
+  }
+  return best4;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Folds: what is_free / accumulate_cost / max do with cells (outline, ray, cell-list paths) and with
+// whole row spans (area path).  `cell`/`span` return false when the walk may stop.
+// ---------------------------------------------------------------------------------------------------
+
+template <int OP>
+struct Fold;
+
+template <>
+struct Fold<OP_IS_FREE> {  // std::none_of(is_lethal): out of the map counts as lethal (costmap.hpp:81-91)
+  bool hit = false;
+  __device__ __forceinline__ bool cell(const MapView& m, int x, int y) {
+    if (static_cast<unsigned>(x) >= static_cast<unsigned>(m.size_x) || static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) ||
+        __ldg(m.data + static_cast<size_t>(y) * m.pitch + x) == kLethal) {
+      hit = true;
+      return false;
+    }
+    return true;
+  }
+  __device__ __forceinline__ bool span(const MapView& m, int y, int lo, int hi) {
+    if (static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) || lo < 0 || hi >= m.size_x ||
+        row_any_eq(m.data + static_cast<size_t>(y) * m.pitch, lo, hi, 0xFEFEFEFEu)) {
+      hit = true;
+      return false;
+    }
+    return true;
+  }
+  __device__ __forceinline__ void store(const OutView& o, long long i) const {
+    if (o.is_free) o.is_free[i] = hit ? 0 : 1;
+  }
+};
+
+template <>
+struct Fold<OP_ACCUMULATE> {  // impl/costmap.hpp:50-63: first negative value in generator order wins
+  unsigned long long sum = 0;
+  int early = 0;
+  __device__ __forceinline__ bool cell(const MapView& m, int x, int y) {
+    if (static_cast<unsigned>(x) >= static_cast<unsigned>(m.size_x) || static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y)) {
+      early = -3;
+      return false;
+    }
+    const int v = __ldg(m.data + static_cast<size_t>(y) * m.pitch + x);
+    if (v >= kLethal) {
+      early = v == kLethal ? -1 : -2;
+      return false;
+    }
+    sum += v;
+    return true;
+  }
+  __device__ __forceinline__ bool span(const MapView& m, int y, int lo, int hi) {
+    if (static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) || lo < 0 || lo >= m.size_x) {
+      early = -3;  // the first cell of the span is already outside
+      return false;
+    }
+    const int hc = min(hi, m.size_x - 1);
+    early = row_accumulate(m.data + static_cast<size_t>(y) * m.pitch, lo, hc, sum);
+    if (early == 0 && hi >= m.size_x) early = -3;
+    return early == 0;
+  }
+  __device__ __forceinline__ void store(const OutView& o, long long i) const {
+    const double c = early ? static_cast<double>(early) : static_cast<double>(sum);
+    if (o.cost) o.cost[i] = c;
+    if (o.is_free) o.is_free[i] = early ? 0 : 1;
+  }
+};
+
+template <>
+struct Fold<OP_MAX> {  // extension: max of get_cell_cost; any cell outside the map -> -3
+  uint32_t best4 = 0;
+  bool outside = false;
+  __device__ __forceinline__ bool cell(const MapView& m, int x, int y) {
+    if (static_cast<unsigned>(x) >= static_cast<unsigned>(m.size_x) || static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y)) {
+      outside = true;
+      return false;
+    }
+    best4 = max(best4, static_cast<uint32_t>(__ldg(m.data + static_cast<size_t>(y) * m.pitch + x)));
+    return true;
+  }
+  __device__ __forceinline__ bool span(const MapView& m, int y, int lo, int hi) {
+    if (static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) || lo < 0 || hi >= m.size_x) {
+      outside = true;
+      return false;
+    }
+    best4 = row_max(m.data + static_cast<size_t>(y) * m.pitch, lo, hi, best4);
+    return true;
+  }
+  __device__ __forceinline__ int value() const {
+    const uint32_t a = max(best4 & 0xFFu, (best4 >> 8) & 0xFFu), b = max((best4 >> 16) & 0xFFu, best4 >> 24);
+    return static_cast<int>(max(a, b));
+  }
+  __device__ __forceinline__ void store(const OutView& o, long long i) const {
+    const int v = value();
+    if (o.cost) o.cost[i] = outside ? -3.0 : static_cast<double>(v);
+    if (o.is_free) o.is_free[i] = (!outside && v != kLethal) ? 1 : 0;
+  }
+};
+
+__device__ __forceinline__ void store_failure(const OutView& o, long long i, int status) {
+  if (o.is_free) o.is_free[i] = 0;
+  if (o.cost) o.cost[i] = __longlong_as_double(0x7FF8000000000000LL);  // quiet NaN
+  if (o.status) o.status[i] = static_cast<uint8_t>(status);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Bresenham walkers.
+// ---------------------------------------------------------------------------------------------------
+
+/// ray_generator: `size = max(|dx|,|dy|)` cells from (bx,by), end excluded; ties make x the major axis.
+template <class Sink>
+__device__ __forceinline__ bool walk_ray(int bx, int by, int ex, int ey, Sink& sink) {
+  const int dx = ex - bx, dy = ey - by;
+  const int adx = abs(dx), ady = abs(dy);
+  const int sx = (dx > 0) - (dx < 0), sy = (dy > 0) - (dy < 0);
+  const bool x_major = adx >= ady;
+  const int size = x_major ? adx : ady, add = x_major ? ady : adx;
+  const int major_x = x_major ? sx : 0, major_y = x_major ? 0 : sy;
+  const int minor_x = x_major ? 0 : sx, minor_y = x_major ? sy : 0;
+  int x = bx, y = by, num = size >> 1;
+  for (int k = 0; k < size; ++k) {
+    if (!sink.cell(x, y)) return false;
+    num += add;
+    if (num >= size) {
+      num -= size;
+      x += minor_x;
+      y += minor_y;
+    }
+    x += major_x;
+    y += major_y;
+  }
+  return true;
+}
+
+/// outline_generator over the transformed polygon; vertices are discretised on the fly (two live
+/// vertices + the first).  `poly` = column-major xy in shared memory.
+template <int XF, class Sink>
+__device__ __forceinline__ bool walk_outline(const double* __restrict__ poly, int nv, const Pose& T, const MapView& m,
+                                             Sink& sink) {
+  if (nv == 0) return true;
+  int fx, fy;
+  to_cell<XF>(T, poly[0], poly[1], m, fx, fy);
+  int px = fx, py = fy, rays = 0;
+  for (int i = 1; i < nv; ++i) {
+    int cx, cy;
+    to_cell<XF>(T, poly[2 * i], poly[2 * i + 1], m, cx, cy);
+    if (cx != px || cy != py) {  // degenerate rays are skipped (generators.cpp:86-93)
+      ++rays;
+      if (!walk_ray(px, py, cx, cy, sink)) return false;
+    }
+    px = cx, py = cy;
+  }
+  if (rays > 1) {  // close the outline (generators.cpp:69-71)
+    if (px != fx || py != fy) return walk_ray(px, py, fx, fy, sink);
+    return true;
+  }
+  return sink.cell(px, py);  // one-cell dummy ray holding the last point (generators.cpp:72-78)
+}
+
+/// Integer bounding box of the discretised vertices + the coordinate-range check.
+template <int XF>
+__device__ __forceinline__ bool polygon_bbox(const double* __restrict__ poly, int nv, const Pose& T, const MapView& m, int& x0,
+                                             int& y0, int& x1, int& y1) {
+  bool ok = true;
+  x0 = y0 = 0x7FFFFFFF;
+  x1 = y1 = -0x7FFFFFFF - 1;
+  for (int i = 0; i < nv; ++i) {
+    int cx, cy;
+    ok &= to_cell<XF>(T, poly[2 * i], poly[2 * i + 1], m, cx, cy);
+    x0 = min(x0, cx), x1 = max(x1, cx);
+    y0 = min(y0, cy), y1 = max(y1, cy);
+  }
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Run detection: outline cell stream -> scan-line ranges (generators.cpp:189-232).
+//
+// A run is a maximal cyclic stretch of consecutive outline cells on one row.  Each run contributes the
+// range (x of its first cell, x of its last cell); a run where y turns around (cusp) counts twice.  The
+// reference inserts ranges in the order of the runs' END indices, starting with the run that contains
+// outline cell 0 — whose beginning may lie at the tail of the outline.  We stream: every run but that
+// first one is emitted when it closes; the first run is emitted last through `add_first`, which gives
+// it the rank the reference gives it (it wins ties of equal `min`).
+// ---------------------------------------------------------------------------------------------------
+template <class Store>
+struct RunDetector {
+  Store& store;
+  int seq_base;                                  // outline cell index offset (multi-outline order)
+  int idx = 0;                                   // cells seen so far
+  int y_run = 0, x_first = 0, x_prev = 0;        // current run
+  int y_before = 0;                              // y of the cell before the current run
+  int x0 = 0, y0 = 0;                            // outline cell 0
+  int f_xlast = 0, f_ynext = 0, f_end = 0;       // the first run, closed
+  bool in_first = true;
+  int min_x, max_x;  // x extent of the vertices = x extent of the outline when every cell is on one row
+
+  __device__ __forceinline__ RunDetector(Store& s, int base, int bbox_x0, int bbox_x1) :
+      store(s), seq_base(base), min_x(bbox_x0), max_x(bbox_x1) {}
+
+  __device__ __forceinline__ void emit(int y, int a, int b, int yp, int yn, int end_idx, bool first) {
+    const int lo = min(a, b), hi = max(a, b);
+    const bool cusp = (yp - y) * (y - yn) < 0;  // generators.cpp:100-103
+    store.add(y, lo, hi, seq_base + end_idx, first);
+    if (cusp) store.add(y, lo, hi, seq_base + end_idx, first);
+  }
+
+  __device__ __forceinline__ bool cell(int x, int y) {
+    if (idx == 0) {
+      y_run = y0 = y;
+      x_first = x0 = x;
+    } else if (y != y_run) {
+      if (in_first) {
+        f_xlast = x_prev, f_ynext = y, f_end = idx - 1;
+        in_first = false;
+      } else {
+        emit(y_run, x_first, x_prev, y_before, y, idx - 1, false);
+      }
+      y_before = y_run;
+      y_run = y;
+      x_first = x;
+    }
+    x_prev = x;
+    ++idx;
+    return true;
+  }
+
+  __device__ __forceinline__ void finish() {
+    if (idx == 0) return;
+    if (in_first) {  // every cell on one row (generators.cpp:197-204)
+      store.add(y0, min_x, min_x, seq_base, false);
+      store.add(y0, max_x, max_x, seq_base, false);
+      return;
+    }
+    if (y_run == y0) {  // the tail run continues into cell 0: one run, ending where the first run ended
+      emit(y0, x_first, f_xlast, y_before, f_ynext, f_end, true);
+    } else {
+      emit(y_run, x_first, x_prev, y_before, y0, idx - 1, false);
+      emit(y0, x0, f_xlast, y_run, f_ynext, f_end, true);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Row stores.
+// ---------------------------------------------------------------------------------------------------
+
+/// Two ranges per row, packed in ONE shared-memory word per (row, thread): bits 0-14 lo, 15-29 hi
+/// (relative to the vertex bounding box), 30-31 count.  The pair is merged the moment the second range
+/// arrives: sorted by `min` with insertion order breaking ties, result [first.min, second.max]
+/// (generators.cpp:236-255).  A third range marks the pose for the list store.
+struct PackedStore {
+  uint32_t* tab;  // &table[0][threadIdx.x]
+  int stride;     // threads per block
+  int xb, yb;     // bounding-box origin
+  bool overflow = false;
+
+  __device__ __forceinline__ void clear(int rows) {
+    for (int r = 0; r < rows; ++r) tab[r * stride] = 0;
+  }
+  __device__ __forceinline__ void add(int y, int lo, int hi, int /*seq*/, bool first) {
+    uint32_t& w = tab[(y - yb) * stride];
+    const uint32_t cnt = w >> 30;
+    const uint32_t nlo = static_cast<uint32_t>(lo - xb), nhi = static_cast<uint32_t>(hi - xb);
+    if (cnt == 0) {
+      w = nlo | (nhi << 15) | (1u << 30);
+    } else if (cnt == 1) {
+      const uint32_t olo = w & 0x7FFFu, ohi = (w >> 15) & 0x7FFFu;
+      uint32_t rlo, rhi;
+      if (first) {  // the new range was inserted BEFORE the stored one
+        if (olo < nlo) rlo = olo, rhi = nhi;
+        else rlo = nlo, rhi = ohi;
+      } else {
+        if (nlo < olo) rlo = nlo, rhi = ohi;
+        else rlo = olo, rhi = nhi;
+      }
+      w = rlo | (rhi << 15) | (2u << 30);
+    } else {
+      overflow = true;
+    }
+  }
+};
+
+/// Sorted range lists per row in global scratch, interleaved across the resident threads
+/// ([row][slot][thread]) so that a warp's accesses to the same (row, slot) coalesce.  Insertion keeps
+/// the list ordered by (min, outline order) = what a stable sort by `min` produces.
+struct ListStore {
+  int* cnt;   // [rows_cap][nthreads]
+  int2* rng;  // [rows_cap][kMaxRanges][nthreads]
+  int* seq;   // [rows_cap][kMaxRanges][nthreads]
+  long long nthreads;
+  long long me;
+  int yb, rows_cap;
+  bool overflow = false;   // a row needed more than kMaxRanges entries
+  bool out_of_rows = false;
+
+  __device__ __forceinline__ long long at(int row, int k) const { return (static_cast<long long>(row) * kMaxRanges + k) * nthreads + me; }
+  __device__ __forceinline__ void clear(int rows) {
+    for (int r = 0; r < rows; ++r) cnt[static_cast<long long>(r) * nthreads + me] = 0;
+  }
+  __device__ __forceinline__ void add(int y, int lo, int hi, int s, bool /*first*/) {
+    const int row = y - yb;
+    if (row < 0 || row >= rows_cap) {
+      out_of_rows = true;
+      return;
+    }
+    int& n = cnt[static_cast<long long>(row) * nthreads + me];
+    if (n >= kMaxRanges) {  // keep counting: the parity still decides std::logic_error
+      overflow = true;
+      ++n;
+      return;
+    }
+    int k = n;
+    while (k > 0) {
+      const int2 e = rng[at(row, k - 1)];
+      const int es = seq[at(row, k - 1)];
+      if (e.x < lo || (e.x == lo && es <= s)) break;
+      rng[at(row, k)] = e;
+      seq[at(row, k)] = es;
+      --k;
+    }
+    rng[at(row, k)] = make_int2(lo, hi);
+    seq[at(row, k)] = s;
+    ++n;
+  }
+};
+
+}  // namespace cvr

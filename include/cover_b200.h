@@ -1,0 +1,177 @@
+/* cover_b200.h — C ABI of the B200-native batched footprint collision checker.
+ *
+ * This is the drop-in boundary for ONE hot path of magazino/cover: cell generators
+ * (src/cover/generators.hpp) feeding the costmap pose checks (src/cover/costmap.hpp) and the split
+ * footprint checks (src/cover/footprints.hpp), batched as MANY POSES x ONE COSTMAP.
+ * The reference has no FFI today (it is a header-heavy C++ library); each entry below names the
+ * reference function it batches (paths relative to the reference tree) and INTEGRATION.md shows the
+ * C++ overload a maintainer adds next to that function to call it.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns 0 (COVER_OK) or a negative cover_error;
+ *    nothing throws across this boundary; cover_last_error(ctx) holds the message.
+ *  - polygons are 2 x V doubles, COLUMN-major (x0,y0,x1,y1,...) = Eigen's layout of cover::polygon
+ *    (src/cover/base.hpp:26); cell lists are 2 x N int32 column-major = cover::discrete_polygon
+ *    (src/cover/base.hpp:30).
+ *  - poses: COVER_POSE_CS = count x {cos, sin, tx, ty} doubles, i.e. the Eigen::Isometry2d
+ *    Translation2d(tx,ty) * Rotation2Dd with the trig evaluated BY THE CALLER on the host (device
+ *    sin/cos differ from glibc in the last ulp); COVER_POSE_LATTICE = a descriptor expanded on the
+ *    device: pose index p = (it*ny + iy)*nx + ix, t = (x0 + ix*dx, y0 + iy*dy) (multiply then add,
+ *    no FMA), heading (cos,sin) = cs[it]; COVER_POSE_NONE = the no-pose overloads (one check).
+ *  - outputs are caller-owned arrays of `count` elements, host or device (cover_results.mem); any of
+ *    them may be NULL.  status[i] is a cover_status; for a status other than COVER_STATUS_OK the
+ *    verdict is 0 and the cost NaN (the scalar reference would have thrown, see each status).
+ *  - a cover_ctx is single-threaded and owns one CUDA stream; all work of a call is enqueued on it
+ *    and, when any argument or result lives on the host, completed before the call returns.  With
+ *    device-resident arguments and results the call is asynchronous (cover_ctx_synchronize).
+ *  - maps, cell lists and footprints are immutable once uploaded and may be shared by calls on the
+ *    same context.  One context per GPU; contexts are independent (pose sharding across GPUs is done
+ *    by the caller: replicate the map, split the pose range, see cover_poses.first).
+ *  - there is NO CPU fallback: without a CUDA device every entry fails with COVER_E_CUDA.
+ */
+#ifndef COVER_B200_H
+#define COVER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COVER_B200_ABI_VERSION 1
+
+typedef struct cover_ctx cover_ctx;
+typedef struct cover_map cover_map;
+typedef struct cover_cells cover_cells;
+typedef struct cover_footprints cover_footprints;
+typedef struct cover_split cover_split;
+
+typedef enum cover_error {
+  COVER_OK = 0,
+  COVER_E_INVALID_ARG = -1, /* std::invalid_argument in the reference (e.g. resolution <= 0, base.hpp:54) */
+  COVER_E_CUDA = -2,
+  COVER_E_NOMEM = -3,
+  COVER_E_UNSUPPORTED = -4
+} cover_error;
+
+typedef enum cover_status {
+  COVER_STATUS_OK = 0,
+  COVER_STATUS_LOGIC_ERROR = 1,    /* area_generator threw std::logic_error (generators.cpp:246-249) */
+  COVER_STATUS_ROW_COMPLEXITY = 2, /* > 16 ranges on one scan row: std::sort is no longer insertion-stable
+                                      (generators.cpp:236-241); the result would depend on libstdc++ */
+  COVER_STATUS_COORD_RANGE = 3     /* |cell coordinate| >= 2^22: outside any costmap (int cast UB upstream) */
+} cover_status;
+
+typedef enum cover_mem { COVER_MEM_HOST = 0, COVER_MEM_DEVICE = 1 } cover_mem;
+typedef enum cover_pose_format { COVER_POSE_CS = 0, COVER_POSE_LATTICE = 1, COVER_POSE_NONE = 2 } cover_pose_format;
+
+typedef struct cover_lattice {
+  double x0, dx; /* tx = x0 + ix*dx */
+  double y0, dy; /* ty = y0 + iy*dy */
+  const double* cs; /* HOST pointer: ntheta x {cos, sin} */
+  int32_t nx, ny, ntheta;
+} cover_lattice;
+
+typedef struct cover_poses {
+  int32_t format;        /* cover_pose_format */
+  int32_t mem;           /* cover_mem of `data` (COVER_POSE_CS only) */
+  int64_t first;         /* LATTICE: index of the first pose of this batch (pose sharding); else 0 */
+  int64_t count;         /* number of poses in this batch */
+  const void* data;      /* CS: count x 4 doubles */
+  cover_lattice lattice; /* LATTICE */
+} cover_poses;
+
+typedef struct cover_results {
+  int32_t mem;      /* cover_mem of the three arrays */
+  uint8_t* is_free; /* 1 = free */
+  double* cost;     /* accumulate_cost / max_cost value */
+  uint8_t* status;  /* cover_status */
+} cover_results;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int cover_abi_version(void);
+int cover_ctx_create(int device, cover_ctx** out);
+void cover_ctx_destroy(cover_ctx* ctx);
+const char* cover_last_error(const cover_ctx* ctx);
+void* cover_ctx_stream(cover_ctx* ctx); /* the cudaStream_t all work of this context is enqueued on */
+int cover_ctx_synchronize(cover_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t cover_ctx_launch_count(const cover_ctx* ctx);
+
+/* ---- costmap: stands in for `const costmap_2d::Costmap2D&` ----------------------------------------
+ * size/resolution/origin = getSizeInCellsX/Y, getResolution, getOriginX/Y; bytes = getCharMap(),
+ * row-major, index = y*size_x + x (call sites src/cover/costmap.hpp:52,89,105,122).
+ * cover_map_create fails with COVER_E_INVALID_ARG for resolution <= 0 (base.hpp:54-55). */
+int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double resolution, double origin_x, double origin_y,
+                     cover_map** out);
+int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem);
+/* re-upload the window [x0,x0+w) x [y0,y0+h) from a full-size HOST image (dirty-rectangle update). */
+int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x0, int32_t y0, int32_t w, int32_t h);
+void cover_map_destroy(cover_map* map);
+
+/* ---- polygon x poses: path A transform ((pose*polygon) - origin, src/cover/costmap.cpp:71-85) ---- */
+/* is_free(const polygon&, const Eigen::Isometry2d&, const Costmap2D&)  costmap.cpp:78-85 (POSE_NONE: :71-76) */
+int cover_area_is_free(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t n_vertices,
+                       const cover_poses* poses, const cover_results* out);
+/* accumulate_cost(area_generator(res, pose*polygon - origin), map)  impl/costmap.hpp:50-70 over generators.cpp:137-268 */
+int cover_area_accumulate_cost(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t n_vertices,
+                               const cover_poses* poses, const cover_results* out);
+/* EXTENSION (no reference function): max of detail::get_cell_cost (costmap.hpp:113-124) over the area;
+ * a cell outside the map gives -3. */
+int cover_area_max_cost(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t n_vertices,
+                        const cover_poses* poses, const cover_results* out);
+/* is_free(outline_generator(res, pose*polygon - origin), map)  impl/costmap.hpp:23-27 over generators.cpp:54-93 */
+int cover_outline_is_free(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t n_vertices,
+                          const cover_poses* poses, const cover_results* out);
+int cover_outline_accumulate_cost(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t n_vertices,
+                                  const cover_poses* poses, const cover_results* out);
+int cover_outline_max_cost(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t n_vertices,
+                           const cover_poses* poses, const cover_results* out);
+
+/* ---- rays: is_free / accumulate_cost(ray_generator(begin,end)[, offset], map) ---------------------
+ * impl/costmap.hpp:23-35,65-81 over generators.cpp:30-52.  segments = count x {x0,y0,x1,y1} cells
+ * (end exclusive); offset = 2 ints added to every cell, or NULL. */
+int cover_ray_is_free(cover_ctx* ctx, const cover_map* map, const int32_t* segments, int32_t mem, int64_t count,
+                      const int32_t* offset, const cover_results* out);
+int cover_ray_accumulate_cost(cover_ctx* ctx, const cover_map* map, const int32_t* segments, int32_t mem, int64_t count,
+                              const int32_t* offset, const cover_results* out);
+int cover_ray_max_cost(cover_ctx* ctx, const cover_map* map, const int32_t* segments, int32_t mem, int64_t count,
+                       const int32_t* offset, const cover_results* out);
+
+/* ---- cached cell lists x offsets: is_free(const discrete_polygon&, const cell& offset, map) -------
+ * src/cover/costmap.cpp:59-69.  offsets = count x {x,y}. */
+int cover_cells_create(cover_ctx* ctx, const int32_t* cells, int64_t n_cells, cover_cells** out);
+void cover_cells_destroy(cover_cells* cells);
+int cover_cells_is_free(cover_ctx* ctx, const cover_map* map, const cover_cells* cells, const int32_t* offsets, int32_t mem,
+                        int64_t count, const cover_results* out);
+/* EXTENSIONS: the accumulate_cost / max folds over the same cached list, in list order. */
+int cover_cells_accumulate_cost(cover_ctx* ctx, const cover_map* map, const cover_cells* cells, const int32_t* offsets,
+                                int32_t mem, int64_t count, const cover_results* out);
+int cover_cells_max_cost(cover_ctx* ctx, const cover_map* map, const cover_cells* cells, const int32_t* offsets, int32_t mem,
+                         int64_t count, const cover_results* out);
+
+/* ---- split footprints, offset form: generator_footprint / discrete_footprint::is_free(offset, map)
+ * src/cover/footprints.cpp:214-247.  A BANK of n_footprints footprints (one per heading bin):
+ * footprint k owns outline cells [o_starts[k], o_starts[k+1]) (checked for 253 or 254) and area cells
+ * [a_starts[k], a_starts[k+1]) (checked for 254); a cell outside the map collides.
+ * `which` (count int32, NULL = all 0) selects the footprint of each offset. */
+int cover_footprints_create(cover_ctx* ctx, const int32_t* outline_cells, const int64_t* o_starts, const int32_t* area_cells,
+                            const int64_t* a_starts, int32_t n_footprints, cover_footprints** out);
+void cover_footprints_destroy(cover_footprints* fps);
+int cover_footprints_is_free(cover_ctx* ctx, const cover_map* map, const cover_footprints* fps, const int32_t* offsets,
+                             const int32_t* which, int32_t mem, int64_t count, const cover_results* out);
+
+/* ---- split footprint, pose form: continuous_footprint::is_free(pose, map) -------------------------
+ * src/cover/footprints.cpp:130-196 (path B transform: t' = t + (-origin), q = t' + R*p).  The split
+ * itself (outlines = always-inscribed sub-regions, areas = remainder) is given as packed polygon lists:
+ * polygon k of a list = vertices [starts[k], starts[k+1]) of its xy buffer. */
+int cover_split_create(cover_ctx* ctx, const double* outline_xy, const int32_t* outline_starts, int32_t n_outlines,
+                       const double* area_xy, const int32_t* area_starts, int32_t n_areas, cover_split** out);
+void cover_split_destroy(cover_split* split);
+int cover_split_is_free(cover_ctx* ctx, const cover_map* map, const cover_split* split, const cover_poses* poses,
+                        const cover_results* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COVER_B200_H */

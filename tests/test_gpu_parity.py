@@ -1,0 +1,332 @@
+"""GPU parity: every C-ABI entry (through the ctypes host layer) against the CPU oracle on identical
+seeded inputs.  Integer/byte work -> the bar is BIT-EXACT verdicts, costs and statuses.
+Run on the B200 box: `python -m pytest tests -m gpu`.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.fixtures import FOOTPRINTS, FOOTPRINT_NAMES, RECT, head_polygons
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import cover_b200
+    return cover_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(cb):
+    c = cb.Context(0)
+    yield c
+    c.close()
+
+
+def mixed_map(rng, sx, sy, lethal=0.002):
+    data = rng.integers(0, 253, (sy, sx), dtype=np.uint8)
+    r = rng.random((sy, sx))
+    data[r < lethal] = 254
+    data[(r >= lethal) & (r < 1.5 * lethal)] = 255
+    data[(r >= 1.5 * lethal) & (r < 2.5 * lethal)] = 253
+    return data
+
+
+def poses_around(rng, n, lo, hi):
+    th = rng.uniform(-math.pi, math.pi, n)
+    return np.stack([np.cos(th), np.sin(th), rng.uniform(lo, hi, n), rng.uniform(lo, hi, n)], axis=1)
+
+
+def assert_same(gpu, cpu, cost=False, what=""):
+    np.testing.assert_array_equal(gpu.status, cpu.status, err_msg=f"status {what}")
+    np.testing.assert_array_equal(gpu.is_free, cpu.is_free, err_msg=f"is_free {what}")
+    if cost:
+        np.testing.assert_array_equal(gpu.cost, cpu.cost, err_msg=f"cost {what}")  # NaN == NaN positionally
+
+
+OPS = [("is_free", po.OP_IS_FREE, False), ("accumulate_cost", po.OP_ACCUMULATE, True), ("max_cost", po.OP_MAX, True)]
+
+
+@pytest.mark.parametrize("name,op,has_cost", OPS)
+def test_rect_area_random_poses(cb, ctx, name, op, has_cost):
+    """C1 shape: 1.0 x 0.6 m rectangle, 5 cm, 1000 x 1000 map, random poses (some leave the map)."""
+    rng = np.random.default_rng(1)
+    data = mixed_map(rng, 1000, 1000)
+    poses = poses_around(rng, 100_000, -0.5, 50.5)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    gpu = getattr(cmap, f"area_{name}")(RECT, poses)
+    cpu = po.polygon_batch(po.Costmap(data, 0.05), RECT, poses, shape=po.SHAPE_AREA, op=op, threads=8)
+    assert_same(gpu, cpu, has_cost, name)
+    assert 0.05 < cpu.is_free.mean() < 0.95
+
+
+@pytest.mark.parametrize("name,op,has_cost", OPS)
+def test_rect_outline_random_poses(cb, ctx, name, op, has_cost):
+    rng = np.random.default_rng(2)
+    data = mixed_map(rng, 700, 500, lethal=0.01)
+    poses = poses_around(rng, 50_000, -0.5, 30.0)
+    cmap = cb.Costmap(ctx, data, 0.05, -1.25, 0.7)
+    gpu = getattr(cmap, f"outline_{name}")(RECT, poses)
+    cpu = po.polygon_batch(po.Costmap(data, 0.05, -1.25, 0.7), RECT, poses, shape=po.SHAPE_OUTLINE, op=op, threads=8)
+    assert_same(gpu, cpu, has_cost, name)
+
+
+def test_rect_lattice_matches_oracle_and_explicit_poses(cb, ctx):
+    """C4 shape at reduced size: lattice descriptor == the same poses materialised on the host == oracle."""
+    rng = np.random.default_rng(3)
+    data = mixed_map(rng, 400, 400, lethal=0.001)
+    th = -math.pi + 2 * math.pi * np.arange(9) / 9
+    cs = np.stack([np.cos(th), np.sin(th)], 1)
+    lat = cb.Lattice(0.31, 0.05, 150, 0.47, 0.05, 120, cs)
+    olat = po.Lattice(0.31, 0.05, 150, 0.47, 0.05, 120, cs)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    gpu = cmap.area_is_free(RECT, lat)
+    cpu = po.polygon_batch(po.Costmap(data, 0.05), RECT, olat, threads=8)
+    assert_same(gpu, cpu)
+    explicit = cmap.area_is_free(RECT, olat.poses_cs())
+    np.testing.assert_array_equal(gpu.is_free, explicit.is_free)
+    # a sub-range (pose sharding across GPUs uses first/count)
+    part = cmap.area_is_free(RECT, lat, first=12_345, count=50_000)
+    np.testing.assert_array_equal(part.is_free, gpu.is_free[12_345:62_345])
+    acc = cmap.area_accumulate_cost(RECT, lat, first=1000, count=20_000)
+    cpu_acc = po.polygon_batch(po.Costmap(data, 0.05), RECT, olat, op=po.OP_ACCUMULATE, first=1000, count=20_000, threads=8)
+    assert_same(acc, cpu_acc, True)
+
+
+@pytest.mark.parametrize("idx", range(7))
+@pytest.mark.parametrize("shape,prefix", [(po.SHAPE_AREA, "area"), (po.SHAPE_OUTLINE, "outline")])
+def test_reference_footprints_all_ops(cb, ctx, idx, shape, prefix):
+    """The reference's 7 test footprints (non-convex ones exercise cusps, ties and the list store)."""
+    rng = np.random.default_rng(10 + idx)
+    data = mixed_map(rng, 600, 500, lethal=0.0004)
+    poses = poses_around(rng, 4000, -1.0, 27.0)
+    cmap = cb.Costmap(ctx, data, 0.05, -0.5, 1.0)
+    omap = po.Costmap(data, 0.05, -0.5, 1.0)
+    for name, op, has_cost in OPS:
+        gpu = getattr(cmap, f"{prefix}_{name}")(FOOTPRINTS[idx], poses)
+        cpu = po.polygon_batch(omap, FOOTPRINTS[idx], poses, shape=shape, op=op, threads=8)
+        assert_same(gpu, cpu, has_cost, f"{FOOTPRINT_NAMES[idx]} {prefix} {name}")
+
+
+@pytest.mark.parametrize("res", [0.2, 0.1, 0.025])
+def test_resolutions_and_small_scale(cb, ctx, res):
+    rng = np.random.default_rng(20)
+    data = mixed_map(rng, 300, 260, lethal=0.003)
+    cmap = cb.Costmap(ctx, data, res)
+    omap = po.Costmap(data, res)
+    span = 300 * res
+    for fp in (FOOTPRINTS[5], FOOTPRINTS[6], RECT, FOOTPRINTS[0] * 0.4):
+        poses = poses_around(rng, 3000, 0.0, span)
+        assert_same(cmap.area_accumulate_cost(fp, poses), po.polygon_batch(omap, fp, poses, op=po.OP_ACCUMULATE, threads=8), True)
+
+
+def test_degenerate_polygons_and_statuses(cb, ctx):
+    """Empty / 1-point / 2-point / collinear polygons; open outlines give LOGIC_ERROR (generators.cpp:246-249)."""
+    rng = np.random.default_rng(30)
+    data = mixed_map(rng, 200, 200, lethal=0.01)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    omap = po.Costmap(data, 0.05)
+    poses = poses_around(rng, 2000, 0.5, 9.5)
+    polys = [
+        np.zeros((2, 0)),
+        np.array([[0.2], [0.1]]),
+        np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 0.0]]),
+        np.array([[0.0, 0.4], [0.0, 0.0]]),
+        np.array([[0.0, 0.3], [0.0, 0.45]]),
+        np.array([[0.0, 0.3, 0.6], [0.0, 0.3, 0.6]]),
+        np.array([[0.0, 0.05, 0.1, 0.05], [0.0, 0.05, 0.0, 0.05]]),
+        np.array([[0.0, 0.3, 0.3, 0.0, 0.0, 0.3], [0.0, 0.0, 0.3, 0.3, 0.0, 0.0]]),
+    ]
+    saw_logic_error = False
+    for poly in polys:
+        for shape, prefix in ((po.SHAPE_AREA, "area"), (po.SHAPE_OUTLINE, "outline")):
+            for name, op, has_cost in OPS:
+                gpu = getattr(cmap, f"{prefix}_{name}")(poly, poses)
+                cpu = po.polygon_batch(omap, poly, poses, shape=shape, op=op, threads=4)
+                assert_same(gpu, cpu, has_cost, f"{poly.tolist()} {prefix} {name}")
+                saw_logic_error |= bool((cpu.status == po.LOGIC_ERROR).any())
+    assert saw_logic_error
+
+
+def test_random_small_polygons_fuzz(cb, ctx):
+    """Random 3..9-gons on a coarse grid: provokes every scan-line quirk through the full pipeline."""
+    rng = np.random.default_rng(31)
+    data = mixed_map(rng, 120, 120, lethal=0.01)
+    cmap = cb.Costmap(ctx, data, 0.1)
+    omap = po.Costmap(data, 0.1)
+    poses = poses_around(rng, 300, 1.0, 11.0)
+    for _ in range(120):
+        n = int(rng.integers(3, 10))
+        poly = rng.uniform(-0.9, 0.9, (2, n))
+        gpu = cmap.area_accumulate_cost(poly, poses)
+        cpu = po.polygon_batch(omap, poly, poses, op=po.OP_ACCUMULATE, threads=4)
+        assert_same(gpu, cpu, True, str(poly.tolist()))
+
+
+def test_no_pose_overload_and_coord_range(cb, ctx):
+    """is_free(polygon, map) (costmap.cpp:71-76) and the COORD_RANGE status."""
+    data = np.zeros((100, 100), dtype=np.uint8)
+    data[40, 40] = 254
+    cmap = cb.Costmap(ctx, data, 0.1, -2.0, -3.0)
+    omap = po.Costmap(data, 0.1, -2.0, -3.0)
+    for poly in (FOOTPRINTS[6] * 0.5 + 1.0, FOOTPRINTS[6] * 0.5 + np.array([[2.0], [1.0]]), RECT + 50.0):
+        gpu, cpu = cmap.area_is_free(poly, None), po.polygon_batch(omap, poly, None)
+        assert_same(gpu, cpu)
+        gpu, cpu = cmap.outline_accumulate_cost(poly, None), po.polygon_batch(omap, poly, None, shape=po.SHAPE_OUTLINE, op=po.OP_ACCUMULATE)
+        assert_same(gpu, cpu, True)
+    far = np.array([[1.0, 0.0, 1e7, 0.0], [1.0, 0.0, 5.0, 5.0], [float("nan"), 0.0, 1.0, 1.0]])
+    gpu, cpu = cmap.area_accumulate_cost(RECT, far), po.polygon_batch(omap, RECT, far, op=po.OP_ACCUMULATE)
+    assert cpu.status.tolist() == [po.COORD_RANGE, po.OK, po.COORD_RANGE]
+    assert_same(gpu, cpu, True)
+
+
+def test_golden_vectors_through_the_gpu(cb, ctx):
+    """test/costmap.cpp:106-194 known answers, evaluated by the CUDA kernels."""
+    data = np.zeros((20, 10), dtype=np.uint8)
+    data[5, 5], data[6, 5], data[7, 5] = 254, 255, 253
+    cmap = cb.Costmap(ctx, data, 1.0)
+    assert cmap.ray_is_free([(4, 0, 4, 9)]).is_free[0] == 1
+    assert cmap.ray_is_free([(5, 0, 5, 9)]).is_free[0] == 0
+    assert cmap.ray_is_free([(-4, -4, -4, 4)]).is_free[0] == 0
+    assert cmap.ray_is_free([(-4, -4, -4, 4)], offset=(4, 4)).is_free[0] == 1
+    tens = cb.Costmap(ctx, np.full((20, 10), 10, dtype=np.uint8), 1.0)
+    sparse = np.array([(0, 0), (9, 0), (9, 19), (0, 19)], dtype=np.int32)
+    area = cb.DiscretePolygon(ctx, po.area_cells([po.outline_cells(sparse)]))
+    assert area.accumulate_cost(tens, [(0, 0)]).cost[0] == 2000
+    shifted = cb.DiscretePolygon(ctx, po.area_cells([po.outline_cells(sparse - np.array([4, 4], dtype=np.int32))]))
+    assert shifted.accumulate_cost(tens, [(0, 0)]).cost[0] == -3
+    assert shifted.accumulate_cost(tens, [(4, 4)]).cost[0] == 2000
+    assert tens.ray_accumulate_cost([(-1, -1, 5, 5)]).cost[0] == -3
+    # box polygon covering the whole map through the polygon entry: sum = 10 * 200
+    box = np.array([[0.5, 9.5, 9.5, 0.5], [0.5, 0.5, 19.5, 19.5]])
+    assert tens.area_accumulate_cost(box, None).cost[0] == 2000
+
+
+def test_rays_cells_and_footprint_bank(cb, ctx):
+    rng = np.random.default_rng(40)
+    data = mixed_map(rng, 256, 192, lethal=0.01)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    omap = po.Costmap(data, 0.05)
+    segs = rng.integers(-10, 270, (50_000, 4)).astype(np.int32)
+    for name, op, has_cost in OPS:
+        for off in (None, (7, -3)):
+            gpu = getattr(cmap, f"ray_{name}")(segs, off)
+            cpu = po.rays_batch(omap, segs, off, op, threads=8)
+            assert_same(gpu, cpu, has_cost, f"ray {name} {off}")
+    cells = po.area_cells([po.outline_cells(po.to_discrete(0.05, FOOTPRINTS[5]))])
+    offs = rng.integers(-20, 280, (40_000, 2)).astype(np.int32)
+    dp = cb.DiscretePolygon(ctx, cells)
+    for name, op, has_cost in OPS:
+        assert_same(getattr(dp, name)(cmap, offs), po.cells_batch(omap, cells, offs, op, threads=8), has_cost, f"cells {name}")
+
+    toru = FOOTPRINTS[5]
+    outlines, areas = [toru * 0.45], [toru, RECT * 0.4 + np.array([[0.5], [0.0]])]
+    bank = []
+    for k in range(12):
+        th = 2 * math.pi * k / 12
+        R = np.array([[math.cos(th), -math.sin(th)], [math.sin(th), math.cos(th)]])
+        bank.append(po.make_discrete_footprint(0.05, [R @ o for o in outlines], [R @ a for a in areas]))
+    which = rng.integers(0, 12, len(offs)).astype(np.int32)
+    fb = cb.FootprintBank(ctx, bank)
+    gpu = fb.is_free(cmap, offs, which)
+    cpu = po.discrete_footprint_batch(omap, bank, offs, which, threads=8)
+    np.testing.assert_array_equal(gpu.is_free, cpu.is_free)
+    assert 0 < cpu.is_free.mean() < 1
+    np.testing.assert_array_equal(fb.is_free(cmap, offs).is_free, po.discrete_footprint_batch(omap, bank, offs, None, threads=8).is_free)
+
+
+def test_split_footprint_pose_form(cb, ctx):
+    """continuous_footprint::is_free(pose, map) with hand-made splits, incl. test/footprints.cpp:244-305."""
+    rng = np.random.default_rng(50)
+    data = np.zeros((200, 100), dtype=np.uint8)
+    box = np.array([[0, 1, 1, 0], [0, 0, 2, 2]], dtype=np.float64) - np.array([[0.5], [1.0]])
+    ident = np.array([[1.0, 0.0, 0.0, 0.0]])
+
+    def both(d, outlines, areas, poses):
+        g = cb.SplitFootprint(ctx, outlines, areas).is_free(cb.Costmap(ctx, d, 0.1, -5.0, -10.0), poses)
+        c = po.continuous_footprint_batch(po.Costmap(d, 0.1, -5.0, -10.0), outlines, areas, poses)
+        np.testing.assert_array_equal(g.is_free, c.is_free)
+        np.testing.assert_array_equal(g.status, c.status)
+        return g.is_free
+
+    assert both(data, [box], [], ident)[0] == 1
+    data[100, 50] = 254
+    assert both(data, [box], [], ident)[0] == 1
+    data[90, 45] = 253
+    assert both(data, [box], [], ident)[0] == 0
+    assert both(data, [], [box], ident)[0] == 0
+    data[100, 50] = 253
+    assert both(data, [], [box], ident)[0] == 1
+    assert both(data, [box * 0.5], [box], np.array([[1.0, 0.0, 5.0, 10.0]]))[0] == 0
+
+    big = mixed_map(rng, 500, 400, lethal=0.0008)
+    toru = FOOTPRINTS[5]
+    outlines = [toru * 0.4, toru * 0.2 + np.array([[0.3], [0.0]])]
+    areas = [toru, FOOTPRINTS[6] * 0.8, RECT * 0.5 + np.array([[-0.2], [0.1]])]
+    poses = poses_around(rng, 30_000, -1.0, 24.0)
+    g = cb.SplitFootprint(ctx, outlines, areas).is_free(cb.Costmap(ctx, big, 0.05, -1.0, 0.5), poses)
+    c = po.continuous_footprint_batch(po.Costmap(big, 0.05, -1.0, 0.5), outlines, areas, poses, threads=8)
+    np.testing.assert_array_equal(g.status, c.status)
+    np.testing.assert_array_equal(g.is_free, c.is_free)
+    assert 0.02 < c.is_free.mean() < 0.98
+
+
+def test_device_resident_inputs_and_outputs(cb, ctx):
+    """Same numbers when poses/results stay on the device (the bench's `value` path)."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(60)
+    data = mixed_map(rng, 512, 512)
+    poses = poses_around(rng, 20_000, 0.0, 25.6)
+    cmap = cb.Costmap(ctx, torch.from_numpy(data).cuda(), 0.05)
+    host = cmap.area_accumulate_cost(RECT, poses)
+    dposes = torch.from_numpy(poses).cuda()
+    out = cb.Result(torch.empty(len(poses), dtype=torch.uint8, device="cuda"), torch.empty(len(poses), dtype=torch.float64, device="cuda"),
+                    torch.empty(len(poses), dtype=torch.uint8, device="cuda"))
+    cmap.area_accumulate_cost(RECT, dposes, out=out)
+    ctx.synchronize()
+    np.testing.assert_array_equal(out.is_free.cpu().numpy(), host.is_free)
+    np.testing.assert_array_equal(out.cost.cpu().numpy(), host.cost)
+    cpu = po.polygon_batch(po.Costmap(data, 0.05), RECT, poses, op=po.OP_ACCUMULATE, threads=8)
+    assert_same(host, cpu, True)
+
+
+def test_map_window_update(cb, ctx):
+    rng = np.random.default_rng(70)
+    data = mixed_map(rng, 300, 300, lethal=0.0)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    poses = poses_around(rng, 5000, 1.0, 14.0)
+    assert cmap.area_is_free(RECT, poses).is_free.all()
+    data[100:140, 120:170] = 254
+    cmap.upload_window(data, 120, 100, 50, 40)
+    assert_same(cmap.area_is_free(RECT, poses), po.polygon_batch(po.Costmap(data, 0.05), RECT, poses, threads=8))
+
+
+def test_full_size_lattice_properties(cb, ctx):
+    """BASELINE config 4 at FULL size (4000 x 4000 map, 1180 x 1180 x 72 lattice = 1.0e8 poses): sampled
+    oracle comparison + size-independent properties (idempotence, verdict <-> max_cost consistency)."""
+    from cover_b200 import workloads as wl
+    data = wl.inflated_costmap(4000, 4000, 0.05, seed=3)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    desc = wl.dwa_lattice()
+    lat = cb.Lattice(**desc)
+    first = cmap.area_is_free(RECT, lat)
+    assert len(first.is_free) == 1180 * 1180 * 72
+    assert (first.status == 0).all()
+    again = cmap.area_is_free(RECT, lat)
+    np.testing.assert_array_equal(first.is_free, again.is_free)
+    frac = first.is_free.mean()
+    assert 0.5 < frac < 0.999
+    # sampled parity against the oracle
+    rng = np.random.default_rng(4)
+    olat = po.Lattice(**desc)
+    omap = po.Costmap(data, 0.05)
+    for start in rng.integers(0, lat.count - 40_000, 6).tolist():
+        cpu = po.polygon_batch(omap, RECT, olat, first=start, count=40_000, threads=8)
+        np.testing.assert_array_equal(first.is_free[start:start + 40_000], cpu.is_free)
+    # verdict <-> max consistency on a slab: no 255 in this map, so is_free == (0 <= max < 254)
+    n = 3_000_000
+    mx = cmap.area_max_cost(RECT, lat, first=5_000_000, count=n)
+    np.testing.assert_array_equal(first.is_free[5_000_000:5_000_000 + n], ((mx.cost >= 0) & (mx.cost < 254)).astype(np.uint8))
