@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -130,6 +131,232 @@ __global__ void __launch_bounds__(kBlock) k_area_packed(MapView m, const double*
   }
   fold.store(out, i);
   if (out.status) out.status[i] = ST_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Lattice kernel (is_free on a POSE_LATTICE batch): the DWA-style headline path.
+//
+// On an (x, y, heading) lattice almost every pose of one heading has the SAME discretised polygon up to
+// a translation: the vertices' cell offsets relative to vertex 0 only change where a coordinate sits
+// within rounding noise of a cell boundary.  The kernel therefore
+//   1. discretises every pose's vertices exactly (FP64, per thread) and hashes the relative shape,
+//   2. deduplicates the relative shapes of a 128 x 8 pose tile in shared memory,
+//   3. rasterises each DISTINCT shape once (one thread per shape: same run detector / packed row table
+//      as k_area_packed, so the scan-line semantics are literally the same code),
+//   4. verifies each pose's relative vertices against its shape's canonical ones (exactness never
+//      rests on the hash) and then tests 32 x-adjacent poses at once: per scan row the warp loads the
+//      row segment one byte per lane, ballots "lethal or outside" into a 64-cell bit window, and every
+//      pose ANDs its own sub-window — ~25 warp instructions per row for 32 poses.
+// Poses whose shape needs more than two ranges on a row, or does not fit the window, go to the todo
+// list and are finished by k_area_list.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kLatTileX = 128, kLatTileY = 8, kLatThreads = 256, kLatSlots = 32, kLatTasks = 4;
+constexpr int kLatMaxVertices = 64;
+constexpr int kLatMaxWidth = 32;  // widest scan row (cells) the 64-cell window handles with 32 lane offsets
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+struct LatShape {
+  int xb, yb, rows, wmax, status;  // status: ST_OK, ST_LOGIC_ERROR, or -1 = not representable here
+};
+
+struct LatGeom {
+  long long row_first;  // first lattice row (it*ny + iy) touched by this batch
+  int n_rows, tiles_x;
+};
+
+__device__ __forceinline__ unsigned long long lat_mix(unsigned long long h, int v) {
+  return (h ^ static_cast<unsigned int>(v)) * 0x100000001B3ull;  // FNV-1a step
+}
+
+__device__ __forceinline__ Pose lattice_pose(const PoseSource& src, long long row, int ix) {
+  const int it = static_cast<int>(row / src.ny);
+  const int iy = static_cast<int>(row - static_cast<long long>(it) * src.ny);
+  Pose T;
+  T.tx = __dadd_rn(src.x0, __dmul_rn(static_cast<double>(ix), src.dx));
+  T.ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(iy), src.dy));
+  const double2 cs = __ldg(reinterpret_cast<const double2*>(src.theta_cs) + it);
+  T.c = cs.x, T.s = cs.y;
+  return T;
+}
+
+__global__ void __launch_bounds__(kLatThreads) k_area_lattice_free(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
+                                                                  long long count, OutView out, int rows_cap,
+                                                                  unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count,
+                                                                  LatGeom g) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv, smem_d);
+  unsigned long long* slot_hash = reinterpret_cast<unsigned long long*>(smem_d + 2 * nv);
+  int2* canon = reinterpret_cast<int2*>(slot_hash + kLatSlots);                // [slot][vertex] relative cells
+  uint32_t* rowtab = reinterpret_cast<uint32_t*>(canon + kLatSlots * nv);      // [slot][row] packed ranges
+  LatShape* meta = reinterpret_cast<LatShape*>(rowtab + kLatSlots * rows_cap);  // [slot]
+  if (threadIdx.x < kLatSlots) slot_hash[threadIdx.x] = 0ull;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_y = blockIdx.x / g.tiles_x, tile_x = blockIdx.x - tile_y * g.tiles_x;
+
+  int vx0[kLatTasks], vy0[kLatTasks], slot[kLatTasks];
+  long long oidx[kLatTasks];
+
+  // ---- phases 1 + 2: exact vertices, shape hash, tile-wide deduplication ---------------------------
+#pragma unroll
+  for (int k = 0; k < kLatTasks; ++k) {
+    const int t = warp + 8 * k, row_rel = tile_y * kLatTileY + (t >> 2);
+    const int ix = tile_x * kLatTileX + (t & 3) * 32 + lane;
+    const long long row = g.row_first + row_rel;
+    const long long i = row * src.nx + ix - src.first;
+    const bool active = row_rel < g.n_rows && ix < src.nx && i >= 0 && i < count;
+    oidx[k] = active ? i : -1;
+    slot[k] = -2;
+    vx0[k] = vy0[k] = 0;
+    bool valid = false;
+    unsigned long long h = 0xCBF29CE484222325ull;
+    Pose T{1, 0, 0, 0};
+    if (active) {
+      T = lattice_pose(src, row, ix);
+      bool ok = true;
+      int ax = 0, ay = 0;
+      for (int v = 0; v < nv; ++v) {
+        int cx, cy;
+        ok &= to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
+        if (v == 0) {
+          ax = cx, ay = cy;
+        } else {
+          h = lat_mix(lat_mix(h, cx - ax), cy - ay);
+        }
+      }
+      if (h == 0ull) h = 1ull;
+      vx0[k] = ax, vy0[k] = ay;
+      valid = ok;
+      if (!ok) {
+        store_failure(out, i, ST_COORD_RANGE);
+        oidx[k] = -1;
+      }
+    }
+    unsigned pending = __ballot_sync(kFull, valid);
+    while (pending) {
+      const int leader = __ffs(pending) - 1;
+      const unsigned long long hl = __shfl_sync(kFull, h, leader);
+      const bool same = valid && h == hl;
+      const unsigned grp = __ballot_sync(kFull, same);
+      int s = -1;
+      if (lane == leader) {  // find or insert the shape in the tile's table
+        for (int j = 0; j < kLatSlots && s < 0; ++j) {
+          const int idx = static_cast<int>((hl + j) & (kLatSlots - 1));
+          const unsigned long long old = atomicCAS(&slot_hash[idx], 0ull, hl);
+          if (old == 0ull) {  // we own the slot: publish the canonical relative vertices
+            for (int v = 0; v < nv; ++v) {
+              int cx, cy;
+              to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
+              canon[idx * nv + v] = make_int2(cx - vx0[k], cy - vy0[k]);
+            }
+            s = idx;
+          } else if (old == hl) {
+            s = idx;
+          }
+        }
+      }
+      s = __shfl_sync(kFull, s, leader);
+      if (same) slot[k] = s;
+      pending &= ~grp;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: one thread rasterises one distinct shape ------------------------------------------
+  if (threadIdx.x < kLatSlots && slot_hash[threadIdx.x] != 0ull) {
+    const int2* verts = canon + threadIdx.x * nv;
+    int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, x1 = -0x7FFFFFFF - 1, y1 = -0x7FFFFFFF - 1;
+    for (int v = 0; v < nv; ++v) {
+      x0 = min(x0, verts[v].x), x1 = max(x1, verts[v].x);
+      y0 = min(y0, verts[v].y), y1 = max(y1, verts[v].y);
+    }
+    LatShape sh{x0, y0, y1 - y0 + 1, 0, ST_OK};
+    if (sh.rows > rows_cap || (x1 - x0) > kPackedMaxWidth) {
+      sh.status = -1;
+    } else {
+      PackedStore store{rowtab + threadIdx.x * rows_cap, 1, x0, y0};
+      store.clear(sh.rows);
+      RunDetector<PackedStore> runs(store, 0, x0, x1);
+      walk_outline_cells(verts, nv, runs);
+      runs.finish();
+      if (store.overflow) {
+        sh.status = -1;
+      } else {
+        for (int r = 0; r < sh.rows; ++r) {
+          const uint32_t w = store.tab[r];
+          if ((w >> 30) == 1u) sh.status = ST_LOGIC_ERROR;
+          if ((w >> 30) == 2u) sh.wmax = max(sh.wmax, static_cast<int>(((w >> 15) & 0x7FFFu) - (w & 0x7FFFu)) + 1);
+        }
+        if (sh.status == ST_OK && sh.wmax > kLatMaxWidth) sh.status = -1;
+      }
+    }
+    meta[threadIdx.x] = sh;
+  }
+  __syncthreads();
+
+  // ---- phase 4: verify, then 32 x-adjacent poses per bit window -----------------------------------
+#pragma unroll
+  for (int k = 0; k < kLatTasks; ++k) {
+    const long long i = oidx[k];
+    int s = slot[k];
+    if (i >= 0 && s >= 0) {  // the hash only proposed the shape: compare the actual relative vertices
+      const int t = warp + 8 * k;
+      const Pose T = lattice_pose(src, g.row_first + tile_y * kLatTileY + (t >> 2), tile_x * kLatTileX + (t & 3) * 32 + lane);
+      for (int v = 0; v < nv; ++v) {
+        int cx, cy;
+        to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
+        const int2 c = canon[s * nv + v];
+        if (cx - vx0[k] != c.x || cy - vy0[k] != c.y) s = -1;
+      }
+    }
+    const int st = s >= 0 ? meta[s].status : 0;
+    if (i >= 0 && (s == -1 || st == -1)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i);
+    if (i >= 0 && s >= 0 && st == ST_LOGIC_ERROR) store_failure(out, i, ST_LOGIC_ERROR);
+    const bool go = i >= 0 && s >= 0 && st == ST_OK;
+    unsigned pending = __ballot_sync(kFull, go);
+    while (pending) {
+      const int leader = __ffs(pending) - 1;
+      const int sl = __shfl_sync(kFull, s, leader), yl = __shfl_sync(kFull, vy0[k], leader);
+      const LatShape sh = meta[sl];
+      const bool same = go && ((pending >> lane) & 1u) && s == sl && vy0[k] == yl;
+      const int xmin = __reduce_min_sync(kFull, same ? vx0[k] : 0x7FFFFFFF);
+      const int off = vx0[k] - xmin;
+      const bool fits = same && off <= 64 - sh.wmax;  // the lane holding xmin always fits (wmax <= 32)
+      const unsigned grp = __ballot_sync(kFull, fits);
+      const int maxoff = __reduce_max_sync(kFull, fits ? off : 0);
+      const uint32_t* tab = rowtab + sl * rows_cap;
+      uint32_t hit = 0;
+      for (int r = 0; r < sh.rows; ++r) {
+        const uint32_t w = tab[r];
+        if ((w >> 30) != 2u) continue;
+        const int lo = sh.xb + static_cast<int>(w & 0x7FFFu), width = static_cast<int>(((w >> 15) & 0x7FFFu) - (w & 0x7FFFu)) + 1;
+        const int y = yl + sh.yb + r;
+        const bool y_in = static_cast<unsigned>(y) < static_cast<unsigned>(m.size_y);
+        const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y_in ? y : 0) * m.pitch;
+        int x = xmin + lo + lane;
+        bool lethal = true;  // outside the map counts as lethal (costmap.hpp:81-91)
+        if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
+        const uint32_t m0 = __ballot_sync(kFull, lethal);
+        uint32_t m1 = 0;
+        if (width + maxoff > 32) {
+          x += 32;
+          lethal = true;
+          if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
+          m1 = __ballot_sync(kFull, lethal);
+        }
+        const uint32_t bits = off < 32 ? __funnelshift_r(m0, m1, off) : (m1 >> (off - 32));
+        const uint32_t wmask = width >= 32 ? 0xFFFFFFFFu : ((1u << width) - 1u);
+        hit |= bits & wmask;
+      }
+      if (fits) {
+        if (out.is_free) out.is_free[i] = hit ? 0 : 1;
+        if (out.status) out.status[i] = ST_OK;
+      }
+      pending &= ~grp;
+    }
+  }
 }
 
 struct ListScratch {
@@ -376,6 +603,7 @@ struct cover_ctx {
   cudaStream_t stream = nullptr;
   std::string error;
   int64_t launches = 0;
+  bool disable_lattice_kernel = false;  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
   DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, todo, todo_count, list_cnt, list_rng, list_seq;
 };
 
@@ -592,6 +820,7 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_list<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_list<OP_MAX>));
   set(reinterpret_cast<const void*>(&k_split));
+  set(reinterpret_cast<const void*>(&k_area_lattice_free));
   return e;
 }
 
@@ -612,9 +841,25 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     CU(ctx->todo.ensure(static_cast<size_t>(count) * sizeof(unsigned int)));
     CU(ctx->todo_count.ensure(sizeof(unsigned int)));
     CU(cudaMemsetAsync(ctx->todo_count.ptr, 0, sizeof(unsigned int), ctx->stream));
-    const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint32_t);
-    k_area_packed<OP><<<grid_for(count), kBlock, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
-                                                                      ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
+    // Lattice batches of small footprints: shape-deduplicating warp-cooperative kernel.
+    const bool lattice = OP == OP_IS_FREE && src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices &&
+                         rows_cap - 3 <= kLatMaxWidth && !ctx->disable_lattice_kernel;
+    if (lattice) {
+      LatGeom g;
+      g.row_first = src.first / src.nx;
+      const long long row_last = (src.first + count - 1) / src.nx;
+      g.n_rows = static_cast<int>(row_last - g.row_first + 1);
+      g.tiles_x = (src.nx + kLatTileX - 1) / kLatTileX;
+      const long long tiles_y = (g.n_rows + kLatTileY - 1) / kLatTileY;
+      const size_t smem = poly_bytes + kLatSlots * (sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) +
+                                                     static_cast<size_t>(rows_cap) * sizeof(uint32_t) + sizeof(LatShape));
+      k_area_lattice_free<<<static_cast<unsigned int>(tiles_y * g.tiles_x), kLatThreads, smem, ctx->stream>>>(
+          map->view, poly_dev, nv, src, count, out, rows_cap, ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g);
+    } else {
+      const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint32_t);
+      k_area_packed<OP><<<grid_for(count), kBlock, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
+                                                                        ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
+    }
     ++ctx->launches;
     // Drain whatever the packed kernel deferred (usually nothing) with a small persistent grid.
     const unsigned int grid = list_grid(ctx, count, rows_cap, 1);
@@ -752,6 +997,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
     return COVER_E_CUDA;
   }
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* e = std::getenv("COVER_B200_NO_LATTICE_KERNEL")) ctx->disable_lattice_kernel = e[0] == '1';
   *out = ctx;
   return COVER_OK;
 }

@@ -337,6 +337,29 @@ __device__ __forceinline__ bool walk_outline(const double* __restrict__ poly, in
   return sink.cell(px, py);  // one-cell dummy ray holding the last point (generators.cpp:72-78)
 }
 
+/// outline_generator over an already discretised vertex list (`verts[0]` is implicitly (0,0) when
+/// `first_is_origin`): used by the lattice kernel, which rasterises each distinct RELATIVE shape once.
+template <class Sink>
+__device__ __forceinline__ bool walk_outline_cells(const int2* __restrict__ verts, int nv, Sink& sink) {
+  if (nv == 0) return true;
+  const int2 f = verts[0];
+  int2 p = f;
+  int rays = 0;
+  for (int i = 1; i < nv; ++i) {
+    const int2 c = verts[i];
+    if (c.x != p.x || c.y != p.y) {
+      ++rays;
+      if (!walk_ray(p.x, p.y, c.x, c.y, sink)) return false;
+    }
+    p = c;
+  }
+  if (rays > 1) {
+    if (p.x != f.x || p.y != f.y) return walk_ray(p.x, p.y, f.x, f.y, sink);
+    return true;
+  }
+  return sink.cell(p.x, p.y);
+}
+
 /// Integer bounding box of the discretised vertices + the coordinate-range check.
 template <int XF>
 __device__ __forceinline__ bool polygon_bbox(const double* __restrict__ poly, int nv, const Pose& T, const MapView& m, int& x0,

@@ -96,6 +96,42 @@ def test_rect_lattice_matches_oracle_and_explicit_poses(cb, ctx):
     assert_same(acc, cpu_acc, True)
 
 
+@pytest.mark.parametrize("pitch", [0.05, 0.025, 0.1, 0.07])
+def test_lattice_axis_aligned_headings_and_map_border(cb, ctx, pitch):
+    """Headings where the vertices sit exactly on cell boundaries (the relative shape flips with rounding
+    noise from pose to pose) on a lattice that sticks out of the map on every side, at cell pitch and at
+    pitches that are not the cell size."""
+    rng = np.random.default_rng(33)
+    data = mixed_map(rng, 300, 240, lethal=0.002)
+    th = np.array([0.0, math.pi / 2, math.pi, -math.pi / 2, 0.3, math.atan2(3, 4), 1e-9])
+    cs = np.stack([np.cos(th), np.sin(th)], 1)
+    nx, ny = int(17.0 / pitch), int(14.0 / pitch)
+    nx, ny = min(nx, 400), min(ny, 330)
+    for origin in ((0.0, 0.0), (-1.3, 0.65)):
+        desc = dict(x0=origin[0] - 1.0, dx=pitch, nx=nx, y0=origin[1] - 1.0, dy=pitch, ny=ny, cs=cs)
+        cmap = cb.Costmap(ctx, data, 0.05, *origin)
+        gpu = cmap.area_is_free(RECT, cb.Lattice(**desc))
+        cpu = po.polygon_batch(po.Costmap(data, 0.05, *origin), RECT, po.Lattice(**desc), threads=8)
+        assert_same(gpu, cpu, what=f"pitch {pitch} origin {origin}")
+        assert 0.05 < cpu.is_free.mean() < 0.95
+
+
+def test_lattice_other_small_footprints(cb, ctx):
+    """Triangles, the L-shape scaled down, a 1-cell polygon and a degenerate (open) outline on a lattice."""
+    rng = np.random.default_rng(34)
+    data = mixed_map(rng, 256, 256, lethal=0.004)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    omap = po.Costmap(data, 0.05)
+    th = -math.pi + 2 * math.pi * np.arange(12) / 12
+    desc = dict(x0=0.2, dx=0.05, nx=230, y0=0.3, dy=0.05, ny=100, cs=np.stack([np.cos(th), np.sin(th)], 1))
+    polys = [np.array([[0.4, -0.3, -0.3], [0.0, 0.25, -0.25]]), FOOTPRINTS[6] * 0.8, np.array([[0.01], [0.01]]),
+             np.array([[0.0, 0.3], [0.0, 0.45]]), np.array([[0.6, 0.6, -0.6, -0.6], [0.05, -0.05, -0.05, 0.05]])]
+    for poly in polys:
+        gpu = cmap.area_is_free(poly, cb.Lattice(**desc))
+        cpu = po.polygon_batch(omap, poly, po.Lattice(**desc), threads=8)
+        assert_same(gpu, cpu, what=str(poly.tolist()))
+
+
 @pytest.mark.parametrize("idx", range(7))
 @pytest.mark.parametrize("shape,prefix", [(po.SHAPE_AREA, "area"), (po.SHAPE_OUTLINE, "outline")])
 def test_reference_footprints_all_ops(cb, ctx, idx, shape, prefix):
