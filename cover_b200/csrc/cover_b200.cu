@@ -139,223 +139,277 @@ __global__ void __launch_bounds__(kBlock) k_area_packed(MapView m, const double*
 //
 // On an (x, y, heading) lattice almost every pose of one heading has the SAME discretised polygon up to
 // a translation: the vertices' cell offsets relative to vertex 0 only change where a coordinate sits
-// within rounding noise of a cell boundary.  The kernel therefore
-//   1. discretises every pose's vertices exactly (FP64, per thread) and hashes the relative shape,
-//   2. deduplicates the relative shapes of a 128 x 8 pose tile in shared memory,
-//   3. rasterises each DISTINCT shape once (one thread per shape: same run detector / packed row table
-//      as k_area_packed, so the scan-line semantics are literally the same code),
-//   4. verifies each pose's relative vertices against its shape's canonical ones (exactness never
-//      rests on the hash) and then tests 32 x-adjacent poses at once: per scan row the warp loads the
-//      row segment one byte per lane, ballots "lethal or outside" into a 64-cell bit window, and every
-//      pose ANDs its own sub-window — ~25 warp instructions per row for 32 poses.
-// Poses whose shape needs more than two ranges on a row, or does not fit the window, go to the todo
-// list and are finished by k_area_list.
+// within rounding noise of a cell boundary.  A persistent CTA walks 128 x 8 pose tiles and
+//   1. discretises every pose's vertices exactly (FP64, per thread) and forms the key of the RELATIVE
+//      shape (the packed vertex offsets themselves for <= 4 vertices, else a 64-bit hash),
+//   2. looks the shape up in a shared-memory cache that persists across the CTA's tiles,
+//   3. rasterises each NEW shape once (one thread per shape: the same run detector / packed row table
+//      as k_area_packed, so the scan-line semantics are literally the same code) — rare after a CTA's
+//      first tile of a heading,
+//   4. (hashed keys only) verifies each pose's relative vertices against the cached canonical ones, so
+//      exactness never rests on the hash, and then tests up to 32 x-adjacent poses at once: per scan row
+//      the warp loads the row segment one byte per lane (two coalesced 32-byte pieces), ballots "lethal
+//      or outside" into a 64-cell bit window, and every pose ANDs its own sub-window.
+// Poses whose shape needs more than two ranges on a row, is wider than 32 cells, or finds the cache
+// full go to the todo list and are finished by k_area_list.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kLatTileX = 128, kLatTileY = 8, kLatThreads = 256, kLatSlots = 32, kLatTasks = 4;
+constexpr int kLatTileX = 128, kLatTileY = 8, kLatThreads = 256, kLatSlots = 64, kLatTasks = 4;
 constexpr int kLatMaxVertices = 64;
-constexpr int kLatMaxWidth = 32;  // widest scan row (cells) the 64-cell window handles with 32 lane offsets
+constexpr int kLatMaxWidth = 32;   // widest scan row (cells): 32 lane offsets + 32 cells = one 64-cell window
+constexpr int kLatPending = -2;    // shape inserted, not rasterised yet
+constexpr int kLatUnfit = -1;      // shape not representable by this kernel
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 struct LatShape {
-  int xb, yb, rows, wmax, status;  // status: ST_OK, ST_LOGIC_ERROR, or -1 = not representable here
+  int xb, x1, yb, rows, status;  // bbox of the relative vertices (x: [xb, x1], y: [yb, yb+rows-1])
 };
 
 struct LatGeom {
   long long row_first;  // first lattice row (it*ny + iy) touched by this batch
   int n_rows, tiles_x;
+  long long n_tiles;
 };
 
 __device__ __forceinline__ unsigned long long lat_mix(unsigned long long h, int v) {
   return (h ^ static_cast<unsigned int>(v)) * 0x100000001B3ull;  // FNV-1a step
 }
 
-__device__ __forceinline__ Pose lattice_pose(const PoseSource& src, long long row, int ix) {
-  const int it = static_cast<int>(row / src.ny);
-  const int iy = static_cast<int>(row - static_cast<long long>(it) * src.ny);
-  Pose T;
-  T.tx = __dadd_rn(src.x0, __dmul_rn(static_cast<double>(ix), src.dx));
-  T.ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(iy), src.dy));
-  const double2 cs = __ldg(reinterpret_cast<const double2*>(src.theta_cs) + it);
-  T.c = cs.x, T.s = cs.y;
-  return T;
+template <bool FAST>
+__device__ __forceinline__ uint32_t lattice_rows(const MapView& m, const int* __restrict__ row_a, const uint32_t* __restrict__ row_m,
+                                                 int rows, int x_base, int y_base, int off, int lane) {
+  uint32_t hit = 0;
+  if (FAST) {  // every needed cell of every pose of the group is inside the map: no per-cell bounds tests
+    const uint8_t* __restrict__ p = m.data + static_cast<size_t>(y_base) * m.pitch + (x_base + lane);
+    for (int r = 0; r < rows; ++r, p += m.pitch) {
+      const int lo = static_cast<short>(row_a[r] & 0xFFFF);
+      const uint32_t m0 = __ballot_sync(kFull, __ldg(p + lo) == kLethal);
+      const uint32_t m1 = __ballot_sync(kFull, __ldg(p + lo + 32) == kLethal);
+      hit |= __funnelshift_r(m0, m1, off) & row_m[r];
+    }
+  } else {
+    for (int r = 0; r < rows; ++r) {
+      const int lo = static_cast<short>(row_a[r] & 0xFFFF);
+      const int y = y_base + r;
+      const bool y_in = static_cast<unsigned>(y) < static_cast<unsigned>(m.size_y);
+      const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y_in ? y : 0) * m.pitch;
+      int x = x_base + lo + lane;
+      bool lethal = true;  // outside the map counts as lethal (costmap.hpp:81-91)
+      if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
+      const uint32_t m0 = __ballot_sync(kFull, lethal);
+      x += 32;
+      lethal = true;
+      if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
+      const uint32_t m1 = __ballot_sync(kFull, lethal);
+      hit |= __funnelshift_r(m0, m1, off) & row_m[r];
+    }
+  }
+  return hit;
 }
 
-__global__ void __launch_bounds__(kLatThreads) k_area_lattice_free(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
-                                                                  long long count, OutView out, int rows_cap,
-                                                                  unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count,
-                                                                  LatGeom g) {
+__global__ void __launch_bounds__(kLatThreads, 4) k_area_lattice_free(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
+                                                                     long long count, OutView out, int rows_cap,
+                                                                     unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count,
+                                                                     LatGeom g) {
   extern __shared__ double smem_d[];
   const double* poly = stage_polygon(poly_g, nv, smem_d);
-  unsigned long long* slot_hash = reinterpret_cast<unsigned long long*>(smem_d + 2 * nv);
-  int2* canon = reinterpret_cast<int2*>(slot_hash + kLatSlots);                // [slot][vertex] relative cells
-  uint32_t* rowtab = reinterpret_cast<uint32_t*>(canon + kLatSlots * nv);      // [slot][row] packed ranges
-  LatShape* meta = reinterpret_cast<LatShape*>(rowtab + kLatSlots * rows_cap);  // [slot]
-  if (threadIdx.x < kLatSlots) slot_hash[threadIdx.x] = 0ull;
+  unsigned long long* slot_key = reinterpret_cast<unsigned long long*>(smem_d + 2 * nv);  // 0 = empty
+  int2* canon = reinterpret_cast<int2*>(slot_key + kLatSlots);                          // [slot][vertex] relative cells
+  int* row_a = reinterpret_cast<int*>(canon + kLatSlots * nv);                          // [slot][row] lo (int16) | width << 16
+  uint32_t* row_m = reinterpret_cast<uint32_t*>(row_a + kLatSlots * rows_cap);          // [slot][row] width mask (0 = no range)
+  LatShape* meta = reinterpret_cast<LatShape*>(row_m + kLatSlots * rows_cap);           // [slot]
+  int* ctl = reinterpret_cast<int*>(meta + kLatSlots);                                  // [0] used slots, [1] dirty
+  int2* tile_rows = reinterpret_cast<int2*>(ctl + 2);                                   // [kLatTileY] (it, iy) of the tile's rows
+  if (threadIdx.x < kLatSlots) slot_key[threadIdx.x] = 0ull;
+  if (threadIdx.x < 2) ctl[threadIdx.x] = 0;
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_y = blockIdx.x / g.tiles_x, tile_x = blockIdx.x - tile_y * g.tiles_x;
+  const bool exact_key = nv <= 4;  // 3 x 2 offsets of 8 bits: the key IS the shape, no verification pass
 
-  int vx0[kLatTasks], vy0[kLatTasks], slot[kLatTasks];
-  long long oidx[kLatTasks];
-
-  // ---- phases 1 + 2: exact vertices, shape hash, tile-wide deduplication ---------------------------
-#pragma unroll
-  for (int k = 0; k < kLatTasks; ++k) {
-    const int t = warp + 8 * k, row_rel = tile_y * kLatTileY + (t >> 2);
-    const int ix = tile_x * kLatTileX + (t & 3) * 32 + lane;
-    const long long row = g.row_first + row_rel;
-    const long long i = row * src.nx + ix - src.first;
-    const bool active = row_rel < g.n_rows && ix < src.nx && i >= 0 && i < count;
-    oidx[k] = active ? i : -1;
-    slot[k] = -2;
-    vx0[k] = vy0[k] = 0;
-    bool valid = false;
-    unsigned long long h = 0xCBF29CE484222325ull;
-    Pose T{1, 0, 0, 0};
-    if (active) {
-      T = lattice_pose(src, row, ix);
-      bool ok = true;
-      int ax = 0, ay = 0;
-      for (int v = 0; v < nv; ++v) {
-        int cx, cy;
-        ok &= to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
-        if (v == 0) {
-          ax = cx, ay = cy;
-        } else {
-          h = lat_mix(lat_mix(h, cx - ax), cy - ay);
-        }
-      }
-      if (h == 0ull) h = 1ull;
-      vx0[k] = ax, vy0[k] = ay;
-      valid = ok;
-      if (!ok) {
-        store_failure(out, i, ST_COORD_RANGE);
-        oidx[k] = -1;
-      }
+  for (long long tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+    const int tile_y = static_cast<int>(tile / g.tiles_x), tile_x = static_cast<int>(tile - static_cast<long long>(tile_y) * g.tiles_x);
+    if (ctl[0] > kLatSlots - 16) {  // cache nearly full: start over (uniform decision, taken after a barrier)
+      __syncthreads();
+      if (threadIdx.x < kLatSlots) slot_key[threadIdx.x] = 0ull;
+      if (threadIdx.x == 0) ctl[0] = 0;
     }
-    unsigned pending = __ballot_sync(kFull, valid);
-    while (pending) {
-      const int leader = __ffs(pending) - 1;
-      const unsigned long long hl = __shfl_sync(kFull, h, leader);
-      const bool same = valid && h == hl;
-      const unsigned grp = __ballot_sync(kFull, same);
-      int s = -1;
-      if (lane == leader) {  // find or insert the shape in the tile's table
-        for (int j = 0; j < kLatSlots && s < 0; ++j) {
-          const int idx = static_cast<int>((hl + j) & (kLatSlots - 1));
-          const unsigned long long old = atomicCAS(&slot_hash[idx], 0ull, hl);
-          if (old == 0ull) {  // we own the slot: publish the canonical relative vertices
-            for (int v = 0; v < nv; ++v) {
-              int cx, cy;
-              to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
-              canon[idx * nv + v] = make_int2(cx - vx0[k], cy - vy0[k]);
-            }
-            s = idx;
-          } else if (old == hl) {
-            s = idx;
+    if (threadIdx.x < kLatTileY) {
+      const long long row = g.row_first + static_cast<long long>(tile_y) * kLatTileY + threadIdx.x;
+      const int it = static_cast<int>(row / src.ny);
+      tile_rows[threadIdx.x] = make_int2(it, static_cast<int>(row - static_cast<long long>(it) * src.ny));
+    }
+    __syncthreads();
+
+    int vx0[kLatTasks], vy0[kLatTasks], slot[kLatTasks];
+    long long oidx[kLatTasks];
+
+    // ---- phases 1 + 2: exact vertices, shape key, cache lookup / insert ----------------------------
+#pragma unroll
+    for (int k = 0; k < kLatTasks; ++k) {
+      const int t = warp + 8 * k, rit = t >> 2, row_rel = tile_y * kLatTileY + rit;
+      const int ix = tile_x * kLatTileX + (t & 3) * 32 + lane;
+      const long long i = (g.row_first + row_rel) * src.nx + ix - src.first;
+      const bool active = row_rel < g.n_rows && ix < src.nx && i >= 0 && i < count;
+      oidx[k] = active ? i : -1;
+      slot[k] = -2;  // -2: nothing to do, -1: todo list, >= 0: cache slot
+      vx0[k] = vy0[k] = 0;
+      bool valid = false;
+      unsigned long long key = 0;
+      Pose T{1, 0, 0, 0};
+      if (active) {
+        const int2 rr = tile_rows[rit];
+        T.tx = __dadd_rn(src.x0, __dmul_rn(static_cast<double>(ix), src.dx));
+        T.ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(rr.y), src.dy));
+        const double2 cs = __ldg(reinterpret_cast<const double2*>(src.theta_cs) + rr.x);
+        T.c = cs.x, T.s = cs.y;
+        bool ok = true;
+        int ax = 0, ay = 0;
+        unsigned long long h = 0xCBF29CE484222325ull;
+        for (int v = 0; v < nv; ++v) {
+          int cx, cy;
+          ok &= to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
+          if (v == 0) {
+            ax = cx, ay = cy;
+          } else if (exact_key) {
+            const int dx = cx - ax, dy = cy - ay;
+            if (dx < -128 || dx > 127 || dy < -128 || dy > 127) key = ~0ull;  // cannot be packed: todo list
+            if (key != ~0ull) key = (key << 16) | (static_cast<unsigned long long>(dx & 0xFF) << 8) | static_cast<unsigned long long>(dy & 0xFF);
+          } else {
+            h = lat_mix(lat_mix(h, cx - ax), cy - ay);
           }
         }
-      }
-      s = __shfl_sync(kFull, s, leader);
-      if (same) slot[k] = s;
-      pending &= ~grp;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 3: one thread rasterises one distinct shape ------------------------------------------
-  if (threadIdx.x < kLatSlots && slot_hash[threadIdx.x] != 0ull) {
-    const int2* verts = canon + threadIdx.x * nv;
-    int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, x1 = -0x7FFFFFFF - 1, y1 = -0x7FFFFFFF - 1;
-    for (int v = 0; v < nv; ++v) {
-      x0 = min(x0, verts[v].x), x1 = max(x1, verts[v].x);
-      y0 = min(y0, verts[v].y), y1 = max(y1, verts[v].y);
-    }
-    LatShape sh{x0, y0, y1 - y0 + 1, 0, ST_OK};
-    if (sh.rows > rows_cap || (x1 - x0) > kPackedMaxWidth) {
-      sh.status = -1;
-    } else {
-      PackedStore store{rowtab + threadIdx.x * rows_cap, 1, x0, y0};
-      store.clear(sh.rows);
-      RunDetector<PackedStore> runs(store, 0, x0, x1);
-      walk_outline_cells(verts, nv, runs);
-      runs.finish();
-      if (store.overflow) {
-        sh.status = -1;
-      } else {
-        for (int r = 0; r < sh.rows; ++r) {
-          const uint32_t w = store.tab[r];
-          if ((w >> 30) == 1u) sh.status = ST_LOGIC_ERROR;
-          if ((w >> 30) == 2u) sh.wmax = max(sh.wmax, static_cast<int>(((w >> 15) & 0x7FFFu) - (w & 0x7FFFu)) + 1);
+        vx0[k] = ax, vy0[k] = ay;
+        if (!ok) {
+          store_failure(out, i, ST_COORD_RANGE);
+          oidx[k] = -1;
+        } else if (exact_key && key == ~0ull) {
+          slot[k] = -1;
+        } else {
+          key = exact_key ? (key | (1ull << 63)) : (h | 1ull);
+          valid = true;
         }
-        if (sh.status == ST_OK && sh.wmax > kLatMaxWidth) sh.status = -1;
+      }
+      unsigned pending = __ballot_sync(kFull, valid);
+      while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const unsigned long long kl = __shfl_sync(kFull, key, leader);
+        const bool same = valid && key == kl;
+        const unsigned grp = __ballot_sync(kFull, same);
+        int s = -1;
+        if (lane == leader) {  // find the shape in the cache, or insert it
+          const int home = static_cast<int>((kl * 0x9E3779B97F4A7C15ull) >> 58);
+          for (int j = 0; j < kLatSlots && s < 0; ++j) {
+            const int idx = (home + j) & (kLatSlots - 1);
+            unsigned long long old = slot_key[idx];
+            if (old == 0ull) old = atomicCAS(&slot_key[idx], 0ull, kl);
+            if (old == 0ull) {  // we own the slot: publish the canonical relative vertices
+              for (int v = 0; v < nv; ++v) {
+                int cx, cy;
+                to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
+                canon[idx * nv + v] = make_int2(cx - vx0[k], cy - vy0[k]);
+              }
+              meta[idx].status = kLatPending;
+              atomicAdd(&ctl[0], 1);
+              ctl[1] = 1;
+              s = idx;
+            } else if (old == kl) {
+              s = idx;
+            }
+          }
+        }
+        s = __shfl_sync(kFull, s, leader);
+        if (same) slot[k] = s;
+        pending &= ~grp;
       }
     }
-    meta[threadIdx.x] = sh;
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- phase 4: verify, then 32 x-adjacent poses per bit window -----------------------------------
+    // ---- phase 3: one thread rasterises one NEW shape ----------------------------------------------
+    if (ctl[1]) {
+      if (threadIdx.x < kLatSlots && slot_key[threadIdx.x] != 0ull && meta[threadIdx.x].status == kLatPending) {
+        const int2* verts = canon + threadIdx.x * nv;
+        int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, x1 = -0x7FFFFFFF - 1, y1 = -0x7FFFFFFF - 1;
+        for (int v = 0; v < nv; ++v) {
+          x0 = min(x0, verts[v].x), x1 = max(x1, verts[v].x);
+          y0 = min(y0, verts[v].y), y1 = max(y1, verts[v].y);
+        }
+        LatShape sh{x0, x1, y0, y1 - y0 + 1, ST_OK};
+        int* ra = row_a + threadIdx.x * rows_cap;
+        uint32_t* rm = row_m + threadIdx.x * rows_cap;
+        if (sh.rows > rows_cap || (x1 - x0) > kPackedMaxWidth || x0 < -30000 || x1 > 30000) {
+          sh.status = kLatUnfit;
+        } else {
+          // the packed table is built in place in row_m, then converted to (lo, width) + width mask
+          PackedStore store{rm, 1, x0, y0};
+          store.clear(sh.rows);
+          RunDetector<PackedStore> runs(store, 0, x0, x1);
+          walk_outline_cells(verts, nv, runs);
+          runs.finish();
+          if (store.overflow) sh.status = kLatUnfit;
+          for (int r = 0; r < sh.rows && sh.status != kLatUnfit; ++r) {
+            const uint32_t w = rm[r];
+            const uint32_t cnt = w >> 30;
+            if (cnt == 1u) sh.status = ST_LOGIC_ERROR;
+            const int lo = x0 + static_cast<int>(w & 0x7FFFu), width = cnt == 2u ? static_cast<int>(((w >> 15) & 0x7FFFu) - (w & 0x7FFFu)) + 1 : 0;
+            if (width > kLatMaxWidth) sh.status = kLatUnfit;
+            ra[r] = (lo & 0xFFFF) | (width << 16);
+            rm[r] = width >= 32 ? 0xFFFFFFFFu : ((1u << width) - 1u);
+          }
+        }
+        meta[threadIdx.x] = sh;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) ctl[1] = 0;
+    }
+
+    // ---- phase 4: up to 32 x-adjacent poses per 64-cell bit window ---------------------------------
 #pragma unroll
-  for (int k = 0; k < kLatTasks; ++k) {
-    const long long i = oidx[k];
-    int s = slot[k];
-    if (i >= 0 && s >= 0) {  // the hash only proposed the shape: compare the actual relative vertices
-      const int t = warp + 8 * k;
-      const Pose T = lattice_pose(src, g.row_first + tile_y * kLatTileY + (t >> 2), tile_x * kLatTileX + (t & 3) * 32 + lane);
-      for (int v = 0; v < nv; ++v) {
-        int cx, cy;
-        to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
-        const int2 c = canon[s * nv + v];
-        if (cx - vx0[k] != c.x || cy - vy0[k] != c.y) s = -1;
-      }
-    }
-    const int st = s >= 0 ? meta[s].status : 0;
-    if (i >= 0 && (s == -1 || st == -1)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i);
-    if (i >= 0 && s >= 0 && st == ST_LOGIC_ERROR) store_failure(out, i, ST_LOGIC_ERROR);
-    const bool go = i >= 0 && s >= 0 && st == ST_OK;
-    unsigned pending = __ballot_sync(kFull, go);
-    while (pending) {
-      const int leader = __ffs(pending) - 1;
-      const int sl = __shfl_sync(kFull, s, leader), yl = __shfl_sync(kFull, vy0[k], leader);
-      const LatShape sh = meta[sl];
-      const bool same = go && ((pending >> lane) & 1u) && s == sl && vy0[k] == yl;
-      const int xmin = __reduce_min_sync(kFull, same ? vx0[k] : 0x7FFFFFFF);
-      const int off = vx0[k] - xmin;
-      const bool fits = same && off <= 64 - sh.wmax;  // the lane holding xmin always fits (wmax <= 32)
-      const unsigned grp = __ballot_sync(kFull, fits);
-      const int maxoff = __reduce_max_sync(kFull, fits ? off : 0);
-      const uint32_t* tab = rowtab + sl * rows_cap;
-      uint32_t hit = 0;
-      for (int r = 0; r < sh.rows; ++r) {
-        const uint32_t w = tab[r];
-        if ((w >> 30) != 2u) continue;
-        const int lo = sh.xb + static_cast<int>(w & 0x7FFFu), width = static_cast<int>(((w >> 15) & 0x7FFFu) - (w & 0x7FFFu)) + 1;
-        const int y = yl + sh.yb + r;
-        const bool y_in = static_cast<unsigned>(y) < static_cast<unsigned>(m.size_y);
-        const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y_in ? y : 0) * m.pitch;
-        int x = xmin + lo + lane;
-        bool lethal = true;  // outside the map counts as lethal (costmap.hpp:81-91)
-        if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
-        const uint32_t m0 = __ballot_sync(kFull, lethal);
-        uint32_t m1 = 0;
-        if (width + maxoff > 32) {
-          x += 32;
-          lethal = true;
-          if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
-          m1 = __ballot_sync(kFull, lethal);
+    for (int k = 0; k < kLatTasks; ++k) {
+      const long long i = oidx[k];
+      int s = slot[k];
+      if (!exact_key && i >= 0 && s >= 0) {  // the hash only proposed the shape: compare the actual relative vertices
+        const int t = warp + 8 * k;
+        const int2 rr = tile_rows[t >> 2];
+        const int ix = tile_x * kLatTileX + (t & 3) * 32 + lane;
+        Pose T;
+        T.tx = __dadd_rn(src.x0, __dmul_rn(static_cast<double>(ix), src.dx));
+        T.ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(rr.y), src.dy));
+        const double2 cs = __ldg(reinterpret_cast<const double2*>(src.theta_cs) + rr.x);
+        T.c = cs.x, T.s = cs.y;
+        for (int v = 0; v < nv; ++v) {
+          int cx, cy;
+          to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
+          const int2 c = canon[s * nv + v];
+          if (cx - vx0[k] != c.x || cy - vy0[k] != c.y) s = -1;
         }
-        const uint32_t bits = off < 32 ? __funnelshift_r(m0, m1, off) : (m1 >> (off - 32));
-        const uint32_t wmask = width >= 32 ? 0xFFFFFFFFu : ((1u << width) - 1u);
-        hit |= bits & wmask;
       }
-      if (fits) {
-        if (out.is_free) out.is_free[i] = hit ? 0 : 1;
-        if (out.status) out.status[i] = ST_OK;
+      const int st = s >= 0 ? meta[s].status : ST_OK;
+      if (i >= 0 && (s == -1 || st == kLatUnfit)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i);
+      if (i >= 0 && s >= 0 && st == ST_LOGIC_ERROR) store_failure(out, i, ST_LOGIC_ERROR);
+      const bool go = i >= 0 && s >= 0 && st == ST_OK;
+      unsigned pending = __ballot_sync(kFull, go);
+      while (pending) {
+        const int leader = __ffs(pending) - 1;
+        const int sl = __shfl_sync(kFull, s, leader), yl = __shfl_sync(kFull, vy0[k], leader);
+        const LatShape sh = meta[sl];
+        const bool same = ((pending >> lane) & 1u) && s == sl && vy0[k] == yl;
+        const int xmin = __reduce_min_sync(kFull, same ? vx0[k] : 0x7FFFFFFF);
+        const int off = vx0[k] - xmin;
+        const bool fits = same && off < 32;  // the lane holding xmin always fits
+        const unsigned grp = __ballot_sync(kFull, fits);
+        const int y_base = yl + sh.yb;
+        // every cell any pose of the group needs lies in x: [xmin + xb, xmin + 31 + x1]
+        const bool inside = y_base >= 0 && y_base + sh.rows <= m.size_y && xmin + sh.xb >= 0 && xmin + 31 + sh.x1 < m.size_x;
+        const uint32_t hit = inside ? lattice_rows<true>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, sh.rows, xmin, y_base, off & 31, lane)
+                                    : lattice_rows<false>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, sh.rows, xmin, y_base, off & 31, lane);
+        if (fits) {
+          if (out.is_free) out.is_free[i] = hit ? 0 : 1;
+          if (out.status) out.status[i] = ST_OK;
+        }
+        pending &= ~grp;
       }
-      pending &= ~grp;
     }
+    __syncthreads();
   }
 }
 
@@ -850,11 +904,13 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       const long long row_last = (src.first + count - 1) / src.nx;
       g.n_rows = static_cast<int>(row_last - g.row_first + 1);
       g.tiles_x = (src.nx + kLatTileX - 1) / kLatTileX;
-      const long long tiles_y = (g.n_rows + kLatTileY - 1) / kLatTileY;
+      g.n_tiles = static_cast<long long>((g.n_rows + kLatTileY - 1) / kLatTileY) * g.tiles_x;
       const size_t smem = poly_bytes + kLatSlots * (sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) +
-                                                     static_cast<size_t>(rows_cap) * sizeof(uint32_t) + sizeof(LatShape));
-      k_area_lattice_free<<<static_cast<unsigned int>(tiles_y * g.tiles_x), kLatThreads, smem, ctx->stream>>>(
-          map->view, poly_dev, nv, src, count, out, rows_cap, ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g);
+                                                     static_cast<size_t>(rows_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape)) +
+                          2 * sizeof(int) + kLatTileY * sizeof(int2);
+      const unsigned int grid = static_cast<unsigned int>(std::min<long long>(g.n_tiles, static_cast<long long>(ctx->sm_count) * 4));
+      k_area_lattice_free<<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
+                                                                   ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g);
     } else {
       const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint32_t);
       k_area_packed<OP><<<grid_for(count), kBlock, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
@@ -1033,8 +1089,9 @@ int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double reso
   Bind bind(ctx->device);
   const int pitch = (size_x + 15) & ~15;
   uint8_t* dev = nullptr;
-  CU(cudaMalloc(reinterpret_cast<void**>(&dev), static_cast<size_t>(pitch) * size_y));
-  CU(cudaMemsetAsync(dev, 0, static_cast<size_t>(pitch) * size_y, ctx->stream));
+  // + 128 bytes: k_area_lattice_free's unchecked loop reads (and masks off) up to 63 bytes past the last needed cell
+  CU(cudaMalloc(reinterpret_cast<void**>(&dev), static_cast<size_t>(pitch) * size_y + 128));
+  CU(cudaMemsetAsync(dev, 0, static_cast<size_t>(pitch) * size_y + 128, ctx->stream));
   cover_map* m = new (std::nothrow) cover_map();
   if (!m) {
     cudaFree(dev);
