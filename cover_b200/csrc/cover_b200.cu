@@ -139,17 +139,19 @@ __global__ void __launch_bounds__(kBlock) k_area_packed(MapView m, const double*
 //
 // On an (x, y, heading) lattice almost every pose of one heading has the SAME discretised polygon up to
 // a translation: the vertices' cell offsets relative to vertex 0 only change where a coordinate sits
-// within rounding noise of a cell boundary.  A persistent CTA walks 128 x 8 pose tiles and
+// within rounding noise of a cell boundary.  A persistent CTA walks a contiguous range of 128 x 8 pose
+// tiles; each warp takes 32 x-adjacent poses of one lattice row at a time and
 //   1. discretises every pose's vertices exactly (FP64, per thread) and forms the key of the RELATIVE
 //      shape (the packed vertex offsets themselves for <= 4 vertices, else a 64-bit hash),
-//   2. looks the shape up in a shared-memory cache that persists across the CTA's tiles,
-//   3. rasterises each NEW shape once (one thread per shape: the same run detector / packed row table
-//      as k_area_packed, so the scan-line semantics are literally the same code) — rare after a CTA's
-//      first tile of a heading,
-//   4. (hashed keys only) verifies each pose's relative vertices against the cached canonical ones, so
-//      exactness never rests on the hash, and then tests up to 32 x-adjacent poses at once: per scan row
-//      the warp loads the row segment one byte per lane (two coalesced 32-byte pieces), ballots "lethal
-//      or outside" into a 64-cell bit window, and every pose ANDs its own sub-window.
+//   2. looks the shape up in a shared-memory cache that persists across the CTA's tiles; the lane that
+//      inserts a NEW shape rasterises it on the spot (the same run detector / packed row table as
+//      k_area_packed, so the scan-line semantics are literally the same code) and publishes it; warps
+//      that meet a shape still being rasterised wait for its status word — no CTA-wide barrier,
+//   3. (hashed keys only) verifies each pose's relative vertices against the cached canonical ones, so
+//      exactness never rests on the hash,
+//   4. tests up to 32 x-adjacent poses at once: per scan row the warp loads the row segment one byte per
+//      lane (two coalesced 32-byte pieces), ballots "lethal or outside" into a 64-cell bit window, and
+//      every pose ANDs its own sub-window.
 // Poses whose shape needs more than two ranges on a row, is wider than 32 cells, or finds the cache
 // full go to the todo list and are finished by k_area_list.
 // ---------------------------------------------------------------------------------------------------
@@ -181,14 +183,14 @@ __device__ __forceinline__ uint32_t lattice_rows(const MapView& m, const int* __
   if (FAST) {  // every needed cell of every pose of the group is inside the map: no per-cell bounds tests
     const uint8_t* __restrict__ p = m.data + static_cast<size_t>(y_base) * m.pitch + (x_base + lane);
     for (int r = 0; r < rows; ++r, p += m.pitch) {
-      const int lo = static_cast<short>(row_a[r] & 0xFFFF);
+      const int lo = row_a[r];
       const uint32_t m0 = __ballot_sync(kFull, __ldg(p + lo) == kLethal);
       const uint32_t m1 = __ballot_sync(kFull, __ldg(p + lo + 32) == kLethal);
       hit |= __funnelshift_r(m0, m1, off) & row_m[r];
     }
   } else {
     for (int r = 0; r < rows; ++r) {
-      const int lo = static_cast<short>(row_a[r] & 0xFFFF);
+      const int lo = row_a[r];
       const int y = y_base + r;
       const bool y_in = static_cast<unsigned>(y) < static_cast<unsigned>(m.size_y);
       const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y_in ? y : 0) * m.pitch;
@@ -206,6 +208,38 @@ __device__ __forceinline__ uint32_t lattice_rows(const MapView& m, const int* __
   return hit;
 }
 
+/// Rasterises the relative shape `verts` into (row_a = first cell of the merged range, relative to vertex
+/// 0; row_m = width mask) and returns its descriptor.  Runs in ONE lane.
+__device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ verts, int nv, int rows_cap, int* __restrict__ ra,
+                                                   uint32_t* __restrict__ rm) {
+  int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, x1 = -0x7FFFFFFF - 1, y1 = -0x7FFFFFFF - 1;
+  for (int v = 0; v < nv; ++v) {
+    x0 = min(x0, verts[v].x), x1 = max(x1, verts[v].x);
+    y0 = min(y0, verts[v].y), y1 = max(y1, verts[v].y);
+  }
+  LatShape sh{x0, x1, y0, y1 - y0 + 1, ST_OK};
+  if (sh.rows > rows_cap || (x1 - x0) > kPackedMaxWidth || x0 < -30000 || x1 > 30000) {
+    sh.status = kLatUnfit;
+    return sh;
+  }
+  PackedStore store{rm, 1, x0, y0};  // the packed table is built in place in row_m, then converted
+  store.clear(sh.rows);
+  RunDetector<PackedStore> runs(store, 0, x0, x1);
+  walk_outline_cells(verts, nv, runs);
+  runs.finish();
+  if (store.overflow) sh.status = kLatUnfit;
+  for (int r = 0; r < sh.rows && sh.status != kLatUnfit; ++r) {
+    const uint32_t w = rm[r];
+    const uint32_t cnt = w >> 30;
+    if (cnt == 1u) sh.status = ST_LOGIC_ERROR;  // odd number of ranges: std::logic_error upstream
+    const int width = cnt == 2u ? static_cast<int>(((w >> 15) & 0x7FFFu) - (w & 0x7FFFu)) + 1 : 0;
+    if (width > kLatMaxWidth) sh.status = kLatUnfit;
+    ra[r] = x0 + static_cast<int>(w & 0x7FFFu);
+    rm[r] = width >= 32 ? 0xFFFFFFFFu : ((1u << width) - 1u);
+  }
+  return sh;
+}
+
 __global__ void __launch_bounds__(kLatThreads, 4) k_area_lattice_free(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
                                                                      long long count, OutView out, int rows_cap,
                                                                      unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count,
@@ -214,81 +248,81 @@ __global__ void __launch_bounds__(kLatThreads, 4) k_area_lattice_free(MapView m,
   const double* poly = stage_polygon(poly_g, nv, smem_d);
   unsigned long long* slot_key = reinterpret_cast<unsigned long long*>(smem_d + 2 * nv);  // 0 = empty
   int2* canon = reinterpret_cast<int2*>(slot_key + kLatSlots);                          // [slot][vertex] relative cells
-  int* row_a = reinterpret_cast<int*>(canon + kLatSlots * nv);                          // [slot][row] lo (int16) | width << 16
+  int* row_a = reinterpret_cast<int*>(canon + kLatSlots * nv);                          // [slot][row] first cell of the range
   uint32_t* row_m = reinterpret_cast<uint32_t*>(row_a + kLatSlots * rows_cap);          // [slot][row] width mask (0 = no range)
   LatShape* meta = reinterpret_cast<LatShape*>(row_m + kLatSlots * rows_cap);           // [slot]
-  int* ctl = reinterpret_cast<int*>(meta + kLatSlots);                                  // [0] used slots, [1] dirty
-  int2* tile_rows = reinterpret_cast<int2*>(ctl + 2);                                   // [kLatTileY] (it, iy) of the tile's rows
-  if (threadIdx.x < kLatSlots) slot_key[threadIdx.x] = 0ull;
-  if (threadIdx.x < 2) ctl[threadIdx.x] = 0;
+  if (threadIdx.x < kLatSlots) {
+    slot_key[threadIdx.x] = 0ull;
+    meta[threadIdx.x].status = kLatPending;
+  }
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool exact_key = nv <= 4;  // 3 x 2 offsets of 8 bits: the key IS the shape, no verification pass
+  const long long chunk = (g.n_tiles + gridDim.x - 1) / gridDim.x;
+  const long long tile_begin = blockIdx.x * chunk, tile_end = min(g.n_tiles, tile_begin + chunk);
+  int cached_heading = -1;
 
-  for (long long tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+  for (long long tile = tile_begin; tile < tile_end; ++tile) {
     const int tile_y = static_cast<int>(tile / g.tiles_x), tile_x = static_cast<int>(tile - static_cast<long long>(tile_y) * g.tiles_x);
-    if (ctl[0] > kLatSlots - 16) {  // cache nearly full: start over (uniform decision, taken after a barrier)
-      __syncthreads();
-      if (threadIdx.x < kLatSlots) slot_key[threadIdx.x] = 0ull;
-      if (threadIdx.x == 0) ctl[0] = 0;
+    const long long row0 = g.row_first + static_cast<long long>(tile_y) * kLatTileY;
+    const int it0 = static_cast<int>(row0 / src.ny), iy0 = static_cast<int>(row0 - static_cast<long long>(it0) * src.ny);
+    if (it0 != cached_heading) {  // new heading: start the shape cache over (depends on the tile index only: uniform)
+      if (cached_heading >= 0) {
+        __syncthreads();
+        if (threadIdx.x < kLatSlots) {
+          slot_key[threadIdx.x] = 0ull;
+          meta[threadIdx.x].status = kLatPending;
+        }
+        __syncthreads();
+      }
+      cached_heading = it0;
     }
-    if (threadIdx.x < kLatTileY) {
-      const long long row = g.row_first + static_cast<long long>(tile_y) * kLatTileY + threadIdx.x;
-      const int it = static_cast<int>(row / src.ny);
-      tile_rows[threadIdx.x] = make_int2(it, static_cast<int>(row - static_cast<long long>(it) * src.ny));
-    }
-    __syncthreads();
 
-    int vx0[kLatTasks], vy0[kLatTasks], slot[kLatTasks];
-    long long oidx[kLatTasks];
-
-    // ---- phases 1 + 2: exact vertices, shape key, cache lookup / insert ----------------------------
-#pragma unroll
     for (int k = 0; k < kLatTasks; ++k) {
       const int t = warp + 8 * k, rit = t >> 2, row_rel = tile_y * kLatTileY + rit;
       const int ix = tile_x * kLatTileX + (t & 3) * 32 + lane;
-      const long long i = (g.row_first + row_rel) * src.nx + ix - src.first;
+      const long long i = (row0 + rit) * src.nx + ix - src.first;
       const bool active = row_rel < g.n_rows && ix < src.nx && i >= 0 && i < count;
-      oidx[k] = active ? i : -1;
-      slot[k] = -2;  // -2: nothing to do, -1: todo list, >= 0: cache slot
-      vx0[k] = vy0[k] = 0;
+
+      // ---- exact vertices and the key of the relative shape ---------------------------------------
+      int vx0 = 0, vy0 = 0, slot = -2;  // slot -2: nothing to do, -1: todo list, >= 0: cache slot
       bool valid = false;
       unsigned long long key = 0;
       Pose T{1, 0, 0, 0};
       if (active) {
-        const int2 rr = tile_rows[rit];
+        int it = it0, iy = iy0 + rit;
+        while (iy >= src.ny) iy -= src.ny, ++it;
         T.tx = __dadd_rn(src.x0, __dmul_rn(static_cast<double>(ix), src.dx));
-        T.ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(rr.y), src.dy));
-        const double2 cs = __ldg(reinterpret_cast<const double2*>(src.theta_cs) + rr.x);
+        T.ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(iy), src.dy));
+        const double2 cs = __ldg(reinterpret_cast<const double2*>(src.theta_cs) + it);
         T.c = cs.x, T.s = cs.y;
-        bool ok = true;
-        int ax = 0, ay = 0;
+        bool ok = true, packable = true;
         unsigned long long h = 0xCBF29CE484222325ull;
         for (int v = 0; v < nv; ++v) {
           int cx, cy;
           ok &= to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
           if (v == 0) {
-            ax = cx, ay = cy;
+            vx0 = cx, vy0 = cy;
           } else if (exact_key) {
-            const int dx = cx - ax, dy = cy - ay;
-            if (dx < -128 || dx > 127 || dy < -128 || dy > 127) key = ~0ull;  // cannot be packed: todo list
-            if (key != ~0ull) key = (key << 16) | (static_cast<unsigned long long>(dx & 0xFF) << 8) | static_cast<unsigned long long>(dy & 0xFF);
+            const int dx = cx - vx0, dy = cy - vy0;
+            packable &= dx >= -128 && dx <= 127 && dy >= -128 && dy <= 127;
+            key = (key << 16) | (static_cast<unsigned long long>(dx & 0xFF) << 8) | static_cast<unsigned long long>(dy & 0xFF);
           } else {
-            h = lat_mix(lat_mix(h, cx - ax), cy - ay);
+            h = lat_mix(lat_mix(h, cx - vx0), cy - vy0);
           }
         }
-        vx0[k] = ax, vy0[k] = ay;
         if (!ok) {
           store_failure(out, i, ST_COORD_RANGE);
-          oidx[k] = -1;
-        } else if (exact_key && key == ~0ull) {
-          slot[k] = -1;
+        } else if (!packable) {
+          slot = -1;
         } else {
           key = exact_key ? (key | (1ull << 63)) : (h | 1ull);
           valid = true;
         }
       }
+
+      // ---- shape cache: find, or insert + rasterise -----------------------------------------------
       unsigned pending = __ballot_sync(kFull, valid);
       while (pending) {
         const int leader = __ffs(pending) - 1;
@@ -296,21 +330,22 @@ __global__ void __launch_bounds__(kLatThreads, 4) k_area_lattice_free(MapView m,
         const bool same = valid && key == kl;
         const unsigned grp = __ballot_sync(kFull, same);
         int s = -1;
-        if (lane == leader) {  // find the shape in the cache, or insert it
+        if (lane == leader) {
           const int home = static_cast<int>((kl * 0x9E3779B97F4A7C15ull) >> 58);
           for (int j = 0; j < kLatSlots && s < 0; ++j) {
             const int idx = (home + j) & (kLatSlots - 1);
-            unsigned long long old = slot_key[idx];
+            unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(&slot_key[idx]);
             if (old == 0ull) old = atomicCAS(&slot_key[idx], 0ull, kl);
-            if (old == 0ull) {  // we own the slot: publish the canonical relative vertices
+            if (old == 0ull) {  // we own the slot: publish the canonical relative vertices and the row table
               for (int v = 0; v < nv; ++v) {
                 int cx, cy;
                 to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
-                canon[idx * nv + v] = make_int2(cx - vx0[k], cy - vy0[k]);
+                canon[idx * nv + v] = make_int2(cx - vx0, cy - vy0);
               }
-              meta[idx].status = kLatPending;
-              atomicAdd(&ctl[0], 1);
-              ctl[1] = 1;
+              const LatShape sh = lattice_rasterise(canon + idx * nv, nv, rows_cap, row_a + idx * rows_cap, row_m + idx * rows_cap);
+              meta[idx].xb = sh.xb, meta[idx].x1 = sh.x1, meta[idx].yb = sh.yb, meta[idx].rows = sh.rows;
+              __threadfence_block();
+              *reinterpret_cast<volatile int*>(&meta[idx].status) = sh.status;
               s = idx;
             } else if (old == kl) {
               s = idx;
@@ -318,90 +353,43 @@ __global__ void __launch_bounds__(kLatThreads, 4) k_area_lattice_free(MapView m,
           }
         }
         s = __shfl_sync(kFull, s, leader);
-        if (same) slot[k] = s;
+        if (same) slot = s;
         pending &= ~grp;
       }
-    }
-    __syncthreads();
 
-    // ---- phase 3: one thread rasterises one NEW shape ----------------------------------------------
-    if (ctl[1]) {
-      if (threadIdx.x < kLatSlots && slot_key[threadIdx.x] != 0ull && meta[threadIdx.x].status == kLatPending) {
-        const int2* verts = canon + threadIdx.x * nv;
-        int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, x1 = -0x7FFFFFFF - 1, y1 = -0x7FFFFFFF - 1;
-        for (int v = 0; v < nv; ++v) {
-          x0 = min(x0, verts[v].x), x1 = max(x1, verts[v].x);
-          y0 = min(y0, verts[v].y), y1 = max(y1, verts[v].y);
+      // ---- wait for shapes other warps are still rasterising, verify hashed keys --------------------
+      int st = ST_OK;
+      if (slot >= 0) {
+        while ((st = *reinterpret_cast<volatile int*>(&meta[slot].status)) == kLatPending) {
         }
-        LatShape sh{x0, x1, y0, y1 - y0 + 1, ST_OK};
-        int* ra = row_a + threadIdx.x * rows_cap;
-        uint32_t* rm = row_m + threadIdx.x * rows_cap;
-        if (sh.rows > rows_cap || (x1 - x0) > kPackedMaxWidth || x0 < -30000 || x1 > 30000) {
-          sh.status = kLatUnfit;
-        } else {
-          // the packed table is built in place in row_m, then converted to (lo, width) + width mask
-          PackedStore store{rm, 1, x0, y0};
-          store.clear(sh.rows);
-          RunDetector<PackedStore> runs(store, 0, x0, x1);
-          walk_outline_cells(verts, nv, runs);
-          runs.finish();
-          if (store.overflow) sh.status = kLatUnfit;
-          for (int r = 0; r < sh.rows && sh.status != kLatUnfit; ++r) {
-            const uint32_t w = rm[r];
-            const uint32_t cnt = w >> 30;
-            if (cnt == 1u) sh.status = ST_LOGIC_ERROR;
-            const int lo = x0 + static_cast<int>(w & 0x7FFFu), width = cnt == 2u ? static_cast<int>(((w >> 15) & 0x7FFFu) - (w & 0x7FFFu)) + 1 : 0;
-            if (width > kLatMaxWidth) sh.status = kLatUnfit;
-            ra[r] = (lo & 0xFFFF) | (width << 16);
-            rm[r] = width >= 32 ? 0xFFFFFFFFu : ((1u << width) - 1u);
+        __threadfence_block();
+        if (!exact_key) {  // the hash only proposed the shape: compare the actual relative vertices
+          for (int v = 0; v < nv; ++v) {
+            int cx, cy;
+            to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
+            const int2 c = canon[slot * nv + v];
+            if (cx - vx0 != c.x || cy - vy0 != c.y) slot = -1;
           }
         }
-        meta[threadIdx.x] = sh;
       }
-      __syncthreads();
-      if (threadIdx.x == 0) ctl[1] = 0;
-    }
+      if (slot == -1 || (slot >= 0 && st == kLatUnfit)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i);
+      if (slot >= 0 && st == ST_LOGIC_ERROR) store_failure(out, i, ST_LOGIC_ERROR);
 
-    // ---- phase 4: up to 32 x-adjacent poses per 64-cell bit window ---------------------------------
-#pragma unroll
-    for (int k = 0; k < kLatTasks; ++k) {
-      const long long i = oidx[k];
-      int s = slot[k];
-      if (!exact_key && i >= 0 && s >= 0) {  // the hash only proposed the shape: compare the actual relative vertices
-        const int t = warp + 8 * k;
-        const int2 rr = tile_rows[t >> 2];
-        const int ix = tile_x * kLatTileX + (t & 3) * 32 + lane;
-        Pose T;
-        T.tx = __dadd_rn(src.x0, __dmul_rn(static_cast<double>(ix), src.dx));
-        T.ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(rr.y), src.dy));
-        const double2 cs = __ldg(reinterpret_cast<const double2*>(src.theta_cs) + rr.x);
-        T.c = cs.x, T.s = cs.y;
-        for (int v = 0; v < nv; ++v) {
-          int cx, cy;
-          to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
-          const int2 c = canon[s * nv + v];
-          if (cx - vx0[k] != c.x || cy - vy0[k] != c.y) s = -1;
-        }
-      }
-      const int st = s >= 0 ? meta[s].status : ST_OK;
-      if (i >= 0 && (s == -1 || st == kLatUnfit)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i);
-      if (i >= 0 && s >= 0 && st == ST_LOGIC_ERROR) store_failure(out, i, ST_LOGIC_ERROR);
-      const bool go = i >= 0 && s >= 0 && st == ST_OK;
-      unsigned pending = __ballot_sync(kFull, go);
+      // ---- up to 32 x-adjacent poses per 64-cell bit window ----------------------------------------
+      pending = __ballot_sync(kFull, slot >= 0 && st == ST_OK);
       while (pending) {
         const int leader = __ffs(pending) - 1;
-        const int sl = __shfl_sync(kFull, s, leader), yl = __shfl_sync(kFull, vy0[k], leader);
-        const LatShape sh = meta[sl];
-        const bool same = ((pending >> lane) & 1u) && s == sl && vy0[k] == yl;
-        const int xmin = __reduce_min_sync(kFull, same ? vx0[k] : 0x7FFFFFFF);
-        const int off = vx0[k] - xmin;
+        const int sl = __shfl_sync(kFull, slot, leader), yl = __shfl_sync(kFull, vy0, leader);
+        const bool same = ((pending >> lane) & 1u) && slot == sl && vy0 == yl;
+        const int xmin = __reduce_min_sync(kFull, same ? vx0 : 0x7FFFFFFF);
+        const int off = vx0 - xmin;
         const bool fits = same && off < 32;  // the lane holding xmin always fits
         const unsigned grp = __ballot_sync(kFull, fits);
-        const int y_base = yl + sh.yb;
+        const int xb = meta[sl].xb, x1 = meta[sl].x1, rows = meta[sl].rows, y_base = yl + meta[sl].yb;
         // every cell any pose of the group needs lies in x: [xmin + xb, xmin + 31 + x1]
-        const bool inside = y_base >= 0 && y_base + sh.rows <= m.size_y && xmin + sh.xb >= 0 && xmin + 31 + sh.x1 < m.size_x;
-        const uint32_t hit = inside ? lattice_rows<true>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, sh.rows, xmin, y_base, off & 31, lane)
-                                    : lattice_rows<false>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, sh.rows, xmin, y_base, off & 31, lane);
+        const bool inside = y_base >= 0 && y_base + rows <= m.size_y && xmin + xb >= 0 && xmin + 31 + x1 < m.size_x;
+        const uint32_t hit = inside ? lattice_rows<true>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, off & 31, lane)
+                                    : lattice_rows<false>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, off & 31, lane);
         if (fits) {
           if (out.is_free) out.is_free[i] = hit ? 0 : 1;
           if (out.status) out.status[i] = ST_OK;
@@ -409,7 +397,6 @@ __global__ void __launch_bounds__(kLatThreads, 4) k_area_lattice_free(MapView m,
         pending &= ~grp;
       }
     }
-    __syncthreads();
   }
 }
 
@@ -906,8 +893,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       g.tiles_x = (src.nx + kLatTileX - 1) / kLatTileX;
       g.n_tiles = static_cast<long long>((g.n_rows + kLatTileY - 1) / kLatTileY) * g.tiles_x;
       const size_t smem = poly_bytes + kLatSlots * (sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) +
-                                                     static_cast<size_t>(rows_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape)) +
-                          2 * sizeof(int) + kLatTileY * sizeof(int2);
+                                                     static_cast<size_t>(rows_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape));
       const unsigned int grid = static_cast<unsigned int>(std::min<long long>(g.n_tiles, static_cast<long long>(ctx->sm_count) * 4));
       k_area_lattice_free<<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
                                                                    ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g);
