@@ -55,7 +55,8 @@ class _Poses(C.Structure):
 
 
 class _Results(C.Structure):
-    _fields_ = [("mem", C.c_int32), ("is_free", C.c_void_p), ("cost", C.c_void_p), ("status", C.c_void_p)]
+    _fields_ = [("mem", C.c_int32), ("is_free", C.c_void_p), ("cost", C.c_void_p), ("status", C.c_void_p),
+                ("free_bits", C.c_void_p), ("not_ok", C.c_void_p)]
 
 
 _lib = None
@@ -130,9 +131,19 @@ class Lattice:
 
 @dataclass
 class Result:
-    is_free: Optional[object]
-    cost: Optional[object]
-    status: Optional[object]
+    """Caller-owned outputs.  Any field may be None.  `free_bits` is the bit-packed verdict array
+    (uint32 words, bit i & 31 of word i >> 5); `not_ok` a one-element int64 array counting poses whose
+    status is not STATUS_OK."""
+    is_free: Optional[object] = None
+    cost: Optional[object] = None
+    status: Optional[object] = None
+    free_bits: Optional[object] = None
+    not_ok: Optional[object] = None
+
+    def unpack_bits(self, count: int) -> np.ndarray:
+        """free_bits -> uint8 verdicts [count] (host arrays only)."""
+        words = np.asarray(self.free_bits, dtype=np.uint32)
+        return np.unpackbits(words.view(np.uint8), bitorder="little")[:count]
 
 
 class Context:
@@ -199,15 +210,16 @@ class Context:
 
     def _results(self, n: int, want_free: bool, want_cost: bool, want_status: bool, out: Optional[Result]):
         if out is not None:
-            arrays = [a for a in (out.is_free, out.cost, out.status) if a is not None]
+            arrays = [a for a in (out.is_free, out.cost, out.status, out.free_bits, out.not_ok) if a is not None]
             dev = any(_is_device(a) for a in arrays)
             if dev and not all(_is_device(a) for a in arrays):
                 raise ValueError("result arrays must all be host or all be device memory")
-            r = _Results(_MEM_DEVICE if dev else _MEM_HOST, _ptr(out.is_free), _ptr(out.cost), _ptr(out.status))
+            r = _Results(_MEM_DEVICE if dev else _MEM_HOST, _ptr(out.is_free), _ptr(out.cost), _ptr(out.status),
+                         _ptr(out.free_bits), _ptr(out.not_ok))
             return r, out
         res = Result(np.empty(n, dtype=np.uint8) if want_free else None, np.empty(n, dtype=np.float64) if want_cost else None,
                      np.empty(n, dtype=np.uint8) if want_status else None)
-        return _Results(_MEM_HOST, _ptr(res.is_free), _ptr(res.cost), _ptr(res.status)), res
+        return _Results(_MEM_HOST, _ptr(res.is_free), _ptr(res.cost), _ptr(res.status), None, None), res
 
 
 class Costmap:

@@ -394,6 +394,17 @@ __global__ void __launch_bounds__(kLatThreads, 4) k_area_lattice_free(MapView m,
           if (out.is_free) out.is_free[i] = hit ? 0 : 1;
           if (out.status) out.status[i] = ST_OK;
         }
+        if (out.free_bits) {  // the group's poses are consecutive: they touch at most two output words
+          const int gl = __ffs(grp) - 1;
+          const long long w = i >> 5, wl = __shfl_sync(kFull, w, gl);
+          const uint32_t bit = (fits && !hit) ? (1u << (i & 31)) : 0u;
+          const uint32_t lo_word = __reduce_or_sync(kFull, (fits && w == wl) ? bit : 0u);
+          const uint32_t hi_word = __reduce_or_sync(kFull, (fits && w != wl) ? bit : 0u);
+          if (lane == gl) {
+            if (lo_word) atomicOr(out.free_bits + wl, lo_word);
+            if (hi_word) atomicOr(out.free_bits + wl + 1, hi_word);
+          }
+        }
         pending &= ~grp;
       }
     }
@@ -525,7 +536,7 @@ __global__ void __launch_bounds__(kBlock) k_footprints(MapView m, const int2* __
     hit = static_cast<unsigned>(x) >= static_cast<unsigned>(m.size_x) || static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) ||
           __ldg(m.data + static_cast<size_t>(y) * m.pitch + x) == kLethal;
   }
-  if (out.is_free) out.is_free[i] = hit ? 0 : 1;
+  emit_free(out, i, !hit);
   if (out.status) out.status[i] = ST_OK;
 }
 
@@ -603,7 +614,7 @@ __global__ void __launch_bounds__(kBlock) k_split(MapView m, SplitView fp, int n
     if (status != ST_OK) {
       store_failure(out, i, status);
     } else {
-      if (out.is_free) out.is_free[i] = free_ ? 1 : 0;
+      emit_free(out, i, free_);
       if (out.status) out.status[i] = ST_OK;
     }
   }
@@ -645,7 +656,7 @@ struct cover_ctx {
   std::string error;
   int64_t launches = 0;
   bool disable_lattice_kernel = false;  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
-  DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, todo, todo_count, list_cnt, list_rng, list_seq;
+  DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, list_cnt, list_rng, list_seq;
 };
 
 struct cover_map {
@@ -707,7 +718,7 @@ struct Bind {  // makes `device` current for the duration of a call
 
 /// Results staged on the device when the caller's arrays are host memory.
 struct OutStage {
-  OutView dev{nullptr, nullptr, nullptr};
+  OutView dev{nullptr, nullptr, nullptr, nullptr, nullptr};
   const cover_results* user = nullptr;
   bool host = false;
 };
@@ -716,11 +727,14 @@ int stage_out(cover_ctx* ctx, const cover_results* out, int64_t count, OutStage&
   st.user = out;
   if (!out) return fail(ctx, COVER_E_INVALID_ARG, "results must not be NULL");
   st.host = out->mem == COVER_MEM_HOST;
+  const size_t n = static_cast<size_t>(std::max<int64_t>(count, 1));
+  const size_t bit_bytes = ((n + 31) / 32) * sizeof(uint32_t);
   if (!st.host) {
-    st.dev = OutView{out->is_free, out->cost, out->status};
+    st.dev = OutView{out->is_free, out->cost, out->status, out->free_bits, reinterpret_cast<unsigned long long*>(out->not_ok)};
+    if (out->free_bits) CU(cudaMemsetAsync(out->free_bits, 0, bit_bytes, ctx->stream));
+    if (out->not_ok) CU(cudaMemsetAsync(out->not_ok, 0, sizeof(int64_t), ctx->stream));
     return COVER_OK;
   }
-  const size_t n = static_cast<size_t>(std::max<int64_t>(count, 1));
   if (out->is_free) {
     CU(ctx->out_free.ensure(n));
     st.dev.is_free = ctx->out_free.as<uint8_t>();
@@ -733,6 +747,16 @@ int stage_out(cover_ctx* ctx, const cover_results* out, int64_t count, OutStage&
     CU(ctx->out_status.ensure(n));
     st.dev.status = ctx->out_status.as<uint8_t>();
   }
+  if (out->free_bits) {
+    CU(ctx->out_bits.ensure(bit_bytes));
+    CU(cudaMemsetAsync(ctx->out_bits.ptr, 0, bit_bytes, ctx->stream));
+    st.dev.free_bits = ctx->out_bits.as<uint32_t>();
+  }
+  if (out->not_ok) {
+    CU(ctx->out_not_ok.ensure(sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(ctx->out_not_ok.ptr, 0, sizeof(unsigned long long), ctx->stream));
+    st.dev.not_ok = ctx->out_not_ok.as<unsigned long long>();
+  }
   return COVER_OK;
 }
 
@@ -744,7 +768,9 @@ int finish_out(cover_ctx* ctx, const OutStage& st, int64_t count) {
     if (st.user->is_free) CU(cudaMemcpyAsync(st.user->is_free, st.dev.is_free, n, cudaMemcpyDeviceToHost, ctx->stream));
     if (st.user->cost) CU(cudaMemcpyAsync(st.user->cost, st.dev.cost, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (st.user->status) CU(cudaMemcpyAsync(st.user->status, st.dev.status, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (st.user->free_bits) CU(cudaMemcpyAsync(st.user->free_bits, st.dev.free_bits, ((n + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   }
+  if (st.user->not_ok) CU(cudaMemcpyAsync(st.user->not_ok, st.dev.not_ok, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return COVER_OK;
 }
@@ -1048,7 +1074,7 @@ void cover_ctx_destroy(cover_ctx* ctx) {
   if (!ctx) return;
   Bind bind(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (DeviceBuffer* b : {&ctx->poses, &ctx->theta, &ctx->poly, &ctx->in_a, &ctx->in_b, &ctx->out_free, &ctx->out_cost, &ctx->out_status,
+  for (DeviceBuffer* b : {&ctx->poses, &ctx->theta, &ctx->poly, &ctx->in_a, &ctx->in_b, &ctx->out_free, &ctx->out_cost, &ctx->out_status, &ctx->out_bits, &ctx->out_not_ok,
                           &ctx->todo, &ctx->todo_count, &ctx->list_cnt, &ctx->list_rng, &ctx->list_seq})
     b->release();
   cudaStreamDestroy(ctx->stream);

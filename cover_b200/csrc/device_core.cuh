@@ -58,7 +58,15 @@ struct OutView {
   uint8_t* is_free;
   double* cost;
   uint8_t* status;
+  uint32_t* free_bits;          // optional bit-packed verdicts (pre-zeroed): bit (i & 31) of word (i >> 5)
+  unsigned long long* not_ok;   // optional counter of poses whose status is not ST_OK (pre-zeroed)
 };
+
+/// Verdict of pose i: byte array and/or bit-packed word (bits are only ever set, the buffer starts zeroed).
+__device__ __forceinline__ void emit_free(const OutView& o, long long i, bool is_free) {
+  if (o.is_free) o.is_free[i] = is_free ? 1 : 0;
+  if (o.free_bits && is_free) atomicOr(o.free_bits + (i >> 5), 1u << (i & 31));
+}
 
 __device__ __forceinline__ Pose load_pose(const PoseSource& src, long long i) {
   Pose T;
@@ -207,9 +215,7 @@ struct Fold<OP_IS_FREE> {  // std::none_of(is_lethal): out of the map counts as 
     }
     return true;
   }
-  __device__ __forceinline__ void store(const OutView& o, long long i) const {
-    if (o.is_free) o.is_free[i] = hit ? 0 : 1;
-  }
+  __device__ __forceinline__ void store(const OutView& o, long long i) const { emit_free(o, i, !hit); }
 };
 
 template <>
@@ -242,7 +248,7 @@ struct Fold<OP_ACCUMULATE> {  // impl/costmap.hpp:50-63: first negative value in
   __device__ __forceinline__ void store(const OutView& o, long long i) const {
     const double c = early ? static_cast<double>(early) : static_cast<double>(sum);
     if (o.cost) o.cost[i] = c;
-    if (o.is_free) o.is_free[i] = early ? 0 : 1;
+    emit_free(o, i, early == 0);
   }
 };
 
@@ -273,7 +279,7 @@ struct Fold<OP_MAX> {  // extension: max of get_cell_cost; any cell outside the 
   __device__ __forceinline__ void store(const OutView& o, long long i) const {
     const int v = value();
     if (o.cost) o.cost[i] = outside ? -3.0 : static_cast<double>(v);
-    if (o.is_free) o.is_free[i] = (!outside && v != kLethal) ? 1 : 0;
+    emit_free(o, i, !outside && v != kLethal);
   }
 };
 
@@ -281,6 +287,7 @@ __device__ __forceinline__ void store_failure(const OutView& o, long long i, int
   if (o.is_free) o.is_free[i] = 0;
   if (o.cost) o.cost[i] = __longlong_as_double(0x7FF8000000000000LL);  // quiet NaN
   if (o.status) o.status[i] = static_cast<uint8_t>(status);
+  if (o.not_ok) atomicAdd(o.not_ok, 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------------

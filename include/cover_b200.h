@@ -18,8 +18,8 @@
  *    sin/cos differ from glibc in the last ulp); COVER_POSE_LATTICE = a descriptor expanded on the
  *    device: pose index p = (it*ny + iy)*nx + ix, t = (x0 + ix*dx, y0 + iy*dy) (multiply then add,
  *    no FMA), heading (cos,sin) = cs[it]; COVER_POSE_NONE = the no-pose overloads (one check).
- *  - outputs are caller-owned arrays of `count` elements, host or device (cover_results.mem); any of
- *    them may be NULL.  status[i] is a cover_status; for a status other than COVER_STATUS_OK the
+ *  - outputs are caller-owned arrays (sizes in cover_results), host or device (cover_results.mem); any
+ *    of them may be NULL.  status[i] is a cover_status; for a status other than COVER_STATUS_OK the
  *    verdict is 0 and the cost NaN (the scalar reference would have thrown, see each status).
  *  - a cover_ctx is single-threaded and owns one CUDA stream; all work of a call is enqueued on it
  *    and, when any argument or result lives on the host, completed before the call returns.  With
@@ -82,10 +82,14 @@ typedef struct cover_poses {
 } cover_poses;
 
 typedef struct cover_results {
-  int32_t mem;      /* cover_mem of the three arrays */
-  uint8_t* is_free; /* 1 = free */
-  double* cost;     /* accumulate_cost / max_cost value */
-  uint8_t* status;  /* cover_status */
+  int32_t mem;         /* cover_mem of every pointer below */
+  uint8_t* is_free;    /* count bytes, 1 = free */
+  double* cost;        /* count doubles: accumulate_cost / max_cost value */
+  uint8_t* status;     /* count bytes: cover_status */
+  uint32_t* free_bits; /* (count + 31) / 32 words: bit (i & 31) of word (i >> 5) = is_free[i]; 8x less
+                          device->host traffic than is_free for verdict-only sweeps (1e8 poses = 12.5 MB) */
+  int64_t* not_ok;     /* ONE counter: number of poses whose status is not COVER_STATUS_OK, so that a caller
+                          who skips `status` still learns whether the scalar reference would have thrown */
 } cover_results;
 
 /* ---- context ------------------------------------------------------------------------------------ */

@@ -73,3 +73,14 @@ def test_product_never_imports_the_oracle():
                     text = open(os.path.join(dirpath, f), errors="ignore").read()
                     for needle in ("import oracle", "from oracle", "pyoracle", "liboracle", "cover_oracle", "oracle/"):
                         assert needle not in text, (os.path.join(dirpath, f), needle)
+
+
+def test_cpp_host_layer_compiles_and_links(lib, tmp_path):
+    """include/cover_b200.hpp (the C++ mirror of the reference's surface) builds against the C ABI."""
+    import cover_b200
+    exe = tmp_path / "host_api_test"
+    libdir = os.path.dirname(cover_b200.library_path())
+    proc = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "host_api_test.cpp"), "-o", str(exe), "-L", libdir, "-lcover_b200",
+                           f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr

@@ -366,3 +366,54 @@ def test_full_size_lattice_properties(cb, ctx):
     n = 3_000_000
     mx = cmap.area_max_cost(RECT, lat, first=5_000_000, count=n)
     np.testing.assert_array_equal(first.is_free[5_000_000:5_000_000 + n], ((mx.cost >= 0) & (mx.cost < 254)).astype(np.uint8))
+
+
+def test_bit_packed_verdicts_and_not_ok_counter(cb, ctx):
+    """free_bits / not_ok (cover_results) agree with the byte arrays on every kernel family."""
+    rng = np.random.default_rng(80)
+    data = mixed_map(rng, 400, 400, lethal=0.002)
+    cmap = cb.Costmap(ctx, data, 0.05)
+
+    def packed(n):
+        return cb.Result(free_bits=np.full((n + 31) // 32, 0xFFFFFFFF, dtype=np.uint32), not_ok=np.full(1, -7, dtype=np.int64))
+
+    # lattice kernel (unaligned sub-range), thread-per-pose kernel, list kernel, outline, rays
+    th = -math.pi + 2 * math.pi * np.arange(5) / 5
+    lat = cb.Lattice(0.4, 0.05, 333, 0.4, 0.05, 61, np.stack([np.cos(th), np.sin(th)], 1))
+    ref = cmap.area_is_free(RECT, lat, first=777, count=90_001)
+    out = packed(90_001)
+    cmap.area_is_free(RECT, lat, first=777, count=90_001, out=out)
+    np.testing.assert_array_equal(out.unpack_bits(90_001), ref.is_free)
+    assert out.not_ok[0] == 0
+    poses = poses_around(rng, 33_333, -0.5, 20.5)
+    for poly in (RECT, FOOTPRINTS[0] * 0.3, np.array([[0.0, 0.3], [0.0, 0.45]])):
+        for fn in (cmap.area_is_free, cmap.area_accumulate_cost, cmap.outline_is_free):
+            ref = fn(poly, poses)
+            out = packed(len(poses))
+            fn(poly, poses, out=out)
+            np.testing.assert_array_equal(out.unpack_bits(len(poses)), ref.is_free)
+            assert out.not_ok[0] == int((ref.status != 0).sum())
+    bad = np.array([[1.0, 0.0, 1e7, 0.0], [1.0, 0.0, 5.0, 5.0], [float("nan"), 0.0, 1.0, 1.0]])
+    out = packed(3)
+    cmap.area_is_free(RECT, bad, out=out)
+    assert out.not_ok[0] == 2
+    segs = rng.integers(-10, 410, (10_001, 4)).astype(np.int32)
+    ref = cmap.ray_is_free(segs)
+    out = packed(len(segs))
+    cmap.ray_is_free(segs, out=out)
+    np.testing.assert_array_equal(out.unpack_bits(len(segs)), ref.is_free)
+
+
+def test_cpp_host_layer_runs_the_reference_unit_tests(cb, tmp_path):
+    """tests/cpp/host_api_test.cpp: test/costmap.cpp + test/footprints.cpp known answers through
+    include/cover_b200.hpp -> C ABI -> CUDA kernels."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(cb.library_path())
+    exe = tmp_path / "host_api_test"
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "host_api_test.cpp"),
+                            "-o", str(exe), "-L", libdir, "-lcover_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
