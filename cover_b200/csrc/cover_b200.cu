@@ -14,6 +14,7 @@
 //   k_split             continuous_footprint::is_free (a14)
 // There is no CPU path in this file: without a CUDA device every entry returns COVER_E_CUDA.
 #include "../../include/cover_b200.h"
+#include "area_rows.cuh"
 #include "device_core.cuh"
 
 #include <algorithm>
@@ -482,6 +483,40 @@ __global__ void __launch_bounds__(kBlock) k_area_list(MapView m, const double* _
   }
 }
 
+
+/// Area checks for any polygon, one WARP per pose (area_rows.cuh); also drains the poses the packed and
+/// lattice kernels deferred (`todo`).  Persistent grid.
+constexpr int kRowsWarps = 4;
+template <int OP>
+__global__ void __launch_bounds__(kRowsWarps * 32) k_area_rows(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
+                                                              long long count, OutView out, const unsigned int* __restrict__ todo,
+                                                              const unsigned int* __restrict__ todo_count) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv, smem_d);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RayRec* rays = reinterpret_cast<RayRec*>(smem_d + 2 * nv) + warp * (nv + 1);
+  int2* verts = reinterpret_cast<int2*>(reinterpret_cast<RayRec*>(smem_d + 2 * nv) + kRowsWarps * (nv + 1)) + warp * nv;
+  const long long n_warps = static_cast<long long>(gridDim.x) * kRowsWarps;
+  const long long n_items = todo ? static_cast<long long>(*todo_count) : count;
+  const bool none = src.format == POSE_NONE;
+  for (long long item = static_cast<long long>(blockIdx.x) * kRowsWarps + warp; item < n_items; item += n_warps) {
+    const long long i = todo ? static_cast<long long>(todo[item]) : item;
+    const Pose T = load_pose(src, i);
+    WarpFold<OP> wf;
+    const int status = none ? area_rows_pose<OP, XF_NONE>(poly, nv, T, m, verts, rays, lane, wf)
+                            : area_rows_pose<OP, XF_PATH_A>(poly, nv, T, m, verts, rays, lane, wf);
+    if (lane == 0) {
+      if (status != ST_OK) {
+        store_failure(out, i, status);
+      } else {
+        wf.store(out, i);
+        if (out.status) out.status[i] = ST_OK;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int OP>
 __global__ void __launch_bounds__(kBlock) k_rays(MapView m, const int4* __restrict__ segments, long long count, int offx, int offy,
                                                 OutView out) {
@@ -655,7 +690,9 @@ struct cover_ctx {
   cudaStream_t stream = nullptr;
   std::string error;
   int64_t launches = 0;
-  bool disable_lattice_kernel = false;  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
+  bool disable_lattice_kernel = false;
+  bool force_list_kernel = false;
+  bool always_try_packed = true;        // COVER_B200_PACKED_ONLY_CONVEX=1 restricts the packed pass to convex polygons       // COVER_B200_FORCE_LIST_KERNEL=1: A/B measurements and tests of k_area_list  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
   DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, list_cnt, list_rng, list_seq;
 };
 
@@ -843,6 +880,11 @@ bool is_convex(const double* xy, int n) {
   return true;
 }
 
+/// Dynamic shared memory of k_area_rows: polygon + per-warp ray records and vertices.
+size_t rows_smem(int nv) {
+  return static_cast<size_t>(nv) * 16 + kRowsWarps * (static_cast<size_t>(nv + 1) * sizeof(RayRec) + static_cast<size_t>(nv) * sizeof(int2));
+}
+
 unsigned int grid_for(int64_t count) { return static_cast<unsigned int>((count + kBlock - 1) / kBlock); }
 
 /// Global scratch of the list store for `nthreads` resident threads.
@@ -887,6 +929,9 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_list<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_list<OP_MAX>));
   set(reinterpret_cast<const void*>(&k_split));
+  set(reinterpret_cast<const void*>(&k_area_rows<OP_IS_FREE>));
+  set(reinterpret_cast<const void*>(&k_area_rows<OP_ACCUMULATE>));
+  set(reinterpret_cast<const void*>(&k_area_rows<OP_MAX>));
   set(reinterpret_cast<const void*>(&k_area_lattice_free));
   return e;
 }
@@ -902,9 +947,16 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     return COVER_OK;
   }
   const int rows_cap = rows_bound(polygon_diameter(poly_host, nv), map->view.inv_res);
-  const bool packed = is_convex(poly_host, nv) && rows_cap <= kPackedMaxRows;
-  ListScratch scratch{};
-  if (packed) {
+  // 1. fast pass: poses whose scan rows all have <= 2 ranges (every pose of a convex polygon, many poses of a
+  //    mildly concave one) are finished by the packed / lattice kernel; the rest lands on the todo list.
+  //    Polygons that are far from convex skip it (the pass would defer almost everything).
+  const bool fast = rows_cap <= kPackedMaxRows && (is_convex(poly_host, nv) || ctx->always_try_packed);
+  // 2. general pass over everything (or the todo list): one warp per pose when the outline has few rays
+  //    relative to its rows, else one thread per pose with per-row lists in global scratch.
+  const bool rows_kernel = nv <= kRowsMaxVertices && rows_cap <= 30000 && !ctx->force_list_kernel && (nv <= 16 || rows_cap > 48);
+  const unsigned int* todo = nullptr;
+  const unsigned int* todo_count = nullptr;
+  if (fast) {
     CU(ctx->todo.ensure(static_cast<size_t>(count) * sizeof(unsigned int)));
     CU(ctx->todo_count.ensure(sizeof(unsigned int)));
     CU(cudaMemsetAsync(ctx->todo_count.ptr, 0, sizeof(unsigned int), ctx->stream));
@@ -929,20 +981,23 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
                                                                         ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
     }
     ++ctx->launches;
-    // Drain whatever the packed kernel deferred (usually nothing) with a small persistent grid.
-    const unsigned int grid = list_grid(ctx, count, rows_cap, 1);
-    const int rc = ensure_list_scratch(ctx, rows_cap, static_cast<long long>(grid) * kBlock, scratch);
-    if (rc) return rc;
-    k_area_list<OP><<<grid, kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, scratch,
-                                                             ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
-    ++ctx->launches;
-  } else {
-    const unsigned int grid = list_grid(ctx, count, rows_cap, 4);
-    const int rc = ensure_list_scratch(ctx, rows_cap, static_cast<long long>(grid) * kBlock, scratch);
-    if (rc) return rc;
-    k_area_list<OP><<<grid, kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, scratch, nullptr, nullptr);
-    ++ctx->launches;
+    todo = ctx->todo.as<unsigned int>();
+    todo_count = ctx->todo_count.as<unsigned int>();
   }
+  // A convex polygon defers (almost) nothing: a small persistent grid is enough to drain the list.
+  const bool small_drain = fast && is_convex(poly_host, nv);
+  if (rows_kernel) {
+    const long long blocks = small_drain ? ctx->sm_count : static_cast<long long>(ctx->sm_count) * 12;
+    const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(blocks, (count + kRowsWarps - 1) / kRowsWarps)));
+    k_area_rows<OP><<<grid, kRowsWarps * 32, rows_smem(nv), ctx->stream>>>(map->view, poly_dev, nv, src, count, out, todo, todo_count);
+  } else {
+    ListScratch scratch{};
+    const unsigned int grid = list_grid(ctx, count, rows_cap, small_drain ? 1 : 4);
+    const int rc = ensure_list_scratch(ctx, rows_cap, static_cast<long long>(grid) * kBlock, scratch);
+    if (rc) return rc;
+    k_area_list<OP><<<grid, kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, scratch, todo, todo_count);
+  }
+  ++ctx->launches;
   return COVER_OK;
 }
 
@@ -1066,6 +1121,8 @@ int cover_ctx_create(int device, cover_ctx** out) {
   }
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = std::getenv("COVER_B200_NO_LATTICE_KERNEL")) ctx->disable_lattice_kernel = e[0] == '1';
+  if (const char* e = std::getenv("COVER_B200_PACKED_ONLY_CONVEX")) ctx->always_try_packed = e[0] != '1';
+  if (const char* e = std::getenv("COVER_B200_FORCE_LIST_KERNEL")) ctx->force_list_kernel = e[0] == '1';
   *out = ctx;
   return COVER_OK;
 }

@@ -417,3 +417,38 @@ def test_cpp_host_layer_runs_the_reference_unit_tests(cb, tmp_path):
     assert build.returncode == 0, build.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert run.returncode == 0, run.stdout + run.stderr
+
+
+def test_list_kernel_still_exact(cb, monkeypatch):
+    """k_area_list (per-thread sorted lists in global scratch) is only used for polygons with more than 256
+    vertices now; force it for ordinary polygons so that it stays covered."""
+    monkeypatch.setenv("COVER_B200_FORCE_LIST_KERNEL", "1")
+    c = cb.Context(0)
+    try:
+        rng = np.random.default_rng(90)
+        data = mixed_map(rng, 500, 400, lethal=0.0005)
+        cmap = cb.Costmap(c, data, 0.05)
+        omap = po.Costmap(data, 0.05)
+        poses = poses_around(rng, 2500, -1.0, 24.0)
+        for idx in (0, 3, 6):
+            for name, op, has_cost in OPS:
+                gpu = getattr(cmap, f"area_{name}")(FOOTPRINTS[idx], poses)
+                cpu = po.polygon_batch(omap, FOOTPRINTS[idx], poses, op=op, threads=8)
+                assert_same(gpu, cpu, has_cost, f"list kernel {FOOTPRINT_NAMES[idx]} {name}")
+    finally:
+        c.close()
+
+
+def test_many_vertex_polygons(cb, ctx):
+    """64-, 256- and 300-vertex polygons (the last one exceeds the warp-per-pose kernel's vertex table)."""
+    rng = np.random.default_rng(91)
+    data = mixed_map(rng, 400, 400, lethal=0.001)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    omap = po.Costmap(data, 0.05)
+    poses = poses_around(rng, 1500, 0.0, 20.0)
+    from cover_b200 import workloads as wl
+    for nv in (64, 256, 300):
+        poly = wl.potato(nv) * 1.7
+        assert_same(cmap.area_accumulate_cost(poly, poses), po.polygon_batch(omap, poly, poses, op=po.OP_ACCUMULATE, threads=8), True, f"potato {nv}")
+        star = poly * (1.0 + 0.35 * np.cos(9 * 2 * math.pi * np.arange(nv) / nv))
+        assert_same(cmap.area_is_free(star, poses), po.polygon_batch(omap, star, poses, threads=8), False, f"star {nv}")
