@@ -138,27 +138,38 @@ __global__ void __launch_bounds__(kBlock) k_area_packed(MapView m, const double*
 // ---------------------------------------------------------------------------------------------------
 // Lattice kernel (is_free on a POSE_LATTICE batch): the DWA-style headline path.
 //
-// On an (x, y, heading) lattice almost every pose of one heading has the SAME discretised polygon up to
-// a translation: the vertices' cell offsets relative to vertex 0 only change where a coordinate sits
-// within rounding noise of a cell boundary.  A persistent CTA walks a contiguous range of 128 x 8 pose
-// tiles; each warp takes 32 x-adjacent poses of one lattice row at a time and
-//   1. discretises every pose's vertices exactly (FP64, per thread) and forms the key of the RELATIVE
-//      shape (the packed vertex offsets themselves for <= 4 vertices, else a 64-bit hash),
-//   2. looks the shape up in a shared-memory cache that persists across the CTA's tiles; the lane that
+// Two facts about an (x, y, heading) lattice make the work shareable without giving up per-pose exactness:
+//  * the pose transform separates: the x cells of the vertices depend only on (heading, ix), the y cells
+//    only on (heading, iy) — a unit of 64 columns x 8 rows needs 64 x-profiles + 8 y-profiles, not 512
+//    vertex transforms;
+//  * almost every pose of one heading has the SAME discretised polygon up to a translation: the vertices'
+//    cell offsets relative to vertex 0 only change where a coordinate sits within rounding noise of a
+//    cell boundary.
+// A persistent CTA walks a contiguous range of units; each warp owns one unit at a time (lane = two
+// columns, ix and ix+32) and, per lattice row,
+//   1. combines the exact x- and y-profiles into the key of the RELATIVE shape (the packed vertex offsets
+//      themselves for <= 4 vertices, else a 64-bit hash),
+//   2. looks the shape up in a shared-memory cache that persists across the CTA's units; the lane that
 //      inserts a NEW shape rasterises it on the spot (the same run detector / packed row table as
-//      k_area_packed, so the scan-line semantics are literally the same code) and publishes it; warps
-//      that meet a shape still being rasterised wait for its status word — no CTA-wide barrier,
+//      k_area_packed, so the scan-line semantics are literally the same code) and publishes it; warps that
+//      meet a shape still being rasterised wait for its status word — no CTA-wide barrier,
 //   3. (hashed keys only) verifies each pose's relative vertices against the cached canonical ones, so
 //      exactness never rests on the hash,
-//   4. tests up to 32 x-adjacent poses at once: per scan row the warp loads the row segment one byte per
-//      lane (two coalesced 32-byte pieces), ballots "lethal or outside" into a 64-cell bit window, and
+//   4. tests up to 64 x-adjacent poses at once: per scan row the warp loads the row segment one byte per
+//      lane (three coalesced 32-byte pieces), ballots "lethal or outside" into a 96-cell bit window, and
 //      every pose ANDs its own sub-window.
 // Poses whose shape needs more than two ranges on a row, is wider than 32 cells, or finds the cache
-// full go to the todo list and are finished by k_area_list.
+// full go to the todo list and are finished by the general kernels.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kLatTileX = 128, kLatTileY = 8, kLatThreads = 256, kLatSlots = 64, kLatTasks = 4;
+#ifndef LAT_ROWS_INLINE
+#define LAT_ROWS_INLINE __forceinline__
+#endif
+#ifndef LAT_MIN_BLOCKS
+#define LAT_MIN_BLOCKS 3
+#endif
+constexpr int kLatSegX = 64, kLatRows = 8, kLatWarps = 8, kLatThreads = kLatWarps * 32, kLatSlots = 64;
 constexpr int kLatMaxVertices = 64;
-constexpr int kLatMaxWidth = 32;   // widest scan row (cells): 32 lane offsets + 32 cells = one 64-cell window
+constexpr int kLatMaxWidth = 32;   // widest scan row (cells): 64 pose offsets + 32 cells = one 96-cell window
 constexpr int kLatPending = -2;    // shape inserted, not rasterised yet
 constexpr int kLatUnfit = -1;      // shape not representable by this kernel
 constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -169,44 +180,95 @@ struct LatShape {
 
 struct LatGeom {
   long long row_first;  // first lattice row (it*ny + iy) touched by this batch
-  int n_rows, tiles_x;
-  long long n_tiles;
+  int n_rows, segs;     // lattice rows touched; 64-column segments per row
+  long long n_units;    // segs * ceil(n_rows / 8)
 };
 
 __device__ __forceinline__ unsigned long long lat_mix(unsigned long long h, int v) {
   return (h ^ static_cast<unsigned int>(v)) * 0x100000001B3ull;  // FNV-1a step
 }
 
+/// x cell of one vertex: the x half of to_cell<XF_PATH_A> (same operations in the same order).
+__device__ __forceinline__ bool lat_cell_x(double c, double s, double tx, double px, double py, const MapView& m, int& cx) {
+  const double q = __dsub_rn(__dadd_rn(tx, __dadd_rn(__dmul_rn(c, px), __dmul_rn(-s, py))), m.origin_x);
+  const double sc = __dmul_rn(q, m.inv_res);
+  cx = __double2int_rz(sc);
+  return fabs(sc) < kCoordLimit;
+}
+/// y cell of one vertex: the y half of to_cell<XF_PATH_A>.
+__device__ __forceinline__ bool lat_cell_y(double c, double s, double ty, double px, double py, const MapView& m, int& cy) {
+  const double q = __dsub_rn(__dadd_rn(ty, __dadd_rn(__dmul_rn(s, px), __dmul_rn(c, py))), m.origin_y);
+  const double sc = __dmul_rn(q, m.inv_res);
+  cy = __double2int_rz(sc);
+  return fabs(sc) < kCoordLimit;
+}
+
+/// One coordinate's profile of a column (x) or row (y): cell of vertex 0 + key of the offsets of the others.
+struct LatProfile {
+  int c0;                  // cell coordinate of vertex 0
+  unsigned long long key;  // exact mode: offsets packed 8 bits each; hash mode: FNV of the offsets
+  bool ok, packable;       // all coordinates in range; all offsets fit 8 bits (exact mode)
+};
+
+template <bool IS_X>
+__device__ __forceinline__ LatProfile lat_profile(const double* __restrict__ poly, int nv, double c, double s, double t, const MapView& m,
+                                                  bool exact_key) {
+  LatProfile p{0, exact_key ? 0ull : 0xCBF29CE484222325ull, true, true};
+  for (int v = 0; v < nv; ++v) {
+    int cell;
+    p.ok &= IS_X ? lat_cell_x(c, s, t, poly[2 * v], poly[2 * v + 1], m, cell) : lat_cell_y(c, s, t, poly[2 * v], poly[2 * v + 1], m, cell);
+    if (v == 0) {
+      p.c0 = cell;
+    } else if (exact_key) {
+      const int d = cell - p.c0;
+      p.packable &= d >= -128 && d <= 127;
+      p.key = (p.key << 8) | static_cast<unsigned long long>(d & 0xFF);
+    } else {
+      p.key = lat_mix(p.key, cell - p.c0);
+    }
+  }
+  return p;
+}
+
 template <bool FAST>
-__device__ __forceinline__ uint32_t lattice_rows(const MapView& m, const int* __restrict__ row_a, const uint32_t* __restrict__ row_m,
-                                                 int rows, int x_base, int y_base, int off, int lane) {
-  uint32_t hit = 0;
+__device__ LAT_ROWS_INLINE void lattice_rows(const MapView& m, const int* __restrict__ row_a, const uint32_t* __restrict__ row_m, int rows,
+                                             int x_base, int y_base, int lane, bool third, int off_a, int off_b, uint32_t& hit_a, uint32_t& hit_b) {
+  // lane constants: which two of the three 32-cell pieces a pose's window starts in, and its shift
+  const bool hi_a = off_a >= 32, hi_b = off_b >= 32;
+  const int sh_a = off_a & 31, sh_b = off_b & 31;
   if (FAST) {  // every needed cell of every pose of the group is inside the map: no per-cell bounds tests
     const uint8_t* __restrict__ p = m.data + static_cast<size_t>(y_base) * m.pitch + (x_base + lane);
-    for (int r = 0; r < rows; ++r, p += m.pitch) {
-      const int lo = row_a[r];
-      const uint32_t m0 = __ballot_sync(kFull, __ldg(p + lo) == kLethal);
-      const uint32_t m1 = __ballot_sync(kFull, __ldg(p + lo + 32) == kLethal);
-      hit |= __funnelshift_r(m0, m1, off) & row_m[r];
+    // unrolled by 4: the 12 byte loads of four scan rows are in flight together (few resident warps, so the
+    // memory-level parallelism has to come from inside the warp)
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) {
+      const uint8_t* __restrict__ q = p + static_cast<size_t>(r) * m.pitch + row_a[r];
+      const uint8_t b0 = __ldg(q), b1 = __ldg(q + 32), b2 = third ? __ldg(q + 64) : static_cast<uint8_t>(0);
+      const uint32_t m0 = __ballot_sync(kFull, b0 == kLethal);
+      const uint32_t m1 = __ballot_sync(kFull, b1 == kLethal);
+      const uint32_t m2 = __ballot_sync(kFull, b2 == kLethal);
+      const uint32_t wm = row_m[r];
+      hit_a |= __funnelshift_r(hi_a ? m1 : m0, hi_a ? m2 : m1, sh_a) & wm;
+      hit_b |= __funnelshift_r(hi_b ? m1 : m0, hi_b ? m2 : m1, sh_b) & wm;
     }
   } else {
     for (int r = 0; r < rows; ++r) {
-      const int lo = row_a[r];
       const int y = y_base + r;
       const bool y_in = static_cast<unsigned>(y) < static_cast<unsigned>(m.size_y);
       const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y_in ? y : 0) * m.pitch;
-      int x = x_base + lo + lane;
-      bool lethal = true;  // outside the map counts as lethal (costmap.hpp:81-91)
-      if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
-      const uint32_t m0 = __ballot_sync(kFull, lethal);
-      x += 32;
-      lethal = true;
-      if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
-      const uint32_t m1 = __ballot_sync(kFull, lethal);
-      hit |= __funnelshift_r(m0, m1, off) & row_m[r];
+      uint32_t piece[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int x = x_base + row_a[r] + lane + 32 * j;
+        bool lethal = true;  // outside the map counts as lethal (costmap.hpp:81-91)
+        if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
+        piece[j] = __ballot_sync(kFull, lethal);
+      }
+      const uint32_t wm = row_m[r];
+      hit_a |= __funnelshift_r(hi_a ? piece[1] : piece[0], hi_a ? piece[2] : piece[1], sh_a) & wm;
+      hit_b |= __funnelshift_r(hi_b ? piece[1] : piece[0], hi_b ? piece[2] : piece[1], sh_b) & wm;
     }
   }
-  return hit;
 }
 
 /// Rasterises the relative shape `verts` into (row_a = first cell of the merged range, relative to vertex
@@ -241,7 +303,21 @@ __device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ vert
   return sh;
 }
 
-__global__ void __launch_bounds__(kLatThreads, 4) k_area_lattice_free(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
+/// Bit-packed verdicts of one plane of a group (consecutive pose indices: at most two output words).
+__device__ __forceinline__ void lat_store_bits(const OutView& out, unsigned grp, bool fits, bool is_free, long long i, int lane) {
+  if (grp == 0u) return;
+  const int gl = __ffs(grp) - 1;
+  const long long w = i >> 5, wl = __shfl_sync(kFull, w, gl);
+  const uint32_t bit = (fits && is_free) ? (1u << (i & 31)) : 0u;
+  const uint32_t lo_word = __reduce_or_sync(kFull, (fits && w == wl) ? bit : 0u);
+  const uint32_t hi_word = __reduce_or_sync(kFull, (fits && w != wl) ? bit : 0u);
+  if (lane == gl) {
+    if (lo_word) atomicOr(out.free_bits + wl, lo_word);
+    if (hi_word) atomicOr(out.free_bits + wl + 1, hi_word);
+  }
+}
+
+__global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice_free(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
                                                                      long long count, OutView out, int rows_cap,
                                                                      unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count,
                                                                      LatGeom g) {
@@ -259,154 +335,216 @@ __global__ void __launch_bounds__(kLatThreads, 4) k_area_lattice_free(MapView m,
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool exact_key = nv <= 4;  // 3 x 2 offsets of 8 bits: the key IS the shape, no verification pass
-  const long long chunk = (g.n_tiles + gridDim.x - 1) / gridDim.x;
-  const long long tile_begin = blockIdx.x * chunk, tile_end = min(g.n_tiles, tile_begin + chunk);
+  const bool exact_key = nv <= 4;  // 2 x 3 offsets of 8 bits: the key IS the shape, no verification pass
+  const long long chunk = (g.n_units + gridDim.x - 1) / gridDim.x;
+  const long long unit_begin = blockIdx.x * chunk, unit_end = min(g.n_units, unit_begin + chunk);
   int cached_heading = -1;
 
-  for (long long tile = tile_begin; tile < tile_end; ++tile) {
-    const int tile_y = static_cast<int>(tile / g.tiles_x), tile_x = static_cast<int>(tile - static_cast<long long>(tile_y) * g.tiles_x);
-    const long long row0 = g.row_first + static_cast<long long>(tile_y) * kLatTileY;
-    const int it0 = static_cast<int>(row0 / src.ny), iy0 = static_cast<int>(row0 - static_cast<long long>(it0) * src.ny);
-    if (it0 != cached_heading) {  // new heading: start the shape cache over (depends on the tile index only: uniform)
-      if (cached_heading >= 0) {
-        __syncthreads();
-        if (threadIdx.x < kLatSlots) {
-          slot_key[threadIdx.x] = 0ull;
-          meta[threadIdx.x].status = kLatPending;
+  for (long long round = unit_begin; round < unit_end; round += kLatWarps) {
+    {  // new heading at the start of this round: start the shape cache over (depends on `round` only: CTA-uniform)
+      const long long row0 = g.row_first + (round / g.segs) * kLatRows;
+      const int it0 = static_cast<int>(row0 / src.ny);
+      if (it0 != cached_heading) {
+        if (cached_heading >= 0) {
+          __syncthreads();
+          if (threadIdx.x < kLatSlots) {
+            slot_key[threadIdx.x] = 0ull;
+            meta[threadIdx.x].status = kLatPending;
+          }
+          __syncthreads();
         }
-        __syncthreads();
+        cached_heading = it0;
       }
-      cached_heading = it0;
+    }
+    const long long unit = round + warp;
+    if (unit >= unit_end) continue;
+    const int group = static_cast<int>(unit / g.segs), seg = static_cast<int>(unit - static_cast<long long>(group) * g.segs);
+    const int ix_a = seg * kLatSegX + lane, ix_b = ix_a + 32;
+    auto column_tx = [&src](int ix) { return __dadd_rn(src.x0, __dmul_rn(static_cast<double>(ix), src.dx)); };
+    auto heading_cs = [&src](int it) { return __ldg(reinterpret_cast<const double2*>(src.theta_cs) + it); };
+
+    // y-profiles of the unit's 8 rows: lane r owns row r
+    int my_it = 0;
+    LatProfile my_y{0, 0ull, false, false};
+    {
+      const int row_rel = group * kLatRows + (lane & (kLatRows - 1));
+      const long long row = g.row_first + row_rel;
+      if (row_rel < g.n_rows) {
+        my_it = static_cast<int>(row / src.ny);
+        const int iy = static_cast<int>(row - static_cast<long long>(my_it) * src.ny);
+        const double2 cs = heading_cs(my_it);
+        my_y = lat_profile<false>(poly, nv, cs.x, cs.y, __dadd_rn(src.y0, __dmul_rn(static_cast<double>(iy), src.dy)), m, exact_key);
+      }
     }
 
-    for (int k = 0; k < kLatTasks; ++k) {
-      const int t = warp + 8 * k, rit = t >> 2, row_rel = tile_y * kLatTileY + rit;
-      const int ix = tile_x * kLatTileX + (t & 3) * 32 + lane;
-      const long long i = (row0 + rit) * src.nx + ix - src.first;
-      const bool active = row_rel < g.n_rows && ix < src.nx && i >= 0 && i < count;
+    int x_heading = -1;
+    LatProfile xa{0, 0ull, false, false}, xb{0, 0ull, false, false};
+    // memo: a column's slot stays valid while the heading (x-profile) and the row's y-key do not change
+    unsigned long long memo_ykey = 0ull;
+    bool memo_valid = false;
+    int memo_slot_a = -1, memo_slot_b = -1;
 
-      // ---- exact vertices and the key of the relative shape ---------------------------------------
-      int vx0 = 0, vy0 = 0, slot = -2;  // slot -2: nothing to do, -1: todo list, >= 0: cache slot
-      bool valid = false;
-      unsigned long long key = 0;
-      Pose T{1, 0, 0, 0};
-      if (active) {
-        int it = it0, iy = iy0 + rit;
-        while (iy >= src.ny) iy -= src.ny, ++it;
-        T.tx = __dadd_rn(src.x0, __dmul_rn(static_cast<double>(ix), src.dx));
-        T.ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(iy), src.dy));
-        const double2 cs = __ldg(reinterpret_cast<const double2*>(src.theta_cs) + it);
-        T.c = cs.x, T.s = cs.y;
-        bool ok = true, packable = true;
-        unsigned long long h = 0xCBF29CE484222325ull;
-        for (int v = 0; v < nv; ++v) {
-          int cx, cy;
-          ok &= to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
-          if (v == 0) {
-            vx0 = cx, vy0 = cy;
-          } else if (exact_key) {
-            const int dx = cx - vx0, dy = cy - vy0;
-            packable &= dx >= -128 && dx <= 127 && dy >= -128 && dy <= 127;
-            key = (key << 16) | (static_cast<unsigned long long>(dx & 0xFF) << 8) | static_cast<unsigned long long>(dy & 0xFF);
-          } else {
-            h = lat_mix(lat_mix(h, cx - vx0), cy - vy0);
-          }
-        }
-        if (!ok) {
-          store_failure(out, i, ST_COORD_RANGE);
-        } else if (!packable) {
-          slot = -1;
+    for (int r = 0; r < kLatRows; ++r) {
+      const int row_rel = group * kLatRows + r;
+      if (row_rel >= g.n_rows) break;
+      const int it = __shfl_sync(kFull, my_it, r);
+      const int vy0 = __shfl_sync(kFull, my_y.c0, r);
+      const unsigned long long ykey = __shfl_sync(kFull, my_y.key, r);
+      const bool y_ok = __shfl_sync(kFull, static_cast<int>(my_y.ok), r) != 0, y_pack = __shfl_sync(kFull, static_cast<int>(my_y.packable), r) != 0;
+      if (it != x_heading) {  // x-profiles depend on the heading only: once per unit (twice on a heading boundary)
+        const double2 cs = heading_cs(it);
+        xa = lat_profile<true>(poly, nv, cs.x, cs.y, column_tx(ix_a), m, exact_key);
+        xb = lat_profile<true>(poly, nv, cs.x, cs.y, column_tx(ix_b), m, exact_key);
+        x_heading = it;
+        memo_valid = false;
+      }
+      if (ykey != memo_ykey) memo_valid = false;
+      memo_ykey = ykey;
+      const long long i_a = (g.row_first + row_rel) * src.nx + ix_a - src.first, i_b = i_a + 32;
+      const bool act_a = ix_a < src.nx && i_a >= 0 && i_a < count, act_b = ix_b < src.nx && i_b >= 0 && i_b < count;
+
+      // ---- key of the relative shape; -2: nothing to do, -1: todo list, >= 0: cache slot ------------
+      int slot_a = -2, slot_b = -2;
+      unsigned long long key_a = 0ull, key_b = 0ull;
+      bool look_a = false, look_b = false;
+      if (act_a) {
+        if (!(xa.ok && y_ok)) {
+          store_failure(out, i_a, ST_COORD_RANGE);
+        } else if (exact_key && !(xa.packable && y_pack)) {
+          slot_a = -1;
         } else {
-          key = exact_key ? (key | (1ull << 63)) : (h | 1ull);
-          valid = true;
+          key_a = exact_key ? ((1ull << 63) | (xa.key << 24) | ykey) : ((lat_mix(xa.key, static_cast<int>(ykey)) ^ (ykey >> 32)) | 1ull);
+          if (memo_valid && memo_slot_a >= 0) slot_a = memo_slot_a;
+          else look_a = true;
+        }
+      }
+      if (act_b) {
+        if (!(xb.ok && y_ok)) {
+          store_failure(out, i_b, ST_COORD_RANGE);
+        } else if (exact_key && !(xb.packable && y_pack)) {
+          slot_b = -1;
+        } else {
+          key_b = exact_key ? ((1ull << 63) | (xb.key << 24) | ykey) : ((lat_mix(xb.key, static_cast<int>(ykey)) ^ (ykey >> 32)) | 1ull);
+          if (memo_valid && memo_slot_b >= 0) slot_b = memo_slot_b;
+          else look_b = true;
         }
       }
 
-      // ---- shape cache: find, or insert + rasterise -----------------------------------------------
-      unsigned pending = __ballot_sync(kFull, valid);
-      while (pending) {
-        const int leader = __ffs(pending) - 1;
-        const unsigned long long kl = __shfl_sync(kFull, key, leader);
-        const bool same = valid && key == kl;
-        const unsigned grp = __ballot_sync(kFull, same);
-        int s = -1;
+      // ---- shape cache: find, or insert + rasterise (only for keys the lane has not just looked up) ---
+      unsigned pend_a = __ballot_sync(kFull, look_a), pend_b = __ballot_sync(kFull, look_b);
+      while (pend_a | pend_b) {
+        const bool from_a = pend_a != 0u;
+        const int leader = __ffs(from_a ? pend_a : pend_b) - 1;
+        const unsigned long long kl = __shfl_sync(kFull, from_a ? key_a : key_b, leader);
+        const bool same_a = look_a && key_a == kl, same_b = look_b && key_b == kl;
+        int sfound = -1;
         if (lane == leader) {
           const int home = static_cast<int>((kl * 0x9E3779B97F4A7C15ull) >> 58);
-          for (int j = 0; j < kLatSlots && s < 0; ++j) {
+          for (int j = 0; j < kLatSlots && sfound < 0; ++j) {
             const int idx = (home + j) & (kLatSlots - 1);
             unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(&slot_key[idx]);
             if (old == 0ull) old = atomicCAS(&slot_key[idx], 0ull, kl);
             if (old == 0ull) {  // we own the slot: publish the canonical relative vertices and the row table
+              const double2 cs = heading_cs(it);
+              const double c = cs.x, s = cs.y;
+              const double tx = column_tx(from_a ? ix_a : ix_b);
+              const double ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>((g.row_first + row_rel) - static_cast<long long>(it) * src.ny), src.dy));
+              int ax = 0, ay = 0;
               for (int v = 0; v < nv; ++v) {
                 int cx, cy;
-                to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
-                canon[idx * nv + v] = make_int2(cx - vx0, cy - vy0);
+                lat_cell_x(c, s, tx, poly[2 * v], poly[2 * v + 1], m, cx);
+                lat_cell_y(c, s, ty, poly[2 * v], poly[2 * v + 1], m, cy);
+                if (v == 0) ax = cx, ay = cy;
+                canon[idx * nv + v] = make_int2(cx - ax, cy - ay);
               }
               const LatShape sh = lattice_rasterise(canon + idx * nv, nv, rows_cap, row_a + idx * rows_cap, row_m + idx * rows_cap);
               meta[idx].xb = sh.xb, meta[idx].x1 = sh.x1, meta[idx].yb = sh.yb, meta[idx].rows = sh.rows;
               __threadfence_block();
               *reinterpret_cast<volatile int*>(&meta[idx].status) = sh.status;
-              s = idx;
+              sfound = idx;
             } else if (old == kl) {
-              s = idx;
+              sfound = idx;
             }
           }
         }
-        s = __shfl_sync(kFull, s, leader);
-        if (same) slot = s;
-        pending &= ~grp;
+        sfound = __shfl_sync(kFull, sfound, leader);
+        if (same_a) slot_a = sfound, look_a = false;
+        if (same_b) slot_b = sfound, look_b = false;
+        pend_a &= ~__ballot_sync(kFull, same_a);
+        pend_b &= ~__ballot_sync(kFull, same_b);
       }
+      memo_slot_a = slot_a, memo_slot_b = slot_b;  // (slots < 0 are looked up / re-decided again next row)
+      memo_valid = true;
 
-      // ---- wait for shapes other warps are still rasterising, verify hashed keys --------------------
-      int st = ST_OK;
-      if (slot >= 0) {
-        while ((st = *reinterpret_cast<volatile int*>(&meta[slot].status)) == kLatPending) {
+      // ---- wait for shapes other warps are still rasterising; verify hashed keys ----------------------
+      int st_a = ST_OK, st_b = ST_OK;
+      if (slot_a >= 0) {
+        while ((st_a = *reinterpret_cast<volatile int*>(&meta[slot_a].status)) == kLatPending) {
         }
-        __threadfence_block();
-        if (!exact_key) {  // the hash only proposed the shape: compare the actual relative vertices
-          for (int v = 0; v < nv; ++v) {
-            int cx, cy;
-            to_cell<XF_PATH_A>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
-            const int2 c = canon[slot * nv + v];
-            if (cx - vx0 != c.x || cy - vy0 != c.y) slot = -1;
+      }
+      if (slot_b >= 0) {
+        while ((st_b = *reinterpret_cast<volatile int*>(&meta[slot_b].status)) == kLatPending) {
+        }
+      }
+      __threadfence_block();
+      if (!exact_key) {  // the hash only proposed the shape: compare the actual relative vertices
+        const double2 cs = heading_cs(it);
+        const double c = cs.x, s = cs.y, tx_a = column_tx(ix_a), tx_b = column_tx(ix_b);
+        const double ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>((g.row_first + row_rel) - static_cast<long long>(it) * src.ny), src.dy));
+        for (int v = 0; v < nv; ++v) {
+          int cy, cx;
+          lat_cell_y(c, s, ty, poly[2 * v], poly[2 * v + 1], m, cy);
+          if (slot_a >= 0) {
+            lat_cell_x(c, s, tx_a, poly[2 * v], poly[2 * v + 1], m, cx);
+            const int2 q = canon[slot_a * nv + v];
+            if (cx - xa.c0 != q.x || cy - vy0 != q.y) slot_a = -1;
+          }
+          if (slot_b >= 0) {
+            lat_cell_x(c, s, tx_b, poly[2 * v], poly[2 * v + 1], m, cx);
+            const int2 q = canon[slot_b * nv + v];
+            if (cx - xb.c0 != q.x || cy - vy0 != q.y) slot_b = -1;
           }
         }
       }
-      if (slot == -1 || (slot >= 0 && st == kLatUnfit)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i);
-      if (slot >= 0 && st == ST_LOGIC_ERROR) store_failure(out, i, ST_LOGIC_ERROR);
+      if (slot_a == -1 || (slot_a >= 0 && st_a == kLatUnfit)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
+      if (slot_b == -1 || (slot_b >= 0 && st_b == kLatUnfit)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
+      if (slot_a >= 0 && st_a == ST_LOGIC_ERROR) store_failure(out, i_a, ST_LOGIC_ERROR);
+      if (slot_b >= 0 && st_b == ST_LOGIC_ERROR) store_failure(out, i_b, ST_LOGIC_ERROR);
 
-      // ---- up to 32 x-adjacent poses per 64-cell bit window ----------------------------------------
-      pending = __ballot_sync(kFull, slot >= 0 && st == ST_OK);
-      while (pending) {
-        const int leader = __ffs(pending) - 1;
-        const int sl = __shfl_sync(kFull, slot, leader), yl = __shfl_sync(kFull, vy0, leader);
-        const bool same = ((pending >> lane) & 1u) && slot == sl && vy0 == yl;
-        const int xmin = __reduce_min_sync(kFull, same ? vx0 : 0x7FFFFFFF);
-        const int off = vx0 - xmin;
-        const bool fits = same && off < 32;  // the lane holding xmin always fits
-        const unsigned grp = __ballot_sync(kFull, fits);
-        const int xb = meta[sl].xb, x1 = meta[sl].x1, rows = meta[sl].rows, y_base = yl + meta[sl].yb;
-        // every cell any pose of the group needs lies in x: [xmin + xb, xmin + 31 + x1]
-        const bool inside = y_base >= 0 && y_base + rows <= m.size_y && xmin + xb >= 0 && xmin + 31 + x1 < m.size_x;
-        const uint32_t hit = inside ? lattice_rows<true>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, off & 31, lane)
-                                    : lattice_rows<false>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, off & 31, lane);
-        if (fits) {
-          if (out.is_free) out.is_free[i] = hit ? 0 : 1;
-          if (out.status) out.status[i] = ST_OK;
+      // ---- up to 64 x-adjacent poses per 96-cell bit window -------------------------------------------
+      const bool go_a = slot_a >= 0 && st_a == ST_OK, go_b = slot_b >= 0 && st_b == ST_OK;
+      pend_a = __ballot_sync(kFull, go_a), pend_b = __ballot_sync(kFull, go_b);
+      while (pend_a | pend_b) {
+        const bool from_a = pend_a != 0u;
+        const int leader = __ffs(from_a ? pend_a : pend_b) - 1;
+        const int sl = __shfl_sync(kFull, from_a ? slot_a : slot_b, leader);
+        const bool same_a = ((pend_a >> lane) & 1u) && slot_a == sl, same_b = ((pend_b >> lane) & 1u) && slot_b == sl;
+        const int xmin = __reduce_min_sync(kFull, min(same_a ? xa.c0 : 0x7FFFFFFF, same_b ? xb.c0 : 0x7FFFFFFF));
+        const int off_a = xa.c0 - xmin, off_b = xb.c0 - xmin;
+        const bool fits_a = same_a && off_a < 64, fits_b = same_b && off_b < 64;  // the pose holding xmin always fits
+        const unsigned grp_a = __ballot_sync(kFull, fits_a), grp_b = __ballot_sync(kFull, fits_b);
+        const int maxoff = __reduce_max_sync(kFull, max(fits_a ? off_a : 0, fits_b ? off_b : 0));
+        const int xb_s = meta[sl].xb, x1_s = meta[sl].x1, rows = meta[sl].rows, y_base = vy0 + meta[sl].yb;
+        // every cell any pose of the group needs lies in x: [xmin + xb, xmin + maxoff + x1]
+        const bool inside = y_base >= 0 && y_base + rows <= m.size_y && xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x;
+        uint32_t hit_a = 0, hit_b = 0;
+        const int oa = fits_a ? off_a : 0, ob = fits_b ? off_b : 0;
+        if (inside) lattice_rows<true>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, ob, hit_a, hit_b);
+        else lattice_rows<false>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, true, oa, ob, hit_a, hit_b);
+        if (fits_a) {
+          if (out.is_free) out.is_free[i_a] = hit_a ? 0 : 1;
+          if (out.status) out.status[i_a] = ST_OK;
         }
-        if (out.free_bits) {  // the group's poses are consecutive: they touch at most two output words
-          const int gl = __ffs(grp) - 1;
-          const long long w = i >> 5, wl = __shfl_sync(kFull, w, gl);
-          const uint32_t bit = (fits && !hit) ? (1u << (i & 31)) : 0u;
-          const uint32_t lo_word = __reduce_or_sync(kFull, (fits && w == wl) ? bit : 0u);
-          const uint32_t hi_word = __reduce_or_sync(kFull, (fits && w != wl) ? bit : 0u);
-          if (lane == gl) {
-            if (lo_word) atomicOr(out.free_bits + wl, lo_word);
-            if (hi_word) atomicOr(out.free_bits + wl + 1, hi_word);
-          }
+        if (fits_b) {
+          if (out.is_free) out.is_free[i_b] = hit_b ? 0 : 1;
+          if (out.status) out.status[i_b] = ST_OK;
         }
-        pending &= ~grp;
+        if (out.free_bits) {
+          lat_store_bits(out, grp_a, fits_a, hit_a == 0u, i_a, lane);
+          lat_store_bits(out, grp_b, fits_b, hit_b == 0u, i_b, lane);
+        }
+        pend_a &= ~grp_a;
+        pend_b &= ~grp_b;
       }
     }
   }
@@ -968,11 +1106,11 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       g.row_first = src.first / src.nx;
       const long long row_last = (src.first + count - 1) / src.nx;
       g.n_rows = static_cast<int>(row_last - g.row_first + 1);
-      g.tiles_x = (src.nx + kLatTileX - 1) / kLatTileX;
-      g.n_tiles = static_cast<long long>((g.n_rows + kLatTileY - 1) / kLatTileY) * g.tiles_x;
+      g.segs = (src.nx + kLatSegX - 1) / kLatSegX;
+      g.n_units = static_cast<long long>((g.n_rows + kLatRows - 1) / kLatRows) * g.segs;
       const size_t smem = poly_bytes + kLatSlots * (sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) +
                                                      static_cast<size_t>(rows_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape));
-      const unsigned int grid = static_cast<unsigned int>(std::min<long long>(g.n_tiles, static_cast<long long>(ctx->sm_count) * 4));
+      const unsigned int grid = static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_MIN_BLOCKS));
       k_area_lattice_free<<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
                                                                    ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g);
     } else {
@@ -1158,7 +1296,7 @@ int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double reso
   Bind bind(ctx->device);
   const int pitch = (size_x + 15) & ~15;
   uint8_t* dev = nullptr;
-  // + 128 bytes: k_area_lattice_free's unchecked loop reads (and masks off) up to 63 bytes past the last needed cell
+  // + 128 bytes: k_area_lattice_free's unchecked loop reads (and masks off) up to 95 bytes past the last needed cell
   CU(cudaMalloc(reinterpret_cast<void**>(&dev), static_cast<size_t>(pitch) * size_y + 128));
   CU(cudaMemsetAsync(dev, 0, static_cast<size_t>(pitch) * size_y + 128, ctx->stream));
   cover_map* m = new (std::nothrow) cover_map();
