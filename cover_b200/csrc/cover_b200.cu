@@ -682,32 +682,48 @@ __global__ void __launch_bounds__(kBlock) k_cells(MapView m, const int2* __restr
   if (out.status) out.status[i] = ST_OK;
 }
 
+/// is_free(discrete_polygon, offset, map) over the host-precomputed row spans of the cell SET (an
+/// any-reduction does not care about order or duplicates).
+__global__ void __launch_bounds__(kBlock) k_cells_free(MapView m, const int4* __restrict__ spans, int n_spans, const int2* __restrict__ offsets,
+                                                      long long count, OutView out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int2 off = __ldg(offsets + i);
+  bool hit = false;
+  for (int j = 0; j < n_spans && !hit; ++j) {
+    const int4 sp = __ldg(spans + j);
+    const int y = sp.x + off.y, lo = sp.y + off.x, hi = sp.z + off.x;
+    hit = static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) || lo < 0 || hi >= m.size_x ||
+          row_any_eq(m.data + static_cast<size_t>(y) * m.pitch, lo, hi, 0xFEFEFEFEu);
+  }
+  emit_free(out, i, !hit);
+  if (out.status) out.status[i] = ST_OK;
+}
+
 /// discrete_footprint::is_free(offset, map): outline cells collide on 253/254/outside, area cells on
-/// 254/outside (footprints.cpp:240-247).
-__global__ void __launch_bounds__(kBlock) k_footprints(MapView m, const int2* __restrict__ ocells, const long long* __restrict__ ostarts,
-                                                      const int2* __restrict__ acells, const long long* __restrict__ astarts,
+/// 254/outside (footprints.cpp:240-247).  The verdict is an any-reduction, so the order of the cells is
+/// irrelevant: at upload the host turned each footprint's cell SET into row spans {y, x_lo, x_hi}
+/// ("the polygon split precomputed once on the host per footprint"), which are scanned 4 cells per word.
+__global__ void __launch_bounds__(kBlock) k_footprints(MapView m, const int4* __restrict__ spans, const int2* __restrict__ ranges,
                                                       const int2* __restrict__ offsets, const int* __restrict__ which, long long count,
                                                       OutView out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const int2 off = __ldg(offsets + i);
   const int k = which ? __ldg(which + i) : 0;
+  const int2 o_rng = __ldg(ranges + 2 * k), a_rng = __ldg(ranges + 2 * k + 1);  // [begin, end) of outline / area spans
   bool hit = false;
-  for (long long j = __ldg(ostarts + k), e = __ldg(ostarts + k + 1); j < e && !hit; ++j) {
-    const int2 c = __ldg(ocells + j);
-    const int x = c.x + off.x, y = c.y + off.y;
-    if (static_cast<unsigned>(x) >= static_cast<unsigned>(m.size_x) || static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y)) {
-      hit = true;
-    } else {
-      const int v = __ldg(m.data + static_cast<size_t>(y) * m.pitch + x);
-      hit = v == kInscribed || v == kLethal;
-    }
+  for (int j = o_rng.x; j < o_rng.y && !hit; ++j) {
+    const int4 sp = __ldg(spans + j);
+    const int y = sp.x + off.y, lo = sp.y + off.x, hi = sp.z + off.x;
+    hit = static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) || lo < 0 || hi >= m.size_x ||
+          row_any_inflated(m.data + static_cast<size_t>(y) * m.pitch, lo, hi);
   }
-  for (long long j = __ldg(astarts + k), e = __ldg(astarts + k + 1); j < e && !hit; ++j) {
-    const int2 c = __ldg(acells + j);
-    const int x = c.x + off.x, y = c.y + off.y;
-    hit = static_cast<unsigned>(x) >= static_cast<unsigned>(m.size_x) || static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) ||
-          __ldg(m.data + static_cast<size_t>(y) * m.pitch + x) == kLethal;
+  for (int j = a_rng.x; j < a_rng.y && !hit; ++j) {
+    const int4 sp = __ldg(spans + j);
+    const int y = sp.x + off.y, lo = sp.y + off.x, hi = sp.z + off.x;
+    hit = static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) || lo < 0 || hi >= m.size_x ||
+          row_any_eq(m.data + static_cast<size_t>(y) * m.pitch, lo, hi, 0xFEFEFEFEu);
   }
   emit_free(out, i, !hit);
   if (out.status) out.status[i] = ST_OK;
@@ -843,14 +859,16 @@ struct cover_map {
 
 struct cover_cells {
   cover_ctx* ctx;
-  int2* dev;
+  int2* dev;     // the cells in list order (accumulate_cost / max_cost)
   int64_t n;
+  int4* spans;   // {y, x_lo, x_hi, 0} row spans of the cell set (is_free)
+  int n_spans;
 };
 
 struct cover_footprints {
   cover_ctx* ctx;
-  int2 *ocells, *acells;
-  long long *ostarts, *astarts;
+  int4* spans;   // {y, x_lo, x_hi, 0} row spans of every footprint's outline and area cell sets
+  int2* ranges;  // per footprint: [2k] = outline span range, [2k+1] = area span range
   int32_t n;
 };
 
@@ -1215,7 +1233,7 @@ int cells_check(cover_ctx* ctx, const cover_map* map, const cover_cells* cells, 
   if (rc) return rc;
   if (count) {
     const int2* off = reinterpret_cast<const int2*>(dev);
-    if (op == OP_IS_FREE) k_cells<OP_IS_FREE><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->dev, cells->n, off, count, st.dev);
+    if (op == OP_IS_FREE) k_cells_free<<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->spans, cells->n_spans, off, count, st.dev);
     else if (op == OP_ACCUMULATE) k_cells<OP_ACCUMULATE><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->dev, cells->n, off, count, st.dev);
     else k_cells<OP_MAX><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->dev, cells->n, off, count, st.dev);
     ++ctx->launches;
@@ -1237,6 +1255,23 @@ int upload_new(cover_ctx* ctx, const T* host, size_t n, T** dev) {
 // ===================================================================================================
 // C ABI
 // ===================================================================================================
+
+namespace {
+/// Cells [b, e) of a 2 x N list -> sorted, merged row spans {y, x_lo, x_hi, 0} appended to `spans`.
+void append_row_spans(std::vector<int4>& spans, const int32_t* cells, int64_t b, int64_t e) {
+  std::vector<std::pair<int, int>> yx;
+  yx.reserve(static_cast<size_t>(e - b));
+  for (int64_t i = b; i < e; ++i) yx.emplace_back(cells[2 * i + 1], cells[2 * i]);
+  std::sort(yx.begin(), yx.end());
+  yx.erase(std::unique(yx.begin(), yx.end()), yx.end());
+  for (size_t i = 0; i < yx.size();) {
+    size_t j = i;
+    while (j + 1 < yx.size() && yx[j + 1].first == yx[i].first && yx[j + 1].second == yx[j].second + 1) ++j;
+    spans.push_back(make_int4(yx[i].first, yx[i].second, yx[j].second, 0));
+    i = j + 1;
+  }
+}
+}  // namespace
 
 extern "C" {
 
@@ -1379,9 +1414,17 @@ int cover_cells_create(cover_ctx* ctx, const int32_t* cells, int64_t n_cells, co
   if (n_cells < 0 || (n_cells && !cells)) return fail(ctx, COVER_E_INVALID_ARG, "bad cell list");
   Bind bind(ctx->device);
   int2* dev = nullptr;
-  const int rc = upload_new(ctx, reinterpret_cast<const int2*>(cells), static_cast<size_t>(n_cells), &dev);
+  int rc = upload_new(ctx, reinterpret_cast<const int2*>(cells), static_cast<size_t>(n_cells), &dev);
   if (rc) return rc;
-  *out = new cover_cells{ctx, dev, n_cells};
+  std::vector<int4> spans;
+  append_row_spans(spans, cells, 0, n_cells);
+  int4* dev_spans = nullptr;
+  rc = upload_new(ctx, spans.data(), spans.size(), &dev_spans);
+  if (rc) {
+    cudaFree(dev);
+    return rc;
+  }
+  *out = new cover_cells{ctx, dev, n_cells, dev_spans, static_cast<int>(spans.size())};
   return COVER_OK;
 }
 
@@ -1390,6 +1433,7 @@ void cover_cells_destroy(cover_cells* cells) {
   Bind bind(cells->ctx->device);
   cudaStreamSynchronize(cells->ctx->stream);
   cudaFree(cells->dev);
+  cudaFree(cells->spans);
   delete cells;
 }
 
@@ -1412,13 +1456,22 @@ int cover_footprints_create(cover_ctx* ctx, const int32_t* outline_cells, const 
   for (int k = 0; k < n; ++k)
     if (o_starts[k + 1] < o_starts[k] || a_starts[k + 1] < a_starts[k]) return fail(ctx, COVER_E_INVALID_ARG, "starts must be non-decreasing");
   if ((o_starts[n] && !outline_cells) || (a_starts[n] && !area_cells)) return fail(ctx, COVER_E_INVALID_ARG, "missing cells");
+  // cell set -> sorted, merged row spans (exact for the any-reduction; duplicates and order do not matter)
+  std::vector<int4> spans;
+  std::vector<int2> ranges;
+  auto append_spans = [&spans](const int32_t* cells, int64_t b, int64_t e) { append_row_spans(spans, cells, b, e); };
+  for (int k = 0; k < n; ++k) {
+    const int ob = static_cast<int>(spans.size());
+    append_spans(outline_cells, o_starts[k], o_starts[k + 1]);
+    const int ab = static_cast<int>(spans.size());
+    append_spans(area_cells, a_starts[k], a_starts[k + 1]);
+    ranges.push_back(make_int2(ob, ab));
+    ranges.push_back(make_int2(ab, static_cast<int>(spans.size())));
+  }
   Bind bind(ctx->device);
-  cover_footprints* f = new cover_footprints{ctx, nullptr, nullptr, nullptr, nullptr, n};
-  std::vector<long long> os(o_starts, o_starts + n + 1), as(a_starts, a_starts + n + 1);
-  int rc = upload_new(ctx, reinterpret_cast<const int2*>(outline_cells), static_cast<size_t>(o_starts[n]), &f->ocells);
-  if (!rc) rc = upload_new(ctx, reinterpret_cast<const int2*>(area_cells), static_cast<size_t>(a_starts[n]), &f->acells);
-  if (!rc) rc = upload_new(ctx, os.data(), os.size(), &f->ostarts);
-  if (!rc) rc = upload_new(ctx, as.data(), as.size(), &f->astarts);
+  cover_footprints* f = new cover_footprints{ctx, nullptr, nullptr, n};
+  int rc = upload_new(ctx, spans.data(), spans.size(), &f->spans);
+  if (!rc) rc = upload_new(ctx, ranges.data(), ranges.size(), &f->ranges);
   if (rc) {
     cover_footprints_destroy(f);
     return rc;
@@ -1431,10 +1484,8 @@ void cover_footprints_destroy(cover_footprints* f) {
   if (!f) return;
   Bind bind(f->ctx->device);
   cudaStreamSynchronize(f->ctx->stream);
-  cudaFree(f->ocells);
-  cudaFree(f->acells);
-  cudaFree(f->ostarts);
-  cudaFree(f->astarts);
+  cudaFree(f->spans);
+  cudaFree(f->ranges);
   delete f;
 }
 
@@ -1458,8 +1509,8 @@ int cover_footprints_is_free(cover_ctx* ctx, const cover_map* map, const cover_f
     if (rc) return rc;
   }
   if (count) {
-    k_footprints<<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, fps->ocells, fps->ostarts, fps->acells, fps->astarts,
-                                                             reinterpret_cast<const int2*>(off_dev), which_dev, count, st.dev);
+    k_footprints<<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, fps->spans, fps->ranges, reinterpret_cast<const int2*>(off_dev),
+                                                             which_dev, count, st.dev);
     ++ctx->launches;
   }
   return finish_out(ctx, st, count);

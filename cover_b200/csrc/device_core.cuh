@@ -149,6 +149,19 @@ __device__ __forceinline__ bool row_any_eq(const uint8_t* __restrict__ row, int 
   return acc != 0;
 }
 
+/// true iff some cell of [lo,hi] is INSCRIBED_INFLATED (253) or LETHAL (254): is_lethal_or_inflated (costmap.hpp:96-109).
+__device__ __forceinline__ bool row_any_inflated(const uint8_t* __restrict__ row, int lo, int hi) {
+  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(row);
+  const int w0 = lo >> 2, w1 = hi >> 2;
+  uint32_t acc = 0;
+  for (int w = w0; w <= w1; ++w) {
+    uint32_t v = __ldg(p + w);
+    if (w == w0 || w == w1) v &= keep_mask(w, lo, hi);  // excluded bytes become 0: neither 253 nor 254
+    acc |= zero_bytes(v ^ 0xFEFEFEFEu) | zero_bytes(v ^ 0xFDFDFDFDu);
+  }
+  return acc != 0;
+}
+
 /// accumulate_cost over [lo,hi] in x order: adds costs to `sum`; returns 0, or -1 / -2 for the first
 /// LETHAL / NO_INFORMATION cell (costmap.cpp:35-46).
 __device__ __forceinline__ int row_accumulate(const uint8_t* __restrict__ row, int lo, int hi, unsigned long long& sum) {
