@@ -299,6 +299,33 @@ class Costmap:
     def outline_max_cost(self, polygon, poses, first=0, count=None, out=None) -> Result:
         return self._polygon("cover_outline_max_cost", polygon, poses, first, count, out, True)
 
+    # -- expand (to_outline / to_area, batched) ------------------------------------------------
+    def _expand(self, fn: str, polygon, poses, first, count):
+        ctx = self.ctx
+        xy = polygon_xy(polygon)
+        p, keep = ctx._poses(poses, first, count)
+        n = int(p.count)
+        starts = np.zeros(n + 1, dtype=np.int64)
+        status = np.zeros(max(n, 1), dtype=np.uint8)
+        call = getattr(ctx._lib, fn)
+        args = (ctx._h, self._h, C.c_void_p(xy.ctypes.data), C.c_int32(xy.size // 2), C.byref(p))
+        ctx._check(call(*args, None, C.c_int64(0), C.c_void_p(starts.ctypes.data), C.c_void_p(status.ctypes.data), C.c_int32(_MEM_HOST)))
+        total = int(starts[n])
+        cells = np.empty((max(total, 1), 2), dtype=np.int32)
+        ctx._check(call(*args, C.c_void_p(cells.ctypes.data), C.c_int64(total), C.c_void_p(starts.ctypes.data),
+                        C.c_void_p(status.ctypes.data), C.c_int32(_MEM_HOST)))
+        del keep
+        return cells[:total], starts, status[:n]
+
+    def area_cells(self, polygon, poses, first=0, count=None):
+        """Batched to_area(res, pose*polygon - origin) (expand.hpp:75-80): (cells [total, 2] in generator order,
+        starts [N + 1], status [N])."""
+        return self._expand("cover_area_expand", polygon, poses, first, count)
+
+    def outline_cells(self, polygon, poses, first=0, count=None):
+        """Batched to_outline(res, pose*polygon - origin) (expand.hpp:68-72)."""
+        return self._expand("cover_outline_expand", polygon, poses, first, count)
+
     # -- rays ----------------------------------------------------------------------------------
     def _rays(self, fn: str, segments, offset, out, want_cost):
         ctx = self.ctx

@@ -289,4 +289,52 @@ __device__ __forceinline__ int area_rows_pose(const double* __restrict__ poly, i
   return ST_OK;
 }
 
+
+/// expand(area_generator): counts (cells == nullptr) or writes the area cells of one pose in generator
+/// order — rows ascending, merged ranges in sorted order, x ascending (generators.hpp:417-423,
+/// impl/expand.hpp:23-39).  One warp; returns the status, `total` = number of cells.
+template <int XF>
+__device__ __forceinline__ int area_rows_expand(const double* __restrict__ poly, int nv, const Pose& T, const MapView& m, int2* verts,
+                                                RayRec* rays, int lane, int2* __restrict__ cells, long long& total) {
+  total = 0;
+  bool ok;
+  int x0, y0, x1, y1;
+  const int n_rays = build_rays<XF>(poly, nv, T, m, verts, rays, lane, ok, x0, y0, x1, y1);
+  if (!ok) return ST_COORD_RANGE;
+  if (n_rays == 0) return ST_OK;
+  if (y0 == y1) {  // single row: [min, max]
+    total = x1 - x0 + 1;
+    if (cells)
+      for (int x = x0 + lane; x <= x1; x += 32) cells[x - x0] = make_int2(x, y0);
+    return ST_OK;
+  }
+  bool odd = false, overflow = false;
+  long long base = 0;
+  for (int yb = y0; yb <= y1; yb += 32) {
+    const int y = yb + lane;
+    RowList L;
+    if (y <= y1) build_row(rays, n_rays, y, L);
+    odd |= (L.n & 1) != 0;
+    overflow |= L.overflow;
+    int mine = 0;
+    if (!(L.n & 1) && !L.overflow)
+      for (int k = 0; k + 1 < L.n; k += 2) mine += L.hi[k + 1] - L.lo[k] + 1;
+    int incl = mine;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += up;
+    }
+    if (cells && !(L.n & 1) && !L.overflow) {
+      long long at = base + incl - mine;
+      for (int k = 0; k + 1 < L.n; k += 2)
+        for (int x = L.lo[k]; x <= L.hi[k + 1]; ++x) cells[at++] = make_int2(x, y);
+    }
+    base += __shfl_sync(0xFFFFFFFFu, incl, 31);
+  }
+  if (__any_sync(0xFFFFFFFFu, odd)) return ST_LOGIC_ERROR;
+  if (__any_sync(0xFFFFFFFFu, overflow)) return ST_ROW_COMPLEXITY;
+  total = base;
+  return ST_OK;
+}
+
 }  // namespace cvr

@@ -655,6 +655,69 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_area_rows(MapView m, const 
   }
 }
 
+
+/// expand(area_generator(res, pose*polygon - origin)) — to_area (expand.hpp:75-80).  One warp per pose.
+/// Pass 1 (cells == nullptr) fills counts[]; pass 2 writes the cells of pose i at cells + starts[i].
+__global__ void __launch_bounds__(kRowsWarps * 32) k_area_expand(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
+                                                                long long count, long long* __restrict__ counts, uint8_t* __restrict__ status,
+                                                                const long long* __restrict__ starts, int2* __restrict__ cells) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv, smem_d);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RayRec* rays = reinterpret_cast<RayRec*>(smem_d + 2 * nv) + warp * (nv + 1);
+  int2* verts = reinterpret_cast<int2*>(reinterpret_cast<RayRec*>(smem_d + 2 * nv) + kRowsWarps * (nv + 1)) + warp * nv;
+  const long long n_warps = static_cast<long long>(gridDim.x) * kRowsWarps;
+  const bool none = src.format == POSE_NONE;
+  for (long long i = static_cast<long long>(blockIdx.x) * kRowsWarps + warp; i < count; i += n_warps) {
+    const Pose T = load_pose(src, i);
+    long long total = 0;
+    int2* dst = cells ? cells + starts[i] : nullptr;
+    if (cells && starts[i + 1] == starts[i]) dst = nullptr;  // nothing to write (empty or failed pose)
+    const int st = (cells && !dst) ? ST_OK
+                   : none          ? area_rows_expand<XF_NONE>(poly, nv, T, m, verts, rays, lane, dst, total)
+                                   : area_rows_expand<XF_PATH_A>(poly, nv, T, m, verts, rays, lane, dst, total);
+    if (!cells && lane == 0) {
+      counts[i] = st == ST_OK ? total : 0;
+      if (status) status[i] = static_cast<uint8_t>(st);
+    }
+    __syncwarp();
+  }
+}
+
+/// Sink that stores the outline cells in order.
+struct CellWriter {
+  int2* __restrict__ dst;
+  long long n = 0;
+  __device__ __forceinline__ bool cell(int x, int y) {
+    if (dst) dst[n] = make_int2(x, y);
+    ++n;
+    return true;
+  }
+};
+
+/// expand(outline_generator(res, pose*polygon - origin)) — to_outline (expand.hpp:68-72).  One thread per pose.
+__global__ void __launch_bounds__(kBlock) k_outline_expand(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src, long long count,
+                                                          long long* __restrict__ counts, uint8_t* __restrict__ status,
+                                                          const long long* __restrict__ starts, int2* __restrict__ cells) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv, smem_d);
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const Pose T = load_pose(src, i);
+  int x0, y0, x1, y1;
+  const bool none = src.format == POSE_NONE;
+  const bool ok = none ? polygon_bbox<XF_NONE>(poly, nv, T, m, x0, y0, x1, y1) : polygon_bbox<XF_PATH_A>(poly, nv, T, m, x0, y0, x1, y1);
+  CellWriter w{cells ? cells + starts[i] : nullptr};
+  if (ok && !(cells && starts[i + 1] == starts[i])) {
+    if (none) walk_outline<XF_NONE>(poly, nv, T, m, w);
+    else walk_outline<XF_PATH_A>(poly, nv, T, m, w);
+  }
+  if (!cells) {
+    counts[i] = ok ? w.n : 0;
+    if (status) status[i] = ok ? ST_OK : ST_COORD_RANGE;
+  }
+}
+
 template <int OP>
 __global__ void __launch_bounds__(kBlock) k_rays(MapView m, const int4* __restrict__ segments, long long count, int offx, int offy,
                                                 OutView out) {
@@ -1089,6 +1152,8 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_rows<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_rows<OP_MAX>));
   set(reinterpret_cast<const void*>(&k_area_lattice_free));
+  set(reinterpret_cast<const void*>(&k_area_expand));
+  set(reinterpret_cast<const void*>(&k_outline_expand));
   return e;
 }
 
@@ -1256,6 +1321,57 @@ int upload_new(cover_ctx* ctx, const T* host, size_t n, T** dev) {
 // C ABI
 // ===================================================================================================
 
+
+namespace {
+/// Shared implementation of cover_area_expand / cover_outline_expand (two kernel passes + a host prefix sum).
+int expand_cells(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t nv, bool area, const cover_poses* poses,
+                 int32_t* cells, int64_t capacity, int64_t* starts, uint8_t* status, int32_t mem) {
+  if (!ctx) return COVER_E_INVALID_ARG;
+  if (!map || map->ctx != ctx) return fail(ctx, COVER_E_INVALID_ARG, "map does not belong to this context");
+  if (nv < 0 || (nv > 0 && !polygon_xy) || !starts) return fail(ctx, COVER_E_INVALID_ARG, "bad arguments");
+  if (nv > kRowsMaxVertices) return fail(ctx, COVER_E_UNSUPPORTED, "expand supports at most 256 vertices");
+  if (mem != COVER_MEM_HOST) return fail(ctx, COVER_E_UNSUPPORTED, "expand returns host arrays (it is a per-footprint precompute)");
+  Bind bind(ctx->device);
+  PoseSource src;
+  int rc = stage_poses(ctx, poses, src);
+  if (rc) return rc;
+  const int64_t n = poses->count;
+  const size_t poly_bytes = static_cast<size_t>(nv) * 2 * sizeof(double);
+  CU(ctx->poly.ensure(std::max<size_t>(poly_bytes, 16)));
+  if (poly_bytes) CU(cudaMemcpyAsync(ctx->poly.ptr, polygon_xy, poly_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx->in_a.ensure(static_cast<size_t>(n + 1) * sizeof(long long)));  // counts, then starts
+  CU(ctx->out_status.ensure(static_cast<size_t>(std::max<int64_t>(n, 1))));
+  long long* d_counts = ctx->in_a.as<long long>();
+  uint8_t* d_status = ctx->out_status.as<uint8_t>();
+  const unsigned int rows_grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(static_cast<long long>(ctx->sm_count) * 12, (n + kRowsWarps - 1) / kRowsWarps)));
+  auto launch = [&](const long long* d_starts, int2* d_cells) {
+    if (n == 0) return;
+    if (area) k_area_expand<<<rows_grid, kRowsWarps * 32, rows_smem(nv), ctx->stream>>>(map->view, ctx->poly.as<double>(), nv, src, n, d_counts, d_status, d_starts, d_cells);
+    else k_outline_expand<<<grid_for(n), kBlock, poly_bytes, ctx->stream>>>(map->view, ctx->poly.as<double>(), nv, src, n, d_counts, d_status, d_starts, d_cells);
+    ++ctx->launches;
+  };
+  launch(nullptr, nullptr);
+  CU(cudaGetLastError());
+  std::vector<long long> counts(static_cast<size_t>(n));
+  if (n) CU(cudaMemcpyAsync(counts.data(), d_counts, static_cast<size_t>(n) * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  if (status && n) CU(cudaMemcpyAsync(status, d_status, static_cast<size_t>(n), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::vector<long long> st(static_cast<size_t>(n) + 1, 0);
+  for (int64_t i = 0; i < n; ++i) st[i + 1] = st[i] + counts[i];
+  for (int64_t i = 0; i <= n; ++i) starts[i] = st[i];
+  if (!cells) return COVER_OK;  // size query
+  if (st[n] > capacity) return fail(ctx, COVER_E_INVALID_ARG, "cells buffer too small (call with cells = NULL to get the size)");
+  if (st[n] == 0) return COVER_OK;
+  CU(ctx->in_b.ensure(static_cast<size_t>(st[n]) * sizeof(int2)));
+  CU(cudaMemcpyAsync(d_counts, st.data(), st.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  launch(d_counts, ctx->in_b.as<int2>());
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(cells, ctx->in_b.ptr, static_cast<size_t>(st[n]) * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return COVER_OK;
+}
+}  // namespace
+
 namespace {
 /// Cells [b, e) of a 2 x N list -> sorted, merged row spans {y, x_lo, x_hi, 0} appended to `spans`.
 void append_row_spans(std::vector<int4>& spans, const int32_t* cells, int64_t b, int64_t e) {
@@ -1406,6 +1522,15 @@ int cover_ray_accumulate_cost(cover_ctx* ctx, const cover_map* map, const int32_
 }
 int cover_ray_max_cost(cover_ctx* ctx, const cover_map* map, const int32_t* seg, int32_t mem, int64_t count, const int32_t* offset, const cover_results* out) {
   return rays_check(ctx, map, seg, mem, count, offset, OP_MAX, out);
+}
+
+int cover_area_expand(cover_ctx* ctx, const cover_map* map, const double* xy, int32_t nv, const cover_poses* poses, int32_t* cells,
+                      int64_t capacity, int64_t* starts, uint8_t* status, int32_t mem) {
+  return expand_cells(ctx, map, xy, nv, true, poses, cells, capacity, starts, status, mem);
+}
+int cover_outline_expand(cover_ctx* ctx, const cover_map* map, const double* xy, int32_t nv, const cover_poses* poses, int32_t* cells,
+                         int64_t capacity, int64_t* starts, uint8_t* status, int32_t mem) {
+  return expand_cells(ctx, map, xy, nv, false, poses, cells, capacity, starts, status, mem);
 }
 
 int cover_cells_create(cover_ctx* ctx, const int32_t* cells, int64_t n_cells, cover_cells** out) {

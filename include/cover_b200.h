@@ -132,6 +132,18 @@ int cover_outline_accumulate_cost(cover_ctx* ctx, const cover_map* map, const do
 int cover_outline_max_cost(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t n_vertices,
                            const cover_poses* poses, const cover_results* out);
 
+/* ---- expand: to_outline / to_area (src/cover/expand.hpp:68-80, impl/expand.hpp:23-39), batched over poses ----
+ * The dense cells of outline_generator / area_generator(res, pose*polygon - origin) in GENERATOR ORDER
+ * (the per-heading discrete-footprint cache is built from these on the device).
+ * starts[count + 1] receives the prefix offsets (pose i owns cells [starts[i], starts[i+1])); with
+ * cells == NULL only starts/status are produced (size query), else 2 x starts[count] int32 are written
+ * (capacity = number of cells the buffer holds).  A pose whose status is not OK contributes 0 cells.
+ * Host arrays only (mem must be COVER_MEM_HOST): this is a per-footprint precompute, not a per-pose check. */
+int cover_area_expand(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t n_vertices, const cover_poses* poses,
+                      int32_t* cells, int64_t capacity, int64_t* starts, uint8_t* status, int32_t mem);
+int cover_outline_expand(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t n_vertices, const cover_poses* poses,
+                         int32_t* cells, int64_t capacity, int64_t* starts, uint8_t* status, int32_t mem);
+
 /* ---- rays: is_free / accumulate_cost(ray_generator(begin,end)[, offset], map) ---------------------
  * impl/costmap.hpp:23-35,65-81 over generators.cpp:30-52.  segments = count x {x0,y0,x1,y1} cells
  * (end exclusive); offset = 2 ints added to every cell, or NULL. */

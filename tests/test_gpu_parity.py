@@ -452,3 +452,72 @@ def test_many_vertex_polygons(cb, ctx):
         assert_same(cmap.area_accumulate_cost(poly, poses), po.polygon_batch(omap, poly, poses, op=po.OP_ACCUMULATE, threads=8), True, f"potato {nv}")
         star = poly * (1.0 + 0.35 * np.cos(9 * 2 * math.pi * np.arange(nv) / nv))
         assert_same(cmap.area_is_free(star, poses), po.polygon_batch(omap, star, poses, threads=8), False, f"star {nv}")
+
+
+def _sparse_cells(poly, pose, res, ox, oy):
+    """Path-A discretisation in numpy (every operation individually rounded, like the reference)."""
+    c, s, tx, ty = pose
+    px, py = np.asarray(poly, dtype=np.float64)
+    qx = (tx + ((c * px) + ((-s) * py))) - ox
+    qy = (ty + ((s * px) + (c * py))) - oy
+    inv = 1.0 / res
+    return np.stack([np.trunc(qx * inv), np.trunc(qy * inv)], 1).astype(np.int32)
+
+
+def test_expand_matches_to_area_and_to_outline(cb, ctx):
+    """cover_area_expand / cover_outline_expand == to_area / to_outline (expand.hpp:68-80) cell for cell, in
+    generator order, for every reference footprint and for degenerate polygons."""
+    rng = np.random.default_rng(95)
+    cmap = cb.Costmap(ctx, np.zeros((50, 50), dtype=np.uint8), 0.05, -0.4, 0.3)
+    poses = poses_around(rng, 60, -3.0, 3.0)
+    polys = list(FOOTPRINTS) + [RECT, np.array([[0.0, 0.3], [0.0, 0.45]]), np.array([[0.1], [0.1]]), np.array([[0.0, 0.4], [0.0, 0.0]])]
+    for poly in polys:
+        a_cells, a_starts, a_status = cmap.area_cells(poly, poses)
+        o_cells, o_starts, o_status = cmap.outline_cells(poly, poses)
+        assert (o_status == 0).all()
+        for i, pose in enumerate(poses):
+            dense = po.outline_cells(_sparse_cells(poly, pose, 0.05, -0.4, 0.3))
+            np.testing.assert_array_equal(o_cells[o_starts[i]:o_starts[i + 1]], dense)
+            try:
+                expect = po.area_cells([dense])
+                assert a_status[i] == 0
+                np.testing.assert_array_equal(a_cells[a_starts[i]:a_starts[i + 1]], expect)
+            except RuntimeError:
+                assert a_status[i] == po.LOGIC_ERROR and a_starts[i + 1] == a_starts[i]
+
+
+@pytest.mark.parametrize("idx", [4, 5])
+def test_grid_split_safety_regression(cb, ctx, idx):
+    """The reference's safety property (test/footprints.cpp:205-242,351-391) for the grid split: with an
+    inflation layer whose inscribed radius equals the split radius, a lethal obstacle on ANY cell of the
+    footprint makes the split check fail (the reference tolerates 2 misses, this construction allows 0),
+    and an empty map is free."""
+    from cover_b200 import split, workloads as wl
+    res, radius = 0.05, 0.2
+    free_map = np.zeros((200, 200), dtype=np.uint8)
+    cmap = cb.Costmap(ctx, free_map, res, -5.0, -5.0)
+    bank, cs = split.heading_bank(cmap, FOOTPRINTS[idx], radius, 8)
+    assert all(len(o) > 0 for o, _ in bank)
+    fb = cb.FootprintBank(ctx, bank)
+    centre = np.array([[100, 100]], dtype=np.int32)
+    rad = int(math.ceil(radius / res))
+    yy, xx = np.mgrid[-rad:rad + 1, -rad:rad + 1]
+    disk = (np.hypot(xx, yy) * res <= radius)
+    for k in (0, 3, 5):
+        which = np.array([k], dtype=np.int32)
+        assert fb.is_free(cmap, centre, which).is_free[0] == 1
+        cells, starts, _ = cmap.area_cells(FOOTPRINTS[idx], np.array([[cs[k, 0], cs[k, 1], -5.0, -5.0]]))
+        misses = 0
+        for (cx, cy) in cells[::7]:  # every 7th footprint cell keeps the test short
+            data = np.zeros((200, 200), dtype=np.uint8)
+            x, y = cx + 100, cy + 100
+            view = data[y - rad:y + rad + 1, x - rad:x + rad + 1]
+            view[disk] = 253
+            data[y, x] = 254
+            cmap.upload(data)
+            misses += int(fb.is_free(cmap, centre, which).is_free[0])
+        cmap.upload(free_map)
+        assert misses == 0
+    # fewer cells are scanned than by the full-area check
+    full = sum(len(cmap.area_cells(FOOTPRINTS[idx], np.array([[c, s, -5.0, -5.0]]))[0]) for c, s in cs)
+    assert sum(len(o) + len(a) for o, a in bank) < full
