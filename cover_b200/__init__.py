@@ -26,7 +26,7 @@ from . import _build
 
 __all__ = [
     "CoverError", "Context", "Costmap", "Lattice", "Result", "DiscretePolygon", "FootprintBank", "SplitFootprint",
-    "STATUS_OK", "STATUS_LOGIC_ERROR", "STATUS_ROW_COMPLEXITY", "STATUS_COORD_RANGE", "library_path", "build",
+    "trajectory_reduce", "STATUS_OK", "STATUS_LOGIC_ERROR", "STATUS_ROW_COMPLEXITY", "STATUS_COORD_RANGE", "library_path", "build",
 ]
 
 STATUS_OK, STATUS_LOGIC_ERROR, STATUS_ROW_COMPLEXITY, STATUS_COORD_RANGE = 0, 1, 2, 3
@@ -220,6 +220,29 @@ class Context:
         res = Result(np.empty(n, dtype=np.uint8) if want_free else None, np.empty(n, dtype=np.float64) if want_cost else None,
                      np.empty(n, dtype=np.uint8) if want_status else None)
         return _Results(_MEM_HOST, _ptr(res.is_free), _ptr(res.cost), _ptr(res.status), None, None), res
+
+
+def trajectory_reduce(ctx: "Context", is_free=None, cost=None, steps: int = 1):
+    """Scores trajectories of `steps` consecutive poses each (extension; see cover_trajectory_reduce).
+    Host (numpy) or device (torch) arrays; returns (first_blocked int32 [T] or None, score float64 [T] or None)."""
+    ref = is_free if is_free is not None else cost
+    n = int(ref.shape[0])
+    if n % steps:
+        raise ValueError("the number of poses must be a multiple of steps")
+    t = n // steps
+    dev = _is_device(ref)
+    if dev:
+        import torch
+        first = torch.empty(t, dtype=torch.int32, device=ref.device) if is_free is not None else None
+        score = torch.empty(t, dtype=torch.float64, device=ref.device) if cost is not None else None
+    else:
+        is_free = None if is_free is None else np.ascontiguousarray(is_free, dtype=np.uint8)
+        cost = None if cost is None else np.ascontiguousarray(cost, dtype=np.float64)
+        first = np.empty(t, dtype=np.int32) if is_free is not None else None
+        score = np.empty(t, dtype=np.float64) if cost is not None else None
+    ctx._check(ctx._lib.cover_trajectory_reduce(ctx._h, C.c_void_p(_ptr(is_free)), C.c_void_p(_ptr(cost)), C.c_int32(_MEM_DEVICE if dev else _MEM_HOST),
+                                                C.c_int64(t), C.c_int32(steps), C.c_void_p(_ptr(first)), C.c_void_p(_ptr(score))))
+    return first, score
 
 
 class Costmap:

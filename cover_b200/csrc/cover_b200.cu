@@ -718,6 +718,45 @@ __global__ void __launch_bounds__(kBlock) k_outline_expand(MapView m, const doub
   }
 }
 
+
+/// Trajectory scoring (the DWA-style caller right after the pose checks).  Poses are grouped as
+/// n_trajectories x steps (pose index = trajectory * steps + step).  One warp per trajectory:
+///   first_blocked[t] = first step whose verdict is 0 (`steps` if the whole trajectory is free)
+///   score[t]         = accumulate_cost semantics lifted to the trajectory: the first negative per-pose cost
+///                      in step order if there is one, else the sum of the per-pose costs (exact: integers).
+__global__ void __launch_bounds__(kBlock) k_trajectories(const uint8_t* __restrict__ is_free, const double* __restrict__ cost, long long n_traj,
+                                                        int steps, int* __restrict__ first_blocked, double* __restrict__ score) {
+  const int lane = threadIdx.x & 31;
+  const long long t = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (t >= n_traj) return;
+  const long long base = t * steps;
+  int blocked = steps, neg_step = steps;
+  double sum = 0.0, neg = 0.0;
+  for (int s0 = 0; s0 < steps; s0 += 32) {
+    const int s = s0 + lane;
+    const bool in = s < steps;
+    if (is_free) {
+      const unsigned b = __ballot_sync(0xFFFFFFFFu, in && is_free[base + s] == 0);
+      if (b && blocked == steps) blocked = s0 + __ffs(b) - 1;
+    }
+    if (cost) {
+      const double c = in ? cost[base + s] : 0.0;
+      const unsigned b = __ballot_sync(0xFFFFFFFFu, in && !(c >= 0.0));  // negative sentinel or NaN (failed pose)
+      if (b && neg_step == steps) {
+        neg_step = s0 + __ffs(b) - 1;
+        neg = __shfl_sync(0xFFFFFFFFu, c, __ffs(b) - 1);
+      }
+      double part = (in && c >= 0.0) ? c : 0.0;
+      for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);
+      sum += part;
+    }
+  }
+  if (lane == 0) {
+    if (first_blocked) first_blocked[t] = blocked;
+    if (score) score[t] = neg_step < steps ? neg : sum;
+  }
+}
+
 template <int OP>
 __global__ void __launch_bounds__(kBlock) k_rays(MapView m, const int4* __restrict__ segments, long long count, int offx, int offy,
                                                 OutView out) {
@@ -1531,6 +1570,50 @@ int cover_area_expand(cover_ctx* ctx, const cover_map* map, const double* xy, in
 int cover_outline_expand(cover_ctx* ctx, const cover_map* map, const double* xy, int32_t nv, const cover_poses* poses, int32_t* cells,
                          int64_t capacity, int64_t* starts, uint8_t* status, int32_t mem) {
   return expand_cells(ctx, map, xy, nv, false, poses, cells, capacity, starts, status, mem);
+}
+
+int cover_trajectory_reduce(cover_ctx* ctx, const uint8_t* is_free, const double* cost, int32_t mem, int64_t n_trajectories, int32_t steps,
+                            int32_t* first_blocked, double* score) {
+  if (!ctx) return COVER_E_INVALID_ARG;
+  if (n_trajectories < 0 || steps <= 0 || (!is_free && !cost) || (first_blocked && !is_free) || (score && !cost))
+    return fail(ctx, COVER_E_INVALID_ARG, "bad trajectory arguments");
+  if (n_trajectories == 0) return COVER_OK;
+  Bind bind(ctx->device);
+  const size_t n = static_cast<size_t>(n_trajectories) * static_cast<size_t>(steps);
+  const uint8_t* d_free = is_free;
+  const double* d_cost = cost;
+  int32_t* d_first = first_blocked;
+  double* d_score = score;
+  if (mem == COVER_MEM_HOST) {
+    if (is_free) {
+      CU(ctx->out_free.ensure(n));
+      CU(cudaMemcpyAsync(ctx->out_free.ptr, is_free, n, cudaMemcpyHostToDevice, ctx->stream));
+      d_free = ctx->out_free.as<uint8_t>();
+    }
+    if (cost) {
+      CU(ctx->out_cost.ensure(n * sizeof(double)));
+      CU(cudaMemcpyAsync(ctx->out_cost.ptr, cost, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      d_cost = ctx->out_cost.as<double>();
+    }
+    if (first_blocked) {
+      CU(ctx->in_a.ensure(static_cast<size_t>(n_trajectories) * sizeof(int32_t)));
+      d_first = ctx->in_a.as<int32_t>();
+    }
+    if (score) {
+      CU(ctx->in_b.ensure(static_cast<size_t>(n_trajectories) * sizeof(double)));
+      d_score = ctx->in_b.as<double>();
+    }
+  }
+  const unsigned int grid = static_cast<unsigned int>((n_trajectories * 32 + kBlock - 1) / kBlock);
+  k_trajectories<<<grid, kBlock, 0, ctx->stream>>>(d_free, d_cost, n_trajectories, steps, d_first, d_score);
+  ++ctx->launches;
+  CU(cudaGetLastError());
+  if (mem == COVER_MEM_HOST) {
+    if (first_blocked) CU(cudaMemcpyAsync(first_blocked, d_first, static_cast<size_t>(n_trajectories) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (score) CU(cudaMemcpyAsync(score, d_score, static_cast<size_t>(n_trajectories) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return COVER_OK;
 }
 
 int cover_cells_create(cover_ctx* ctx, const int32_t* cells, int64_t n_cells, cover_cells** out) {

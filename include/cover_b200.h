@@ -187,6 +187,14 @@ void cover_split_destroy(cover_split* split);
 int cover_split_is_free(cover_ctx* ctx, const cover_map* map, const cover_split* split, const cover_poses* poses,
                         const cover_results* out);
 
+/* ---- trajectory scoring (EXTENSION: the DWA-style caller right after the pose checks) -------
+ * Poses grouped as n_trajectories x steps (pose index = trajectory * steps + step), e.g. the outputs of the
+ * entries above left on the device.  first_blocked[t] = first step with verdict 0 (`steps` if none);
+ * score[t] = the first negative per-pose cost in step order if any, else the sum of the per-pose costs
+ * (accumulate_cost's rule, impl/costmap.hpp:50-63, lifted from cells to poses).  Either output may be NULL. */
+int cover_trajectory_reduce(cover_ctx* ctx, const uint8_t* is_free, const double* cost, int32_t mem, int64_t n_trajectories,
+                            int32_t steps, int32_t* first_blocked, double* score);
+
 #ifdef __cplusplus
 }
 #endif

@@ -521,3 +521,62 @@ def test_grid_split_safety_regression(cb, ctx, idx):
     # fewer cells are scanned than by the full-area check
     full = sum(len(cmap.area_cells(FOOTPRINTS[idx], np.array([[c, s, -5.0, -5.0]]))[0]) for c, s in cs)
     assert sum(len(o) + len(a) for o, a in bank) < full
+
+
+def test_error_codes_and_messages(cb, ctx):
+    """Error behaviour at the boundary: invalid arguments come back as COVER_E_INVALID_ARG (-1, the
+    reference's std::invalid_argument) with a message, never as a crash; handles are context-bound."""
+    with pytest.raises(cb.CoverError) as e:
+        cb.Costmap(ctx, np.zeros((10, 10), dtype=np.uint8), 0.0)
+    assert e.value.code == -1 and "resolution" in str(e.value).lower()
+    with pytest.raises(cb.CoverError):
+        cb.Costmap(ctx, np.zeros((10, 10), dtype=np.uint8), -1.0)
+    cmap = cb.Costmap(ctx, np.zeros((64, 64), dtype=np.uint8), 0.05)
+    th = np.array([[1.0, 0.0]])
+    with pytest.raises(cb.CoverError) as e:  # lattice sub-range outside the lattice
+        cmap.area_is_free(RECT, cb.Lattice(0.5, 0.05, 10, 0.5, 0.05, 10, th), first=50, count=100)
+    assert e.value.code == -1
+    with pytest.raises(cb.CoverError):  # more vertices than any kernel supports
+        cmap.area_is_free(np.zeros((2, 5000)), np.array([[1.0, 0.0, 1.0, 1.0]]))
+    other = cb.Context(0)
+    try:
+        with pytest.raises(cb.CoverError) as e:  # a cell list of another context
+            cb.DiscretePolygon(other, [(0, 0), (1, 0)]).is_free(cmap, [(3, 3)])
+        assert e.value.code == -1
+    finally:
+        other.close()
+    with pytest.raises(cb.CoverError):  # footprint index out of range
+        cb.FootprintBank(ctx, [(np.zeros((0, 2), np.int32), np.array([[0, 0]], np.int32))]).is_free(cmap, [(1, 1)], which=[3])
+    # empty batches are fine
+    r = cmap.area_is_free(RECT, np.zeros((0, 4)))
+    assert len(r.is_free) == 0
+    assert len(cmap.ray_is_free(np.zeros((0, 4), dtype=np.int32)).is_free) == 0
+    # the context is still usable after the errors
+    assert cmap.area_is_free(RECT, np.array([[1.0, 0.0, 1.5, 1.5]])).is_free[0] == 1
+
+
+def test_trajectory_scoring(cb, ctx):
+    """cover_trajectory_reduce against a numpy restatement: rollouts of 37 poses along arcs."""
+    rng = np.random.default_rng(97)
+    data = mixed_map(rng, 600, 600, lethal=0.0015)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    n_traj, steps = 3001, 37
+    x0, y0, th0 = rng.uniform(2, 28, n_traj), rng.uniform(2, 28, n_traj), rng.uniform(-math.pi, math.pi, n_traj)
+    v, w = rng.uniform(0.05, 0.25, n_traj), rng.uniform(-0.2, 0.2, n_traj)
+    k = np.arange(steps)
+    th = th0[:, None] + w[:, None] * k
+    poses = np.stack([np.cos(th), np.sin(th), x0[:, None] + v[:, None] * k * np.cos(th), y0[:, None] + v[:, None] * k * np.sin(th)], axis=-1).reshape(-1, 4)
+    r = cmap.area_accumulate_cost(RECT, poses)
+    first, score = cb.trajectory_reduce(ctx, r.is_free, r.cost, steps)
+    fr, co = r.is_free.reshape(n_traj, steps), r.cost.reshape(n_traj, steps)
+    exp_first = np.where((fr == 0).any(1), (fr == 0).argmax(1), steps)
+    neg = ~(co >= 0)
+    exp_score = np.where(neg.any(1), co[np.arange(n_traj), neg.argmax(1)], np.where(neg, 0.0, co).sum(1))
+    np.testing.assert_array_equal(first, exp_first)
+    np.testing.assert_array_equal(score, exp_score)
+    assert 0 < (exp_first < steps).mean() < 1
+    torch = pytest.importorskip("torch")
+    dfirst, dscore = cb.trajectory_reduce(ctx, torch.from_numpy(r.is_free).cuda(), torch.from_numpy(r.cost).cuda(), steps)
+    ctx.synchronize()
+    np.testing.assert_array_equal(dfirst.cpu().numpy(), exp_first)
+    np.testing.assert_array_equal(dscore.cpu().numpy(), exp_score)
