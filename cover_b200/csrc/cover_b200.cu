@@ -230,36 +230,46 @@ __device__ __forceinline__ LatProfile lat_profile(const double* __restrict__ pol
   return p;
 }
 
-template <bool FAST>
+/// Scan-row walk of one group.  `row_a[r]` = r * pitch + (first cell of row r's range, relative to vertex 0),
+/// `row_m[r]` = width mask.  MODE 0: every needed cell is inside the map and plane A's windows start in piece 0,
+/// plane B's in piece 1 (the usual full 64-pose group): no bounds tests, no piece selection.  MODE 1: inside
+/// the map, arbitrary offsets.  MODE 2: per-cell bounds tests (outside the map counts as lethal).
+template <int MODE>
 __device__ LAT_ROWS_INLINE void lattice_rows(const MapView& m, const int* __restrict__ row_a, const uint32_t* __restrict__ row_m, int rows,
                                              int x_base, int y_base, int lane, bool third, int off_a, int off_b, uint32_t& hit_a, uint32_t& hit_b) {
   // lane constants: which two of the three 32-cell pieces a pose's window starts in, and its shift
   const bool hi_a = off_a >= 32, hi_b = off_b >= 32;
   const int sh_a = off_a & 31, sh_b = off_b & 31;
-  if (FAST) {  // every needed cell of every pose of the group is inside the map: no per-cell bounds tests
+  if (MODE != 2) {
     const uint8_t* __restrict__ p = m.data + static_cast<size_t>(y_base) * m.pitch + (x_base + lane);
     // unrolled by 4: the 12 byte loads of four scan rows are in flight together (few resident warps, so the
     // memory-level parallelism has to come from inside the warp)
 #pragma unroll 4
     for (int r = 0; r < rows; ++r) {
-      const uint8_t* __restrict__ q = p + static_cast<size_t>(r) * m.pitch + row_a[r];
+      const uint8_t* __restrict__ q = p + row_a[r];
       const uint8_t b0 = __ldg(q), b1 = __ldg(q + 32), b2 = third ? __ldg(q + 64) : static_cast<uint8_t>(0);
       const uint32_t m0 = __ballot_sync(kFull, b0 == kLethal);
       const uint32_t m1 = __ballot_sync(kFull, b1 == kLethal);
       const uint32_t m2 = __ballot_sync(kFull, b2 == kLethal);
       const uint32_t wm = row_m[r];
-      hit_a |= __funnelshift_r(hi_a ? m1 : m0, hi_a ? m2 : m1, sh_a) & wm;
-      hit_b |= __funnelshift_r(hi_b ? m1 : m0, hi_b ? m2 : m1, sh_b) & wm;
+      if (MODE == 0) {
+        hit_a |= __funnelshift_r(m0, m1, sh_a) & wm;
+        hit_b |= __funnelshift_r(m1, m2, sh_b) & wm;
+      } else {
+        hit_a |= __funnelshift_r(hi_a ? m1 : m0, hi_a ? m2 : m1, sh_a) & wm;
+        hit_b |= __funnelshift_r(hi_b ? m1 : m0, hi_b ? m2 : m1, sh_b) & wm;
+      }
     }
   } else {
     for (int r = 0; r < rows; ++r) {
       const int y = y_base + r;
       const bool y_in = static_cast<unsigned>(y) < static_cast<unsigned>(m.size_y);
       const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y_in ? y : 0) * m.pitch;
+      const int lo = row_a[r] - r * m.pitch;
       uint32_t piece[3];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const int x = x_base + row_a[r] + lane + 32 * j;
+        const int x = x_base + lo + lane + 32 * j;
         bool lethal = true;  // outside the map counts as lethal (costmap.hpp:81-91)
         if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
         piece[j] = __ballot_sync(kFull, lethal);
@@ -273,7 +283,7 @@ __device__ LAT_ROWS_INLINE void lattice_rows(const MapView& m, const int* __rest
 
 /// Rasterises the relative shape `verts` into (row_a = first cell of the merged range, relative to vertex
 /// 0; row_m = width mask) and returns its descriptor.  Runs in ONE lane.
-__device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ verts, int nv, int rows_cap, int* __restrict__ ra,
+__device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ verts, int nv, int rows_cap, int pitch, int* __restrict__ ra,
                                                    uint32_t* __restrict__ rm) {
   int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, x1 = -0x7FFFFFFF - 1, y1 = -0x7FFFFFFF - 1;
   for (int v = 0; v < nv; ++v) {
@@ -297,7 +307,7 @@ __device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ vert
     if (cnt == 1u) sh.status = ST_LOGIC_ERROR;  // odd number of ranges: std::logic_error upstream
     const int width = cnt == 2u ? static_cast<int>(((w >> 15) & 0x7FFFu) - (w & 0x7FFFu)) + 1 : 0;
     if (width > kLatMaxWidth) sh.status = kLatUnfit;
-    ra[r] = x0 + static_cast<int>(w & 0x7FFFu);
+    ra[r] = r * pitch + x0 + static_cast<int>(w & 0x7FFFu);  // byte offset of the row's first cell from (vertex 0, row yb)
     rm[r] = width >= 32 ? 0xFFFFFFFFu : ((1u << width) - 1u);
   }
   return sh;
@@ -457,7 +467,7 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice_fr
                 if (v == 0) ax = cx, ay = cy;
                 canon[idx * nv + v] = make_int2(cx - ax, cy - ay);
               }
-              const LatShape sh = lattice_rasterise(canon + idx * nv, nv, rows_cap, row_a + idx * rows_cap, row_m + idx * rows_cap);
+              const LatShape sh = lattice_rasterise(canon + idx * nv, nv, rows_cap, m.pitch, row_a + idx * rows_cap, row_m + idx * rows_cap);
               meta[idx].xb = sh.xb, meta[idx].x1 = sh.x1, meta[idx].yb = sh.yb, meta[idx].rows = sh.rows;
               __threadfence_block();
               *reinterpret_cast<volatile int*>(&meta[idx].status) = sh.status;
@@ -529,8 +539,11 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice_fr
         const bool inside = y_base >= 0 && y_base + rows <= m.size_y && xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x;
         uint32_t hit_a = 0, hit_b = 0;
         const int oa = fits_a ? off_a : 0, ob = fits_b ? off_b : 0;
-        if (inside) lattice_rows<true>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, ob, hit_a, hit_b);
-        else lattice_rows<false>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, true, oa, ob, hit_a, hit_b);
+        // the usual full group: plane A's offsets are 0..31, plane B's 32..63 -> no per-row piece selection
+        const bool split_planes = __all_sync(kFull, (!fits_a || off_a < 32) && (!fits_b || off_b >= 32));
+        if (inside && split_planes) lattice_rows<0>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, fits_b ? ob : 32, hit_a, hit_b);
+        else if (inside) lattice_rows<1>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, ob, hit_a, hit_b);
+        else lattice_rows<2>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, true, oa, ob, hit_a, hit_b);
         if (fits_a) {
           if (out.is_free) out.is_free[i_a] = hit_a ? 0 : 1;
           if (out.status) out.status[i_a] = ST_OK;
