@@ -280,6 +280,19 @@ class Costmap:
         self.ctx._check(self.ctx._lib.cover_map_upload_window(self._h, C.c_void_p(arr.ctypes.data), C.c_int32(x0), C.c_int32(y0),
                                                               C.c_int32(w), C.c_int32(h)))
 
+    def inflate(self, radius_cells: int, cost_by_d2: np.ndarray):
+        """Inflate the lethal cells of the device map in place (see workloads.inflation_lut)."""
+        lut = np.ascontiguousarray(cost_by_d2, dtype=np.uint8)
+        if lut.size != radius_cells * radius_cells + 1:
+            raise ValueError("cost_by_d2 must have radius_cells^2 + 1 entries")
+        self.ctx._check(self.ctx._lib.cover_map_inflate(self._h, C.c_int32(radius_cells), C.c_void_p(lut.ctypes.data)))
+
+    def download(self) -> np.ndarray:
+        """Device map -> host uint8 [size_y, size_x] (e.g. after `inflate`)."""
+        out = np.empty((self.size_y, self.size_x), dtype=np.uint8)
+        self.ctx._check(self.ctx._lib.cover_map_download(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
     def close(self):
         if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
             self.ctx._lib.cover_map_destroy(self._h)

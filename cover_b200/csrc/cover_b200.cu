@@ -770,6 +770,55 @@ __global__ void __launch_bounds__(kBlock) k_trajectories(const uint8_t* __restri
   }
 }
 
+
+/// Inflation layer (the step BEFORE the path, costmap_2d::InflationLayer restated): every cell
+/// within `radius` cells of a LETHAL cell gets lut[d^2] (d = Euclidean cell distance to the nearest lethal
+/// cell; the LUT is built on the host so that no device exp() is involved), combined with the old cost like
+/// InflationLayer::updateCosts: NO_INFORMATION stays unless the new cost is >= INSCRIBED, else max(old, new).
+/// One CTA per 32 x 32 output tile; the (32 + 2R)^2 neighbourhood is staged in shared memory.
+__global__ void __launch_bounds__(256) k_inflate(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int size_x, int size_y, int pitch,
+                                                int radius, const uint8_t* __restrict__ lut) {
+  extern __shared__ double smem_d[];
+  uint8_t* tile = reinterpret_cast<uint8_t*>(smem_d);
+  const int span = 32 + 2 * radius, tx0 = blockIdx.x * 32 - radius, ty0 = blockIdx.y * 32 - radius;
+  __shared__ int any_lethal;
+  if (threadIdx.x == 0) any_lethal = 0;
+  __syncthreads();
+  bool mine = false;
+  for (int idx = threadIdx.x; idx < span * span; idx += blockDim.x) {
+    const int ly = idx / span, lx = idx - ly * span, x = tx0 + lx, y = ty0 + ly;
+    uint8_t v = 0;
+    if (x >= 0 && y >= 0 && x < size_x && y < size_y) v = src[static_cast<size_t>(y) * pitch + x];
+    tile[idx] = v;
+    mine |= v == kLethal;
+  }
+  if (mine) any_lethal = 1;
+  __syncthreads();
+  const bool work = any_lethal != 0;
+  const int r2max = radius * radius;
+  for (int c = threadIdx.x; c < 32 * 32; c += blockDim.x) {
+    const int cy = c >> 5, cx = c & 31, x = blockIdx.x * 32 + cx, y = blockIdx.y * 32 + cy;
+    if (x >= size_x || y >= size_y) continue;
+    const uint8_t old = tile[(cy + radius) * span + cx + radius];
+    uint8_t out = old;
+    if (work) {
+      int best = 0x7FFFFFFF;
+      for (int dy = -radius; dy <= radius; ++dy) {
+        const uint8_t* row = tile + (cy + radius + dy) * span + cx;
+        const int dy2 = dy * dy;
+        for (int dx = -radius; dx <= radius; ++dx)
+          if (row[dx + radius] == kLethal) best = min(best, dy2 + dx * dx);
+      }
+      if (best <= r2max) {
+        const uint8_t cost = lut[best];
+        if (old == kNoInformation) out = cost >= kInscribed ? cost : old;
+        else out = max(old, cost);
+      }
+    }
+    dst[static_cast<size_t>(y) * pitch + x] = out;
+  }
+}
+
 template <int OP>
 __global__ void __launch_bounds__(kBlock) k_rays(MapView m, const int4* __restrict__ segments, long long count, int offx, int offy,
                                                 OutView out) {
@@ -1206,6 +1255,7 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_lattice_free));
   set(reinterpret_cast<const void*>(&k_area_expand));
   set(reinterpret_cast<const void*>(&k_outline_expand));
+  set(reinterpret_cast<const void*>(&k_inflate));
   return e;
 }
 
@@ -1535,6 +1585,38 @@ int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x
   Bind bind(ctx->device);
   CU(cudaMemcpy2DAsync(map->dev + static_cast<size_t>(y0) * v.pitch + x0, v.pitch, full_image + static_cast<size_t>(y0) * v.size_x + x0,
                        v.size_x, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return COVER_OK;
+}
+
+int cover_map_download(const cover_map* map, uint8_t* data) {
+  if (!map || !data) return COVER_E_INVALID_ARG;
+  cover_ctx* ctx = map->ctx;
+  Bind bind(ctx->device);
+  const MapView& v = map->view;
+  CU(cudaMemcpy2DAsync(data, v.size_x, map->dev, v.pitch, v.size_x, v.size_y, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return COVER_OK;
+}
+
+int cover_map_inflate(cover_map* map, int32_t radius_cells, const uint8_t* cost_by_d2) {
+  if (!map || !cost_by_d2) return COVER_E_INVALID_ARG;
+  cover_ctx* ctx = map->ctx;
+  if (radius_cells < 0 || radius_cells > 96) return fail(ctx, COVER_E_INVALID_ARG, "inflation radius must be 0..96 cells");
+  Bind bind(ctx->device);
+  const MapView& v = map->view;
+  const size_t bytes = static_cast<size_t>(v.pitch) * v.size_y;
+  CU(ctx->in_a.ensure(bytes));  // snapshot of the un-inflated map: the kernel reads it and writes the map in place
+  CU(cudaMemcpyAsync(ctx->in_a.ptr, map->dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  const size_t lut_bytes = static_cast<size_t>(radius_cells) * radius_cells + 1;
+  CU(ctx->in_b.ensure(lut_bytes));
+  CU(cudaMemcpyAsync(ctx->in_b.ptr, cost_by_d2, lut_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const int span = 32 + 2 * radius_cells;
+  const dim3 grid((v.size_x + 31) / 32, (v.size_y + 31) / 32);
+  k_inflate<<<grid, 256, static_cast<size_t>(span) * span, ctx->stream>>>(ctx->in_a.as<uint8_t>(), map->dev, v.size_x, v.size_y, v.pitch,
+                                                                         radius_cells, ctx->in_b.as<uint8_t>());
+  ++ctx->launches;
+  CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
   return COVER_OK;
 }

@@ -63,6 +63,19 @@ def inflated_costmap(size_x: int, size_y: int, resolution: float, seed: int, obs
     return data
 
 
+def inflation_lut(resolution: float, inscribed_radius: float = 0.3, inflation_radius: float = 1.0, cost_scaling: float = 10.0):
+    """(radius_cells, cost_by_d2) for Costmap.inflate: InflationLayer::computeCost evaluated on the host for
+    every squared cell distance 0..radius_cells^2 (0 beyond the inflation radius)."""
+    rad = int(math.ceil(inflation_radius / resolution))
+    d = np.sqrt(np.arange(rad * rad + 1, dtype=np.float64)) * resolution
+    lut = np.zeros(rad * rad + 1, dtype=np.uint8)
+    band = (d > inscribed_radius) & (d <= inflation_radius)
+    lut[band] = (252.0 * np.exp(-cost_scaling * (d[band] - inscribed_radius))).astype(np.uint8)
+    lut[d <= inscribed_radius] = INSCRIBED
+    lut[0] = LETHAL
+    return rad, lut
+
+
 def random_poses(n: int, seed: int, lo: float, hi: float) -> np.ndarray:
     """[n, 4] = (cos, sin, tx, ty): position uniform in [lo, hi]^2, heading uniform in [-pi, pi)."""
     rng = np.random.default_rng(seed)

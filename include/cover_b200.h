@@ -111,6 +111,14 @@ int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double reso
 int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem);
 /* re-upload the window [x0,x0+w) x [y0,y0+h) from a full-size HOST image (dirty-rectangle update). */
 int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x0, int32_t y0, int32_t w, int32_t h);
+/* EXTENSION (the step before the path; costmap_2d::InflationLayer is not part of the reference):
+ * inflate the LETHAL cells of the device map in place.  cost_by_d2[d2], d2 = 0..radius_cells^2, is the cost of a
+ * cell whose nearest lethal cell is sqrt(d2) cells away (HOST array, built by the caller with the layer's
+ * computeCost so that no device exp() is involved); it is combined with the old cost like
+ * InflationLayer::updateCosts (NO_INFORMATION stays unless the new cost is >= 253, else max). */
+int cover_map_inflate(cover_map* map, int32_t radius_cells, const uint8_t* cost_by_d2);
+/* device map -> size_y x size_x host bytes (row-major, unpadded) */
+int cover_map_download(const cover_map* map, uint8_t* data);
 void cover_map_destroy(cover_map* map);
 
 /* ---- polygon x poses: path A transform ((pose*polygon) - origin, src/cover/costmap.cpp:71-85) ---- */

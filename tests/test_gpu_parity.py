@@ -116,6 +116,25 @@ def test_lattice_axis_aligned_headings_and_map_border(cb, ctx, pitch):
         assert 0.05 < cpu.is_free.mean() < 0.95
 
 
+@pytest.mark.parametrize("geom", [dict(nx=70, ny=3, dx=0.05, dy=0.05), dict(nx=90, ny=40, dx=-0.05, dy=0.05), dict(nx=45, ny=20, dx=0.5, dy=0.35),
+                                  dict(nx=200, ny=5, dx=0.0, dy=0.05), dict(nx=1, ny=1, dx=0.05, dy=0.05), dict(nx=65, ny=9, dx=0.013, dy=-0.021)])
+def test_lattice_odd_geometries(cb, ctx, geom):
+    """Lattices with fewer rows than a unit (several headings inside one unit), decreasing x, coarse and
+    sub-cell pitches, a degenerate pitch and a single pose."""
+    rng = np.random.default_rng(35)
+    data = mixed_map(rng, 320, 300, lethal=0.003)
+    th = -math.pi + 2 * math.pi * np.arange(9) / 9
+    x0 = 12.0 if geom["dx"] < 0 else 0.6
+    desc = dict(x0=x0, dx=geom["dx"], nx=geom["nx"], y0=7.0 if geom["dy"] < 0 else 0.7, dy=geom["dy"], ny=geom["ny"], cs=np.stack([np.cos(th), np.sin(th)], 1))
+    cmap = cb.Costmap(ctx, data, 0.05, 0.1, -0.2)
+    gpu = cmap.area_is_free(RECT, cb.Lattice(**desc))
+    cpu = po.polygon_batch(po.Costmap(data, 0.05, 0.1, -0.2), RECT, po.Lattice(**desc), threads=8)
+    assert_same(gpu, cpu, what=str(geom))
+    out = cb.Result(free_bits=np.zeros((len(cpu.is_free) + 31) // 32, dtype=np.uint32), not_ok=np.zeros(1, dtype=np.int64))
+    cmap.area_is_free(RECT, cb.Lattice(**desc), out=out)
+    np.testing.assert_array_equal(out.unpack_bits(len(cpu.is_free)), cpu.is_free)
+
+
 def test_lattice_other_small_footprints(cb, ctx):
     """Triangles, the L-shape scaled down, a 1-cell polygon and a degenerate (open) outline on a lattice."""
     rng = np.random.default_rng(34)
@@ -580,3 +599,48 @@ def test_trajectory_scoring(cb, ctx):
     ctx.synchronize()
     np.testing.assert_array_equal(dfirst.cpu().numpy(), exp_first)
     np.testing.assert_array_equal(dscore.cpu().numpy(), exp_score)
+
+
+def test_gpu_inflation_layer(cb, ctx):
+    """cover_map_inflate against a numpy restatement of InflationLayer (min Euclidean cell distance to a lethal
+    cell -> cost LUT; NO_INFORMATION stays unless the new cost is >= 253, else max(old, new))."""
+    from cover_b200 import workloads as wl
+    rng = np.random.default_rng(98)
+    sx, sy = 333, 277
+    raw = np.zeros((sy, sx), dtype=np.uint8)
+    obs = rng.random((sy, sx)) < 6e-4
+    raw[obs] = 254
+    raw[(rng.random((sy, sx)) < 0.02) & ~obs] = 255        # unknown cells
+    raw[(rng.random((sy, sx)) < 0.05) & (raw == 0)] = 120   # some other layer's costs
+    raw[0, 0] = raw[sy - 1, sx - 1] = 254                   # obstacles on the border
+    rad, lut = wl.inflation_lut(0.05)
+    cmap = cb.Costmap(ctx, raw, 0.05)
+    cmap.inflate(rad, lut)
+    got = cmap.download()
+    # numpy restatement
+    oy, ox = np.nonzero(raw == 254)
+    yy, xx = np.mgrid[0:sy, 0:sx]
+    d2 = np.full((sy, sx), 10 ** 9, dtype=np.int64)
+    for y, x in zip(oy.tolist(), ox.tolist()):
+        y0, y1, x0, x1 = max(0, y - rad), min(sy, y + rad + 1), max(0, x - rad), min(sx, x + rad + 1)
+        d2[y0:y1, x0:x1] = np.minimum(d2[y0:y1, x0:x1], (yy[y0:y1, x0:x1] - y) ** 2 + (xx[y0:y1, x0:x1] - x) ** 2)
+    cost = np.where(d2 <= rad * rad, lut[np.minimum(d2, rad * rad)], 0).astype(np.uint8)
+    reach = d2 <= rad * rad
+    expect = raw.copy()
+    unknown = raw == 255
+    expect[reach & ~unknown] = np.maximum(raw, cost)[reach & ~unknown]
+    expect[reach & unknown & (cost >= 253)] = cost[reach & unknown & (cost >= 253)]
+    np.testing.assert_array_equal(got, expect)
+    # and the inflated map equals the workload generator's stamping formulation on a clean map
+    clean = np.zeros((sy, sx), dtype=np.uint8)
+    clean[obs] = 254
+    c2 = cb.Costmap(ctx, clean, 0.05)
+    c2.inflate(rad, lut)
+    stamped = np.zeros((sy, sx), dtype=np.uint8)
+    yk, xk = np.mgrid[-rad:rad + 1, -rad:rad + 1]
+    kern = np.where(yk ** 2 + xk ** 2 <= rad * rad, lut[np.minimum(yk ** 2 + xk ** 2, rad * rad)], 0).astype(np.uint8)
+    for y, x in zip(*np.nonzero(obs)):
+        y0, y1, x0, x1 = max(0, y - rad), min(sy, y + rad + 1), max(0, x - rad), min(sx, x + rad + 1)
+        v = stamped[y0:y1, x0:x1]
+        np.maximum(v, kern[y0 - (y - rad):y1 - (y - rad), x0 - (x - rad):x1 - (x - rad)], out=v)
+    np.testing.assert_array_equal(c2.download(), stamped)
