@@ -314,6 +314,19 @@ class Costmap:
         del keep
         return res
 
+    def area_multi(self, outlines: Sequence, poses, op: str = "is_free", first=0, count=None, out=None) -> Result:
+        """Batched is_free / accumulate_cost / max_cost over area_generator(res, polygon_vec): `outlines` is a list
+        of [2, V_k] polygons, nested ones are holes (generators.cpp:126-135)."""
+        ctx = self.ctx
+        xy, starts = _pack(outlines)
+        p, keep = ctx._poses(poses, first, count)
+        code = {"is_free": 0, "accumulate_cost": 1, "max_cost": 2}[op]
+        r, res = ctx._results(int(p.count), True, code != 0, True, out)
+        ctx._check(ctx._lib.cover_area_multi_check(ctx._h, self._h, C.c_void_p(xy.ctypes.data), C.c_void_p(starts.ctypes.data), C.c_int32(len(outlines)),
+                                                   C.c_int32(code), C.byref(p), C.byref(r)))
+        del keep
+        return res
+
     def area_is_free(self, polygon, poses, first=0, count=None, out=None) -> Result:
         """Batched is_free(polygon, pose, map) (costmap.cpp:78-85); poses=None is is_free(polygon, map)."""
         return self._polygon("cover_area_is_free", polygon, poses, first, count, out, False)

@@ -337,4 +337,77 @@ __device__ __forceinline__ int area_rows_expand(const double* __restrict__ poly,
   return ST_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Several outlines: area_generator(resolution, polygon_vec) — nested outlines give holes (generalised
+// even-odd rule, src/cover/generators.cpp:126-135,181-233).  Every outline contributes its own cyclic ray
+// list; all ranges of a row land in ONE list, ordered by (min, outline order, outline index).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kRowsMaxOutlines = 16;
+
+struct OutlineRec {
+  int ray_begin, n_rays;  // slice of the warp's ray table
+  int single_row;         // every cell on one row: ranges (min,min),(max,max) (generators.cpp:197-204)
+  int y, min_x, max_x, seq;
+};
+
+template <int OP, int XF>
+__device__ __forceinline__ int area_rows_multi_pose(const double* __restrict__ poly, const int* __restrict__ starts, int n_outlines,
+                                                    const Pose& T, const MapView& m, int2* verts, RayRec* rays, OutlineRec* recs, int lane,
+                                                    WarpFold<OP>& wf) {
+  bool ok_all = true;
+  int y_lo = 0x7FFFFFFF, y_hi = -0x7FFFFFFF - 1, ray_base = 0, seq_base = 0;
+  for (int o = 0; o < n_outlines; ++o) {
+    const int nv = starts[o + 1] - starts[o];
+    OutlineRec rec{ray_base, 0, 0, 0, 0, 0, seq_base};
+    if (nv > 0) {  // (an empty outline is skipped; the reference reads out of bounds there)
+      bool ok;
+      int x0, y0, x1, y1;
+      const int n = build_rays<XF>(poly + 2 * starts[o], nv, T, m, verts, rays + ray_base, lane, ok, x0, y0, x1, y1);
+      ok_all &= ok;
+      for (int e = lane; e < n; e += 32) rays[ray_base + e].start += seq_base;
+      __syncwarp();
+      const RayRec last = rays[ray_base + n - 1];
+      rec = OutlineRec{ray_base, n, y0 == y1, y0, x0, x1, seq_base};
+      y_lo = min(y_lo, y0), y_hi = max(y_hi, y1);
+      ray_base += n;
+      seq_base = last.start + last.size;
+    }
+    if (lane == 0) recs[o] = rec;
+    __syncwarp();
+  }
+  if (!ok_all) return ST_COORD_RANGE;
+  if (ray_base == 0) return ST_OK;  // no cells at all
+  bool odd = false, overflow = false;
+  for (int yb = y_lo; yb <= y_hi; yb += 32) {
+    const int y = yb + lane;
+    RowList L;
+    if (y <= y_hi) {
+      for (int o = 0; o < n_outlines; ++o) {
+        const OutlineRec rec = recs[o];
+        if (rec.n_rays == 0) continue;
+        if (rec.single_row) {
+          if (y == rec.y) {
+            L.add(rec.min_x, rec.min_x, rec.seq);
+            L.add(rec.max_x, rec.max_x, rec.seq);
+          }
+        } else {
+          build_row(rays + rec.ray_begin, rec.n_rays, y, L);
+        }
+      }
+    }
+    odd |= (L.n & 1) != 0;
+    overflow |= L.overflow;
+    if (!wf.done()) {
+      Fold<OP> f;
+      if (!(L.n & 1) && !L.overflow)
+        for (int k = 0; k + 1 < L.n; k += 2)
+          if (!f.span(m, y, L.lo[k], L.hi[k + 1])) break;
+      wf.merge(f);
+    }
+  }
+  if (__any_sync(0xFFFFFFFFu, odd)) return ST_LOGIC_ERROR;
+  if (__any_sync(0xFFFFFFFFu, overflow)) return ST_ROW_COMPLEXITY;
+  return ST_OK;
+}
+
 }  // namespace cvr

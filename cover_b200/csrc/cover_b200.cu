@@ -819,6 +819,43 @@ __global__ void __launch_bounds__(256) k_inflate(const uint8_t* __restrict__ src
   }
 }
 
+
+/// area checks over SEVERAL outlines (holes): batched is_free / accumulate_cost / max over
+/// area_generator(resolution, polygon_vec) (generators.cpp:126-135).  One warp per pose.
+template <int OP>
+__global__ void __launch_bounds__(kRowsWarps * 32) k_area_rows_multi(MapView m, const double* __restrict__ poly_g, const int* __restrict__ starts_g,
+                                                                    int n_outlines, int nv_total, int nv_max, PoseSource src, long long count,
+                                                                    OutView out) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv_total, smem_d);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rays_per_warp = nv_total + n_outlines;
+  RayRec* rays = reinterpret_cast<RayRec*>(smem_d + 2 * nv_total) + warp * rays_per_warp;
+  int2* verts = reinterpret_cast<int2*>(reinterpret_cast<RayRec*>(smem_d + 2 * nv_total) + kRowsWarps * rays_per_warp) + warp * nv_max;
+  OutlineRec* recs = reinterpret_cast<OutlineRec*>(reinterpret_cast<int2*>(reinterpret_cast<RayRec*>(smem_d + 2 * nv_total) + kRowsWarps * rays_per_warp) +
+                                                   kRowsWarps * nv_max) + warp * kRowsMaxOutlines;
+  __shared__ int starts[kRowsMaxOutlines + 1];
+  if (threadIdx.x <= n_outlines) starts[threadIdx.x] = starts_g[threadIdx.x];
+  __syncthreads();
+  const long long n_warps = static_cast<long long>(gridDim.x) * kRowsWarps;
+  const bool none = src.format == POSE_NONE;
+  for (long long i = static_cast<long long>(blockIdx.x) * kRowsWarps + warp; i < count; i += n_warps) {
+    const Pose T = load_pose(src, i);
+    WarpFold<OP> wf;
+    const int status = none ? area_rows_multi_pose<OP, XF_NONE>(poly, starts, n_outlines, T, m, verts, rays, recs, lane, wf)
+                            : area_rows_multi_pose<OP, XF_PATH_A>(poly, starts, n_outlines, T, m, verts, rays, recs, lane, wf);
+    if (lane == 0) {
+      if (status != ST_OK) {
+        store_failure(out, i, status);
+      } else {
+        wf.store(out, i);
+        if (out.status) out.status[i] = ST_OK;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int OP>
 __global__ void __launch_bounds__(kBlock) k_rays(MapView m, const int4* __restrict__ segments, long long count, int offx, int offy,
                                                 OutView out) {
@@ -1256,6 +1293,9 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_expand));
   set(reinterpret_cast<const void*>(&k_outline_expand));
   set(reinterpret_cast<const void*>(&k_inflate));
+  set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_IS_FREE>));
+  set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_ACCUMULATE>));
+  set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_MAX>));
   return e;
 }
 
@@ -1638,6 +1678,50 @@ int cover_area_accumulate_cost(cover_ctx* ctx, const cover_map* map, const doubl
 int cover_area_max_cost(cover_ctx* ctx, const cover_map* map, const double* xy, int32_t nv, const cover_poses* poses, const cover_results* out) {
   return polygon_check(ctx, map, xy, nv, SHAPE_AREA, OP_MAX, poses, out);
 }
+int cover_area_multi_check(cover_ctx* ctx, const cover_map* map, const double* polygons_xy, const int32_t* starts, int32_t n_outlines, int32_t op,
+                           const cover_poses* poses, const cover_results* out) {
+  if (!ctx) return COVER_E_INVALID_ARG;
+  if (!map || map->ctx != ctx) return fail(ctx, COVER_E_INVALID_ARG, "map does not belong to this context");
+  if (n_outlines < 0 || (n_outlines && !starts) || op < OP_IS_FREE || op > OP_MAX) return fail(ctx, COVER_E_INVALID_ARG, "bad arguments");
+  if (n_outlines > kRowsMaxOutlines) return fail(ctx, COVER_E_UNSUPPORTED, "at most 16 outlines");
+  int nv_total = 0, nv_max = 0;
+  for (int o = 0; o < n_outlines; ++o) {
+    const int n = starts[o + 1] - starts[o];
+    if (n < 0 || starts[0] != 0) return fail(ctx, COVER_E_INVALID_ARG, "starts must begin at 0 and be non-decreasing");
+    nv_total += n;
+    nv_max = std::max(nv_max, n);
+  }
+  if (nv_total > kRowsMaxVertices) return fail(ctx, COVER_E_UNSUPPORTED, "at most 256 vertices in total");
+  if (nv_total && !polygons_xy) return fail(ctx, COVER_E_INVALID_ARG, "missing vertices");
+  Bind bind(ctx->device);
+  PoseSource src;
+  int rc = stage_poses(ctx, poses, src);
+  if (rc) return rc;
+  OutStage st;
+  rc = stage_out(ctx, out, poses->count, st);
+  if (rc) return rc;
+  const size_t poly_bytes = static_cast<size_t>(nv_total) * 2 * sizeof(double);
+  CU(ctx->poly.ensure(std::max<size_t>(poly_bytes, 16)));
+  if (poly_bytes) CU(cudaMemcpyAsync(ctx->poly.ptr, polygons_xy, poly_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx->in_b.ensure((kRowsMaxOutlines + 1) * sizeof(int)));
+  std::vector<int> st_host(starts, starts + n_outlines + 1);
+  if (n_outlines == 0) st_host.assign(1, 0);
+  CU(cudaMemcpyAsync(ctx->in_b.ptr, st_host.data(), st_host.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  const int64_t count = poses->count;
+  if (count) {
+    const size_t smem = poly_bytes + kRowsWarps * (static_cast<size_t>(nv_total + n_outlines) * sizeof(RayRec) + static_cast<size_t>(nv_max) * sizeof(int2) +
+                                                   kRowsMaxOutlines * sizeof(OutlineRec));
+    const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(static_cast<long long>(ctx->sm_count) * 12, (count + kRowsWarps - 1) / kRowsWarps)));
+    const double* pd = ctx->poly.as<double>();
+    const int* sd = ctx->in_b.as<int>();
+    if (op == OP_IS_FREE) k_area_rows_multi<OP_IS_FREE><<<grid, kRowsWarps * 32, smem, ctx->stream>>>(map->view, pd, sd, n_outlines, nv_total, nv_max, src, count, st.dev);
+    else if (op == OP_ACCUMULATE) k_area_rows_multi<OP_ACCUMULATE><<<grid, kRowsWarps * 32, smem, ctx->stream>>>(map->view, pd, sd, n_outlines, nv_total, nv_max, src, count, st.dev);
+    else k_area_rows_multi<OP_MAX><<<grid, kRowsWarps * 32, smem, ctx->stream>>>(map->view, pd, sd, n_outlines, nv_total, nv_max, src, count, st.dev);
+    ++ctx->launches;
+  }
+  return finish_out(ctx, st, count);
+}
+
 int cover_outline_is_free(cover_ctx* ctx, const cover_map* map, const double* xy, int32_t nv, const cover_poses* poses, const cover_results* out) {
   return polygon_check(ctx, map, xy, nv, SHAPE_OUTLINE, OP_IS_FREE, poses, out);
 }

@@ -132,6 +132,13 @@ int cover_area_accumulate_cost(cover_ctx* ctx, const cover_map* map, const doubl
  * a cell outside the map gives -3. */
 int cover_area_max_cost(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t n_vertices,
                         const cover_poses* poses, const cover_results* out);
+/* Several outlines = an area with holes: is_free / accumulate_cost / max over
+ * area_generator(resolution, const polygon_vec&) (src/cover/generators.cpp:126-135; nested outlines follow the
+ * generalised even-odd rule).  Outline k = vertices [starts[k], starts[k+1]) of polygons_xy; every outline is
+ * transformed like the single polygon above.  op: 0 = is_free, 1 = accumulate_cost, 2 = max_cost.
+ * At most 16 outlines and 256 vertices in total. */
+int cover_area_multi_check(cover_ctx* ctx, const cover_map* map, const double* polygons_xy, const int32_t* starts, int32_t n_outlines,
+                           int32_t op, const cover_poses* poses, const cover_results* out);
 /* is_free(outline_generator(res, pose*polygon - origin), map)  impl/costmap.hpp:23-27 over generators.cpp:54-93 */
 int cover_outline_is_free(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t n_vertices,
                           const cover_poses* poses, const cover_results* out);

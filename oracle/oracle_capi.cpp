@@ -230,6 +230,50 @@ int oracle_polygon_batch(const oracle_map* map, const double* poly_xy, int32_t n
   return 0;
 }
 
+/// Several outlines (holes): area_generator(res, polygon_vec) (generators.cpp:126-135) under path A.
+int oracle_multi_polygon_batch(const oracle_map* map, const double* polys_xy, const int32_t* starts, int32_t n_outlines, int32_t op,
+                               int32_t pose_format, const void* poses, const oracle_lattice* lattice, int64_t first, int64_t count,
+                               uint8_t* is_free, double* cost, uint8_t* status, int64_t* cells_read, int32_t threads) {
+  if (!map || map->resolution <= 0) return -1;
+  const MapView m = view(map);
+  const OutSink out{is_free, cost, status};
+  std::vector<int64_t> tallies(static_cast<size_t>(std::max(threads, 1)), 0);
+  parallel_for(count, threads, [&](int64_t b, int64_t e, int tid) {
+    Tally t;
+    for (int64_t i = b; i < e; ++i) {
+      Pose T{};
+      const bool has_pose = pose_format != ORACLE_POSE_NONE;
+      if (has_pose) T = pose_at(pose_format, poses, lattice, first + i);
+      bool in_range = true;
+      for (int32_t o = 0; o < n_outlines; ++o)
+        in_range = in_range && coords_in_range(has_pose ? &T : nullptr, polys_xy + 2 * starts[o], starts[o + 1] - starts[o], m, false);
+      if (!in_range) {
+        out.fail(i, ORACLE_COORD_RANGE);
+        continue;
+      }
+      try {
+        std::vector<Cells> dense;
+        for (int32_t o = 0; o < n_outlines; ++o) {
+          const double* xy = polys_xy + 2 * starts[o];
+          const size_t n = static_cast<size_t>(starts[o + 1] - starts[o]);
+          dense.push_back(dense_outline(has_pose ? transform_path_a(T, xy, n, m) : shift_path_a(xy, n, m)));
+        }
+        const Area a = make_area(dense);
+        run_op(op, [&a](auto&& f) { return walk_area(a, f); }, Cell{0, 0}, m, out, i, &t);
+        if (status) status[i] = static_cast<uint8_t>(a.max_ranges_per_row > 16 ? ORACLE_ROW_COMPLEXITY : ORACLE_OK);
+      } catch (const std::logic_error&) {
+        out.fail(i, ORACLE_LOGIC_ERROR);
+      }
+    }
+    tallies[tid] = t.cells_read;
+  });
+  if (cells_read) {
+    *cells_read = 0;
+    for (int64_t v : tallies) *cells_read += v;
+  }
+  return 0;
+}
+
 // ---- rays (a4 + a10/a13) --------------------------------------------------------------------
 
 /// segments: N x {x0,y0,x1,y1} cells; `offset` (2 ints, may be null) is added to every cell

@@ -220,6 +220,20 @@ class Backend:
 
 
 
+    def multi_polygon_batch(self, cmap: Costmap, outlines, poses, op=OP_IS_FREE, first=0, count=None, threads=1) -> Result:
+        """area_generator(res, polygon_vec) checks (holes); restatement only (not exported by oracle/_ref)."""
+        xy, starts = pack_polygons(outlines)
+        fmt, arr, lat, total, _keep = _pose_args(poses)
+        n = total - first if count is None else count
+        free, cost, status = _outputs(n)
+        read = C.c_int64(0)
+        m = cmap.c()
+        rc = self._lib.oracle_multi_polygon_batch(C.byref(m), _p(xy), _p(starts), C.c_int32(len(outlines)), C.c_int32(op), C.c_int32(fmt), _p(arr),
+                                                   lat, C.c_int64(first), C.c_int64(n), _p(free), _p(cost), _p(status), C.byref(read), C.c_int32(threads))
+        if rc != 0:
+            raise ValueError("oracle_multi_polygon_batch failed")
+        return Result(free, cost, status, read.value)
+
     def rays_batch(self, cmap: Costmap, segments, offset=None, op=OP_IS_FREE, threads=1) -> Result:
         seg = np.ascontiguousarray(segments, dtype=np.int32).reshape(-1, 4)
         off = None if offset is None else np.ascontiguousarray(offset, dtype=np.int32)
@@ -329,5 +343,5 @@ def _delegate(name):
     return f
 
 
-for _n in ['to_discrete', 'ray_cells', 'outline_cells', 'area_cells', 'polygon_batch', 'rays_batch', 'cells_batch', 'make_discrete_footprint', 'discrete_footprint_batch', 'continuous_footprint_batch']:
+for _n in ['to_discrete', 'ray_cells', 'outline_cells', 'area_cells', 'polygon_batch', 'rays_batch', 'cells_batch', 'make_discrete_footprint', 'discrete_footprint_batch', 'continuous_footprint_batch', 'multi_polygon_batch']:
     globals()[_n] = _delegate(_n)

@@ -644,3 +644,27 @@ def test_gpu_inflation_layer(cb, ctx):
         v = stamped[y0:y1, x0:x1]
         np.maximum(v, kern[y0 - (y - rad):y1 - (y - rad), x0 - (x - rad):x1 - (x - rad)], out=v)
     np.testing.assert_array_equal(c2.download(), stamped)
+
+
+def test_area_with_holes(cb, ctx):
+    """area_generator(res, polygon_vec): the reference's 'head' with nested holes (test/expand.cpp:241-279) and
+    random outline sets, all three ops, against the oracle."""
+    rng = np.random.default_rng(99)
+    data = mixed_map(rng, 400, 380, lethal=0.002)
+    cmap = cb.Costmap(ctx, data, 0.05, -0.3, 0.2)
+    omap = po.Costmap(data, 0.05, -0.3, 0.2)
+    poses = poses_around(rng, 3000, 0.0, 18.0)
+    sets = [head_polygons(), [FOOTPRINTS[0] * 0.5, RECT * 0.5], [RECT, RECT * 0.5, RECT * 0.2],
+            [np.array([[0.0, 0.6], [0.1, 0.1]]), RECT], [np.zeros((2, 0)), FOOTPRINTS[6]], [np.array([[0.2], [0.2]]), np.array([[0.25], [0.2]])]]
+    names = {"is_free": po.OP_IS_FREE, "accumulate_cost": po.OP_ACCUMULATE, "max_cost": po.OP_MAX}
+    for outlines in sets:
+        for name, op in names.items():
+            gpu = cmap.area_multi(outlines, poses, op=name)
+            cpu = po.multi_polygon_batch(omap, outlines, poses, op=op, threads=8)
+            assert_same(gpu, cpu, name != "is_free", f"{len(outlines)} outlines {name}")
+    # a single outline through the multi entry equals the single-polygon entry
+    a = cmap.area_multi([FOOTPRINTS[3] * 0.5], poses, op="accumulate_cost")
+    b = cmap.area_accumulate_cost(FOOTPRINTS[3] * 0.5, poses)
+    np.testing.assert_array_equal(a.cost, b.cost)
+    none = cmap.area_multi(head_polygons(), None)
+    assert_same(none, po.multi_polygon_batch(omap, head_polygons(), None))
