@@ -136,6 +136,210 @@ __global__ void __launch_bounds__(kBlock) k_area_packed(MapView m, const double*
 
 
 // ---------------------------------------------------------------------------------------------------
+// k_area_pair<OP>: the per-thread fast path, second generation (replaces k_area_packed on the hot path).
+// Same semantics — a pose is finished here iff every scan row gets at most two ranges — but written as one
+// flat loop nest so that the compiler keeps the walker state in registers:
+//   * the Bresenham loop of a ray is specialised by major axis (in a y-major ray every cell closes a run);
+//   * a closed run is APPENDED to its row (one 64-bit shared-memory word per (row, thread): two 16+16-bit
+//     ranges in insertion order, 0xFFFFFFFF = empty); the pair is merged once, when the row is scanned:
+//     sorted by `min`, insertion order breaking ties, result [first.min, second.max] (generators.cpp:236-255);
+//   * the run containing outline cell 0 is closed last but ranks first: it is inserted in FRONT.
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kPairEmpty = 0xFFFFFFFFu;
+constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+struct PairWalker {
+  uint2* tab;   // &table[0][threadIdx.x], stride = blockDim.x
+  int stride;
+  int xb, yb;   // bounding-box origin: ranges are stored relative to xb
+  int y_run, x_first, x_prev, y_before;
+  int x0, y0, f_xlast, f_ynext;
+  bool in_first, overflow;
+
+  __device__ __forceinline__ void append(int y, int a, int b, int yp, int yn) {
+    const uint32_t e = static_cast<uint32_t>(min(a, b) - xb) | (static_cast<uint32_t>(max(a, b) - xb) << 16);
+    uint2& w = tab[(y - yb) * stride];
+    uint2 v = w;
+    const bool cusp = (yp - y) * (y - yn) < 0;  // generators.cpp:100-103: counted twice
+    if (v.x == kPairEmpty) {
+      v.x = e;
+      if (cusp) v.y = e;
+    } else if (v.y == kPairEmpty && !cusp) {
+      v.y = e;
+    } else {
+      overflow = true;
+    }
+    w = v;
+  }
+  /// the run that contains outline cell 0: inserted BEFORE whatever the row already holds
+  __device__ __forceinline__ void prepend(int y, int a, int b, int yp, int yn) {
+    const uint32_t e = static_cast<uint32_t>(min(a, b) - xb) | (static_cast<uint32_t>(max(a, b) - xb) << 16);
+    uint2& w = tab[(y - yb) * stride];
+    uint2 v = w;
+    const bool cusp = (yp - y) * (y - yn) < 0;
+    if (v.y != kPairEmpty || (cusp && v.x != kPairEmpty)) {
+      overflow = true;
+    } else {
+      v.y = cusp ? e : v.x;
+      v.x = e;
+    }
+    w = v;
+  }
+  /// the outline moves on to row `y` at cell x: close the run that ended at x_prev
+  __device__ __forceinline__ void row_change(int x, int y) {
+    if (in_first) {
+      f_xlast = x_prev, f_ynext = y;
+      in_first = false;
+    } else {
+      append(y_run, x_first, x_prev, y_before, y);
+    }
+    y_before = y_run;
+    y_run = y;
+    x_first = x;
+  }
+  /// One outline cell: a row change closes the run that ended at x_prev.
+  __device__ __forceinline__ void visit(int x, int y) {
+    if (y != y_run) row_change(x, y);
+    x_prev = x;
+  }
+};
+
+/// Per-lane Bresenham ray (generators.cpp:30-52) in step-vector form, so that x-major and y-major rays of
+/// different lanes run through the SAME instructions.
+struct LaneRay {
+  int x, y, size, add, num;
+  int major_x, major_y, minor_x, minor_y;
+  __device__ __forceinline__ void set(int bx, int by, int ex, int ey) {
+    const int dx = ex - bx, dy = ey - by, adx = abs(dx), ady = abs(dy);
+    const int sx = (dx > 0) - (dx < 0), sy = (dy > 0) - (dy < 0);
+    const bool xm = adx >= ady;  // ties: x is the major axis
+    x = bx, y = by;
+    size = xm ? adx : ady, add = xm ? ady : adx, num = size >> 1;
+    major_x = xm ? sx : 0, major_y = xm ? 0 : sy, minor_x = xm ? 0 : sx, minor_y = xm ? sy : 0;
+  }
+  __device__ __forceinline__ void step() {
+    num += add;
+    if (num >= size) {
+      num -= size;
+      x += minor_x, y += minor_y;
+    }
+    x += major_x, y += major_y;
+  }
+};
+
+/// Walks the rays of 32 poses in lock-step: ray e of every lane runs for max-over-lanes(size_e) iterations
+/// (random headings make the per-lane sizes differ; one fused, predicated loop avoids the SIMT divergence of
+/// 32 independently nested loops).  All 32 lanes must call this together.
+template <int XF, int OP>
+__device__ __forceinline__ void area_pair_pose(const double* __restrict__ poly, int nv, const Pose& T, const MapView& m, uint2* table, int rows_cap,
+                                               const OutView& out, long long i, bool valid, unsigned int* __restrict__ todo,
+                                               unsigned int* __restrict__ todo_count) {
+  int x0, y0, x1, y1;
+  const bool in_range = polygon_bbox<XF>(poly, nv, T, m, x0, y0, x1, y1);
+  if (nv == 0) {  // empty generator: nothing is lethal, the sum is 0 (uniform branch: nv is a kernel argument)
+    if (valid) {
+      Fold<OP> fold;
+      fold.store(out, i);
+      if (out.status) out.status[i] = ST_OK;
+    }
+    return;
+  }
+  const int rows = y1 - y0 + 1;
+  const bool too_big = rows > rows_cap || (x1 - x0) > 65000;
+  const bool walk = valid && in_range && !too_big;
+  PairWalker w;
+  w.tab = table + threadIdx.x, w.stride = static_cast<int>(blockDim.x), w.xb = x0, w.yb = y0;
+  const int rows_max = __reduce_max_sync(kFullMask, walk ? rows : 0);
+  for (int r = 0; r < rows_max; ++r)
+    if (walk && r < rows) w.tab[r * w.stride] = make_uint2(kPairEmpty, kPairEmpty);
+  int fx, fy;
+  to_cell<XF>(T, poly[0], poly[1], m, fx, fy);
+  w.y_run = w.y0 = fy, w.x_first = w.x0 = w.x_prev = fx, w.y_before = fy;
+  w.in_first = true, w.overflow = false;
+  w.f_xlast = fx, w.f_ynext = fy;
+  int px = fx, py = fy, rays = 0;
+  LaneRay ray;
+  for (int v = 1; v <= nv; ++v) {  // v == nv: the closing ray, or the one-cell dummy ray of an open outline
+    int cx, cy;
+    if (v < nv) {
+      to_cell<XF>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
+    } else {
+      cx = fx, cy = fy;
+    }
+    ray.set(px, py, cx, cy);
+    if (v < nv) {
+      rays += ray.size != 0;  // degenerate rays are skipped (generators.cpp:86-93)
+    } else if (rays <= 1) {
+      ray.size = 1, ray.add = 0, ray.num = 0;  // dummy ray: the last point itself (generators.cpp:72-78)
+      ray.major_x = ray.major_y = ray.minor_x = ray.minor_y = 0;
+    }
+    if (!walk) ray.size = 0;
+    const int n_iter = __reduce_max_sync(kFullMask, ray.size);
+    for (int k = 0; k < n_iter; ++k) {
+      if (k < ray.size) {
+        w.visit(ray.x, ray.y);
+        ray.step();
+      }
+    }
+    px = cx, py = cy;
+  }
+  if (walk) {
+    if (w.in_first) {  // every cell on one row: ranges (min,min),(max,max) (generators.cpp:197-204)
+      w.tab[(w.y0 - y0) * w.stride] = make_uint2(0u, static_cast<uint32_t>(x1 - x0) | (static_cast<uint32_t>(x1 - x0) << 16));
+    } else if (w.y_run == w.y0) {  // the tail run continues into cell 0
+      w.prepend(w.y0, w.x_first, w.f_xlast, w.y_before, w.f_ynext);
+    } else {
+      w.append(w.y_run, w.x_first, w.x_prev, w.y_before, w.y0);
+      w.prepend(w.y0, w.x0, w.f_xlast, w.y_run, w.f_ynext);
+    }
+  }
+  // statuses and deferrals
+  bool scan = walk && !w.overflow;
+  if (valid && !in_range) store_failure(out, i, ST_COORD_RANGE);
+  if (valid && in_range && (too_big || w.overflow)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i);  // > 2 ranges on a row
+  bool odd = false;
+  for (int r = 0; r < rows_max; ++r) {
+    if (scan && r < rows) {
+      const uint2 v = w.tab[r * w.stride];
+      odd |= v.x != kPairEmpty && v.y == kPairEmpty;
+    }
+  }
+  if (scan && odd) store_failure(out, i, ST_LOGIC_ERROR);  // std::logic_error("Even number of line-pairs expected")
+  scan = scan && !odd;
+  Fold<OP> fold;
+  bool more = scan;
+  for (int r = 0; r < rows_max; ++r) {
+    if (__all_sync(kFullMask, !more)) break;
+    if (more && r < rows) {
+      const uint2 v = w.tab[r * w.stride];
+      if (v.x != kPairEmpty) {
+        const int lo1 = v.x & 0xFFFF, hi1 = v.x >> 16, lo2 = v.y & 0xFFFF, hi2 = v.y >> 16;
+        const int lo = min(lo1, lo2), hi = lo2 < lo1 ? hi1 : hi2;  // stable sort by min, then [first.min, second.max]
+        more = fold.span(m, y0 + r, x0 + lo, x0 + hi);
+      }
+    }
+  }
+  if (scan) {
+    fold.store(out, i);
+    if (out.status) out.status[i] = ST_OK;
+  }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kBlock) k_area_pair(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src, long long count,
+                                                     OutView out, int rows_cap, unsigned int* __restrict__ todo,
+                                                     unsigned int* __restrict__ todo_count) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv, smem_d);
+  uint2* table = reinterpret_cast<uint2*>(smem_d + 2 * nv);
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = i < count;  // no early return: the 32 lanes of a warp walk their outlines in lock-step
+  const Pose T = load_pose(src, valid ? i : 0);
+  if (src.format == POSE_NONE) area_pair_pose<XF_NONE, OP>(poly, nv, T, m, table, rows_cap, out, i, valid, todo, todo_count);
+  else area_pair_pose<XF_PATH_A, OP>(poly, nv, T, m, table, rows_cap, out, i, valid, todo, todo_count);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Lattice kernel (is_free on a POSE_LATTICE batch): the DWA-style headline path.
 //
 // Two facts about an (x, y, heading) lattice make the work shareable without giving up per-pose exactness:
@@ -1046,6 +1250,7 @@ struct cover_ctx {
   std::string error;
   int64_t launches = 0;
   bool disable_lattice_kernel = false;
+  bool old_packed_kernel = false;       // COVER_B200_OLD_PACKED=1: first-generation per-thread kernel (A/B measurements)
   bool force_list_kernel = false;
   bool always_try_packed = true;        // COVER_B200_PACKED_ONLY_CONVEX=1 restricts the packed pass to convex polygons       // COVER_B200_FORCE_LIST_KERNEL=1: A/B measurements and tests of k_area_list  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
   DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, list_cnt, list_rng, list_seq;
@@ -1268,7 +1473,7 @@ unsigned int list_grid(const cover_ctx* ctx, int64_t items, int rows_cap, int bl
 enum Shape { SHAPE_OUTLINE = 1, SHAPE_AREA = 2 };
 
 constexpr int kMaxVertices = 4096;                                          // 64 KB of staged polygon
-constexpr int kMaxDynamicSmem = kMaxVertices * 16 + kPackedMaxRows * kBlock * 4;  // 112 KB
+constexpr int kMaxDynamicSmem = kMaxVertices * 16 + kPackedMaxRows * kBlock * 8;  // 160 KB
 
 /// Opt every kernel that stages a polygon into its dynamic shared-memory budget (once per device).
 cudaError_t configure_kernels() {
@@ -1282,6 +1487,9 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_packed<OP_IS_FREE>));
   set(reinterpret_cast<const void*>(&k_area_packed<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_packed<OP_MAX>));
+  set(reinterpret_cast<const void*>(&k_area_pair<OP_IS_FREE>));
+  set(reinterpret_cast<const void*>(&k_area_pair<OP_ACCUMULATE>));
+  set(reinterpret_cast<const void*>(&k_area_pair<OP_MAX>));
   set(reinterpret_cast<const void*>(&k_area_list<OP_IS_FREE>));
   set(reinterpret_cast<const void*>(&k_area_list<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_list<OP_MAX>));
@@ -1339,9 +1547,15 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       k_area_lattice_free<<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
                                                                    ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g);
     } else {
-      const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint32_t);
-      k_area_packed<OP><<<grid_for(count), kBlock, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
+      if (ctx->old_packed_kernel) {
+        const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint32_t);
+        k_area_packed<OP><<<grid_for(count), kBlock, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
+                                                                          ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
+      } else {
+        const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint2);
+        k_area_pair<OP><<<grid_for(count), kBlock, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
                                                                         ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
+      }
     }
     ++ctx->launches;
     todo = ctx->todo.as<unsigned int>();
@@ -1553,6 +1767,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = std::getenv("COVER_B200_NO_LATTICE_KERNEL")) ctx->disable_lattice_kernel = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_PACKED_ONLY_CONVEX")) ctx->always_try_packed = e[0] != '1';
+  if (const char* e = std::getenv("COVER_B200_OLD_PACKED")) ctx->old_packed_kernel = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_FORCE_LIST_KERNEL")) ctx->force_list_kernel = e[0] == '1';
   *out = ctx;
   return COVER_OK;

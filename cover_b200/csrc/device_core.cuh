@@ -132,54 +132,77 @@ __device__ __forceinline__ uint32_t keep_mask(int w, int lo, int hi) {
   return k;
 }
 
-/// true iff some cell of [lo,hi] equals the byte replicated in pat4.
+/// true iff some cell of [lo,hi] equals the byte replicated in pat4.  The words of the span are loaded in
+/// batches of 8 independent (predicated) loads before any of them is tested: with scattered poses every load
+/// is an L2 round trip, so the memory-level parallelism has to come from inside the thread.
 __device__ __forceinline__ bool row_any_eq(const uint8_t* __restrict__ row, int lo, int hi, uint32_t pat4) {
-  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(row);
-  const int w0 = lo >> 2, w1 = hi >> 2;
-  uint32_t acc;
-  {
-    const uint32_t v = (__ldg(p + w0) ^ pat4) | ~keep_mask(w0, lo, hi);
-    acc = zero_bytes(v);
-  }
-  for (int w = w0 + 1; w < w1; ++w) acc |= zero_bytes(__ldg(p + w) ^ pat4);
-  if (w1 > w0) {
-    const uint32_t v = (__ldg(p + w1) ^ pat4) | ~keep_mask(w1, lo, hi);
-    acc |= zero_bytes(v);
+  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(row) + (lo >> 2);
+  const int last = (hi >> 2) - (lo >> 2);  // index of the last word of the span
+  const uint32_t drop_first = ~(0xFFFFFFFFu << (8 * (lo & 3)));        // bytes before lo
+  const uint32_t drop_last = ~(0xFFFFFFFFu >> (8 * (3 - (hi & 3))));   // bytes after hi
+  uint32_t acc = 0;
+  for (int base = 0; base <= last; base += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (base + j <= last) ? __ldg(p + base + j) : ~pat4;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t t = v[j] ^ pat4;  // a zero byte marks a match
+      if (base + j == 0) t |= drop_first;
+      if (base + j == last) t |= drop_last;
+      acc |= zero_bytes(t);
+    }
   }
   return acc != 0;
 }
 
 /// true iff some cell of [lo,hi] is INSCRIBED_INFLATED (253) or LETHAL (254): is_lethal_or_inflated (costmap.hpp:96-109).
 __device__ __forceinline__ bool row_any_inflated(const uint8_t* __restrict__ row, int lo, int hi) {
-  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(row);
-  const int w0 = lo >> 2, w1 = hi >> 2;
+  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(row) + (lo >> 2);
+  const int last = (hi >> 2) - (lo >> 2);
+  const uint32_t keep_first = 0xFFFFFFFFu << (8 * (lo & 3)), keep_last = 0xFFFFFFFFu >> (8 * (3 - (hi & 3)));
   uint32_t acc = 0;
-  for (int w = w0; w <= w1; ++w) {
-    uint32_t v = __ldg(p + w);
-    if (w == w0 || w == w1) v &= keep_mask(w, lo, hi);  // excluded bytes become 0: neither 253 nor 254
-    acc |= zero_bytes(v ^ 0xFEFEFEFEu) | zero_bytes(v ^ 0xFDFDFDFDu);
+  for (int base = 0; base <= last; base += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (base + j <= last) ? __ldg(p + base + j) : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t t = v[j];  // excluded bytes become 0: neither 253 nor 254
+      if (base + j == 0) t &= keep_first;
+      if (base + j == last) t &= keep_last;
+      acc |= zero_bytes(t ^ 0xFEFEFEFEu) | zero_bytes(t ^ 0xFDFDFDFDu);
+    }
   }
   return acc != 0;
 }
 
 /// accumulate_cost over [lo,hi] in x order: adds costs to `sum`; returns 0, or -1 / -2 for the first
-/// LETHAL / NO_INFORMATION cell (costmap.cpp:35-46).
+/// LETHAL / NO_INFORMATION cell (costmap.cpp:35-46).  Loads are issued 8 words at a time.
 __device__ __forceinline__ int row_accumulate(const uint8_t* __restrict__ row, int lo, int hi, unsigned long long& sum) {
-  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(row);
-  const int w0 = lo >> 2, w1 = hi >> 2;
+  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(row) + (lo >> 2);
+  const int last = (hi >> 2) - (lo >> 2);
+  const uint32_t keep_first = 0xFFFFFFFFu << (8 * (lo & 3)), keep_last = 0xFFFFFFFFu >> (8 * (3 - (hi & 3)));
   unsigned int part = 0;
-  for (int w = w0; w <= w1; ++w) {
-    uint32_t u = __ldg(p + w);
-    if (w == w0 || w == w1) u &= keep_mask(w, lo, hi);
-    if (zero_bytes(~(u | 0x01010101u))) {  // some byte is 254 or 255
-      for (int b = 0; b < 4; ++b) {
-        const uint32_t v = (u >> (8 * b)) & 0xFFu;
-        if (v == kLethal) return -1;
-        if (v == kNoInformation) return -2;
-        part += v;  // excluded bytes are zero
+  for (int base = 0; base <= last; base += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (base + j <= last) ? __ldg(p + base + j) : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t u = v[j];
+      if (base + j == 0) u &= keep_first;
+      if (base + j == last) u &= keep_last;
+      if (zero_bytes(~(u | 0x01010101u))) {  // some byte is 254 or 255: resolve the first one in x order
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t c = (u >> (8 * b)) & 0xFFu;
+          if (c == kLethal) return -1;
+          if (c == kNoInformation) return -2;
+          part += c;  // excluded bytes are zero
+        }
+      } else {
+        part = __dp4a(u, 0x01010101u, part);
       }
-    } else {
-      part = __dp4a(u, 0x01010101u, part);
     }
     if (part > 0x7FFFFFFFu) {
       sum += part;
@@ -191,12 +214,20 @@ __device__ __forceinline__ int row_accumulate(const uint8_t* __restrict__ row, i
 }
 
 __device__ __forceinline__ uint32_t row_max(const uint8_t* __restrict__ row, int lo, int hi, uint32_t best4) {
-  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(row);
-  const int w0 = lo >> 2, w1 = hi >> 2;
-  for (int w = w0; w <= w1; ++w) {
-    uint32_t u = __ldg(p + w);
-    if (w == w0 || w == w1) u &= keep_mask(w, lo, hi);
-    best4 = __vmaxu4(best4, u);
+  const uint32_t* __restrict__ p = reinterpret_cast<const uint32_t*>(row) + (lo >> 2);
+  const int last = (hi >> 2) - (lo >> 2);
+  const uint32_t keep_first = 0xFFFFFFFFu << (8 * (lo & 3)), keep_last = 0xFFFFFFFFu >> (8 * (3 - (hi & 3)));
+  for (int base = 0; base <= last; base += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (base + j <= last) ? __ldg(p + base + j) : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t u = v[j];
+      if (base + j == 0) u &= keep_first;
+      if (base + j == last) u &= keep_last;
+      best4 = __vmaxu4(best4, u);
+    }
   }
   return best4;
 }
