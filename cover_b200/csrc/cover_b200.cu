@@ -1079,9 +1079,20 @@ __global__ void __launch_bounds__(kBlock) k_cells(MapView m, const int2* __restr
   if (i >= count) return;
   const int2 off = __ldg(offsets + i);
   Fold<OP> fold;
-  for (long long j = 0; j < n_cells; ++j) {
-    const int2 c = __ldg(cells + j);
-    if (!fold.cell(m, c.x + off.x, c.y + off.y)) break;
+  bool more = true;
+  for (long long j0 = 0; j0 < n_cells && more; j0 += 8) {  // 8 independent loads, consumed in list order
+    int v[8];
+    bool in[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int2 c = j0 + j < n_cells ? __ldg(cells + j0 + j) : make_int2(0, 0);
+      const int x = c.x + off.x, y = c.y + off.y;
+      in[j] = static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x) && static_cast<unsigned>(y) < static_cast<unsigned>(m.size_y);
+      v[j] = (j0 + j < n_cells && in[j]) ? __ldg(m.data + static_cast<size_t>(y) * m.pitch + x) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (more && j0 + j < n_cells) more = fold.consume(in[j], v[j]);
   }
   fold.store(out, i);
   if (out.status) out.status[i] = ST_OK;

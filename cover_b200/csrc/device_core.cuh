@@ -243,6 +243,11 @@ struct Fold;
 template <>
 struct Fold<OP_IS_FREE> {  // std::none_of(is_lethal): out of the map counts as lethal (costmap.hpp:81-91)
   bool hit = false;
+  /// one cell whose cost byte was already fetched (`inside` = the cell is inside the map)
+  __device__ __forceinline__ bool consume(bool inside, int v) {
+    hit = !inside || v == kLethal;
+    return !hit;
+  }
   __device__ __forceinline__ bool cell(const MapView& m, int x, int y) {
     if (static_cast<unsigned>(x) >= static_cast<unsigned>(m.size_x) || static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) ||
         __ldg(m.data + static_cast<size_t>(y) * m.pitch + x) == kLethal) {
@@ -266,6 +271,16 @@ template <>
 struct Fold<OP_ACCUMULATE> {  // impl/costmap.hpp:50-63: first negative value in generator order wins
   unsigned long long sum = 0;
   int early = 0;
+  __device__ __forceinline__ bool consume(bool inside, int v) {
+    if (!inside) {
+      early = -3;
+    } else if (v >= kLethal) {
+      early = v == kLethal ? -1 : -2;
+    } else {
+      sum += v;
+    }
+    return early == 0;
+  }
   __device__ __forceinline__ bool cell(const MapView& m, int x, int y) {
     if (static_cast<unsigned>(x) >= static_cast<unsigned>(m.size_x) || static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y)) {
       early = -3;
@@ -300,6 +315,11 @@ template <>
 struct Fold<OP_MAX> {  // extension: max of get_cell_cost; any cell outside the map -> -3
   uint32_t best4 = 0;
   bool outside = false;
+  __device__ __forceinline__ bool consume(bool inside, int v) {
+    if (!inside) outside = true;
+    else best4 = max(best4, static_cast<uint32_t>(v));
+    return inside;
+  }
   __device__ __forceinline__ bool cell(const MapView& m, int x, int y) {
     if (static_cast<unsigned>(x) >= static_cast<unsigned>(m.size_x) || static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y)) {
       outside = true;
