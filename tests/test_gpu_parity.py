@@ -135,6 +135,25 @@ def test_lattice_odd_geometries(cb, ctx, geom):
     np.testing.assert_array_equal(out.unpack_bits(len(cpu.is_free)), cpu.is_free)
 
 
+def test_lattice_many_distinct_shapes(cb, ctx):
+    """Sub-cell pitches make the relative shape change from pose to pose: hundreds of distinct shapes per
+    heading overflow the 64-slot shape cache, so poses spill to the todo list / general kernel; 5- and
+    12-vertex polygons take the hashed-key path with verification."""
+    rng = np.random.default_rng(36)
+    data = mixed_map(rng, 200, 200, lethal=0.004)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    omap = po.Costmap(data, 0.05)
+    th = np.array([0.0, 0.7, -2.1])
+    ang = 2 * math.pi * np.arange(12) / 12
+    polys = [RECT, np.stack([0.45 * np.cos(ang), 0.45 * np.sin(ang)]), np.array([[0.4, 0.1, -0.4, -0.2, 0.3], [0.0, 0.35, 0.2, -0.3, -0.3]])]
+    for poly in polys:
+        desc = dict(x0=0.8, dx=0.0137, nx=300, y0=0.8, dy=0.0211, ny=40, cs=np.stack([np.cos(th), np.sin(th)], 1))
+        gpu = cmap.area_is_free(poly, cb.Lattice(**desc))
+        cpu = po.polygon_batch(omap, poly, po.Lattice(**desc), threads=8)
+        assert_same(gpu, cpu, what=f"{poly.shape[1]} vertices")
+        assert 0.02 < cpu.is_free.mean() < 0.98
+
+
 def test_lattice_other_small_footprints(cb, ctx):
     """Triangles, the L-shape scaled down, a 1-cell polygon and a degenerate (open) outline on a lattice."""
     rng = np.random.default_rng(34)
