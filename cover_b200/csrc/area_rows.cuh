@@ -29,7 +29,21 @@ struct RayRec {
   int start;      // outline index of the first cell
   int ylast;      // y of the last cell (k = size - 1)
   int xmajor;     // |dx| >= |dy| (ties: x is the major axis)
+  double rcp_size, rcp_add;  // 1/size, 1/add (0 when add == 0): seeds of the exact divisions
 };
+
+/// floor(a / b) for 0 <= a < 2^31, 0 < b: one FP64 multiply by a precomputed 1/b plus an exact integer fix-up
+/// (the product is within one unit of the true quotient), instead of the ~20-instruction integer division.
+__device__ __forceinline__ int floor_div_pos(int a, int b, double rcp_b) {
+  int q = __double2int_rd(__dmul_rn(static_cast<double>(a), rcp_b));
+  const int r = a - q * b;
+  q += (r >= b) - (r < 0);
+  return q;
+}
+/// ceil(a / b) for b > 0 and any a (|a| < 2^31 - b).
+__device__ __forceinline__ int ceil_div(int a, int b, double rcp_b) {
+  return a > 0 ? floor_div_pos(a + b - 1, b, rcp_b) : -floor_div_pos(-a, b, rcp_b);
+}
 
 __device__ __forceinline__ RayRec make_ray_rec(int2 b, int2 e) {
   const int dx = e.x - b.x, dy = e.y - b.y, adx = abs(dx), ady = abs(dy);
@@ -41,16 +55,15 @@ __device__ __forceinline__ RayRec make_ray_rec(int2 b, int2 e) {
   r.sx = (dx > 0) - (dx < 0);
   r.sy = (dy > 0) - (dy < 0);
   r.start = 0;
+  r.rcp_size = 1.0 / static_cast<double>(r.size);
+  r.rcp_add = r.add ? 1.0 / static_cast<double>(r.add) : 0.0;
   const int k = r.size - 1;
-  r.ylast = r.xmajor ? b.y + r.sy * (((r.size >> 1) + k * r.add) / r.size) : b.y + r.sy * k;
+  r.ylast = r.xmajor ? b.y + r.sy * floor_div_pos((r.size >> 1) + k * r.add, r.size, r.rcp_size) : b.y + r.sy * k;
   return r;
 }
 
 /// The one-cell dummy ray that keeps the last point of an open outline (generators.cpp:72-78).
-__device__ __forceinline__ RayRec dummy_ray_rec(int2 p) { return RayRec{p.x, p.y, 1, 0, 0, 0, 0, p.y, 1}; }
-
-/// ceil(a / b) for b > 0 and any a.
-__device__ __forceinline__ int ceil_div(int a, int b) { return a > 0 ? (a + b - 1) / b : -((-a) / b); }
+__device__ __forceinline__ RayRec dummy_ray_rec(int2 p) { return RayRec{p.x, p.y, 1, 0, 0, 0, 0, p.y, 1, 1.0, 0.0}; }
 
 /// Cells of ray r on scan row y: indices [k_lo, k_hi] and the x of both ends.  false = none.
 __device__ __forceinline__ bool ray_row_interval(const RayRec& r, int y, int& k_lo, int& k_hi, int& x_lo, int& x_hi) {
@@ -63,9 +76,9 @@ __device__ __forceinline__ bool ray_row_interval(const RayRec& r, int y, int& k_
       k_lo = 0, k_hi = r.size - 1;
     } else {
       // minor offset of cell k is floor((h + k*add) / size) == m  <=>  m*size <= h + k*add < (m+1)*size
-      k_lo = m == 0 ? 0 : ceil_div(m * r.size - h, r.add);
+      k_lo = m == 0 ? 0 : ceil_div(m * r.size - h, r.add, r.rcp_add);
       if (k_lo >= r.size) return false;
-      k_hi = min(r.size - 1, ceil_div((m + 1) * r.size - h, r.add) - 1);
+      k_hi = min(r.size - 1, ceil_div((m + 1) * r.size - h, r.add, r.rcp_add) - 1);
     }
     x_lo = r.bx + r.sx * k_lo;
     x_hi = r.bx + r.sx * k_hi;
@@ -73,7 +86,7 @@ __device__ __forceinline__ bool ray_row_interval(const RayRec& r, int y, int& k_
     const int k = (y - r.by) * r.sy;  // y-major rays have sy != 0 and exactly one cell per row
     if (k < 0 || k >= r.size) return false;
     k_lo = k_hi = k;
-    x_lo = x_hi = r.bx + r.sx * ((h + k * r.add) / r.size);
+    x_lo = x_hi = r.bx + r.sx * floor_div_pos(h + k * r.add, r.size, r.rcp_size);
   }
   return true;
 }
