@@ -1,17 +1,21 @@
 // cover_b200.cu — kernels and the C ABI (include/cover_b200.h) of the batched footprint checker.
 //
-// One THREAD per pose.  Adjacent threads take adjacent poses, so on a pose lattice (x fastest) a warp
-// walks 32 copies of the same outline shifted by one cell: control flow is uniform and every load of the
-// warp falls into one or two 32-byte sectors of the costmap.  The costmap (<= 64 MB) lives in the 126 MB
-// L2; HBM only sees the first touch.  Kernels:
-//   k_outline<OP>       outline_generator checks   (a5 + a10/a13)
-//   k_area_packed<OP>   area checks, rows with <= 2 ranges: packed shared-memory row table
-//   k_area_list<OP>     area checks, any polygon: sorted per-row lists in global scratch (persistent grid);
-//                       also drains the poses k_area_packed could not finish
-//   k_rays<OP>          ray_generator checks       (a4)
-//   k_cells<OP>         cached discrete_polygon x offsets (a11)
-//   k_footprints        discrete/generator footprint bank x offsets (a15/a16)
-//   k_split             continuous_footprint::is_free (a14)
+// The costmap (<= 64 MB) lives in the 126 MB L2; HBM only sees the first touch.  Kernels:
+//   k_area_lattice_free  is_free on a pose lattice: warp = 64 x-adjacent poses, separable exact vertex profiles,
+//                        per-CTA shape cache, ballot bit windows (the headline path)
+//   k_area_pair<OP>      area checks, arbitrary poses, rows with <= 2 ranges: thread = pose, the warp's 32 outline
+//                        walks fused in lock-step, 64-bit pair table in shared memory
+//   k_area_rows<OP>      area checks, any polygon <= 256 vertices: warp = pose, lane = scan row (area_rows.cuh);
+//                        also drains the poses the two kernels above defer;  k_area_rows_multi<OP>: holes
+//   k_area_list<OP>      area checks for > 256 vertices / many short edges: per-thread sorted lists in global scratch
+//   k_area_packed<OP>    first-generation per-thread kernel (COVER_B200_OLD_PACKED=1, A/B measurements only)
+//   k_outline<OP>        outline_generator checks   (a5 + a10/a13)
+//   k_rays<OP>           ray_generator checks       (a4)
+//   k_cells_free / k_cells<OP>   cached discrete_polygon x offsets (a11): row spans / ordered list
+//   k_footprints         discrete/generator footprint bank x offsets (a15/a16): host-precomputed row spans
+//   k_split              continuous_footprint::is_free (a14)
+//   k_area_expand, k_outline_expand   to_area / to_outline, batched
+//   k_trajectories       trajectory scoring (8f-4);  k_inflate: inflation layer (8f-3)
 // There is no CPU path in this file: without a CUDA device every entry returns COVER_E_CUDA.
 #include "../../include/cover_b200.h"
 #include "area_rows.cuh"
