@@ -84,3 +84,12 @@ def test_cpp_host_layer_compiles_and_links(lib, tmp_path):
                            os.path.join(ROOT, "tests", "cpp", "host_api_test.cpp"), "-o", str(exe), "-L", libdir, "-lcover_b200",
                            f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
     assert proc.returncode == 0, proc.stderr
+
+
+def test_plain_c_client_compiles_and_links(lib, tmp_path):
+    """tests/c/abi_smoke.c: the ABI consumed from C99 (no C++ in the client)."""
+    import cover_b200
+    libdir = os.path.dirname(cover_b200.library_path())
+    proc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_smoke.c"),
+                           "-o", str(tmp_path / "abi_smoke"), "-L", libdir, "-lcover_b200", f"-Wl,-rpath,{libdir}", "-lm"], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr

@@ -687,3 +687,17 @@ def test_area_with_holes(cb, ctx):
     np.testing.assert_array_equal(a.cost, b.cost)
     none = cmap.area_multi(head_polygons(), None)
     assert_same(none, po.multi_polygon_batch(omap, head_polygons(), None))
+
+
+def test_plain_c_client(cb, tmp_path):
+    """tests/c/abi_smoke.c through gcc -std=c99: hand-computable answers via the raw C ABI."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(cb.library_path())
+    exe = tmp_path / "abi_smoke"
+    build = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c", "abi_smoke.c"), "-o", str(exe),
+                            "-L", libdir, "-lcover_b200", f"-Wl,-rpath,{libdir}", "-lm"], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
