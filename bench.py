@@ -312,7 +312,7 @@ def run_gpu(args) -> None:
             alg_bytes = (cells_per_pose + B_OUT) * n_poses
             achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": recorded_traffic(), "peak_kind": peak_kind, "kernel": "k_area_lattice_free",
+                        "traffic": recorded_traffic(), "peak_kind": peak_kind, "kernel": "k_area_lattice<OP_IS_FREE>",
                         "algorithmic_bytes_per_check": cells_per_pose + B_OUT}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

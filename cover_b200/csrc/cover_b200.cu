@@ -1,7 +1,7 @@
 // cover_b200.cu — kernels and the C ABI (include/cover_b200.h) of the batched footprint checker.
 //
 // The costmap (<= 64 MB) lives in the 126 MB L2; HBM only sees the first touch.  Kernels:
-//   k_area_lattice_free  is_free on a pose lattice: warp = 64 x-adjacent poses, separable exact vertex profiles,
+//   k_area_lattice<OP>   pose-lattice checks: warp = 64 x-adjacent poses, separable exact vertex profiles,
 //                        per-CTA shape cache, ballot bit windows (the headline path)
 //   k_area_pair<OP>      area checks, arbitrary poses, rows with <= 2 ranges: thread = pose, the warp's 32 outline
 //                        walks fused in lock-step, 64-bit pair table in shared memory
@@ -521,6 +521,62 @@ __device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ vert
   return sh;
 }
 
+
+/// accumulate_cost / max_cost for one group of the lattice kernel (all needed cells inside the map): per scan row
+/// the warp stages the 96-byte row segment in shared memory (one byte per lane and piece, coalesced loads), then
+/// every pose folds its own window [off, off + width) word by word — 4 cells per 32-bit shared-memory load, in x
+/// order, so accumulate_cost's "first negative value in generator order" rule is kept (rows ascend, x ascends).
+template <int OP>
+__device__ __forceinline__ void lattice_rows_fold(const MapView& m, const int* __restrict__ row_a, const uint32_t* __restrict__ row_m, int rows,
+                                                  int x_base, int y_base, int lane, bool third, int off_a, int off_b, uint8_t* rowbuf,
+                                                  Fold<OP>& fa, Fold<OP>& fb) {
+  const uint8_t* __restrict__ p = m.data + static_cast<size_t>(y_base) * m.pitch + (x_base + lane);
+  const uint32_t* buf32 = reinterpret_cast<const uint32_t*>(rowbuf);
+  bool more_a = true, more_b = true;
+  for (int r = 0; r < rows; ++r) {
+    const uint8_t* __restrict__ q = p + row_a[r];
+    const uint8_t b0 = __ldg(q), b1 = __ldg(q + 32), b2 = third ? __ldg(q + 64) : static_cast<uint8_t>(0);
+    __syncwarp();
+    rowbuf[lane] = b0, rowbuf[32 + lane] = b1, rowbuf[64 + lane] = b2;
+    __syncwarp();
+    const int width = __popc(row_m[r]);
+    if (width == 0) continue;
+#pragma unroll
+    for (int plane = 0; plane < 2; ++plane) {
+      const int lo = plane ? off_b : off_a, hi = lo + width - 1;
+      Fold<OP>& f = plane ? fb : fa;
+      bool& more = plane ? more_b : more_a;
+      const int w0 = lo >> 2, last = (hi >> 2) - w0;
+      const uint32_t keep_first = 0xFFFFFFFFu << (8 * (lo & 3)), keep_last = 0xFFFFFFFFu >> (8 * (3 - (hi & 3)));
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {  // width <= 32 cells: at most 9 words
+        if (more && j <= last) {
+          uint32_t u = buf32[w0 + j];
+          if (j == 0) u &= keep_first;
+          if (j == last) u &= keep_last;
+          if constexpr (OP == OP_MAX) {
+            f.best4 = __vmaxu4(f.best4, u);
+          } else if constexpr (OP == OP_ACCUMULATE) {
+            if (zero_bytes(~(u | 0x01010101u))) {  // some cell is LETHAL or NO_INFORMATION: the first one in x order wins
+              for (int b = 0; b < 4 && more; ++b) {
+                const uint32_t c = (u >> (8 * b)) & 0xFFu;
+                if (c >= static_cast<uint32_t>(kLethal)) {
+                  f.early = c == static_cast<uint32_t>(kLethal) ? -1 : -2;
+                  more = false;
+                } else {
+                  f.sum += c;
+                }
+              }
+            } else {
+              f.sum += __dp4a(u, 0x01010101u, 0u);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 /// Bit-packed verdicts of one plane of a group (consecutive pose indices: at most two output words).
 __device__ __forceinline__ void lat_store_bits(const OutView& out, unsigned grp, bool fits, bool is_free, long long i, int lane) {
   if (grp == 0u) return;
@@ -535,7 +591,8 @@ __device__ __forceinline__ void lat_store_bits(const OutView& out, unsigned grp,
   }
 }
 
-__global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice_free(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
+template <int OP>
+__global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
                                                                      long long count, OutView out, int rows_cap,
                                                                      unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count,
                                                                      LatGeom g) {
@@ -546,6 +603,7 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice_fr
   int* row_a = reinterpret_cast<int*>(canon + kLatSlots * nv);                          // [slot][row] first cell of the range
   uint32_t* row_m = reinterpret_cast<uint32_t*>(row_a + kLatSlots * rows_cap);          // [slot][row] width mask (0 = no range)
   LatShape* meta = reinterpret_cast<LatShape*>(row_m + kLatSlots * rows_cap);           // [slot]
+  uint8_t* rowbufs = reinterpret_cast<uint8_t*>(meta + kLatSlots);                      // [warp][96 (+32 pad)] staged row bytes
   if (threadIdx.x < kLatSlots) {
     slot_key[threadIdx.x] = 0ull;
     meta[threadIdx.x].status = kLatPending;
@@ -553,6 +611,7 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice_fr
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* rowbuf = rowbufs + warp * 128;
   const bool exact_key = nv <= 4;  // 2 x 3 offsets of 8 bits: the key IS the shape, no verification pass
   const long long chunk = (g.n_units + gridDim.x - 1) / gridDim.x;
   const long long unit_begin = blockIdx.x * chunk, unit_end = min(g.n_units, unit_begin + chunk);
@@ -745,24 +804,40 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice_fr
         const int xb_s = meta[sl].xb, x1_s = meta[sl].x1, rows = meta[sl].rows, y_base = vy0 + meta[sl].yb;
         // every cell any pose of the group needs lies in x: [xmin + xb, xmin + maxoff + x1]
         const bool inside = y_base >= 0 && y_base + rows <= m.size_y && xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x;
-        uint32_t hit_a = 0, hit_b = 0;
         const int oa = fits_a ? off_a : 0, ob = fits_b ? off_b : 0;
-        // the usual full group: plane A's offsets are 0..31, plane B's 32..63 -> no per-row piece selection
-        const bool split_planes = __all_sync(kFull, (!fits_a || off_a < 32) && (!fits_b || off_b >= 32));
-        if (inside && split_planes) lattice_rows<0>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, fits_b ? ob : 32, hit_a, hit_b);
-        else if (inside) lattice_rows<1>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, ob, hit_a, hit_b);
-        else lattice_rows<2>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, true, oa, ob, hit_a, hit_b);
-        if (fits_a) {
-          if (out.is_free) out.is_free[i_a] = hit_a ? 0 : 1;
-          if (out.status) out.status[i_a] = ST_OK;
-        }
-        if (fits_b) {
-          if (out.is_free) out.is_free[i_b] = hit_b ? 0 : 1;
-          if (out.status) out.status[i_b] = ST_OK;
-        }
-        if (out.free_bits) {
-          lat_store_bits(out, grp_a, fits_a, hit_a == 0u, i_a, lane);
-          lat_store_bits(out, grp_b, fits_b, hit_b == 0u, i_b, lane);
+        if constexpr (OP == OP_IS_FREE) {
+          uint32_t hit_a = 0, hit_b = 0;
+          // the usual full group: plane A's offsets are 0..31, plane B's 32..63 -> no per-row piece selection
+          const bool split_planes = __all_sync(kFull, (!fits_a || off_a < 32) && (!fits_b || off_b >= 32));
+          if (inside && split_planes) lattice_rows<0>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, fits_b ? ob : 32, hit_a, hit_b);
+          else if (inside) lattice_rows<1>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, ob, hit_a, hit_b);
+          else lattice_rows<2>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, true, oa, ob, hit_a, hit_b);
+          if (fits_a) {
+            if (out.is_free) out.is_free[i_a] = hit_a ? 0 : 1;
+            if (out.status) out.status[i_a] = ST_OK;
+          }
+          if (fits_b) {
+            if (out.is_free) out.is_free[i_b] = hit_b ? 0 : 1;
+            if (out.status) out.status[i_b] = ST_OK;
+          }
+          if (out.free_bits) {
+            lat_store_bits(out, grp_a, fits_a, hit_a == 0u, i_a, lane);
+            lat_store_bits(out, grp_b, fits_b, hit_b == 0u, i_b, lane);
+          }
+        } else if (inside) {  // (discarded for OP_IS_FREE: the whole else-chain hangs off an `if constexpr`)
+          Fold<OP> fa, fb;
+          lattice_rows_fold<OP>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, ob, rowbuf, fa, fb);
+          if (fits_a) {
+            fa.store(out, i_a);
+            if (out.status) out.status[i_a] = ST_OK;
+          }
+          if (fits_b) {
+            fb.store(out, i_b);
+            if (out.status) out.status[i_b] = ST_OK;
+          }
+        } else {  // a pose of the group touches the map border: the general kernel resolves out-of-map cells in order
+          if (fits_a) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
+          if (fits_b) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
         }
         pend_a &= ~grp_a;
         pend_b &= ~grp_b;
@@ -1512,7 +1587,9 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_rows<OP_IS_FREE>));
   set(reinterpret_cast<const void*>(&k_area_rows<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_rows<OP_MAX>));
-  set(reinterpret_cast<const void*>(&k_area_lattice_free));
+  set(reinterpret_cast<const void*>(&k_area_lattice<OP_IS_FREE>));
+  set(reinterpret_cast<const void*>(&k_area_lattice<OP_ACCUMULATE>));
+  set(reinterpret_cast<const void*>(&k_area_lattice<OP_MAX>));
   set(reinterpret_cast<const void*>(&k_area_expand));
   set(reinterpret_cast<const void*>(&k_outline_expand));
   set(reinterpret_cast<const void*>(&k_inflate));
@@ -1547,7 +1624,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     CU(ctx->todo_count.ensure(sizeof(unsigned int)));
     CU(cudaMemsetAsync(ctx->todo_count.ptr, 0, sizeof(unsigned int), ctx->stream));
     // Lattice batches of small footprints: shape-deduplicating warp-cooperative kernel.
-    const bool lattice = OP == OP_IS_FREE && src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices &&
+    const bool lattice = src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices &&
                          rows_cap - 3 <= kLatMaxWidth && !ctx->disable_lattice_kernel;
     if (lattice) {
       LatGeom g;
@@ -1557,9 +1634,10 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       g.segs = (src.nx + kLatSegX - 1) / kLatSegX;
       g.n_units = static_cast<long long>((g.n_rows + kLatRows - 1) / kLatRows) * g.segs;
       const size_t smem = poly_bytes + kLatSlots * (sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) +
-                                                     static_cast<size_t>(rows_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape));
+                                                     static_cast<size_t>(rows_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape)) +
+                          kLatWarps * 128;
       const unsigned int grid = static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_MIN_BLOCKS));
-      k_area_lattice_free<<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
+      k_area_lattice<OP><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
                                                                    ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g);
     } else {
       if (ctx->old_packed_kernel) {
@@ -1819,7 +1897,7 @@ int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double reso
   Bind bind(ctx->device);
   const int pitch = (size_x + 15) & ~15;
   uint8_t* dev = nullptr;
-  // + 128 bytes: k_area_lattice_free's unchecked loop reads (and masks off) up to 95 bytes past the last needed cell
+  // + 128 bytes: k_area_lattice's unchecked loop reads (and masks off) up to 95 bytes past the last needed cell
   CU(cudaMalloc(reinterpret_cast<void**>(&dev), static_cast<size_t>(pitch) * size_y + 128));
   CU(cudaMemsetAsync(dev, 0, static_cast<size_t>(pitch) * size_y + 128, ctx->stream));
   cover_map* m = new (std::nothrow) cover_map();

@@ -114,6 +114,10 @@ def test_lattice_axis_aligned_headings_and_map_border(cb, ctx, pitch):
         cpu = po.polygon_batch(po.Costmap(data, 0.05, *origin), RECT, po.Lattice(**desc), threads=8)
         assert_same(gpu, cpu, what=f"pitch {pitch} origin {origin}")
         assert 0.05 < cpu.is_free.mean() < 0.95
+        for name, op in (("accumulate_cost", po.OP_ACCUMULATE), ("max_cost", po.OP_MAX)):  # the value folds of the lattice kernel
+            gpu = getattr(cmap, f"area_{name}")(RECT, cb.Lattice(**desc))
+            cpu = po.polygon_batch(po.Costmap(data, 0.05, *origin), RECT, po.Lattice(**desc), op=op, threads=8)
+            assert_same(gpu, cpu, True, what=f"{name} pitch {pitch} origin {origin}")
 
 
 @pytest.mark.parametrize("geom", [dict(nx=70, ny=3, dx=0.05, dy=0.05), dict(nx=90, ny=40, dx=-0.05, dy=0.05), dict(nx=45, ny=20, dx=0.5, dy=0.35),
@@ -133,6 +137,9 @@ def test_lattice_odd_geometries(cb, ctx, geom):
     out = cb.Result(free_bits=np.zeros((len(cpu.is_free) + 31) // 32, dtype=np.uint32), not_ok=np.zeros(1, dtype=np.int64))
     cmap.area_is_free(RECT, cb.Lattice(**desc), out=out)
     np.testing.assert_array_equal(out.unpack_bits(len(cpu.is_free)), cpu.is_free)
+    for name, op in (("accumulate_cost", po.OP_ACCUMULATE), ("max_cost", po.OP_MAX)):
+        assert_same(getattr(cmap, f"area_{name}")(RECT, cb.Lattice(**desc)),
+                    po.polygon_batch(po.Costmap(data, 0.05, 0.1, -0.2), RECT, po.Lattice(**desc), op=op, threads=8), True, f"{name} {geom}")
 
 
 def test_lattice_many_distinct_shapes(cb, ctx):
@@ -152,6 +159,7 @@ def test_lattice_many_distinct_shapes(cb, ctx):
         cpu = po.polygon_batch(omap, poly, po.Lattice(**desc), threads=8)
         assert_same(gpu, cpu, what=f"{poly.shape[1]} vertices")
         assert 0.02 < cpu.is_free.mean() < 0.98
+        assert_same(cmap.area_accumulate_cost(poly, cb.Lattice(**desc)), po.polygon_batch(omap, poly, po.Lattice(**desc), op=po.OP_ACCUMULATE, threads=8), True)
 
 
 def test_lattice_other_small_footprints(cb, ctx):
@@ -168,6 +176,9 @@ def test_lattice_other_small_footprints(cb, ctx):
         gpu = cmap.area_is_free(poly, cb.Lattice(**desc))
         cpu = po.polygon_batch(omap, poly, po.Lattice(**desc), threads=8)
         assert_same(gpu, cpu, what=str(poly.tolist()))
+        for name, op in (("accumulate_cost", po.OP_ACCUMULATE), ("max_cost", po.OP_MAX)):
+            assert_same(getattr(cmap, f"area_{name}")(poly, cb.Lattice(**desc)), po.polygon_batch(omap, poly, po.Lattice(**desc), op=op, threads=8),
+                        True, f"{name} {poly.tolist()}")
 
 
 @pytest.mark.parametrize("idx", range(7))
