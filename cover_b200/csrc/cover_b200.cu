@@ -5,6 +5,7 @@
 //                        per-CTA shape cache, ballot bit windows (the headline path)
 //   k_area_pair<OP>      area checks, arbitrary poses, rows with <= 2 ranges: thread = pose, the warp's 32 outline
 //                        walks fused in lock-step, 64-bit pair table in shared memory
+//   k_area_slots<OP,4>   second per-thread pass over the poses k_area_pair deferred (non-convex polygons): 4 ranges/row
 //   k_area_rows<OP>      area checks, any polygon <= 256 vertices: warp = pose, lane = scan row (area_rows.cuh);
 //                        also drains the poses the two kernels above defer;  k_area_rows_multi<OP>: holes
 //   k_area_list<OP>      area checks for > 256 vertices / many short edges: per-thread sorted lists in global scratch
@@ -208,6 +209,69 @@ struct PairWalker {
   }
 };
 
+/// Row table of the second per-thread pass: SLOTS (4) 32-bit ranges per (row, thread) in insertion order,
+/// laid out [row][slot][thread] so that a warp's accesses never conflict.  0xFFFFFFFF = empty.
+template <int SLOTS>
+struct SlotWalker {
+  uint32_t* tab;  // &table[0][0][threadIdx.x]
+  int stride;     // threads per block
+  int xb, yb;     // bounding-box origin: ranges are stored relative to xb
+  int y_run, x_first, x_prev, y_before;
+  int x0, y0, f_xlast, f_ynext;
+  bool in_first, overflow;
+
+  __device__ __forceinline__ uint32_t& slot(int row, int k) { return tab[(row * SLOTS + k) * stride]; }
+  __device__ __forceinline__ int count(int row) {
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) n += slot(row, k) != kPairEmpty;
+    return n;
+  }
+  __device__ __forceinline__ void append(int y, int a, int b, int yp, int yn) {
+    const uint32_t e = static_cast<uint32_t>(min(a, b) - xb) | (static_cast<uint32_t>(max(a, b) - xb) << 16);
+    const int row = y - yb;
+    const int need = ((yp - y) * (y - yn) < 0) ? 2 : 1;  // a cusp counts twice (generators.cpp:100-103)
+    const int n = count(row);
+    if (n + need > SLOTS) {
+      overflow = true;
+      return;
+    }
+    slot(row, n) = e;
+    if (need == 2) slot(row, n + 1) = e;
+  }
+  /// the run that contains outline cell 0: inserted BEFORE whatever the row already holds
+  __device__ __forceinline__ void prepend(int y, int a, int b, int yp, int yn) {
+    const uint32_t e = static_cast<uint32_t>(min(a, b) - xb) | (static_cast<uint32_t>(max(a, b) - xb) << 16);
+    const int row = y - yb;
+    const int need = ((yp - y) * (y - yn) < 0) ? 2 : 1;
+    const int n = count(row);
+    if (n + need > SLOTS) {
+      overflow = true;
+      return;
+    }
+    for (int k = n - 1; k >= 0; --k) slot(row, k + need) = slot(row, k);
+    slot(row, 0) = e;
+    if (need == 2) slot(row, 1) = e;
+  }
+  /// the outline moves on to row `y` at cell x: close the run that ended at x_prev
+  __device__ __forceinline__ void row_change(int x, int y) {
+    if (in_first) {
+      f_xlast = x_prev, f_ynext = y;
+      in_first = false;
+    } else {
+      append(y_run, x_first, x_prev, y_before, y);
+    }
+    y_before = y_run;
+    y_run = y;
+    x_first = x;
+  }
+  /// One outline cell: a row change closes the run that ended at x_prev.
+  __device__ __forceinline__ void visit(int x, int y) {
+    if (y != y_run) row_change(x, y);
+    x_prev = x;
+  }
+};
+
 /// Per-lane Bresenham ray (generators.cpp:30-52) in step-vector form, so that x-major and y-major rays of
 /// different lanes run through the SAME instructions.
 struct LaneRay {
@@ -341,6 +405,142 @@ __global__ void __launch_bounds__(kBlock) k_area_pair(MapView m, const double* _
   const Pose T = load_pose(src, valid ? i : 0);
   if (src.format == POSE_NONE) area_pair_pose<XF_NONE, OP>(poly, nv, T, m, table, rows_cap, out, i, valid, todo, todo_count);
   else area_pair_pose<XF_PATH_A, OP>(poly, nv, T, m, table, rows_cap, out, i, valid, todo, todo_count);
+}
+
+/// Second per-thread pass: the poses k_area_pair deferred (more than two ranges on a row) are walked again with
+/// SLOTS ranges per row — an L, a notch or a kidney rarely needs more than four; what still overflows goes to the
+/// general kernels.  Same lock-step walk as area_pair_pose.
+template <int XF, int OP, int SLOTS>
+__device__ __forceinline__ void area_slot_pose(const double* __restrict__ poly, int nv, const Pose& T, const MapView& m, uint32_t* table,
+                                               int rows_cap, const OutView& out, long long i, bool valid, unsigned int* __restrict__ todo,
+                                               unsigned int* __restrict__ todo_count) {
+  int x0, y0, x1, y1;
+  const bool in_range = polygon_bbox<XF>(poly, nv, T, m, x0, y0, x1, y1);
+  if (nv == 0) {  // empty generator: nothing is lethal, the sum is 0 (uniform branch: nv is a kernel argument)
+    if (valid) {
+      Fold<OP> fold;
+      fold.store(out, i);
+      if (out.status) out.status[i] = ST_OK;
+    }
+    return;
+  }
+  const int rows = y1 - y0 + 1;
+  const bool too_big = rows > rows_cap || (x1 - x0) > 65000;
+  const bool walk = valid && in_range && !too_big;
+  SlotWalker<SLOTS> w;
+  w.tab = table + threadIdx.x, w.stride = static_cast<int>(blockDim.x), w.xb = x0, w.yb = y0;
+  const int rows_max = __reduce_max_sync(kFullMask, walk ? rows : 0);
+  for (int r = 0; r < rows_max; ++r)
+    if (walk && r < rows) {
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k) w.slot(r, k) = kPairEmpty;
+    }
+  int fx, fy;
+  to_cell<XF>(T, poly[0], poly[1], m, fx, fy);
+  w.y_run = w.y0 = fy, w.x_first = w.x0 = w.x_prev = fx, w.y_before = fy;
+  w.in_first = true, w.overflow = false;
+  w.f_xlast = fx, w.f_ynext = fy;
+  int px = fx, py = fy, rays = 0;
+  LaneRay ray;
+  for (int v = 1; v <= nv; ++v) {  // v == nv: the closing ray, or the one-cell dummy ray of an open outline
+    int cx, cy;
+    if (v < nv) {
+      to_cell<XF>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
+    } else {
+      cx = fx, cy = fy;
+    }
+    ray.set(px, py, cx, cy);
+    if (v < nv) {
+      rays += ray.size != 0;  // degenerate rays are skipped (generators.cpp:86-93)
+    } else if (rays <= 1) {
+      ray.size = 1, ray.add = 0, ray.num = 0;  // dummy ray: the last point itself (generators.cpp:72-78)
+      ray.major_x = ray.major_y = ray.minor_x = ray.minor_y = 0;
+    }
+    if (!walk) ray.size = 0;
+    const int n_iter = __reduce_max_sync(kFullMask, ray.size);
+    for (int k = 0; k < n_iter; ++k) {
+      if (k < ray.size) {
+        w.visit(ray.x, ray.y);
+        ray.step();
+      }
+    }
+    px = cx, py = cy;
+  }
+  if (walk) {
+    if (w.in_first) {  // every cell on one row: ranges (min,min),(max,max) (generators.cpp:197-204)
+      const uint32_t wd = static_cast<uint32_t>(x1 - x0);
+      w.slot(w.y0 - y0, 0) = 0u;
+      w.slot(w.y0 - y0, 1) = wd | (wd << 16);
+    } else if (w.y_run == w.y0) {  // the tail run continues into cell 0
+      w.prepend(w.y0, w.x_first, w.f_xlast, w.y_before, w.f_ynext);
+    } else {
+      w.append(w.y_run, w.x_first, w.x_prev, w.y_before, w.y0);
+      w.prepend(w.y0, w.x0, w.f_xlast, w.y_run, w.f_ynext);
+    }
+  }
+  // statuses and deferrals
+  bool scan = walk && !w.overflow;
+  if (valid && !in_range) store_failure(out, i, ST_COORD_RANGE);
+  if (valid && in_range && (too_big || w.overflow)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i);  // too many ranges on a row
+  bool odd = false;
+  for (int r = 0; r < rows_max; ++r)
+    if (scan && r < rows) odd |= (w.count(r) & 1) != 0;
+  if (scan && odd) store_failure(out, i, ST_LOGIC_ERROR);  // std::logic_error("Even number of line-pairs expected")
+  scan = scan && !odd;
+  Fold<OP> fold;
+  bool more = scan;
+  for (int r = 0; r < rows_max; ++r) {
+    if (__all_sync(kFullMask, !more)) break;
+    if (more && r < rows) {
+      uint32_t e[SLOTS];
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k) e[k] = w.slot(r, k);
+      if (SLOTS == 4 && e[2] != kPairEmpty) {
+        // four ranges: stable insertion sort by `min` (low 16 bits), then [r0.min, r1.max], [r2.min, r3.max]
+#pragma unroll
+        for (int a = 1; a < 4; ++a) {
+#pragma unroll
+          for (int b = a; b > 0; --b) {
+            if ((e[b] & 0xFFFFu) < (e[b - 1] & 0xFFFFu)) {
+              const uint32_t t = e[b];
+              e[b] = e[b - 1], e[b - 1] = t;
+            }
+          }
+        }
+        more = fold.span(m, y0 + r, x0 + static_cast<int>(e[0] & 0xFFFFu), x0 + static_cast<int>(e[1] >> 16));
+        if (more) more = fold.span(m, y0 + r, x0 + static_cast<int>(e[2] & 0xFFFFu), x0 + static_cast<int>(e[3] >> 16));
+      } else if (e[0] != kPairEmpty) {
+        const int lo1 = e[0] & 0xFFFF, hi1 = e[0] >> 16, lo2 = e[1] & 0xFFFF, hi2 = e[1] >> 16;
+        const int lo = min(lo1, lo2), hi = lo2 < lo1 ? hi1 : hi2;  // stable sort by min, then [first.min, second.max]
+        more = fold.span(m, y0 + r, x0 + lo, x0 + hi);
+      }
+    }
+  }
+  if (scan) {
+    fold.store(out, i);
+    if (out.status) out.status[i] = ST_OK;
+  }
+}
+
+template <int OP, int SLOTS>
+__global__ void __launch_bounds__(kBlock) k_area_slots(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src, OutView out,
+                                                      int rows_cap, const unsigned int* __restrict__ in_list,
+                                                      const unsigned int* __restrict__ in_count, unsigned int* __restrict__ todo,
+                                                      unsigned int* __restrict__ todo_count) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv, smem_d);
+  uint32_t* table = reinterpret_cast<uint32_t*>(smem_d + 2 * nv);
+  const long long n_items = *in_count;
+  const long long n_threads = static_cast<long long>(gridDim.x) * blockDim.x;
+  // persistent grid over the deferred poses; whole warps iterate together (lock-step walk)
+  for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x; base < n_items; base += n_threads) {
+    const long long item = base + threadIdx.x;
+    const bool valid = item < n_items;
+    const long long i = valid ? static_cast<long long>(in_list[item]) : 0;
+    const Pose T = load_pose(src, i);
+    if (src.format == POSE_NONE) area_slot_pose<XF_NONE, OP, SLOTS>(poly, nv, T, m, table, rows_cap, out, i, valid, todo, todo_count);
+    else area_slot_pose<XF_PATH_A, OP, SLOTS>(poly, nv, T, m, table, rows_cap, out, i, valid, todo, todo_count);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1343,7 +1543,7 @@ struct cover_ctx {
   bool old_packed_kernel = false;       // COVER_B200_OLD_PACKED=1: first-generation per-thread kernel (A/B measurements)
   bool force_list_kernel = false;
   bool always_try_packed = true;        // COVER_B200_PACKED_ONLY_CONVEX=1 restricts the packed pass to convex polygons       // COVER_B200_FORCE_LIST_KERNEL=1: A/B measurements and tests of k_area_list  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
-  DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, list_cnt, list_rng, list_seq;
+  DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, todo2, todo2_count, list_cnt, list_rng, list_seq;
 };
 
 struct cover_map {
@@ -1580,6 +1780,9 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_pair<OP_IS_FREE>));
   set(reinterpret_cast<const void*>(&k_area_pair<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_pair<OP_MAX>));
+  set(reinterpret_cast<const void*>(&k_area_slots<OP_IS_FREE, 4>));
+  set(reinterpret_cast<const void*>(&k_area_slots<OP_ACCUMULATE, 4>));
+  set(reinterpret_cast<const void*>(&k_area_slots<OP_MAX, 4>));
   set(reinterpret_cast<const void*>(&k_area_list<OP_IS_FREE>));
   set(reinterpret_cast<const void*>(&k_area_list<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_list<OP_MAX>));
@@ -1619,6 +1822,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   const bool rows_kernel = nv <= kRowsMaxVertices && rows_cap <= 30000 && !ctx->force_list_kernel && (nv <= 16 || rows_cap > 48);
   const unsigned int* todo = nullptr;
   const unsigned int* todo_count = nullptr;
+  bool second_list = false;
   if (fast) {
     CU(ctx->todo.ensure(static_cast<size_t>(count) * sizeof(unsigned int)));
     CU(ctx->todo_count.ensure(sizeof(unsigned int)));
@@ -1648,11 +1852,25 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
         const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint2);
         k_area_pair<OP><<<grid_for(count), kBlock, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
                                                                         ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
+        if (!is_convex(poly_host, nv) && rows_cap <= 64) {
+          // second per-thread pass over the deferred poses with four ranges per row; its own overflow list feeds the
+          // general kernel below
+          CU(ctx->todo2.ensure(static_cast<size_t>(count) * sizeof(unsigned int)));
+          CU(ctx->todo2_count.ensure(sizeof(unsigned int)));
+          CU(cudaMemsetAsync(ctx->todo2_count.ptr, 0, sizeof(unsigned int), ctx->stream));
+          const size_t smem4 = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * 4 * sizeof(uint32_t);
+          const unsigned int grid4 = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(static_cast<long long>(ctx->sm_count) * 4, (count + kBlock - 1) / kBlock)));
+          k_area_slots<OP, 4><<<grid4, kBlock, smem4, ctx->stream>>>(map->view, poly_dev, nv, src, out, rows_cap, ctx->todo.as<unsigned int>(),
+                                                                    ctx->todo_count.as<unsigned int>(), ctx->todo2.as<unsigned int>(),
+                                                                    ctx->todo2_count.as<unsigned int>());
+          ++ctx->launches;
+          second_list = true;
+        }
       }
     }
     ++ctx->launches;
-    todo = ctx->todo.as<unsigned int>();
-    todo_count = ctx->todo_count.as<unsigned int>();
+    todo = second_list ? ctx->todo2.as<unsigned int>() : ctx->todo.as<unsigned int>();
+    todo_count = second_list ? ctx->todo2_count.as<unsigned int>() : ctx->todo_count.as<unsigned int>();
   }
   // A convex polygon defers (almost) nothing: a small persistent grid is enough to drain the list.
   const bool small_drain = fast && is_convex(poly_host, nv);
@@ -1871,7 +2089,7 @@ void cover_ctx_destroy(cover_ctx* ctx) {
   Bind bind(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (DeviceBuffer* b : {&ctx->poses, &ctx->theta, &ctx->poly, &ctx->in_a, &ctx->in_b, &ctx->out_free, &ctx->out_cost, &ctx->out_status, &ctx->out_bits, &ctx->out_not_ok,
-                          &ctx->todo, &ctx->todo_count, &ctx->list_cnt, &ctx->list_rng, &ctx->list_seq})
+                          &ctx->todo, &ctx->todo_count, &ctx->todo2, &ctx->todo2_count, &ctx->list_cnt, &ctx->list_rng, &ctx->list_seq})
     b->release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
