@@ -186,7 +186,7 @@ def recorded_traffic():
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(path):
         try:
-            return json.load(open(path)).get("k_area_lattice_free_dram_bytes_per_launch")
+            return json.load(open(path)).get("k_area_lattice_is_free_dram_bytes_per_launch")
         except Exception:
             return None
     return None
@@ -308,7 +308,7 @@ def run_gpu(args) -> None:
         peak, peak_kind = measured_peak()
         roofline = None
         if cells_per_pose is not None:
-            # dominant kernel = k_area_lattice_free: one launch per step (+ a ~3 us drain launch); its duration ~ the step's event time
+            # dominant kernel = k_area_lattice<OP_IS_FREE>: one launch per step (+ a ~3 us drain launch); its duration ~ the step's event time
             alg_bytes = (cells_per_pose + B_OUT) * n_poses
             achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
