@@ -1443,10 +1443,20 @@ struct SplitView {
 };
 
 /// continuous_footprint::is_free(pose, map) — footprints.cpp:130-196.
+/// Sink that feeds outline cells into a SlotWalker (per-thread walk, no lock-step).
+struct SlotSink {
+  SlotWalker<4>& w;
+  __device__ __forceinline__ bool cell(int x, int y) {
+    w.visit(x, y);
+    return true;
+  }
+};
+
 __global__ void __launch_bounds__(kBlock) k_split(MapView m, SplitView fp, int n_vertices_total, PoseSource src, long long count,
-                                                 OutView out, ListScratch scratch) {
+                                                 OutView out, ListScratch scratch, int slot_rows) {
   extern __shared__ double smem_d[];
   const double* xy = stage_polygon(fp.xy, n_vertices_total, smem_d);
+  uint32_t* slot_table = reinterpret_cast<uint32_t*>(smem_d + 2 * n_vertices_total);  // [slot_rows][4][blockDim.x], 0 rows = disabled
   const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long me = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   for (long long i = me; i < count; i += nthreads) {
@@ -1484,6 +1494,60 @@ __global__ void __launch_bounds__(kBlock) k_split(MapView m, SplitView fp, int n
         if (rows > scratch.rows_cap) {
           status = ST_COORD_RANGE;
           break;
+        }
+        if (rows <= slot_rows && (x1 - x0) <= 65000) {
+          // fast attempt: four ranges per row in shared memory (most remainder areas need no more); on overflow the
+          // sub-polygon is redone below with the sorted lists in global scratch
+          SlotWalker<4> w;
+          w.tab = slot_table + threadIdx.x, w.stride = static_cast<int>(blockDim.x), w.xb = x0, w.yb = y0;
+          for (int r = 0; r < rows; ++r)
+            for (int q = 0; q < 4; ++q) w.slot(r, q) = kPairEmpty;
+          int fx, fy;
+          to_cell<XF_PATH_B>(T, poly[0], poly[1], m, fx, fy);
+          w.y_run = w.y0 = fy, w.x_first = w.x0 = w.x_prev = fx, w.y_before = fy;
+          w.in_first = true, w.overflow = false, w.f_xlast = fx, w.f_ynext = fy;
+          SlotSink sink{w};
+          walk_outline<XF_PATH_B>(poly, nv, T, m, sink);
+          if (w.in_first) {  // every cell on one row
+            const uint32_t wd = static_cast<uint32_t>(x1 - x0);
+            w.slot(w.y0 - y0, 0) = 0u, w.slot(w.y0 - y0, 1) = wd | (wd << 16);
+          } else if (w.y_run == w.y0) {
+            w.prepend(w.y0, w.x_first, w.f_xlast, w.y_before, w.f_ynext);
+          } else {
+            w.append(w.y_run, w.x_first, w.x_prev, w.y_before, w.y0);
+            w.prepend(w.y0, w.x0, w.f_xlast, w.y_run, w.f_ynext);
+          }
+          if (!w.overflow) {
+            bool odd = false;
+            for (int r = 0; r < rows; ++r) odd |= (w.count(r) & 1) != 0;
+            if (odd) {
+              status = ST_LOGIC_ERROR;
+              break;
+            }
+            Fold<OP_IS_FREE> fold;
+            bool more = true;
+            for (int r = 0; r < rows && more; ++r) {
+              uint32_t e[4];
+              for (int q = 0; q < 4; ++q) e[q] = w.slot(r, q);
+              if (e[2] != kPairEmpty) {
+#pragma unroll
+                for (int a = 1; a < 4; ++a)
+#pragma unroll
+                  for (int b = a; b > 0; --b)
+                    if ((e[b] & 0xFFFFu) < (e[b - 1] & 0xFFFFu)) {
+                      const uint32_t t = e[b];
+                      e[b] = e[b - 1], e[b - 1] = t;
+                    }
+                more = fold.span(m, y0 + r, x0 + static_cast<int>(e[0] & 0xFFFFu), x0 + static_cast<int>(e[1] >> 16));
+                if (more) more = fold.span(m, y0 + r, x0 + static_cast<int>(e[2] & 0xFFFFu), x0 + static_cast<int>(e[3] >> 16));
+              } else if (e[0] != kPairEmpty) {
+                const int lo1 = e[0] & 0xFFFF, hi1 = e[0] >> 16, lo2 = e[1] & 0xFFFF, hi2 = e[1] >> 16;
+                more = fold.span(m, y0 + r, x0 + min(lo1, lo2), x0 + (lo2 < lo1 ? hi1 : hi2));
+              }
+            }
+            free_ = !fold.hit;
+            continue;
+          }
         }
         ListStore store{scratch.cnt, scratch.rng, scratch.seq, nthreads, me, y0, scratch.rows_cap};
         store.clear(rows);
@@ -2490,8 +2554,9 @@ int cover_split_is_free(cover_ctx* ctx, const cover_map* map, const cover_split*
     rc = ensure_list_scratch(ctx, rows_cap, static_cast<long long>(grid) * kBlock, scratch);
     if (rc) return rc;
     const SplitView view{split->xy, split->starts, split->n_outlines, split->n_areas};
-    k_split<<<grid, kBlock, static_cast<size_t>(split->n_vertices) * 2 * sizeof(double), ctx->stream>>>(map->view, view, split->n_vertices,
-                                                                                                      src, poses->count, st.dev, scratch);
+    const int slot_rows = rows_cap <= 48 ? rows_cap : 0;  // shared-memory 4-range table: rows x 4 x 128 threads x 4 B
+    const size_t smem = static_cast<size_t>(split->n_vertices) * 2 * sizeof(double) + static_cast<size_t>(slot_rows) * 4 * kBlock * sizeof(uint32_t);
+    k_split<<<grid, kBlock, smem, ctx->stream>>>(map->view, view, split->n_vertices, src, poses->count, st.dev, scratch, slot_rows);
     ++ctx->launches;
   }
   return finish_out(ctx, st, poses->count);
