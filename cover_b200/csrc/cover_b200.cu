@@ -1400,12 +1400,16 @@ __global__ void __launch_bounds__(kBlock) k_cells_free(MapView m, const int4* __
 /// irrelevant: at upload the host turned each footprint's cell SET into row spans {y, x_lo, x_hi}
 /// ("the polygon split precomputed once on the host per footprint"), which are scanned 4 cells per word.
 __global__ void __launch_bounds__(kBlock) k_footprints(MapView m, const int4* __restrict__ spans, const int2* __restrict__ ranges,
-                                                      const int2* __restrict__ offsets, const int* __restrict__ which, long long count,
-                                                      OutView out) {
+                                                      int n_footprints, const int2* __restrict__ offsets, const int* __restrict__ which,
+                                                      long long count, OutView out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const int2 off = __ldg(offsets + i);
   const int k = which ? __ldg(which + i) : 0;
+  if (static_cast<unsigned>(k) >= static_cast<unsigned>(n_footprints)) {  // (device-resident `which` cannot be validated on the host)
+    store_failure(out, i, ST_COORD_RANGE);
+    return;
+  }
   const int2 o_rng = __ldg(ranges + 2 * k), a_rng = __ldg(ranges + 2 * k + 1);  // [begin, end) of outline / area spans
   bool hit = false;
   for (int j = o_rng.x; j < o_rng.y && !hit; ++j) {
@@ -2486,7 +2490,7 @@ int cover_footprints_is_free(cover_ctx* ctx, const cover_map* map, const cover_f
     if (rc) return rc;
   }
   if (count) {
-    k_footprints<<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, fps->spans, fps->ranges, reinterpret_cast<const int2*>(off_dev),
+    k_footprints<<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, fps->spans, fps->ranges, fps->n, reinterpret_cast<const int2*>(off_dev),
                                                              which_dev, count, st.dev);
     ++ctx->launches;
   }

@@ -185,7 +185,8 @@ int cover_cells_max_cost(cover_ctx* ctx, const cover_map* map, const cover_cells
  * src/cover/footprints.cpp:214-247.  A BANK of n_footprints footprints (one per heading bin):
  * footprint k owns outline cells [o_starts[k], o_starts[k+1]) (checked for 253 or 254) and area cells
  * [a_starts[k], a_starts[k+1]) (checked for 254); a cell outside the map collides.
- * `which` (count int32, NULL = all 0) selects the footprint of each offset. */
+ * `which` (count int32, NULL = all 0) selects the footprint of each offset; an index outside [0, n_footprints)
+ * is rejected with COVER_E_INVALID_ARG for host arrays and gives status COVER_STATUS_COORD_RANGE for device arrays. */
 int cover_footprints_create(cover_ctx* ctx, const int32_t* outline_cells, const int64_t* o_starts, const int32_t* area_cells,
                             const int64_t* a_starts, int32_t n_footprints, cover_footprints** out);
 void cover_footprints_destroy(cover_footprints* fps);
