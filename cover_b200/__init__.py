@@ -181,6 +181,12 @@ class Context:
     def synchronize(self):
         self._check(self._lib.cover_ctx_synchronize(self._h))
 
+    def probe_read_bandwidth(self, nbytes: int, reps: int = 20) -> float:
+        """Best-of-10 streaming read bandwidth in GB/s over a scratch buffer (16 MB: L2 -> SM path; 1 GB: HBM)."""
+        gbs = C.c_double(0.0)
+        self._check(self._lib.cover_probe_read_bandwidth(self._h, C.c_int64(nbytes), C.c_int32(reps), C.byref(gbs)))
+        return float(gbs.value)
+
     def _check(self, rc: int):
         if rc != 0:
             raise CoverError(rc, self._lib.cover_last_error(self._h).decode())

@@ -1339,6 +1339,19 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_area_rows_multi(MapView m, 
   }
 }
 
+
+/// Streaming 16-byte-vector read of a buffer (bandwidth probe: 16 MB stays in L2, 1 GB streams from HBM).
+__global__ void __launch_bounds__(256) k_probe_read(const uint4* __restrict__ buf, long long n_vec, int reps, unsigned int* __restrict__ sink) {
+  unsigned int acc = 0;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (int r = 0; r < reps; ++r)
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+      const uint4 v = __ldcg(buf + i);  // cache at L2 only: every pass really crosses the L2 -> SM path
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+  if (acc == 0x9E3779B9u) *sink = acc;  // keeps the loads alive
+}
+
 template <int OP>
 __global__ void __launch_bounds__(kBlock) k_rays(MapView m, const int4* __restrict__ segments, long long count, int offx, int offy,
                                                 OutView out) {
@@ -2220,6 +2233,36 @@ int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x
   CU(cudaMemcpy2DAsync(map->dev + static_cast<size_t>(y0) * v.pitch + x0, v.pitch, full_image + static_cast<size_t>(y0) * v.size_x + x0,
                        v.size_x, w, h, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return COVER_OK;
+}
+
+int cover_probe_read_bandwidth(cover_ctx* ctx, int64_t bytes, int32_t reps, double* gb_per_s) {
+  if (!ctx || !gb_per_s || bytes < 4096 || reps < 1) return COVER_E_INVALID_ARG;
+  Bind bind(ctx->device);
+  const long long n_vec = bytes / 16;
+  CU(ctx->list_rng.ensure(static_cast<size_t>(n_vec) * 16 + 16));
+  CU(cudaMemsetAsync(ctx->list_rng.ptr, 1, static_cast<size_t>(n_vec) * 16, ctx->stream));
+  unsigned int* sink = reinterpret_cast<unsigned int*>(static_cast<char*>(ctx->list_rng.ptr) + n_vec * 16);
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  const unsigned int grid = static_cast<unsigned int>(ctx->sm_count * 8);
+  k_probe_read<<<grid, 256, 0, ctx->stream>>>(ctx->list_rng.as<uint4>(), n_vec, 2, sink);  // warm-up (fills the L2)
+  double best = 0;
+  for (int t = 0; t < 10; ++t) {  // best of 10
+    cudaEventRecord(e0, ctx->stream);
+    k_probe_read<<<grid, 256, 0, ctx->stream>>>(ctx->list_rng.as<uint4>(), n_vec, reps, sink);
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms > 0) best = std::max(best, static_cast<double>(n_vec) * 16 * reps / (ms * 1e-3) / 1e9);
+  }
+  ctx->launches += 11;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CU(cudaGetLastError());
+  *gb_per_s = best;
   return COVER_OK;
 }
 

@@ -102,6 +102,11 @@ int cover_ctx_synchronize(cover_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t cover_ctx_launch_count(const cover_ctx* ctx);
 
+/* Measurement helper: best-of-10 streaming read bandwidth (16-byte vectors, L1 bypassed) over a scratch buffer of
+ * `bytes`, `reps` passes per launch.  16 MB measures the L2 -> SM path (the buffer stays in the 126 MB L2), 1 GB the
+ * HBM.  bench.py reports the costmap kernels against both. */
+int cover_probe_read_bandwidth(cover_ctx* ctx, int64_t bytes, int32_t reps, double* gb_per_s);
+
 /* ---- costmap: stands in for `const costmap_2d::Costmap2D&` ----------------------------------------
  * size/resolution/origin = getSizeInCellsX/Y, getResolution, getOriginX/Y; bytes = getCharMap(),
  * row-major, index = y*size_x + x (call sites src/cover/costmap.hpp:52,89,105,122).
