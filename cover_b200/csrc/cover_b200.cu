@@ -722,56 +722,129 @@ __device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ vert
 }
 
 
-/// accumulate_cost / max_cost for one group of the lattice kernel (all needed cells inside the map): per scan row
-/// the warp stages the 96-byte row segment in shared memory (one byte per lane and piece, coalesced loads), then
-/// every pose folds its own window [off, off + width) word by word — 4 cells per 32-bit shared-memory load, in x
-/// order, so accumulate_cost's "first negative value in generator order" rule is kept (rows ascend, x ascends).
+/// accumulate_cost / max_cost for one group of the lattice kernel (all needed cells inside the map).  Per scan
+/// row the warp loads the 96-byte row segment (one byte per lane and piece, coalesced) and turns it into a
+/// structure every pose can query in O(1) for ITS window [off, off + width):
+///   accumulate_cost: exclusive prefix sums of (cost, #cells >= 254) packed in one word (warp scans) — a window
+///                    without LETHAL / NO_INFORMATION cells costs two shared-memory reads and a subtraction; a
+///                    window with one walks its bytes in x order (rows ascend, x ascends: the reference's "first
+///                    negative value in generator order" rule);
+///   max_cost:        sliding-window maxima by doubling (level k holds max over 2^k cells, built with shuffles),
+///                    window max = max(L_k[off], L_k[off + width - 2^k]) with 2^k <= width.
 template <int OP>
 __device__ __forceinline__ void lattice_rows_fold(const MapView& m, const int* __restrict__ row_a, const uint32_t* __restrict__ row_m, int rows,
                                                   int x_base, int y_base, int lane, bool third, int off_a, int off_b, uint8_t* rowbuf,
                                                   Fold<OP>& fa, Fold<OP>& fb) {
-  const uint8_t* __restrict__ p = m.data + static_cast<size_t>(y_base) * m.pitch + (x_base + lane);
-  const uint32_t* buf32 = reinterpret_cast<const uint32_t*>(rowbuf);
-  bool more_a = true, more_b = true;
-  for (int r = 0; r < rows; ++r) {
-    const uint8_t* __restrict__ q = p + row_a[r];
-    const uint8_t b0 = __ldg(q), b1 = __ldg(q + 32), b2 = third ? __ldg(q + 64) : static_cast<uint8_t>(0);
-    __syncwarp();
-    rowbuf[lane] = b0, rowbuf[32 + lane] = b1, rowbuf[64 + lane] = b2;
-    __syncwarp();
-    const int width = __popc(row_m[r]);
-    if (width == 0) continue;
+  uint32_t* table = reinterpret_cast<uint32_t*>(rowbuf);  // 2 x 100 words: prefix tables (accumulate) / window-max level (max)
+  if constexpr (OP == OP_ACCUMULATE) {
+    bool more_a = true, more_b = true;
+    // lane l owns the three consecutive cells 3l .. 3l+2 of the segment: one warp scan of the per-lane totals
+    // gives all 97 exclusive prefixes.  Packed value: low 16 bits cost (<= 96 * 255 in total), high bits the
+    // number of cells >= 254.
+    const uint8_t* __restrict__ p3 = m.data + static_cast<size_t>(y_base) * m.pitch + (x_base + 3 * lane);
+    const int n_cells = third ? 96 : 64;  // cells 64.. are never part of a window when no offset reaches 32
+    uint32_t sum_a = 0, sum_b = 0;
+    // two scan rows per trip: their load -> scan -> table chains are independent and overlap
+    for (int r = 0; r < rows; r += 2) {
+      int width[2];
+      uint32_t v0[2], v1[2], v2[2], s[2];
 #pragma unroll
-    for (int plane = 0; plane < 2; ++plane) {
-      const int lo = plane ? off_b : off_a, hi = lo + width - 1;
-      Fold<OP>& f = plane ? fb : fa;
-      bool& more = plane ? more_b : more_a;
-      const int w0 = lo >> 2, last = (hi >> 2) - w0;
-      const uint32_t keep_first = 0xFFFFFFFFu << (8 * (lo & 3)), keep_last = 0xFFFFFFFFu >> (8 * (3 - (hi & 3)));
+      for (int u = 0; u < 2; ++u) {
+        const bool live = r + u < rows;
+        width[u] = live ? __popc(row_m[r + u]) : 0;
+        const uint8_t* __restrict__ q = p3 + (live ? row_a[r + u] : 0);
+        v0[u] = v1[u] = v2[u] = 0;
+        if (live && 3 * lane < n_cells) v0[u] = __ldg(q), v1[u] = __ldg(q + 1), v2[u] = __ldg(q + 2);  // 64 = 3 * 21 + 1: lane 21 reads two cells more, still inside the segment
+      }
 #pragma unroll
-      for (int j = 0; j < 9; ++j) {  // width <= 32 cells: at most 9 words
-        if (more && j <= last) {
-          uint32_t u = buf32[w0 + j];
-          if (j == 0) u &= keep_first;
-          if (j == last) u &= keep_last;
-          if constexpr (OP == OP_MAX) {
-            f.best4 = __vmaxu4(f.best4, u);
-          } else if constexpr (OP == OP_ACCUMULATE) {
-            if (zero_bytes(~(u | 0x01010101u))) {  // some cell is LETHAL or NO_INFORMATION: the first one in x order wins
-              for (int b = 0; b < 4 && more; ++b) {
-                const uint32_t c = (u >> (8 * b)) & 0xFFu;
-                if (c >= static_cast<uint32_t>(kLethal)) {
-                  f.early = c == static_cast<uint32_t>(kLethal) ? -1 : -2;
-                  more = false;
-                } else {
-                  f.sum += c;
-                }
+      for (int u = 0; u < 2; ++u) {
+        v0[u] |= ((v0[u] + 2u) << 8) & 0x10000u;
+        v1[u] |= ((v1[u] + 2u) << 8) & 0x10000u;
+        v2[u] |= ((v2[u] + 2u) << 8) & 0x10000u;
+        s[u] = v0[u] + v1[u] + v2[u];
+      }
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t ua = __shfl_up_sync(kFull, s[0], d), ub = __shfl_up_sync(kFull, s[1], d);
+        if (lane >= d) s[0] += ua, s[1] += ub;
+      }
+      __syncwarp();  // the previous trip's queries are done
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        uint32_t* t = table + u * 100;
+        const uint32_t e = s[u] - (v0[u] + v1[u] + v2[u]);
+        t[3 * lane] = e, t[3 * lane + 1] = e + v0[u], t[3 * lane + 2] = e + v0[u] + v1[u];
+        if (lane == 31) t[96] = s[u];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t* t = table + u * 100;
+#pragma unroll
+        for (int plane = 0; plane < 2; ++plane) {
+          const int off = plane ? off_b : off_a;
+          Fold<OP>& f = plane ? fb : fa;
+          bool& more = plane ? more_b : more_a;
+          uint32_t& sum = plane ? sum_b : sum_a;
+          const uint32_t d = t[off + width[u]] - t[off];
+          sum += d;  // (meaningless once a sentinel was met: `early` decides then)
+          if ((d >> 16) != 0u && more) {  // the window holds a LETHAL / NO_INFORMATION cell: the first one in x order ends the walk
+            const uint8_t* __restrict__ w = m.data + static_cast<size_t>(y_base) * m.pitch + x_base + row_a[r + u];
+            for (int x = off; x < off + width[u]; ++x) {
+              const int c = __ldg(w + x);
+              if (c >= kLethal) {
+                f.early = c == kLethal ? -1 : -2;
+                break;
               }
-            } else {
-              f.sum += __dp4a(u, 0x01010101u, 0u);
             }
+            more = false;
           }
         }
+      }
+    }
+    fa.sum += sum_a, fb.sum += sum_b;
+  } else {  // OP_MAX
+    const uint8_t* __restrict__ p = m.data + static_cast<size_t>(y_base) * m.pitch + (x_base + lane);
+    for (int r = 0; r < rows; r += 2) {  // two scan rows per trip (independent chains)
+      int width[2], k[2];
+      uint32_t l0[2], l1[2], l2[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const bool live = r + u < rows;
+        width[u] = live ? __popc(row_m[r + u]) : 0;
+        k[u] = 31 - __clz(width[u] | 1);  // 2^k <= width
+        const uint8_t* __restrict__ q = p + (live ? row_a[r + u] : 0);
+        l0[u] = __ldg(q), l1[u] = __ldg(q + 32), l2[u] = third ? __ldg(q + 64) : 0u;
+      }
+      const int k_max = max(k[0], k[1]);
+      for (int j = 0; j < k_max; ++j) {  // level j+1: max over 2^(j+1) cells starting at each position
+        const int d = 1 << j;
+        const bool wraps = lane + d >= 32;  // the partner cell lies in the next 32-cell piece
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t n0 = __shfl_down_sync(kFull, l0[u], d), n1 = __shfl_down_sync(kFull, l1[u], d), n2 = __shfl_down_sync(kFull, l2[u], d);
+          const uint32_t w1 = __shfl_sync(kFull, l1[u], (lane + d) & 31), w2 = __shfl_sync(kFull, l2[u], (lane + d) & 31);
+          if (j < k[u]) {
+            l0[u] = max(l0[u], wraps ? w1 : n0);
+            l1[u] = max(l1[u], wraps ? w2 : n1);
+            l2[u] = max(l2[u], wraps ? 0u : n2);
+          }
+        }
+      }
+      __syncwarp();  // the previous trip's queries are done
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        uint32_t* t = table + u * 100;
+        t[lane] = l0[u], t[32 + lane] = l1[u], t[64 + lane] = l2[u];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (width[u] == 0) continue;
+        const uint32_t* t = table + u * 100;
+        const int tail = width[u] - (1 << k[u]);
+        fa.best4 = max(fa.best4, max(t[off_a], t[off_a + tail]));
+        fb.best4 = max(fb.best4, max(t[off_b], t[off_b + tail]));
       }
     }
   }
@@ -803,7 +876,7 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
   int* row_a = reinterpret_cast<int*>(canon + kLatSlots * nv);                          // [slot][row] first cell of the range
   uint32_t* row_m = reinterpret_cast<uint32_t*>(row_a + kLatSlots * rows_cap);          // [slot][row] width mask (0 = no range)
   LatShape* meta = reinterpret_cast<LatShape*>(row_m + kLatSlots * rows_cap);           // [slot]
-  uint8_t* rowbufs = reinterpret_cast<uint8_t*>(meta + kLatSlots);                      // [warp][96 (+32 pad)] staged row bytes
+  uint8_t* rowbufs = reinterpret_cast<uint8_t*>(meta + kLatSlots);                      // [warp][800]: per-row query tables of the value folds
   if (threadIdx.x < kLatSlots) {
     slot_key[threadIdx.x] = 0ull;
     meta[threadIdx.x].status = kLatPending;
@@ -811,7 +884,7 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* rowbuf = rowbufs + warp * 128;
+  uint8_t* rowbuf = rowbufs + warp * 800;
   const bool exact_key = nv <= 4;  // 2 x 3 offsets of 8 bits: the key IS the shape, no verification pass
   const long long chunk = (g.n_units + gridDim.x - 1) / gridDim.x;
   const long long unit_begin = blockIdx.x * chunk, unit_end = min(g.n_units, unit_begin + chunk);
@@ -1920,7 +1993,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       g.n_units = static_cast<long long>((g.n_rows + kLatRows - 1) / kLatRows) * g.segs;
       const size_t smem = poly_bytes + kLatSlots * (sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) +
                                                      static_cast<size_t>(rows_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape)) +
-                          kLatWarps * 128;
+                          kLatWarps * 800;
       const unsigned int grid = static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_MIN_BLOCKS));
       k_area_lattice<OP><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
                                                                    ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g);
