@@ -268,13 +268,19 @@ def run_gpu(args) -> None:
     host_out = cover_b200.Result(free_bits=host_bits.numpy().view(np.uint32), not_ok=host_not_ok.numpy())
     map_np = pinned_map.numpy()
 
-    def e2e_step():
-        cmap.upload(map_np)                                  # H2D: this planning cycle's costmap (16 MB)
-        # lattice descriptor in; bit-packed verdicts (12.5 MB) + the not-OK counter out (D2H)
+    def e2e_step(image=map_np):
+        # H2D: this planning cycle's costmap (16 MB), queued as row bands; the sweep below starts on the first
+        # bands while the rest is in flight (cover_map_upload_async)
+        cmap.upload_async(image)
+        # lattice descriptor in; bit-packed verdicts (12.5 MB) + the not-OK counter out (D2H); returns when they are on the host
         cmap.area_is_free(wl.RECT, lat, out=host_out)
 
     e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(2):
+    # warm-up, and a check that every step really sees ITS upload: an empty map first (everything free) ...
+    empty_map = torch.zeros_like(pinned_map).pin_memory().numpy()
+    e2e_step(empty_map)
+    assert bool(host_out.unpack_bits(n_poses).all()), "e2e: the sweep did not see the freshly uploaded (empty) costmap"
+    for _ in range(2):  # ... then the real one (compared with the device-resident arm after the timed steps)
         e2e_step()
     barrier()
     t0 = time.perf_counter()

@@ -279,6 +279,16 @@ class Costmap:
                 raise ValueError("costmap shape mismatch")
             self.ctx._check(self.ctx._lib.cover_map_upload(self._h, C.c_void_p(arr.ctypes.data), C.c_int32(_MEM_HOST)))
 
+    def upload_async(self, data: np.ndarray):
+        """Queue a full re-upload from HOST memory and return at once (cover_map_upload_async): the copy runs as row
+        bands on a second stream and later checks start as soon as the bands they need have landed.  `data` (uint8
+        [size_y, size_x], C-contiguous; page-locked for a truly asynchronous copy) must stay alive and unchanged
+        until the next call that returns results to the host, or `Context.synchronize()`."""
+        if not isinstance(data, np.ndarray) or data.dtype != np.uint8 or not data.flags.c_contiguous or data.shape != (self.size_y, self.size_x):
+            raise ValueError("upload_async needs a C-contiguous uint8 [size_y, size_x] numpy array (no conversion copy is made)")
+        self._pending_upload = data  # keep the buffer alive while the copy is in flight
+        self.ctx._check(self.ctx._lib.cover_map_upload_async(self._h, C.c_void_p(data.ctypes.data)))
+
     def upload_window(self, full_image: np.ndarray, x0: int, y0: int, w: int, h: int):
         arr = np.ascontiguousarray(full_image, dtype=np.uint8)
         if arr.shape != (self.size_y, self.size_x):

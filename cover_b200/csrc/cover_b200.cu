@@ -850,18 +850,15 @@ __device__ __forceinline__ void lattice_rows_fold(const MapView& m, const int* _
   }
 }
 
-/// Bit-packed verdicts of one plane of a group (consecutive pose indices: at most two output words).
-__device__ __forceinline__ void lat_store_bits(const OutView& out, unsigned grp, bool fits, bool is_free, long long i, int lane) {
-  if (grp == 0u) return;
-  const int gl = __ffs(grp) - 1;
-  const long long w = i >> 5, wl = __shfl_sync(kFull, w, gl);
-  const uint32_t bit = (fits && is_free) ? (1u << (i & 31)) : 0u;
-  const uint32_t lo_word = __reduce_or_sync(kFull, (fits && w == wl) ? bit : 0u);
-  const uint32_t hi_word = __reduce_or_sync(kFull, (fits && w != wl) ? bit : 0u);
-  if (lane == gl) {
-    if (lo_word) atomicOr(out.free_bits + wl, lo_word);
-    if (hi_word) atomicOr(out.free_bits + wl + 1, hi_word);
-  }
+/// Bit-packed verdicts of one plane of a lattice row: lane l holds pose `base + l`, so the plane's 32 verdicts are
+/// one ballot word, OR-ed into at most two output words (shared with the neighbouring planes, hence atomic).
+__device__ __forceinline__ void lat_store_bits(const OutView& out, uint32_t free_mask, long long base, int lane) {
+  if (lane != 0 || free_mask == 0u) return;
+  const long long w = base >> 5;  // (arithmetic shift: base may be negative for a plane that straddles `first`)
+  const int sh = static_cast<int>(base & 31);
+  const uint32_t lo_word = free_mask << sh, hi_word = sh ? free_mask >> (32 - sh) : 0u;
+  if (lo_word) atomicOr(out.free_bits + w, lo_word);
+  if (hi_word) atomicOr(out.free_bits + w + 1, hi_word);
 }
 
 template <int OP>
@@ -1064,6 +1061,7 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
       // ---- up to 64 x-adjacent poses per 96-cell bit window -------------------------------------------
       const bool go_a = slot_a >= 0 && st_a == ST_OK, go_b = slot_b >= 0 && st_b == ST_OK;
       pend_a = __ballot_sync(kFull, go_a), pend_b = __ballot_sync(kFull, go_b);
+      uint32_t free_a = 0u, free_b = 0u;  // OP_IS_FREE: the row's verdicts, one bit per lane and plane
       while (pend_a | pend_b) {
         const bool from_a = pend_a != 0u;
         const int leader = __ffs(from_a ? pend_a : pend_b) - 1;
@@ -1093,10 +1091,8 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
             if (out.is_free) out.is_free[i_b] = hit_b ? 0 : 1;
             if (out.status) out.status[i_b] = ST_OK;
           }
-          if (out.free_bits) {
-            lat_store_bits(out, grp_a, fits_a, hit_a == 0u, i_a, lane);
-            lat_store_bits(out, grp_b, fits_b, hit_b == 0u, i_b, lane);
-          }
+          free_a |= __ballot_sync(kFull, fits_a && hit_a == 0u);
+          free_b |= __ballot_sync(kFull, fits_b && hit_b == 0u);
         } else if (inside) {  // (discarded for OP_IS_FREE: the whole else-chain hangs off an `if constexpr`)
           Fold<OP> fa, fb;
           lattice_rows_fold<OP>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, ob, rowbuf, fa, fb);
@@ -1114,6 +1110,12 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
         }
         pend_a &= ~grp_a;
         pend_b &= ~grp_b;
+      }
+      if constexpr (OP == OP_IS_FREE) {
+        if (out.free_bits) {
+          lat_store_bits(out, free_a, i_a - lane, lane);
+          lat_store_bits(out, free_b, i_b - lane, lane);
+        }
       }
     }
   }
@@ -1691,6 +1693,8 @@ struct cover_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // banded costmap uploads (cover_map_upload_async) overlap the kernels of `stream`
+  cudaEvent_t fence = nullptr;         // "everything queued on `stream` so far": what a banded upload has to wait for
   std::string error;
   int64_t launches = 0;
   bool disable_lattice_kernel = false;
@@ -1700,11 +1704,23 @@ struct cover_ctx {
   DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, todo2, todo2_count, list_cnt, list_rng, list_seq;
 };
 
+constexpr int kMapBands = 32;
+
 struct cover_map {
   cover_ctx* ctx;
   MapView view;
   uint8_t* dev;
   double resolution;
+  // cover_map_upload_async: the image travels as kMapBands row bands on ctx->copy_stream, one event per band, the
+  // bands the last lattice sweep read first.  While `bands_pending`, every reader of the map is first ordered (on
+  // the device) after the bands it can touch: a lattice sweep after the bands under its pose window, anything else
+  // after the whole image.
+  cudaEvent_t band_done[kMapBands] = {};
+  int band_rows = 0;
+  int issue_pos[kMapBands] = {};  // position of each band in the copy order of the upload in flight
+  int last_band = kMapBands - 1;  // the band copied last
+  mutable bool bands_pending = false;
+  mutable int hint_lo = 0, hint_hi = -1;  // bands the last lattice sweep needed
 };
 
 struct cover_cells {
@@ -1801,6 +1817,42 @@ int stage_out(cover_ctx* ctx, const cover_results* out, int64_t count, OutStage&
     st.dev.not_ok = ctx->out_not_ok.as<unsigned long long>();
   }
   return COVER_OK;
+}
+
+/// Orders `ctx->stream` after an upload that is still in flight on the copy stream (all bands).
+cudaError_t map_ready(cover_ctx* ctx, const cover_map* map) {
+  if (!map->bands_pending) return cudaSuccess;
+  map->bands_pending = false;
+  return cudaStreamWaitEvent(ctx->stream, map->band_done[map->last_band], 0);
+}
+
+/// Same for a reader that touches map rows [row_lo, row_hi] only (rows outside the map are never read).
+cudaError_t map_rows_ready(cover_ctx* ctx, const cover_map* map, long long row_lo, long long row_hi) {
+  if (!map->bands_pending) return cudaSuccess;
+  row_lo = std::max<long long>(row_lo, 0), row_hi = std::min<long long>(row_hi, map->view.size_y - 1);
+  if (row_lo > row_hi) return cudaSuccess;
+  const int b_lo = static_cast<int>(row_lo / map->band_rows), b_hi = static_cast<int>(row_hi / map->band_rows);
+  int latest = b_lo;  // the copy stream is in order: the band issued last among the needed ones covers them all
+  for (int b = b_lo; b <= b_hi; ++b)
+    if (map->issue_pos[b] > map->issue_pos[latest]) latest = b;
+  map->hint_lo = b_lo, map->hint_hi = b_hi;
+  if (latest == map->last_band) map->bands_pending = false;
+  return cudaStreamWaitEvent(ctx->stream, map->band_done[latest], 0);
+}
+
+/// A polygon check over a pose lattice reads map rows under the lattice's y-extent (+ the footprint radius) only.
+cudaError_t lattice_rows_ready(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int nv, const cover_poses* poses) {
+  if (!map->bands_pending) return cudaSuccess;
+  const cover_lattice& L = poses->lattice;
+  double radius = 0, scale = 0;
+  for (int v = 0; v < nv; ++v) radius = std::max(radius, std::hypot(polygon_xy[2 * v], polygon_xy[2 * v + 1]));
+  for (int t = 0; t < L.ntheta; ++t) scale = std::max(scale, std::hypot(L.cs[2 * t], L.cs[2 * t + 1]));  // |(c,s)| need not be 1
+  const double reach = radius * scale;
+  const double ya = L.y0, yb = L.y0 + static_cast<double>(L.ny - 1) * L.dy;
+  const double lo = (std::min(ya, yb) - reach - map->view.origin_y) * map->view.inv_res - 2.0;
+  const double hi = (std::max(ya, yb) + reach - map->view.origin_y) * map->view.inv_res + 2.0;
+  if (!(std::isfinite(lo) && std::isfinite(hi)) || lo < -1e15 || hi > 1e15) return map_ready(ctx, map);
+  return map_rows_ready(ctx, map, static_cast<long long>(std::floor(lo)), static_cast<long long>(std::ceil(hi)));
 }
 
 int finish_out(cover_ctx* ctx, const OutStage& st, int64_t count) {
@@ -1977,15 +2029,15 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   const unsigned int* todo = nullptr;
   const unsigned int* todo_count = nullptr;
   bool second_list = false;
+  // Lattice batches of small footprints: shape-deduplicating warp-cooperative kernel.
+  const bool lattice = fast && src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices &&
+                       rows_cap - 3 <= kLatMaxWidth && !ctx->disable_lattice_kernel;
   if (fast) {
     CU(ctx->todo.ensure(static_cast<size_t>(count) * sizeof(unsigned int)));
     CU(ctx->todo_count.ensure(sizeof(unsigned int)));
     CU(cudaMemsetAsync(ctx->todo_count.ptr, 0, sizeof(unsigned int), ctx->stream));
-    // Lattice batches of small footprints: shape-deduplicating warp-cooperative kernel.
-    const bool lattice = src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices &&
-                         rows_cap - 3 <= kLatMaxWidth && !ctx->disable_lattice_kernel;
     if (lattice) {
-      LatGeom g;
+      LatGeom g{};
       g.row_first = src.first / src.nx;
       const long long row_last = (src.first + count - 1) / src.nx;
       g.n_rows = static_cast<int>(row_last - g.row_first + 1);
@@ -1993,7 +2045,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       g.n_units = static_cast<long long>((g.n_rows + kLatRows - 1) / kLatRows) * g.segs;
       const size_t smem = poly_bytes + kLatSlots * (sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) +
                                                      static_cast<size_t>(rows_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape)) +
-                          kLatWarps * 800;
+                          (OP == OP_IS_FREE ? 0 : kLatWarps * 800);  // the value folds' per-warp query tables
       const unsigned int grid = static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_MIN_BLOCKS));
       k_area_lattice<OP><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
                                                                    ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g);
@@ -2060,6 +2112,9 @@ int polygon_check(cover_ctx* ctx, const cover_map* map, const double* polygon_xy
   CU(ctx->poly.ensure(std::max<size_t>(poly_bytes, 16)));
   if (poly_bytes) CU(cudaMemcpyAsync(ctx->poly.ptr, polygon_xy, poly_bytes, cudaMemcpyHostToDevice, ctx->stream));
   const double* pd = ctx->poly.as<double>();
+  // costmap upload still in flight: a lattice sweep starts as soon as the rows under its window have landed
+  if (poses->format == COVER_POSE_LATTICE && poses->lattice.cs) CU(lattice_rows_ready(ctx, map, polygon_xy, nv, poses));
+  else CU(map_ready(ctx, map));
   switch (op) {
     case OP_IS_FREE: rc = launch_polygon<OP_IS_FREE>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev); break;
     case OP_ACCUMULATE: rc = launch_polygon<OP_ACCUMULATE>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev); break;
@@ -2097,6 +2152,7 @@ int rays_check(cover_ctx* ctx, const cover_map* map, const int32_t* segments, in
   const int ox = offset ? offset[0] : 0, oy = offset ? offset[1] : 0;
   if (count) {
     const int4* seg = reinterpret_cast<const int4*>(dev);
+    CU(map_ready(ctx, map));
     if (op == OP_IS_FREE) k_rays<OP_IS_FREE><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, seg, count, ox, oy, st.dev);
     else if (op == OP_ACCUMULATE) k_rays<OP_ACCUMULATE><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, seg, count, ox, oy, st.dev);
     else k_rays<OP_MAX><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, seg, count, ox, oy, st.dev);
@@ -2119,6 +2175,7 @@ int cells_check(cover_ctx* ctx, const cover_map* map, const cover_cells* cells, 
   if (rc) return rc;
   if (count) {
     const int2* off = reinterpret_cast<const int2*>(dev);
+    CU(map_ready(ctx, map));
     if (op == OP_IS_FREE) k_cells_free<<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->spans, cells->n_spans, off, count, st.dev);
     else if (op == OP_ACCUMULATE) k_cells<OP_ACCUMULATE><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->dev, cells->n, off, count, st.dev);
     else k_cells<OP_MAX><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->dev, cells->n, off, count, st.dev);
@@ -2225,7 +2282,11 @@ int cover_ctx_create(int device, cover_ctx** out) {
   Bind bind(device);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || configure_kernels() != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->fence, cudaEventDisableTiming) != cudaSuccess) {
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
     return COVER_E_CUDA;
   }
@@ -2241,10 +2302,13 @@ int cover_ctx_create(int device, cover_ctx** out) {
 void cover_ctx_destroy(cover_ctx* ctx) {
   if (!ctx) return;
   Bind bind(ctx->device);
+  cudaStreamSynchronize(ctx->copy_stream);
   cudaStreamSynchronize(ctx->stream);
   for (DeviceBuffer* b : {&ctx->poses, &ctx->theta, &ctx->poly, &ctx->in_a, &ctx->in_b, &ctx->out_free, &ctx->out_cost, &ctx->out_status, &ctx->out_bits, &ctx->out_not_ok,
                           &ctx->todo, &ctx->todo_count, &ctx->todo2, &ctx->todo2_count, &ctx->list_cnt, &ctx->list_rng, &ctx->list_seq})
     b->release();
+  cudaEventDestroy(ctx->fence);
+  cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -2256,6 +2320,7 @@ int64_t cover_ctx_launch_count(const cover_ctx* ctx) { return ctx ? ctx->launche
 int cover_ctx_synchronize(cover_ctx* ctx) {
   if (!ctx) return COVER_E_INVALID_ARG;
   Bind bind(ctx->device);
+  CU(cudaStreamSynchronize(ctx->copy_stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return COVER_OK;
 }
@@ -2280,8 +2345,47 @@ int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double reso
   m->ctx = ctx;
   m->dev = dev;
   m->resolution = resolution;
+  m->band_rows = (size_y + kMapBands - 1) / kMapBands;
+  for (cudaEvent_t& e : m->band_done) {
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+      for (cudaEvent_t& d : m->band_done)
+        if (d) cudaEventDestroy(d);
+      cudaFree(dev);
+      delete m;
+      return fail(ctx, COVER_E_CUDA, "cudaEventCreate failed");
+    }
+  }
   m->view = MapView{dev, size_x, size_y, pitch, 1. / resolution, origin_x, origin_y};  // base.hpp:56: x * (1./res)
   *out = m;
+  return COVER_OK;
+}
+
+int cover_map_upload_async(cover_map* map, const uint8_t* host_data) {
+  if (!map || !host_data) return COVER_E_INVALID_ARG;
+  cover_ctx* ctx = map->ctx;
+  Bind bind(ctx->device);
+  const MapView& v = map->view;
+  // the copy may not overtake kernels already queued that still read (or an earlier call that writes) the map
+  CU(cudaEventRecord(ctx->fence, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->fence, 0));
+  // copy order: the bands the last lattice sweep needed first (a planner sweeps the same window every cycle)
+  int order[kMapBands], n = 0;
+  const bool hinted = map->hint_lo >= 0 && map->hint_hi < kMapBands && map->hint_lo <= map->hint_hi;
+  if (hinted)
+    for (int b = map->hint_lo; b <= map->hint_hi; ++b) order[n++] = b;
+  for (int b = 0; b < kMapBands; ++b)
+    if (!hinted || b < map->hint_lo || b > map->hint_hi) order[n++] = b;
+  for (int k = 0; k < kMapBands; ++k) {
+    const int b = order[k];
+    const int y0 = std::min<long long>(v.size_y, static_cast<long long>(b) * map->band_rows), y1 = std::min(v.size_y, y0 + map->band_rows);
+    if (y1 > y0)
+      CU(cudaMemcpy2DAsync(map->dev + static_cast<size_t>(y0) * v.pitch, v.pitch, host_data + static_cast<size_t>(y0) * v.size_x, v.size_x,
+                           v.size_x, y1 - y0, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(cudaEventRecord(map->band_done[b], ctx->copy_stream));
+    map->issue_pos[b] = k;
+  }
+  map->last_band = order[kMapBands - 1];
+  map->bands_pending = true;
   return COVER_OK;
 }
 
@@ -2290,6 +2394,7 @@ int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem) {
   cover_ctx* ctx = map->ctx;
   Bind bind(ctx->device);
   const MapView& v = map->view;
+  CU(map_ready(ctx, map));
   CU(cudaMemcpy2DAsync(map->dev, v.pitch, data, v.size_x, v.size_x, v.size_y,
                        mem == COVER_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
   if (mem == COVER_MEM_HOST) CU(cudaStreamSynchronize(ctx->stream));
@@ -2303,6 +2408,7 @@ int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x
   if (x0 < 0 || y0 < 0 || w < 0 || h < 0 || x0 + w > v.size_x || y0 + h > v.size_y) return fail(ctx, COVER_E_INVALID_ARG, "window outside the map");
   if (w == 0 || h == 0) return COVER_OK;
   Bind bind(ctx->device);
+  CU(map_ready(ctx, map));
   CU(cudaMemcpy2DAsync(map->dev + static_cast<size_t>(y0) * v.pitch + x0, v.pitch, full_image + static_cast<size_t>(y0) * v.size_x + x0,
                        v.size_x, w, h, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -2344,6 +2450,7 @@ int cover_map_download(const cover_map* map, uint8_t* data) {
   cover_ctx* ctx = map->ctx;
   Bind bind(ctx->device);
   const MapView& v = map->view;
+  CU(map_ready(ctx, map));
   CU(cudaMemcpy2DAsync(data, v.size_x, map->dev, v.pitch, v.size_x, v.size_y, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return COVER_OK;
@@ -2356,6 +2463,7 @@ int cover_map_inflate(cover_map* map, int32_t radius_cells, const uint8_t* cost_
   Bind bind(ctx->device);
   const MapView& v = map->view;
   const size_t bytes = static_cast<size_t>(v.pitch) * v.size_y;
+  CU(map_ready(ctx, map));
   CU(ctx->in_a.ensure(bytes));  // snapshot of the un-inflated map: the kernel reads it and writes the map in place
   CU(cudaMemcpyAsync(ctx->in_a.ptr, map->dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   const size_t lut_bytes = static_cast<size_t>(radius_cells) * radius_cells + 1;
@@ -2374,7 +2482,9 @@ int cover_map_inflate(cover_map* map, int32_t radius_cells, const uint8_t* cost_
 void cover_map_destroy(cover_map* map) {
   if (!map) return;
   Bind bind(map->ctx->device);
+  cudaStreamSynchronize(map->ctx->copy_stream);
   cudaStreamSynchronize(map->ctx->stream);
+  for (cudaEvent_t e : map->band_done) cudaEventDestroy(e);
   cudaFree(map->dev);
   delete map;
 }
@@ -2424,6 +2534,7 @@ int cover_area_multi_check(cover_ctx* ctx, const cover_map* map, const double* p
     const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(static_cast<long long>(ctx->sm_count) * 12, (count + kRowsWarps - 1) / kRowsWarps)));
     const double* pd = ctx->poly.as<double>();
     const int* sd = ctx->in_b.as<int>();
+    CU(map_ready(ctx, map));
     if (op == OP_IS_FREE) k_area_rows_multi<OP_IS_FREE><<<grid, kRowsWarps * 32, smem, ctx->stream>>>(map->view, pd, sd, n_outlines, nv_total, nv_max, src, count, st.dev);
     else if (op == OP_ACCUMULATE) k_area_rows_multi<OP_ACCUMULATE><<<grid, kRowsWarps * 32, smem, ctx->stream>>>(map->view, pd, sd, n_outlines, nv_total, nv_max, src, count, st.dev);
     else k_area_rows_multi<OP_MAX><<<grid, kRowsWarps * 32, smem, ctx->stream>>>(map->view, pd, sd, n_outlines, nv_total, nv_max, src, count, st.dev);
@@ -2606,6 +2717,7 @@ int cover_footprints_is_free(cover_ctx* ctx, const cover_map* map, const cover_f
     if (rc) return rc;
   }
   if (count) {
+    CU(map_ready(ctx, map));
     k_footprints<<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, fps->spans, fps->ranges, fps->n, reinterpret_cast<const int2*>(off_dev),
                                                              which_dev, count, st.dev);
     ++ctx->launches;
@@ -2676,6 +2788,7 @@ int cover_split_is_free(cover_ctx* ctx, const cover_map* map, const cover_split*
     const SplitView view{split->xy, split->starts, split->n_outlines, split->n_areas};
     const int slot_rows = rows_cap <= 48 ? rows_cap : 0;  // shared-memory 4-range table: rows x 4 x 128 threads x 4 B
     const size_t smem = static_cast<size_t>(split->n_vertices) * 2 * sizeof(double) + static_cast<size_t>(slot_rows) * 4 * kBlock * sizeof(uint32_t);
+    CU(map_ready(ctx, map));
     k_split<<<grid, kBlock, smem, ctx->stream>>>(map->view, view, split->n_vertices, src, poses->count, st.dev, scratch, slot_rows);
     ++ctx->launches;
   }

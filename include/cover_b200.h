@@ -114,6 +114,12 @@ int cover_probe_read_bandwidth(cover_ctx* ctx, int64_t bytes, int32_t reps, doub
 int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double resolution, double origin_x, double origin_y,
                      cover_map** out);
 int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem);
+/* Same image, HOST source, without waiting for the copy: it is queued as row bands on a second stream and every
+ * later call that reads the map is ordered after the bands it needs on the device - a lattice check of a small
+ * footprint starts on the first rows of the map while the rest is still in flight (the per-planning-cycle
+ * "new costmap, then sweep" sequence).  `host_data` (page-locked memory for a truly asynchronous copy) must stay
+ * unchanged until a later call that returns results to the host, or cover_ctx_synchronize, has returned. */
+int cover_map_upload_async(cover_map* map, const uint8_t* host_data);
 /* re-upload the window [x0,x0+w) x [y0,y0+h) from a full-size HOST image (dirty-rectangle update). */
 int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x0, int32_t y0, int32_t w, int32_t h);
 /* EXTENSION (the step before the path; costmap_2d::InflationLayer is not part of the reference):

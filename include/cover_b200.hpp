@@ -139,6 +139,8 @@ public:
     if (char_map) upload(char_map);
   }
   void upload(const uint8_t* char_map) { detail::check(ctx_.get(), cover_map_upload(map_.get(), char_map, COVER_MEM_HOST)); }
+  /// Queues the copy and returns: `char_map` must stay unchanged until the next check has returned its results.
+  void upload_async(const uint8_t* char_map) { detail::check(ctx_.get(), cover_map_upload_async(map_.get(), char_map)); }
   void upload_window(const uint8_t* char_map, int x0, int y0, int w, int h) {
     detail::check(ctx_.get(), cover_map_upload_window(map_.get(), char_map, x0, y0, w, h));
   }

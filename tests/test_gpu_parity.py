@@ -417,6 +417,73 @@ def test_full_size_lattice_properties(cb, ctx):
     np.testing.assert_array_equal(first.is_free[5_000_000:5_000_000 + n], ((mx.cost >= 0) & (mx.cost < 254)).astype(np.uint8))
 
 
+def test_async_banded_upload_is_ordered_before_every_reader(cb, ctx):
+    """cover_map_upload_async: the image travels as row bands on a second stream (the bands under the last sweep's
+    window first) and a lattice sweep starts once the bands under ITS window have landed.  Alternating two
+    different costmaps and several windows, every check must see exactly the image uploaded just before it -
+    compared with the synchronous upload on a second map object."""
+    import torch
+    from cover_b200 import workloads as wl
+    images = [wl.inflated_costmap(4000, 4000, 0.05, seed=3), wl.inflated_costmap(4000, 4000, 0.05, seed=11, obstacle_p=6e-4)]
+    pinned = [torch.from_numpy(im).pin_memory().numpy() for im in images]
+    sync_map = cb.Costmap(ctx, images[0], 0.05)
+    amap = cb.Costmap(ctx, images[0], 0.05)
+    lattices = [cb.Lattice(**wl.dwa_lattice(n_theta=24)),                                        # low window
+                cb.Lattice(**wl.dwa_lattice(nx=600, ny=500, n_theta=12, x0=100.0, y0=160.0)),  # high window: the hint changes
+                cb.Lattice(**dict(wl.dwa_lattice(nx=800, ny=700, n_theta=10), y0=120.0, dy=-0.05)),  # negative row pitch
+                cb.Lattice(**wl.dwa_lattice(nx=900, ny=2000, n_theta=8, x0=5.0, y0=-2.0, pitch=0.11)),  # leaves the map at both ends
+                cb.Lattice(**dict(wl.dwa_lattice(nx=300, ny=300, n_theta=4), cs=2.5 * wl.heading_table(4)))]  # |(c,s)| != 1: longer reach
+    expected = {}
+    for li, lat in enumerate(lattices):
+        for mi in (0, 1):
+            sync_map.upload(images[mi])
+            expected[li, mi] = sync_map.area_is_free(RECT, lat).is_free
+        assert not np.array_equal(expected[li, 0], expected[li, 1])
+    for rep in range(2):
+        for li, lat in enumerate(lattices):
+            for mi in (1, 0):
+                amap.upload_async(pinned[mi])
+                got = amap.area_is_free(RECT, lat)
+                assert (got.status == 0).all()
+                np.testing.assert_array_equal(got.is_free, expected[li, mi], err_msg=f"lattice {li} image {mi} rep {rep}")
+    # two sweeps over different windows after ONE upload: the second needs bands the first did not wait for
+    amap.upload_async(pinned[1])
+    np.testing.assert_array_equal(amap.area_is_free(RECT, lattices[0]).is_free, expected[0, 1])
+    np.testing.assert_array_equal(amap.area_is_free(RECT, lattices[1]).is_free, expected[1, 1])
+    # a sub-range of the lattice, a value fold, a footprint too big for the lattice kernel, an outline
+    lat = lattices[0]
+    amap.upload_async(pinned[0])
+    part = amap.area_is_free(RECT, lat, first=2_345_678, count=20_000_001)
+    np.testing.assert_array_equal(part.is_free, expected[0, 0][2_345_678:2_345_678 + 20_000_001])
+    big = 3.0 * RECT
+    small_lat = cb.Lattice(**wl.dwa_lattice(nx=400, ny=300, n_theta=5, y0=150.0))
+    for name, poly in (("area_accumulate_cost", RECT), ("area_is_free", big), ("outline_max_cost", big)):
+        sync_map.upload(images[1])
+        want = getattr(sync_map, name)(poly, small_lat)
+        amap.upload_async(pinned[0])
+        amap.area_is_free(RECT, lattices[0])  # moves the hint away from small_lat's window
+        amap.upload_async(pinned[1])
+        got = getattr(amap, name)(poly, small_lat)
+        np.testing.assert_array_equal(got.is_free, want.is_free, err_msg=name)
+        if want.cost is not None:
+            np.testing.assert_array_equal(got.cost, want.cost, err_msg=name)
+    # every other reader of the map waits for the whole image
+    rng = np.random.default_rng(5)
+    poses = poses_around(rng, 200_000, 2.0, 198.0)
+    for mi in (1, 0):
+        sync_map.upload(images[mi])
+        amap.upload_async(pinned[mi])
+        np.testing.assert_array_equal(amap.area_is_free(RECT, poses).is_free, sync_map.area_is_free(RECT, poses).is_free)
+        amap.upload_async(pinned[mi])
+        np.testing.assert_array_equal(amap.outline_accumulate_cost(RECT, poses).cost, sync_map.outline_accumulate_cost(RECT, poses).cost)
+        amap.upload_async(pinned[mi])
+        np.testing.assert_array_equal(amap.download(), images[mi])
+    # a synchronous upload right after an asynchronous one wins
+    amap.upload_async(pinned[1])
+    amap.upload(images[0])
+    np.testing.assert_array_equal(amap.download(), images[0])
+
+
 def test_bit_packed_verdicts_and_not_ok_counter(cb, ctx):
     """free_bits / not_ok (cover_results) agree with the byte arrays on every kernel family."""
     rng = np.random.default_rng(80)
