@@ -28,8 +28,10 @@
 
 #include "cover_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <limits>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -132,7 +134,7 @@ private:
 class costmap {
 public:
   costmap(const context& ctx, int size_x, int size_y, double resolution, double origin_x, double origin_y, const uint8_t* char_map) :
-      ctx_(ctx) {
+      ctx_(ctx), size_x_(size_x), size_y_(size_y), resolution_(resolution), origin_x_(origin_x), origin_y_(origin_y) {
     cover_map* m = nullptr;
     detail::check(ctx.get(), cover_map_create(ctx.get(), size_x, size_y, resolution, origin_x, origin_y, &m));
     map_.reset(m, cover_map_destroy);
@@ -144,12 +146,30 @@ public:
   void upload_window(const uint8_t* char_map, int x0, int y0, int w, int h) {
     detail::check(ctx_.get(), cover_map_upload_window(map_.get(), char_map, x0, y0, w, h));
   }
+  /// Extension (the step before the path): inflate the lethal cells in place; `cost_by_d2[d2]`, d2 = 0..radius_cells^2,
+  /// is the layer's computeCost evaluated on the host for a cell sqrt(d2) cells from the nearest obstacle.
+  void inflate(int radius_cells, const std::vector<uint8_t>& cost_by_d2) {
+    if (cost_by_d2.size() != static_cast<size_t>(radius_cells) * radius_cells + 1) throw std::invalid_argument("cost_by_d2 must have radius_cells^2 + 1 entries");
+    detail::check(ctx_.get(), cover_map_inflate(map_.get(), radius_cells, cost_by_d2.data()));
+  }
+  std::vector<uint8_t> download() const {
+    std::vector<uint8_t> bytes(static_cast<size_t>(size_x_) * size_y_);
+    detail::check(ctx_.get(), cover_map_download(map_.get(), bytes.data()));
+    return bytes;
+  }
   const cover_map* get() const { return map_.get(); }
   const context& ctx() const { return ctx_; }
+  int size_x() const { return size_x_; }
+  int size_y() const { return size_y_; }
+  double resolution() const { return resolution_; }
+  double origin_x() const { return origin_x_; }
+  double origin_y() const { return origin_y_; }
 
 private:
   context ctx_;
   std::shared_ptr<cover_map> map_;
+  int size_x_, size_y_;
+  double resolution_, origin_x_, origin_y_;
 };
 
 namespace detail {
@@ -230,6 +250,66 @@ inline std::vector<double> outline_accumulate_cost(polygon_view poly, const std:
   batch_result r = detail::run(cover_outline_accumulate_cost, poly, detail::make_poses(poses), map, true);
   detail::rethrow_statuses(r.status);
   return std::move(r.cost);
+}
+
+// ---- areas with holes: area_generator(resolution, const polygon_vec&) (generators.cpp:126-135) -----
+
+namespace detail {
+inline batch_result run_multi(const std::vector<polygon>& outlines, int op, const std::vector<pose>& poses, const costmap& map, bool want_cost) {
+  std::vector<double> xy;
+  std::vector<int32_t> starts{0};
+  for (const polygon& o : outlines) {
+    xy.insert(xy.end(), o.v.begin(), o.v.end());
+    starts.push_back(starts.back() + static_cast<int32_t>(o.cols()));
+  }
+  batch_result r;
+  r.is_free.resize(poses.size());
+  r.status.resize(poses.size());
+  if (want_cost) r.cost.resize(poses.size());
+  const cover_poses p = make_poses(poses);
+  const cover_results out{COVER_MEM_HOST, r.is_free.data(), want_cost ? r.cost.data() : nullptr, r.status.data(), nullptr, nullptr};
+  check(map.ctx().get(), cover_area_multi_check(map.ctx().get(), map.get(), xy.data(), starts.data(), static_cast<int32_t>(outlines.size()), op, &p, &out));
+  return r;
+}
+}  // namespace detail
+
+/// is_free over the area between several outlines (outer boundary + holes, even-odd), one verdict per pose.
+inline std::vector<uint8_t> is_free(const std::vector<polygon>& outlines, const std::vector<pose>& poses, const costmap& map) {
+  batch_result r = detail::run_multi(outlines, 0, poses, map, false);
+  detail::rethrow_statuses(r.status);
+  return std::move(r.is_free);
+}
+inline std::vector<double> accumulate_cost(const std::vector<polygon>& outlines, const std::vector<pose>& poses, const costmap& map) {
+  batch_result r = detail::run_multi(outlines, 1, poses, map, true);
+  detail::rethrow_statuses(r.status);
+  return std::move(r.cost);
+}
+
+// ---- expand: to_area / to_outline (expand.hpp:68-80), one discrete_polygon per pose --------------------
+
+namespace detail {
+using expand_entry = int (*)(cover_ctx*, const cover_map*, const double*, int32_t, const cover_poses*, int32_t*, int64_t, int64_t*, uint8_t*, int32_t);
+inline std::vector<discrete_polygon> expand(expand_entry fn, polygon_view poly, const std::vector<pose>& poses, const costmap& map) {
+  const cover_poses p = make_poses(poses);
+  std::vector<int64_t> starts(poses.size() + 1);
+  std::vector<uint8_t> status(poses.size());
+  check(map.ctx().get(), fn(map.ctx().get(), map.get(), poly.xy, poly.n, &p, nullptr, 0, starts.data(), status.data(), COVER_MEM_HOST));
+  rethrow_statuses(status);
+  std::vector<int32_t> cells(static_cast<size_t>(2 * starts.back()) + 2);
+  check(map.ctx().get(), fn(map.ctx().get(), map.get(), poly.xy, poly.n, &p, cells.data(), starts.back(), starts.data(), status.data(), COVER_MEM_HOST));
+  std::vector<discrete_polygon> out(poses.size());
+  for (size_t i = 0; i < poses.size(); ++i) out[i].v.assign(cells.begin() + 2 * starts[i], cells.begin() + 2 * starts[i + 1]);
+  return out;
+}
+}  // namespace detail
+
+/// to_area(resolution, pose * polygon - origin): the dense cells in generator order (y ascending, x ascending).
+inline std::vector<discrete_polygon> to_area(polygon_view poly, const std::vector<pose>& poses, const costmap& map) {
+  return detail::expand(cover_area_expand, poly, poses, map);
+}
+/// to_outline(resolution, pose * polygon - origin): the outline cells in traversal order.
+inline std::vector<discrete_polygon> to_outline(polygon_view poly, const std::vector<pose>& poses, const costmap& map) {
+  return detail::expand(cover_outline_expand, poly, poses, map);
 }
 
 // ---- ray generator ---------------------------------------------------------------------------------
@@ -345,5 +425,138 @@ private:
   context ctx_;
   std::shared_ptr<cover_split> split_;
 };
+
+// ---- grid split: continuous_footprint(radius, polygon) without boost::geometry ---------------------------
+//
+// The reference erodes / dilates the continuous polygon with boost::geometry (footprints.cpp:79-125) and then
+// discretises per heading (discrete_footprint::init, footprints.cpp:233-238).  Here the split is made on the
+// grid, from the exact to_area cells F of one heading:
+//   D  = Euclidean distance (metres, cell centres) to the nearest cell outside F
+//   E  = {c in F : D(c) > r}                    the always-inscribed core
+//   dE = cells of E with a 4-neighbour outside E  -> OUTLINE cells (checked for 253 or 254)
+//   A  = {c in F : dist(c, dE) > r}               -> AREA cells    (checked for 254)
+// A lethal cell inside F is in A or within r of some q in dE, which an inflation layer with inscribed radius >= r
+// marks 253/254: no miss by construction (the reference's regression, test/footprints.cpp:205-242); every q in dE
+// is farther than r from any cell outside F: no false alarm.  Same construction, cell for cell, as
+// cover_b200/split.py.
+
+struct split_cells_result {
+  discrete_polygon outline, area;  ///< both in row-major order (y ascending, then x)
+};
+
+namespace detail {
+/// Exact squared Euclidean distance (cells^2) from every cell of a w x h grid to the nearest cell with feature != 0.
+inline std::vector<int64_t> squared_distance(const std::vector<uint8_t>& feature, int w, int h) {
+  const int64_t inf = std::numeric_limits<int64_t>::max() / 4;
+  std::vector<int64_t> g(static_cast<size_t>(w) * h, inf), d(static_cast<size_t>(w) * h, inf);
+  for (int x = 0; x < w; ++x) {  // per column: distance to the nearest feature cell of the same column
+    int64_t run = inf;
+    for (int y = 0; y < h; ++y) {
+      run = feature[static_cast<size_t>(y) * w + x] ? 0 : (run >= inf ? inf : run + 1);
+      g[static_cast<size_t>(y) * w + x] = run;
+    }
+    run = inf;
+    for (int y = h - 1; y >= 0; --y) {
+      run = feature[static_cast<size_t>(y) * w + x] ? 0 : (run >= inf ? inf : run + 1);
+      int64_t& v = g[static_cast<size_t>(y) * w + x];
+      v = std::min(v, run);
+    }
+  }
+  for (int y = 0; y < h; ++y) {  // per row: min over columns of dx^2 + g^2, scanning outwards until dx^2 alone loses
+    const int64_t* grow = &g[static_cast<size_t>(y) * w];
+    for (int x = 0; x < w; ++x) {
+      int64_t best = grow[x] >= inf ? inf : grow[x] * grow[x];
+      for (int64_t dx = 1; dx * dx < best && (x - dx >= 0 || x + dx < w); ++dx) {
+        if (x - dx >= 0 && grow[x - dx] < inf) best = std::min(best, dx * dx + grow[x - dx] * grow[x - dx]);
+        if (x + dx < w && grow[x + dx] < inf) best = std::min(best, dx * dx + grow[x + dx] * grow[x + dx]);
+      }
+      d[static_cast<size_t>(y) * w + x] = best;
+    }
+  }
+  return d;
+}
+}  // namespace detail
+
+/// Splits one footprint's cell set F (any order, duplicates allowed) into skeleton-outline and remainder-area cells.
+inline split_cells_result split_cells(cells_view cells, double resolution, double radius) {
+  split_cells_result out;
+  if (cells.n == 0) return out;
+  if (!(radius > 0)) throw std::invalid_argument("Radius must be positive");  // footprints.cpp:86-87
+  if (!(resolution > 0)) throw std::invalid_argument("The resolution must be positive");
+  int32_t xmin = cells.xy[0], xmax = xmin, ymin = cells.xy[1], ymax = ymin;
+  for (int64_t i = 0; i < cells.n; ++i) {
+    xmin = std::min(xmin, cells.xy[2 * i]), xmax = std::max(xmax, cells.xy[2 * i]);
+    ymin = std::min(ymin, cells.xy[2 * i + 1]), ymax = std::max(ymax, cells.xy[2 * i + 1]);
+  }
+  const int pad = static_cast<int>(std::ceil(radius / resolution)) + 2;
+  const int x0 = xmin - pad, y0 = ymin - pad, w = xmax - x0 + pad + 1, h = ymax - y0 + pad + 1;
+  const size_t n = static_cast<size_t>(w) * h;
+  std::vector<uint8_t> inside(n, 0), mask(n);
+  for (int64_t i = 0; i < cells.n; ++i) inside[static_cast<size_t>(cells.xy[2 * i + 1] - y0) * w + (cells.xy[2 * i] - x0)] = 1;
+  auto farther_than_radius = [&](int64_t d2) { return std::sqrt(static_cast<double>(d2)) * resolution > radius; };
+  auto emit = [&](const std::vector<uint8_t>& m, discrete_polygon& dst) {
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x)
+        if (m[static_cast<size_t>(y) * w + x]) dst.v.push_back(x + x0), dst.v.push_back(y + y0);
+  };
+  for (size_t i = 0; i < n; ++i) mask[i] = !inside[i];
+  const std::vector<int64_t> d_out = detail::squared_distance(mask, w, h);
+  std::vector<uint8_t> core(n);
+  bool any_core = false;
+  for (size_t i = 0; i < n; ++i) any_core |= (core[i] = inside[i] && farther_than_radius(d_out[i])) != 0;
+  if (!any_core) {  // radius too large: the whole footprint is scanned as area
+    emit(inside, out.area);
+    return out;
+  }
+  std::vector<uint8_t> ring(n, 0);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      const size_t i = static_cast<size_t>(y) * w + x;
+      if (!core[i]) continue;
+      ring[i] = (y > 0 && !core[i - w]) || (y + 1 < h && !core[i + w]) || (x > 0 && !core[i - 1]) || (x + 1 < w && !core[i + 1]);
+    }
+  const std::vector<int64_t> d_ring = detail::squared_distance(ring, w, h);
+  for (size_t i = 0; i < n; ++i) mask[i] = inside[i] && farther_than_radius(d_ring[i]);
+  emit(ring, out.outline);
+  emit(mask, out.area);
+  return out;
+}
+
+/// One discrete_footprint per heading (the reference's per-heading cache of discrete_footprint::init): the polygon is
+/// rotated about the map's origin cell, so the cell offsets passed to `is_free` are the cell of the robot's
+/// reference point.  `headings[k]` needs only (c, s).
+inline discrete_footprints heading_bank(const costmap& map, polygon_view poly, double radius, const std::vector<pose>& headings) {
+  std::vector<pose> poses;
+  for (const pose& h : headings) poses.push_back(pose{h.c, h.s, map.origin_x(), map.origin_y()});
+  const std::vector<discrete_polygon> footprints = to_area(poly, poses, map);
+  std::vector<discrete_polygon> outlines, areas;
+  for (const discrete_polygon& f : footprints) {
+    split_cells_result s = split_cells(f, map.resolution(), radius);
+    outlines.push_back(std::move(s.outline));
+    areas.push_back(std::move(s.area));
+  }
+  return discrete_footprints(map.ctx(), outlines, areas);
+}
+
+// ---- trajectory scoring (extension: the DWA-style caller after the pose checks) ---------------------------
+
+struct trajectory_scores {
+  std::vector<int32_t> first_blocked;  ///< first step whose verdict is 0 (`steps` if none)
+  std::vector<double> score;           ///< first negative per-pose cost in step order, else the sum
+};
+/// Poses grouped as n_trajectories x steps (pose index = trajectory * steps + step); either input may be empty.
+inline trajectory_scores trajectory_reduce(const context& ctx, const std::vector<uint8_t>& is_free, const std::vector<double>& cost, int32_t steps) {
+  const size_t n = is_free.empty() ? cost.size() : is_free.size();
+  if (steps <= 0 || n % static_cast<size_t>(steps) != 0 || (!is_free.empty() && !cost.empty() && is_free.size() != cost.size()))
+    throw std::invalid_argument("poses must be n_trajectories x steps");
+  trajectory_scores out;
+  const int64_t n_traj = static_cast<int64_t>(n / steps);
+  if (!is_free.empty()) out.first_blocked.resize(static_cast<size_t>(n_traj));
+  if (!cost.empty()) out.score.resize(static_cast<size_t>(n_traj));
+  detail::check(ctx.get(), cover_trajectory_reduce(ctx.get(), is_free.empty() ? nullptr : is_free.data(), cost.empty() ? nullptr : cost.data(), COVER_MEM_HOST,
+                                                   n_traj, steps, out.first_blocked.empty() ? nullptr : out.first_blocked.data(),
+                                                   out.score.empty() ? nullptr : out.score.data()));
+  return out;
+}
 
 }  // namespace cover_b200

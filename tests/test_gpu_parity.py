@@ -535,6 +535,53 @@ def test_cpp_host_layer_runs_the_reference_unit_tests(cb, tmp_path):
     assert run.returncode == 0, run.stdout + run.stderr
 
 
+def test_cpp_grid_split_matches_python_and_is_safe(cb, ctx, tmp_path):
+    """tests/cpp/split_bank_test.cpp: the C++ host layer's to_area / split_cells / heading_bank (the Boost-free
+    `continuous_footprint(radius, polygon)` of SURVEY 8f-1) must produce the same outline / area cells as
+    cover_b200/split.py for every heading, and passes the reference's safety regression in C++."""
+    import os
+    import subprocess
+    from cover_b200 import split, workloads as wl
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(cb.library_path())
+    exe = tmp_path / "split_bank_test"
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "split_bank_test.cpp"),
+                            "-o", str(exe), "-L", libdir, "-lcover_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    res, radius, n_headings = 0.05, 0.2, 12
+    polygon = wl.potato(48)
+    cs = wl.heading_table(n_headings)
+    with open(tmp_path / "in.txt", "w") as f:
+        f.write(f"{res!r} {radius!r}\n{polygon.shape[1]}\n")
+        for x, y in polygon.T:
+            f.write(f"{float(x)!r} {float(y)!r}\n")
+        f.write(f"{n_headings}\n")
+        for c, s_ in cs:
+            f.write(f"{float(c)!r} {float(s_)!r}\n")
+    run = subprocess.run([str(exe), str(tmp_path / "in.txt"), str(tmp_path / "out.txt")], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout + run.stderr
+    # the same bank from the Python host layer (same map geometry as the C++ program: 240 x 240, origin at the centre)
+    cmap = cb.Costmap(ctx, np.zeros((240, 240), dtype=np.uint8), res, -120 * res, -120 * res)
+    poses = np.concatenate([cs, np.full((n_headings, 1), cmap.origin_x), np.full((n_headings, 1), cmap.origin_y)], axis=1)
+    cells, starts, status = cmap.area_cells(polygon, poses)
+    assert (status == 0).all()
+    lines = open(tmp_path / "out.txt").read().split("\n")
+    pos = 0
+    for k in range(n_headings):
+        tag, kk, n_out, n_area = lines[pos].split()
+        assert tag == "H" and int(kk) == k
+        n_out, n_area = int(n_out), int(n_area)
+        got = np.array([ln.split() for ln in lines[pos + 1:pos + 1 + n_out + n_area]], dtype=np.int32).reshape(-1, 2)
+        pos += 1 + n_out + n_area
+        want_out, want_area = split.split_cells(cells[starts[k]:starts[k + 1]], res, radius)
+        assert n_out == len(want_out) > 0 and n_area == len(want_area)
+
+        def canon(a):
+            return a[np.lexsort((a[:, 0], a[:, 1]))]
+        np.testing.assert_array_equal(canon(got[:n_out]), canon(want_out), err_msg=f"outline cells, heading {k}")
+        np.testing.assert_array_equal(canon(got[n_out:]), canon(want_area), err_msg=f"area cells, heading {k}")
+
+
 def test_list_kernel_still_exact(cb, monkeypatch):
     """k_area_list (per-thread sorted lists in global scratch) is only used for polygons with more than 256
     vertices now; force it for ordinary polygons so that it stays covered."""
