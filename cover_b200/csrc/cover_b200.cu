@@ -569,9 +569,6 @@ __global__ void __launch_bounds__(kBlock) k_area_slots(MapView m, const double* 
 // Poses whose shape needs more than two ranges on a row, is wider than 32 cells, or finds the cache
 // full go to the todo list and are finished by the general kernels.
 // ---------------------------------------------------------------------------------------------------
-#ifndef LAT_ROWS_INLINE
-#define LAT_ROWS_INLINE __forceinline__
-#endif
 #ifndef LAT_MIN_BLOCKS
 #define LAT_MIN_BLOCKS 3
 #endif
@@ -638,53 +635,106 @@ __device__ __forceinline__ LatProfile lat_profile(const double* __restrict__ pol
   return p;
 }
 
-/// Scan-row walk of one group.  `row_a[r]` = r * pitch + (first cell of row r's range, relative to vertex 0),
-/// `row_m[r]` = width mask.  MODE 0: every needed cell is inside the map and plane A's windows start in piece 0,
-/// plane B's in piece 1 (the usual full 64-pose group): no bounds tests, no piece selection.  MODE 1: inside
-/// the map, arbitrary offsets.  MODE 2: per-cell bounds tests (outside the map counts as lethal).
-template <int MODE>
-__device__ LAT_ROWS_INLINE void lattice_rows(const MapView& m, const int* __restrict__ row_a, const uint32_t* __restrict__ row_m, int rows,
-                                             int x_base, int y_base, int lane, bool third, int off_a, int off_b, uint32_t& hit_a, uint32_t& hit_b) {
+/// Byte walk of one group with per-cell bounds tests (a pose of the group touches the map border, or the bit planes
+/// are unavailable).  `row_a[r]` = r * pitch + (first cell of row r's range, relative to vertex 0), `row_m[r]` =
+/// width mask.  Each lane loads one byte of each of three coalesced 32-cell pieces, `__ballot_sync` turns "lethal or
+/// outside the map" into a 96-cell bit window and every pose ANDs its own sub-window.
+__device__ __noinline__ void lattice_rows_bytes(const MapView& m, const int* __restrict__ row_a, const uint32_t* __restrict__ row_m, int rows,
+                                                int x_base, int y_base, int lane, int off_a, int off_b, uint32_t& hit_a, uint32_t& hit_b) {
   // lane constants: which two of the three 32-cell pieces a pose's window starts in, and its shift
   const bool hi_a = off_a >= 32, hi_b = off_b >= 32;
   const int sh_a = off_a & 31, sh_b = off_b & 31;
-  if (MODE != 2) {
-    const uint8_t* __restrict__ p = m.data + static_cast<size_t>(y_base) * m.pitch + (x_base + lane);
-    // unrolled by 4: the 12 byte loads of four scan rows are in flight together (few resident warps, so the
-    // memory-level parallelism has to come from inside the warp)
-#pragma unroll 4
-    for (int r = 0; r < rows; ++r) {
-      const uint8_t* __restrict__ q = p + row_a[r];
-      const uint8_t b0 = __ldg(q), b1 = __ldg(q + 32), b2 = third ? __ldg(q + 64) : static_cast<uint8_t>(0);
-      const uint32_t m0 = __ballot_sync(kFull, b0 == kLethal);
-      const uint32_t m1 = __ballot_sync(kFull, b1 == kLethal);
-      const uint32_t m2 = __ballot_sync(kFull, b2 == kLethal);
-      const uint32_t wm = row_m[r];
-      if (MODE == 0) {
-        hit_a |= __funnelshift_r(m0, m1, sh_a) & wm;
-        hit_b |= __funnelshift_r(m1, m2, sh_b) & wm;
-      } else {
-        hit_a |= __funnelshift_r(hi_a ? m1 : m0, hi_a ? m2 : m1, sh_a) & wm;
-        hit_b |= __funnelshift_r(hi_b ? m1 : m0, hi_b ? m2 : m1, sh_b) & wm;
-      }
-    }
-  } else {
-    for (int r = 0; r < rows; ++r) {
-      const int y = y_base + r;
-      const bool y_in = static_cast<unsigned>(y) < static_cast<unsigned>(m.size_y);
-      const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y_in ? y : 0) * m.pitch;
-      const int lo = row_a[r] - r * m.pitch;
-      uint32_t piece[3];
+  for (int r = 0; r < rows; ++r) {
+    const int y = y_base + r;
+    const bool y_in = static_cast<unsigned>(y) < static_cast<unsigned>(m.size_y);
+    const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y_in ? y : 0) * m.pitch;
+    const int lo = row_a[r] - r * m.pitch;
+    uint32_t piece[3];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int x = x_base + lo + lane + 32 * j;
-        bool lethal = true;  // outside the map counts as lethal (costmap.hpp:81-91)
-        if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
-        piece[j] = __ballot_sync(kFull, lethal);
-      }
-      const uint32_t wm = row_m[r];
-      hit_a |= __funnelshift_r(hi_a ? piece[1] : piece[0], hi_a ? piece[2] : piece[1], sh_a) & wm;
-      hit_b |= __funnelshift_r(hi_b ? piece[1] : piece[0], hi_b ? piece[2] : piece[1], sh_b) & wm;
+    for (int j = 0; j < 3; ++j) {
+      const int x = x_base + lo + lane + 32 * j;
+      bool lethal = true;  // outside the map counts as lethal (costmap.hpp:81-91)
+      if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
+      piece[j] = __ballot_sync(kFull, lethal);
+    }
+    const uint32_t wm = row_m[r];
+    hit_a |= __funnelshift_r(hi_a ? piece[1] : piece[0], hi_a ? piece[2] : piece[1], sh_a) & wm;
+    hit_b |= __funnelshift_r(hi_b ? piece[1] : piece[0], hi_b ? piece[2] : piece[1], sh_b) & wm;
+  }
+}
+
+/// Lethal bit planes of a costmap (k_lethal_planes): plane k, row y, bit x = "one of the cells x .. x + 2^k - 1
+/// of row y is LETHAL" (k = 0..5; bits past the map edge are 0).  Any window of w <= 32 cells is then the OR of
+/// two overlapping power-of-two windows - two bits - instead of w bytes.
+struct PlaneView {
+  const uint32_t* __restrict__ bits;  // nullptr: planes disabled, the byte walk is used
+  int wpitch;                         // words per plane row (ceil(size_x / 32) + 3 slack words)
+  long long plane_words;              // words per plane
+};
+constexpr int kPlaneCount = 6;
+
+/// is_free walk of one group over the bit planes (every needed cell inside the map): LANE j owns scan row j of the
+/// shape.  For the group's 64 candidate x offsets it fetches the 64-bit window of plane log2(p) that starts at the
+/// row's first cell, and the one that starts `width - p` cells later (p = largest power of two <= width); OR-ing the
+/// lanes' results (one `redux.or` per half) leaves bit `off` = "the pose at offset `off` hits a lethal cell", which
+/// every pose then reads at its own offset.  ~30 warp instructions per 64 poses, whatever the number of rows.
+__device__ __forceinline__ void lattice_rows_planes(const PlaneView& pv, const int* __restrict__ row_a, const uint32_t* __restrict__ row_m, int rows,
+                                                    int pitch, int x_base, int y_base, int lane, bool third, int off_a, int off_b, uint32_t& hit_a,
+                                                    uint32_t& hit_b) {
+  uint32_t r_lo = 0u, r_hi = 0u;
+  for (int j = lane; j < rows; j += 32) {
+    const int width = __popc(row_m[j]);
+    if (width == 0) continue;
+    const int k = 31 - __clz(width), tail = width - (1 << k);
+    const int xs = x_base + (row_a[j] - j * pitch);
+    const uint32_t* __restrict__ rowp = pv.bits + k * pv.plane_words + static_cast<long long>(y_base + j) * pv.wpitch;
+    {
+      const uint32_t* __restrict__ q = rowp + (xs >> 5);
+      const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = third ? __ldg(q + 2) : 0u;
+      r_lo |= __funnelshift_r(w0, w1, xs & 31);
+      r_hi |= __funnelshift_r(w1, w2, xs & 31);
+    }
+    if (tail) {
+      const int xt = xs + tail;
+      const uint32_t* __restrict__ q = rowp + (xt >> 5);
+      const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = third ? __ldg(q + 2) : 0u;
+      r_lo |= __funnelshift_r(w0, w1, xt & 31);
+      r_hi |= __funnelshift_r(w1, w2, xt & 31);
+    }
+  }
+  r_lo = __reduce_or_sync(kFull, r_lo);
+  r_hi = third ? __reduce_or_sync(kFull, r_hi) : 0u;
+  hit_a = ((off_a < 32 ? r_lo : r_hi) >> (off_a & 31)) & 1u;
+  hit_b = ((off_b < 32 ? r_lo : r_hi) >> (off_b & 31)) & 1u;
+}
+
+/// Builds rows [row_lo, row_hi] of the lethal bit planes.  One warp per 1024-cell stretch of a row: 33 coalesced
+/// byte loads + ballots give the lethal words L[i] (lane i keeps word i, plus the first word of the next stretch),
+/// and the doubling V |= V >> 2^k on the 64-bit value L[i] | L[i+1] << 32 yields plane k + 1 in its low word.
+__global__ void __launch_bounds__(256) k_lethal_planes(MapView m, uint32_t* __restrict__ planes, int wpitch, long long plane_words, int row_lo,
+                                                        int row_hi) {
+  const int lane = threadIdx.x & 31;
+  const int stretches = (m.size_x + 1023) / 1024;
+  const long long n_tasks = static_cast<long long>(row_hi - row_lo + 1) * stretches;
+  for (long long task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); task < n_tasks; task += static_cast<long long>(gridDim.x) * (blockDim.x >> 5)) {
+    const int y = row_lo + static_cast<int>(task / stretches), x0 = static_cast<int>(task % stretches) * 1024;
+    const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y) * m.pitch;
+    uint32_t mine = 0u, next = 0u;
+#pragma unroll 11
+    for (int i = 0; i < 33; ++i) {
+      const int x = x0 + 32 * i + lane;
+      const uint32_t word = __ballot_sync(kFull, x < m.size_x && __ldg(rowp + x) == kLethal);
+      if (i == lane) mine = word;
+      if (i == lane + 1) next = word;
+    }
+    const int word_index = (x0 >> 5) + lane;
+    if (word_index >= wpitch) continue;
+    unsigned long long v = static_cast<unsigned long long>(mine) | (static_cast<unsigned long long>(next) << 32);
+    uint32_t* __restrict__ dst = planes + static_cast<long long>(y) * wpitch + word_index;
+#pragma unroll
+    for (int k = 0; k < kPlaneCount; ++k) {
+      dst[k * plane_words] = static_cast<uint32_t>(v);
+      v |= v >> (1 << k);
     }
   }
 }
@@ -865,7 +915,7 @@ template <int OP>
 __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
                                                                      long long count, OutView out, int rows_cap,
                                                                      unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count,
-                                                                     LatGeom g) {
+                                                                     LatGeom g, PlaneView pv) {
   extern __shared__ double smem_d[];
   const double* poly = stage_polygon(poly_g, nv, smem_d);
   unsigned long long* slot_key = reinterpret_cast<unsigned long long*>(smem_d + 2 * nv);  // 0 = empty
@@ -910,213 +960,213 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
     auto column_tx = [&src](int ix) { return __dadd_rn(src.x0, __dmul_rn(static_cast<double>(ix), src.dx)); };
     auto heading_cs = [&src](int it) { return __ldg(reinterpret_cast<const double2*>(src.theta_cs) + it); };
 
-    // y-profiles of the unit's 8 rows: lane r owns row r
-    int my_it = 0;
+    // y-profiles of the unit's 8 rows: lane r owns row r (lanes 8.. mirror rows 0..7)
+    int my_it = 0, my_iy = 0;
     LatProfile my_y{0, 0ull, false, false};
+    bool my_valid = false;
     {
       const int row_rel = group * kLatRows + (lane & (kLatRows - 1));
       const long long row = g.row_first + row_rel;
       if (row_rel < g.n_rows) {
+        my_valid = true;
         my_it = static_cast<int>(row / src.ny);
-        const int iy = static_cast<int>(row - static_cast<long long>(my_it) * src.ny);
+        my_iy = static_cast<int>(row - static_cast<long long>(my_it) * src.ny);
         const double2 cs = heading_cs(my_it);
-        my_y = lat_profile<false>(poly, nv, cs.x, cs.y, __dadd_rn(src.y0, __dmul_rn(static_cast<double>(iy), src.dy)), m, exact_key);
+        my_y = lat_profile<false>(poly, nv, cs.x, cs.y, __dadd_rn(src.y0, __dmul_rn(static_cast<double>(my_iy), src.dy)), m, exact_key);
       }
     }
-
-    int x_heading = -1;
-    LatProfile xa{0, 0ull, false, false}, xb{0, 0ull, false, false};
-    // memo: a column's slot stays valid while the heading (x-profile) and the row's y-key do not change
-    unsigned long long memo_ykey = 0ull;
-    bool memo_valid = false;
-    int memo_slot_a = -1, memo_slot_b = -1;
-
-    for (int r = 0; r < kLatRows; ++r) {
-      const int row_rel = group * kLatRows + r;
-      if (row_rel >= g.n_rows) break;
-      const int it = __shfl_sync(kFull, my_it, r);
-      const int vy0 = __shfl_sync(kFull, my_y.c0, r);
-      const unsigned long long ykey = __shfl_sync(kFull, my_y.key, r);
-      const bool y_ok = __shfl_sync(kFull, static_cast<int>(my_y.ok), r) != 0, y_pack = __shfl_sync(kFull, static_cast<int>(my_y.packable), r) != 0;
-      if (it != x_heading) {  // x-profiles depend on the heading only: once per unit (twice on a heading boundary)
-        const double2 cs = heading_cs(it);
-        xa = lat_profile<true>(poly, nv, cs.x, cs.y, column_tx(ix_a), m, exact_key);
-        xb = lat_profile<true>(poly, nv, cs.x, cs.y, column_tx(ix_b), m, exact_key);
-        x_heading = it;
-        memo_valid = false;
-      }
-      if (ykey != memo_ykey) memo_valid = false;
-      memo_ykey = ykey;
-      const long long i_a = (g.row_first + row_rel) * src.nx + ix_a - src.first, i_b = i_a + 32;
-      const bool act_a = ix_a < src.nx && i_a >= 0 && i_a < count, act_b = ix_b < src.nx && i_b >= 0 && i_b < count;
-
-      // ---- key of the relative shape; -2: nothing to do, -1: todo list, >= 0: cache slot ------------
-      int slot_a = -2, slot_b = -2;
-      unsigned long long key_a = 0ull, key_b = 0ull;
-      bool look_a = false, look_b = false;
-      if (act_a) {
-        if (!(xa.ok && y_ok)) {
-          store_failure(out, i_a, ST_COORD_RANGE);
-        } else if (exact_key && !(xa.packable && y_pack)) {
-          slot_a = -1;
-        } else {
-          key_a = exact_key ? ((1ull << 63) | (xa.key << 24) | ykey) : ((lat_mix(xa.key, static_cast<int>(ykey)) ^ (ykey >> 32)) | 1ull);
-          if (memo_valid && memo_slot_a >= 0) slot_a = memo_slot_a;
-          else look_a = true;
+    // "row r has exactly the y offsets of row r - 1" (same heading): the shape slot of a column group carries over
+    bool my_same_prev;
+    {
+      const int prev_it = __shfl_up_sync(kFull, my_it, 1);
+      const unsigned long long prev_key = __shfl_up_sync(kFull, my_y.key, 1);
+      const bool prev_good = __shfl_up_sync(kFull, static_cast<int>(my_valid && my_y.ok && my_y.packable), 1) != 0;
+      my_same_prev = (lane & (kLatRows - 1)) != 0 && my_valid && my_y.ok && my_y.packable && prev_good && prev_it == my_it && prev_key == my_y.key;
+      if (!exact_key) {  // the key is only a hash of the offsets: compare them
+        const double2 cs = heading_cs(my_it);
+        const double ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(my_iy), src.dy));
+        for (int v = 1; v < nv; ++v) {
+          int cy;
+          lat_cell_y(cs.x, cs.y, ty, poly[2 * v], poly[2 * v + 1], m, cy);
+          const int d = cy - my_y.c0, prev_d = __shfl_up_sync(kFull, d, 1);
+          my_same_prev &= d == prev_d;
         }
       }
-      if (act_b) {
-        if (!(xb.ok && y_ok)) {
-          store_failure(out, i_b, ST_COORD_RANGE);
-        } else if (exact_key && !(xb.packable && y_pack)) {
-          slot_b = -1;
-        } else {
-          key_b = exact_key ? ((1ull << 63) | (xb.key << 24) | ykey) : ((lat_mix(xb.key, static_cast<int>(ykey)) ^ (ykey >> 32)) | 1ull);
-          if (memo_valid && memo_slot_b >= 0) slot_b = memo_slot_b;
-          else look_b = true;
+    }
+    const int rows_here = min(kLatRows, g.n_rows - group * kLatRows);
+    const long long i_base = (g.row_first + static_cast<long long>(group) * kLatRows) * src.nx - src.first;  // pose index of (row 0, column 0)
+    const bool col_a = ix_a < src.nx, col_b = ix_b < src.nx;
+
+    // runs of rows with the same heading (one per unit; two where the unit crosses a heading boundary)
+    for (int r0 = 0; r0 < rows_here;) {
+      const int it = __shfl_sync(kFull, my_it, r0);
+      int r1 = r0 + 1;
+      while (r1 < rows_here && __shfl_sync(kFull, my_it, r1) == it) ++r1;
+      const double2 cs = heading_cs(it);
+      // x-profiles depend on the heading and the column only
+      const LatProfile xa = lat_profile<true>(poly, nv, cs.x, cs.y, column_tx(ix_a), m, exact_key);
+      const LatProfile xb = lat_profile<true>(poly, nv, cs.x, cs.y, column_tx(ix_b), m, exact_key);
+      const bool good_a = col_a && xa.ok && xa.packable, good_b = col_b && xb.ok && xb.packable;
+      const bool row_good = my_valid && my_y.ok && my_y.packable;  // (lane r: row r)
+      const unsigned bad_rows = __ballot_sync(kFull, my_valid && !row_good) & 0xFFu;
+
+      // ---- rare: coordinates out of range (status), offsets that do not fit the packed key (general kernel) ----
+      if (bad_rows != 0u || __any_sync(kFull, (col_a && !good_a) || (col_b && !good_b))) {
+        for (int r = r0; r < r1; ++r) {
+          const bool y_ok = __shfl_sync(kFull, static_cast<int>(my_y.ok), r) != 0, y_good = ((bad_rows >> r) & 1u) == 0u;
+          const long long i_a = i_base + static_cast<long long>(r) * src.nx + ix_a, i_b = i_a + 32;
+          if (col_a && i_a >= 0 && i_a < count && !(good_a && y_good)) {
+            if (!(xa.ok && y_ok)) store_failure(out, i_a, ST_COORD_RANGE);
+            else todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
+          }
+          if (col_b && i_b >= 0 && i_b < count && !(good_b && y_good)) {
+            if (!(xb.ok && y_ok)) store_failure(out, i_b, ST_COORD_RANGE);
+            else todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
+          }
         }
       }
 
-      // ---- shape cache: find, or insert + rasterise (only for keys the lane has not just looked up) ---
-      unsigned pend_a = __ballot_sync(kFull, look_a), pend_b = __ballot_sync(kFull, look_b);
+      // ---- column groups: columns with the same x offsets, at most 64 cells apart ------------------------
+      unsigned pend_a = __ballot_sync(kFull, good_a), pend_b = __ballot_sync(kFull, good_b);
       while (pend_a | pend_b) {
         const bool from_a = pend_a != 0u;
         const int leader = __ffs(from_a ? pend_a : pend_b) - 1;
-        const unsigned long long kl = __shfl_sync(kFull, from_a ? key_a : key_b, leader);
-        const bool same_a = look_a && key_a == kl, same_b = look_b && key_b == kl;
-        int sfound = -1;
-        if (lane == leader) {
-          const int home = static_cast<int>((kl * 0x9E3779B97F4A7C15ull) >> 58);
-          for (int j = 0; j < kLatSlots && sfound < 0; ++j) {
-            const int idx = (home + j) & (kLatSlots - 1);
-            unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(&slot_key[idx]);
-            if (old == 0ull) old = atomicCAS(&slot_key[idx], 0ull, kl);
-            if (old == 0ull) {  // we own the slot: publish the canonical relative vertices and the row table
-              const double2 cs = heading_cs(it);
-              const double c = cs.x, s = cs.y;
-              const double tx = column_tx(from_a ? ix_a : ix_b);
-              const double ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>((g.row_first + row_rel) - static_cast<long long>(it) * src.ny), src.dy));
-              int ax = 0, ay = 0;
-              for (int v = 0; v < nv; ++v) {
-                int cx, cy;
-                lat_cell_x(c, s, tx, poly[2 * v], poly[2 * v + 1], m, cx);
-                lat_cell_y(c, s, ty, poly[2 * v], poly[2 * v + 1], m, cy);
-                if (v == 0) ax = cx, ay = cy;
-                canon[idx * nv + v] = make_int2(cx - ax, cy - ay);
-              }
-              const LatShape sh = lattice_rasterise(canon + idx * nv, nv, rows_cap, m.pitch, row_a + idx * rows_cap, row_m + idx * rows_cap);
-              meta[idx].xb = sh.xb, meta[idx].x1 = sh.x1, meta[idx].yb = sh.yb, meta[idx].rows = sh.rows;
-              __threadfence_block();
-              *reinterpret_cast<volatile int*>(&meta[idx].status) = sh.status;
-              sfound = idx;
-            } else if (old == kl) {
-              sfound = idx;
-            }
+        const unsigned long long kx = __shfl_sync(kFull, from_a ? xa.key : xb.key, leader);
+        bool same_a = ((pend_a >> lane) & 1u) && xa.key == kx, same_b = ((pend_b >> lane) & 1u) && xb.key == kx;
+        const double tx_lead = __shfl_sync(kFull, column_tx(from_a ? ix_a : ix_b), leader);
+        const int c0_lead = __shfl_sync(kFull, from_a ? xa.c0 : xb.c0, leader);
+        if (!exact_key) {  // equal hashes only propose the group: compare the offsets with the leader's
+          const double tx_a = column_tx(ix_a), tx_b = column_tx(ix_b);
+          for (int v = 1; v < nv; ++v) {
+            int cl, ca, cb;
+            lat_cell_x(cs.x, cs.y, tx_lead, poly[2 * v], poly[2 * v + 1], m, cl);
+            lat_cell_x(cs.x, cs.y, tx_a, poly[2 * v], poly[2 * v + 1], m, ca);
+            lat_cell_x(cs.x, cs.y, tx_b, poly[2 * v], poly[2 * v + 1], m, cb);
+            same_a &= ca - xa.c0 == cl - c0_lead;
+            same_b &= cb - xb.c0 == cl - c0_lead;
           }
         }
-        sfound = __shfl_sync(kFull, sfound, leader);
-        if (same_a) slot_a = sfound, look_a = false;
-        if (same_b) slot_b = sfound, look_b = false;
-        pend_a &= ~__ballot_sync(kFull, same_a);
-        pend_b &= ~__ballot_sync(kFull, same_b);
-      }
-      memo_slot_a = slot_a, memo_slot_b = slot_b;  // (slots < 0 are looked up / re-decided again next row)
-      memo_valid = true;
-
-      // ---- wait for shapes other warps are still rasterising; verify hashed keys ----------------------
-      int st_a = ST_OK, st_b = ST_OK;
-      if (slot_a >= 0) {
-        while ((st_a = *reinterpret_cast<volatile int*>(&meta[slot_a].status)) == kLatPending) {
-        }
-      }
-      if (slot_b >= 0) {
-        while ((st_b = *reinterpret_cast<volatile int*>(&meta[slot_b].status)) == kLatPending) {
-        }
-      }
-      __threadfence_block();
-      if (!exact_key) {  // the hash only proposed the shape: compare the actual relative vertices
-        const double2 cs = heading_cs(it);
-        const double c = cs.x, s = cs.y, tx_a = column_tx(ix_a), tx_b = column_tx(ix_b);
-        const double ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>((g.row_first + row_rel) - static_cast<long long>(it) * src.ny), src.dy));
-        for (int v = 0; v < nv; ++v) {
-          int cy, cx;
-          lat_cell_y(c, s, ty, poly[2 * v], poly[2 * v + 1], m, cy);
-          if (slot_a >= 0) {
-            lat_cell_x(c, s, tx_a, poly[2 * v], poly[2 * v + 1], m, cx);
-            const int2 q = canon[slot_a * nv + v];
-            if (cx - xa.c0 != q.x || cy - vy0 != q.y) slot_a = -1;
-          }
-          if (slot_b >= 0) {
-            lat_cell_x(c, s, tx_b, poly[2 * v], poly[2 * v + 1], m, cx);
-            const int2 q = canon[slot_b * nv + v];
-            if (cx - xb.c0 != q.x || cy - vy0 != q.y) slot_b = -1;
-          }
-        }
-      }
-      if (slot_a == -1 || (slot_a >= 0 && st_a == kLatUnfit)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
-      if (slot_b == -1 || (slot_b >= 0 && st_b == kLatUnfit)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
-      if (slot_a >= 0 && st_a == ST_LOGIC_ERROR) store_failure(out, i_a, ST_LOGIC_ERROR);
-      if (slot_b >= 0 && st_b == ST_LOGIC_ERROR) store_failure(out, i_b, ST_LOGIC_ERROR);
-
-      // ---- up to 64 x-adjacent poses per 96-cell bit window -------------------------------------------
-      const bool go_a = slot_a >= 0 && st_a == ST_OK, go_b = slot_b >= 0 && st_b == ST_OK;
-      pend_a = __ballot_sync(kFull, go_a), pend_b = __ballot_sync(kFull, go_b);
-      uint32_t free_a = 0u, free_b = 0u;  // OP_IS_FREE: the row's verdicts, one bit per lane and plane
-      while (pend_a | pend_b) {
-        const bool from_a = pend_a != 0u;
-        const int leader = __ffs(from_a ? pend_a : pend_b) - 1;
-        const int sl = __shfl_sync(kFull, from_a ? slot_a : slot_b, leader);
-        const bool same_a = ((pend_a >> lane) & 1u) && slot_a == sl, same_b = ((pend_b >> lane) & 1u) && slot_b == sl;
         const int xmin = __reduce_min_sync(kFull, min(same_a ? xa.c0 : 0x7FFFFFFF, same_b ? xb.c0 : 0x7FFFFFFF));
         const int off_a = xa.c0 - xmin, off_b = xb.c0 - xmin;
-        const bool fits_a = same_a && off_a < 64, fits_b = same_b && off_b < 64;  // the pose holding xmin always fits
+        const bool fits_a = same_a && off_a < 64, fits_b = same_b && off_b < 64;  // the column holding xmin always fits
         const unsigned grp_a = __ballot_sync(kFull, fits_a), grp_b = __ballot_sync(kFull, fits_b);
         const int maxoff = __reduce_max_sync(kFull, max(fits_a ? off_a : 0, fits_b ? off_b : 0));
-        const int xb_s = meta[sl].xb, x1_s = meta[sl].x1, rows = meta[sl].rows, y_base = vy0 + meta[sl].yb;
-        // every cell any pose of the group needs lies in x: [xmin + xb, xmin + maxoff + x1]
-        const bool inside = y_base >= 0 && y_base + rows <= m.size_y && xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x;
         const int oa = fits_a ? off_a : 0, ob = fits_b ? off_b : 0;
-        if constexpr (OP == OP_IS_FREE) {
-          uint32_t hit_a = 0, hit_b = 0;
-          // the usual full group: plane A's offsets are 0..31, plane B's 32..63 -> no per-row piece selection
-          const bool split_planes = __all_sync(kFull, (!fits_a || off_a < 32) && (!fits_b || off_b >= 32));
-          if (inside && split_planes) lattice_rows<0>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, fits_b ? ob : 32, hit_a, hit_b);
-          else if (inside) lattice_rows<1>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, ob, hit_a, hit_b);
-          else lattice_rows<2>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, true, oa, ob, hit_a, hit_b);
-          if (fits_a) {
-            if (out.is_free) out.is_free[i_a] = hit_a ? 0 : 1;
-            if (out.status) out.status[i_a] = ST_OK;
-          }
-          if (fits_b) {
-            if (out.is_free) out.is_free[i_b] = hit_b ? 0 : 1;
-            if (out.status) out.status[i_b] = ST_OK;
-          }
-          free_a |= __ballot_sync(kFull, fits_a && hit_a == 0u);
-          free_b |= __ballot_sync(kFull, fits_b && hit_b == 0u);
-        } else if (inside) {  // (discarded for OP_IS_FREE: the whole else-chain hangs off an `if constexpr`)
-          Fold<OP> fa, fb;
-          lattice_rows_fold<OP>(m, row_a + sl * rows_cap, row_m + sl * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, ob, rowbuf, fa, fb);
-          if (fits_a) {
-            fa.store(out, i_a);
-            if (out.status) out.status[i_a] = ST_OK;
-          }
-          if (fits_b) {
-            fb.store(out, i_b);
-            if (out.status) out.status[i_b] = ST_OK;
-          }
-        } else {  // a pose of the group touches the map border: the general kernel resolves out-of-map cells in order
-          if (fits_a) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
-          if (fits_b) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
-        }
         pend_a &= ~grp_a;
         pend_b &= ~grp_b;
-      }
-      if constexpr (OP == OP_IS_FREE) {
-        if (out.free_bits) {
-          lat_store_bits(out, free_a, i_a - lane, lane);
-          lat_store_bits(out, free_b, i_b - lane, lane);
+
+        int slot = -1, st = ST_OK;  // the group's shape slot: carried from row to row while the y offsets repeat
+        for (int r = r0; r < r1; ++r) {
+          if ((bad_rows >> r) & 1u) {
+            slot = -1;
+            continue;
+          }
+          const long long i_a = i_base + static_cast<long long>(r) * src.nx + ix_a, i_b = i_a + 32;
+          const bool act_a = fits_a && i_a >= 0 && i_a < count, act_b = fits_b && i_b >= 0 && i_b < count;
+          if (!__any_sync(kFull, act_a || act_b)) {  // (a batch may start / end inside the row)
+            slot = -1;
+            continue;
+          }
+          const int vy0 = __shfl_sync(kFull, my_y.c0, r);
+          if (!(r > r0 && slot >= 0 && __shfl_sync(kFull, static_cast<int>(my_same_prev), r) != 0)) {
+            // ---- shape cache: find, or insert + rasterise ----------------------------------------------
+            const unsigned long long ykey = __shfl_sync(kFull, my_y.key, r);
+            const unsigned long long kl = exact_key ? ((1ull << 63) | (kx << 24) | ykey) : ((lat_mix(kx, static_cast<int>(ykey)) ^ (ykey >> 32)) | 1ull);
+            const int iy = __shfl_sync(kFull, my_iy, r);
+            const double ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(iy), src.dy));
+            int sfound = -1;
+            if (lane == leader) {
+              const int home = static_cast<int>((kl * 0x9E3779B97F4A7C15ull) >> 58);
+              for (int j = 0; j < kLatSlots && sfound < 0; ++j) {
+                const int idx = (home + j) & (kLatSlots - 1);
+                unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(&slot_key[idx]);
+                if (old == 0ull) old = atomicCAS(&slot_key[idx], 0ull, kl);
+                if (old == 0ull) {  // we own the slot: publish the canonical relative vertices and the row table
+                  int ax = 0, ay = 0;
+                  for (int v = 0; v < nv; ++v) {
+                    int cx, cy;
+                    lat_cell_x(cs.x, cs.y, tx_lead, poly[2 * v], poly[2 * v + 1], m, cx);
+                    lat_cell_y(cs.x, cs.y, ty, poly[2 * v], poly[2 * v + 1], m, cy);
+                    if (v == 0) ax = cx, ay = cy;
+                    canon[idx * nv + v] = make_int2(cx - ax, cy - ay);
+                  }
+                  const LatShape sh = lattice_rasterise(canon + idx * nv, nv, rows_cap, m.pitch, row_a + idx * rows_cap, row_m + idx * rows_cap);
+                  meta[idx].xb = sh.xb, meta[idx].x1 = sh.x1, meta[idx].yb = sh.yb, meta[idx].rows = sh.rows;
+                  __threadfence_block();
+                  *reinterpret_cast<volatile int*>(&meta[idx].status) = sh.status;
+                  sfound = idx;
+                } else if (old == kl) {
+                  sfound = idx;
+                }
+              }
+            }
+            slot = __shfl_sync(kFull, sfound, leader);
+            st = ST_OK;
+            if (slot >= 0) {  // wait for a shape another warp is still rasterising
+              while ((st = *reinterpret_cast<volatile int*>(&meta[slot].status)) == kLatPending) {
+              }
+              __threadfence_block();
+              if (!exact_key) {  // the hash only proposed the shape: compare the actual relative vertices
+                bool equal = true;
+                for (int v = lane; v < nv; v += 32) {
+                  int cx, cy;
+                  lat_cell_x(cs.x, cs.y, tx_lead, poly[2 * v], poly[2 * v + 1], m, cx);
+                  lat_cell_y(cs.x, cs.y, ty, poly[2 * v], poly[2 * v + 1], m, cy);
+                  const int2 q = canon[slot * nv + v];
+                  equal &= cx - c0_lead == q.x && cy - vy0 == q.y;
+                }
+                if (!__all_sync(kFull, equal)) slot = -1;
+              }
+            }
+          }
+          if (slot < 0 || st == kLatUnfit) {  // cache full, hash clash or a shape the packed table cannot hold
+            if (act_a) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
+            if (act_b) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
+            continue;
+          }
+          if (st != ST_OK) {  // open outline: std::logic_error in the reference
+            if (act_a) store_failure(out, i_a, st);
+            if (act_b) store_failure(out, i_b, st);
+            continue;
+          }
+          // ---- up to 64 x-adjacent poses per 96-cell bit window ----------------------------------------
+          const int xb_s = meta[slot].xb, x1_s = meta[slot].x1, rows = meta[slot].rows, y_base = vy0 + meta[slot].yb;
+          // every cell any pose of the group needs lies in x: [xmin + xb, xmin + maxoff + x1]
+          const bool inside = y_base >= 0 && y_base + rows <= m.size_y && xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x;
+          if constexpr (OP == OP_IS_FREE) {
+            uint32_t hit_a = 0, hit_b = 0;
+            if (inside && pv.bits) lattice_rows_planes(pv, row_a + slot * rows_cap, row_m + slot * rows_cap, rows, m.pitch, xmin, y_base, lane, maxoff >= 32, oa, ob, hit_a, hit_b);
+            else lattice_rows_bytes(m, row_a + slot * rows_cap, row_m + slot * rows_cap, rows, xmin, y_base, lane, oa, ob, hit_a, hit_b);
+            if (act_a) {
+              if (out.is_free) out.is_free[i_a] = hit_a ? 0 : 1;
+              if (out.status) out.status[i_a] = ST_OK;
+            }
+            if (act_b) {
+              if (out.is_free) out.is_free[i_b] = hit_b ? 0 : 1;
+              if (out.status) out.status[i_b] = ST_OK;
+            }
+            if (out.free_bits) {
+              lat_store_bits(out, __ballot_sync(kFull, act_a && hit_a == 0u), i_a - lane, lane);
+              lat_store_bits(out, __ballot_sync(kFull, act_b && hit_b == 0u), i_b - lane, lane);
+            }
+          } else if (inside) {  // (discarded for OP_IS_FREE: the whole else-chain hangs off an `if constexpr`)
+            Fold<OP> fa, fb;
+            lattice_rows_fold<OP>(m, row_a + slot * rows_cap, row_m + slot * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, ob, rowbuf, fa, fb);
+            if (act_a) {
+              fa.store(out, i_a);
+              if (out.status) out.status[i_a] = ST_OK;
+            }
+            if (act_b) {
+              fb.store(out, i_b);
+              if (out.status) out.status[i_b] = ST_OK;
+            }
+          } else {  // a pose of the group touches the map border: the general kernel resolves out-of-map cells in order
+            if (act_a) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
+            if (act_b) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
+          }
         }
       }
+      r0 = r1;
     }
   }
 }
@@ -1698,6 +1748,7 @@ struct cover_ctx {
   std::string error;
   int64_t launches = 0;
   bool disable_lattice_kernel = false;
+  bool disable_planes = false;          // COVER_B200_NO_PLANES=1: lattice verdicts walk the cost bytes (A/B measurements)
   bool old_packed_kernel = false;       // COVER_B200_OLD_PACKED=1: first-generation per-thread kernel (A/B measurements)
   bool force_list_kernel = false;
   bool always_try_packed = true;        // COVER_B200_PACKED_ONLY_CONVEX=1 restricts the packed pass to convex polygons       // COVER_B200_FORCE_LIST_KERNEL=1: A/B measurements and tests of k_area_list  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
@@ -1721,6 +1772,12 @@ struct cover_map {
   int last_band = kMapBands - 1;  // the band copied last
   mutable bool bands_pending = false;
   mutable int hint_lo = 0, hint_hi = -1;  // bands the last lattice sweep needed
+  // lethal bit planes for lattice verdict sweeps (PlaneView): built lazily for the map rows a sweep can touch,
+  // invalidated by everything that changes the map
+  mutable uint32_t* planes = nullptr;
+  mutable int planes_lo = 0, planes_hi = -1;  // rows whose planes match the current image
+  int wpitch = 0;
+  long long plane_words = 0;
 };
 
 struct cover_cells {
@@ -1840,9 +1897,9 @@ cudaError_t map_rows_ready(cover_ctx* ctx, const cover_map* map, long long row_l
   return cudaStreamWaitEvent(ctx->stream, map->band_done[latest], 0);
 }
 
-/// A polygon check over a pose lattice reads map rows under the lattice's y-extent (+ the footprint radius) only.
-cudaError_t lattice_rows_ready(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int nv, const cover_poses* poses) {
-  if (!map->bands_pending) return cudaSuccess;
+/// Map rows a polygon check over a pose lattice can read: the lattice's y-extent +- the footprint's reach,
+/// clamped to the map (lo > hi: none).  False when the extent is not finite (the caller assumes every row).
+bool lattice_row_range(const cover_map* map, const double* polygon_xy, int nv, const cover_poses* poses, int& row_lo, int& row_hi) {
   const cover_lattice& L = poses->lattice;
   double radius = 0, scale = 0;
   for (int v = 0; v < nv; ++v) radius = std::max(radius, std::hypot(polygon_xy[2 * v], polygon_xy[2 * v + 1]));
@@ -1851,8 +1908,37 @@ cudaError_t lattice_rows_ready(cover_ctx* ctx, const cover_map* map, const doubl
   const double ya = L.y0, yb = L.y0 + static_cast<double>(L.ny - 1) * L.dy;
   const double lo = (std::min(ya, yb) - reach - map->view.origin_y) * map->view.inv_res - 2.0;
   const double hi = (std::max(ya, yb) + reach - map->view.origin_y) * map->view.inv_res + 2.0;
-  if (!(std::isfinite(lo) && std::isfinite(hi)) || lo < -1e15 || hi > 1e15) return map_ready(ctx, map);
-  return map_rows_ready(ctx, map, static_cast<long long>(std::floor(lo)), static_cast<long long>(std::ceil(hi)));
+  row_lo = 0, row_hi = map->view.size_y - 1;
+  if (!(std::isfinite(lo) && std::isfinite(hi))) return false;
+  if (lo > row_lo) row_lo = lo > row_hi ? row_hi + 1 : static_cast<int>(std::floor(lo));
+  if (hi < row_hi) row_hi = hi < 0 ? -1 : static_cast<int>(std::ceil(hi));
+  return true;
+}
+
+/// Lethal bit planes of rows [row_lo, row_hi] (built on ctx->stream when the current ones do not cover them).
+int ensure_planes(cover_ctx* ctx, const cover_map* map, int row_lo, int row_hi, PlaneView& pv) {
+  pv = PlaneView{nullptr, 0, 0};
+  if (ctx->disable_planes || row_lo > row_hi) return COVER_OK;
+  if (!map->planes) {
+    const size_t bytes = static_cast<size_t>(map->plane_words) * kPlaneCount * sizeof(uint32_t);
+    uint32_t* p = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&p), bytes) != cudaSuccess) {
+      cudaGetLastError();  // no memory for the acceleration structure: the byte walk still works
+      return COVER_OK;
+    }
+    CU(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    map->planes = p;
+    map->planes_lo = 0, map->planes_hi = -1;
+  }
+  if (row_lo < map->planes_lo || row_hi > map->planes_hi) {
+    const long long tasks = static_cast<long long>(row_hi - row_lo + 1) * ((map->view.size_x + 1023) / 1024);
+    const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((tasks + 7) / 8, static_cast<long long>(ctx->sm_count) * 8)));
+    k_lethal_planes<<<grid, 256, 0, ctx->stream>>>(map->view, map->planes, map->wpitch, map->plane_words, row_lo, row_hi);
+    ++ctx->launches;
+    map->planes_lo = row_lo, map->planes_hi = row_hi;
+  }
+  pv = PlaneView{map->planes, map->wpitch, map->plane_words};
+  return COVER_OK;
 }
 
 int finish_out(cover_ctx* ctx, const OutStage& st, int64_t count) {
@@ -2002,6 +2088,7 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_expand));
   set(reinterpret_cast<const void*>(&k_outline_expand));
   set(reinterpret_cast<const void*>(&k_inflate));
+  set(reinterpret_cast<const void*>(&k_lethal_planes));
   set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_IS_FREE>));
   set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_MAX>));
@@ -2010,7 +2097,7 @@ cudaError_t configure_kernels() {
 
 template <int OP>
 int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev, const double* poly_host, int nv, int shape,
-                   const PoseSource& src, int64_t count, const OutView& out) {
+                   const PoseSource& src, int64_t count, const OutView& out, int row_lo, int row_hi) {
   const size_t poly_bytes = static_cast<size_t>(nv) * 2 * sizeof(double);
   if (count == 0) return COVER_OK;
   if (shape == SHAPE_OUTLINE) {
@@ -2047,8 +2134,13 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
                                                      static_cast<size_t>(rows_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape)) +
                           (OP == OP_IS_FREE ? 0 : kLatWarps * 800);  // the value folds' per-warp query tables
       const unsigned int grid = static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_MIN_BLOCKS));
+      PlaneView pv{nullptr, 0, 0};
+      if (OP == OP_IS_FREE) {  // verdicts read the lethal bit planes of the rows under the window (built on first use)
+        const int rc = ensure_planes(ctx, map, row_lo, row_hi, pv);
+        if (rc) return rc;
+      }
       k_area_lattice<OP><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
-                                                                   ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g);
+                                                                   ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv);
     } else {
       if (ctx->old_packed_kernel) {
         const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint32_t);
@@ -2113,12 +2205,15 @@ int polygon_check(cover_ctx* ctx, const cover_map* map, const double* polygon_xy
   if (poly_bytes) CU(cudaMemcpyAsync(ctx->poly.ptr, polygon_xy, poly_bytes, cudaMemcpyHostToDevice, ctx->stream));
   const double* pd = ctx->poly.as<double>();
   // costmap upload still in flight: a lattice sweep starts as soon as the rows under its window have landed
-  if (poses->format == COVER_POSE_LATTICE && poses->lattice.cs) CU(lattice_rows_ready(ctx, map, polygon_xy, nv, poses));
-  else CU(map_ready(ctx, map));
+  int row_lo = 0, row_hi = map->view.size_y - 1;  // map rows the check can read
+  if (poses->format == COVER_POSE_LATTICE && poses->lattice.cs && lattice_row_range(map, polygon_xy, nv, poses, row_lo, row_hi))
+    CU(map_rows_ready(ctx, map, row_lo, row_hi));
+  else
+    CU(map_ready(ctx, map));
   switch (op) {
-    case OP_IS_FREE: rc = launch_polygon<OP_IS_FREE>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev); break;
-    case OP_ACCUMULATE: rc = launch_polygon<OP_ACCUMULATE>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev); break;
-    default: rc = launch_polygon<OP_MAX>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev); break;
+    case OP_IS_FREE: rc = launch_polygon<OP_IS_FREE>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev, row_lo, row_hi); break;
+    case OP_ACCUMULATE: rc = launch_polygon<OP_ACCUMULATE>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev, row_lo, row_hi); break;
+    default: rc = launch_polygon<OP_MAX>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev, row_lo, row_hi); break;
   }
   if (rc) return rc;
   return finish_out(ctx, st, poses->count);
@@ -2292,6 +2387,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
   }
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = std::getenv("COVER_B200_NO_LATTICE_KERNEL")) ctx->disable_lattice_kernel = e[0] == '1';
+  if (const char* e = std::getenv("COVER_B200_NO_PLANES")) ctx->disable_planes = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_PACKED_ONLY_CONVEX")) ctx->always_try_packed = e[0] != '1';
   if (const char* e = std::getenv("COVER_B200_OLD_PACKED")) ctx->old_packed_kernel = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_FORCE_LIST_KERNEL")) ctx->force_list_kernel = e[0] == '1';
@@ -2346,6 +2442,8 @@ int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double reso
   m->dev = dev;
   m->resolution = resolution;
   m->band_rows = (size_y + kMapBands - 1) / kMapBands;
+  m->wpitch = (size_x + 31) / 32 + 3;
+  m->plane_words = static_cast<long long>(m->wpitch) * size_y;
   for (cudaEvent_t& e : m->band_done) {
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
       for (cudaEvent_t& d : m->band_done)
@@ -2386,6 +2484,7 @@ int cover_map_upload_async(cover_map* map, const uint8_t* host_data) {
   }
   map->last_band = order[kMapBands - 1];
   map->bands_pending = true;
+  map->planes_hi = -1;  // the bit planes describe the old image
   return COVER_OK;
 }
 
@@ -2395,6 +2494,7 @@ int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem) {
   Bind bind(ctx->device);
   const MapView& v = map->view;
   CU(map_ready(ctx, map));
+  map->planes_hi = -1;
   CU(cudaMemcpy2DAsync(map->dev, v.pitch, data, v.size_x, v.size_x, v.size_y,
                        mem == COVER_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
   if (mem == COVER_MEM_HOST) CU(cudaStreamSynchronize(ctx->stream));
@@ -2409,6 +2509,7 @@ int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x
   if (w == 0 || h == 0) return COVER_OK;
   Bind bind(ctx->device);
   CU(map_ready(ctx, map));
+  map->planes_hi = -1;
   CU(cudaMemcpy2DAsync(map->dev + static_cast<size_t>(y0) * v.pitch + x0, v.pitch, full_image + static_cast<size_t>(y0) * v.size_x + x0,
                        v.size_x, w, h, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -2464,6 +2565,7 @@ int cover_map_inflate(cover_map* map, int32_t radius_cells, const uint8_t* cost_
   const MapView& v = map->view;
   const size_t bytes = static_cast<size_t>(v.pitch) * v.size_y;
   CU(map_ready(ctx, map));
+  map->planes_hi = -1;
   CU(ctx->in_a.ensure(bytes));  // snapshot of the un-inflated map: the kernel reads it and writes the map in place
   CU(cudaMemcpyAsync(ctx->in_a.ptr, map->dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   const size_t lut_bytes = static_cast<size_t>(radius_cells) * radius_cells + 1;
@@ -2485,6 +2587,7 @@ void cover_map_destroy(cover_map* map) {
   cudaStreamSynchronize(map->ctx->copy_stream);
   cudaStreamSynchronize(map->ctx->stream);
   for (cudaEvent_t e : map->band_done) cudaEventDestroy(e);
+  cudaFree(map->planes);
   cudaFree(map->dev);
   delete map;
 }
