@@ -996,6 +996,8 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
     const int rows_here = min(kLatRows, g.n_rows - group * kLatRows);
     const long long i_base = (g.row_first + static_cast<long long>(group) * kLatRows) * src.nx - src.first;  // pose index of (row 0, column 0)
     const bool col_a = ix_a < src.nx, col_b = ix_b < src.nx;
+    // the usual unit lies inside the batch [0, count): no per-pose range tests
+    const bool whole_unit = i_base >= 0 && i_base + static_cast<long long>(rows_here) * src.nx <= count;
 
     // runs of rows with the same heading (one per unit; two where the unit crosses a heading boundary)
     for (int r0 = 0; r0 < rows_here;) {
@@ -1056,16 +1058,21 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
         pend_b &= ~grp_b;
 
         int slot = -1, st = ST_OK;  // the group's shape slot: carried from row to row while the y offsets repeat
-        for (int r = r0; r < r1; ++r) {
+        int xb_s = 0, x1_s = 0, rows = 0, yb_s = 0;  // its bounding box relative to vertex 0
+        long long i_a = i_base + static_cast<long long>(r0) * src.nx + ix_a;
+        for (int r = r0; r < r1; ++r, i_a += src.nx) {
           if ((bad_rows >> r) & 1u) {
             slot = -1;
             continue;
           }
-          const long long i_a = i_base + static_cast<long long>(r) * src.nx + ix_a, i_b = i_a + 32;
-          const bool act_a = fits_a && i_a >= 0 && i_a < count, act_b = fits_b && i_b >= 0 && i_b < count;
-          if (!__any_sync(kFull, act_a || act_b)) {  // (a batch may start / end inside the row)
-            slot = -1;
-            continue;
+          const long long i_b = i_a + 32;
+          bool act_a = fits_a, act_b = fits_b;
+          if (!whole_unit) {  // (a batch may start / end inside the row)
+            act_a = fits_a && i_a >= 0 && i_a < count, act_b = fits_b && i_b >= 0 && i_b < count;
+            if (!__any_sync(kFull, act_a || act_b)) {
+              slot = -1;
+              continue;
+            }
           }
           const int vy0 = __shfl_sync(kFull, my_y.c0, r);
           if (!(r > r0 && slot >= 0 && __shfl_sync(kFull, static_cast<int>(my_same_prev), r) != 0)) {
@@ -1106,6 +1113,7 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
               while ((st = *reinterpret_cast<volatile int*>(&meta[slot].status)) == kLatPending) {
               }
               __threadfence_block();
+              xb_s = meta[slot].xb, x1_s = meta[slot].x1, rows = meta[slot].rows, yb_s = meta[slot].yb;
               if (!exact_key) {  // the hash only proposed the shape: compare the actual relative vertices
                 bool equal = true;
                 for (int v = lane; v < nv; v += 32) {
@@ -1130,7 +1138,7 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
             continue;
           }
           // ---- up to 64 x-adjacent poses per 96-cell bit window ----------------------------------------
-          const int xb_s = meta[slot].xb, x1_s = meta[slot].x1, rows = meta[slot].rows, y_base = vy0 + meta[slot].yb;
+          const int y_base = vy0 + yb_s;
           // every cell any pose of the group needs lies in x: [xmin + xb, xmin + maxoff + x1]
           const bool inside = y_base >= 0 && y_base + rows <= m.size_y && xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x;
           if constexpr (OP == OP_IS_FREE) {
