@@ -572,6 +572,9 @@ __global__ void __launch_bounds__(kBlock) k_area_slots(MapView m, const double* 
 #ifndef LAT_MIN_BLOCKS
 #define LAT_MIN_BLOCKS 3
 #endif
+#ifndef LAT_LEAN_BLOCKS
+#define LAT_LEAN_BLOCKS 3
+#endif
 constexpr int kLatSegX = 64, kLatRows = 8, kLatWarps = 8, kLatThreads = kLatWarps * 32, kLatSlots = 64;
 constexpr int kLatMaxVertices = 64;
 constexpr int kLatMaxWidth = 32;   // widest scan row (cells): 64 pose offsets + 32 cells = one 96-cell window
@@ -911,8 +914,11 @@ __device__ __forceinline__ void lat_store_bits(const OutView& out, uint32_t free
   if (hi_word) atomicOr(out.free_bits + w + 1, hi_word);
 }
 
-template <int OP>
-__global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
+/// LEAN = verdicts of a polygon with at most 4 vertices over the bit planes (the headline case): the shape key is
+/// exact, scan rows are decoded once per slot, and everything unusual (map border, shapes taller than 32 rows) goes
+/// to the todo list - no hashed keys, no byte walk, no out-of-line calls on the hot path.
+template <int OP, bool LEAN>
+__global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_BLOCKS) k_area_lattice(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
                                                                      long long count, OutView out, int rows_cap,
                                                                      unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count,
                                                                      LatGeom g, PlaneView pv) {
@@ -932,7 +938,7 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* rowbuf = rowbufs + warp * 800;
-  const bool exact_key = nv <= 4;  // 2 x 3 offsets of 8 bits: the key IS the shape, no verification pass
+  const bool exact_key = LEAN || nv <= 4;  // 2 x 3 offsets of 8 bits: the key IS the shape, no verification pass
   const long long chunk = (g.n_units + gridDim.x - 1) / gridDim.x;
   const long long unit_begin = blockIdx.x * chunk, unit_end = min(g.n_units, unit_begin + chunk);
   int cached_heading = -1;
@@ -1059,6 +1065,12 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
 
         int slot = -1, st = ST_OK;  // the group's shape slot: carried from row to row while the y offsets repeat
         int xb_s = 0, x1_s = 0, rows = 0, yb_s = 0;  // its bounding box relative to vertex 0
+        // OP_IS_FREE over the bit planes, lane j = scan row j of the slot's shape, decoded once per slot: the two
+        // windows' word pointers for map row 0 (the lattice row only adds y_base * wpitch) and bit shifts
+        const uint32_t* win_s = nullptr;
+        const uint32_t* win_t = nullptr;
+        int sh_s = 0, sh_t = 0;
+        bool lean = false, inside_x = false;
         long long i_a = i_base + static_cast<long long>(r0) * src.nx + ix_a;
         for (int r = r0; r < r1; ++r, i_a += src.nx) {
           if ((bad_rows >> r) & 1u) {
@@ -1109,11 +1121,28 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
             }
             slot = __shfl_sync(kFull, sfound, leader);
             st = ST_OK;
+            lean = false;
             if (slot >= 0) {  // wait for a shape another warp is still rasterising
               while ((st = *reinterpret_cast<volatile int*>(&meta[slot].status)) == kLatPending) {
               }
               __threadfence_block();
               xb_s = meta[slot].xb, x1_s = meta[slot].x1, rows = meta[slot].rows, yb_s = meta[slot].yb;
+              if constexpr (OP == OP_IS_FREE) {
+                lean = pv.bits != nullptr && rows <= 32 && st == ST_OK;
+                if (lean) {
+                  // every cell any pose of the group needs lies in x: [xmin + xb, xmin + maxoff + x1]
+                  inside_x = xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x;
+                  const int width = lane < rows ? __popc(row_m[slot * rows_cap + lane]) : 0;
+                  win_s = win_t = nullptr;
+                  if (width > 0 && inside_x) {
+                    const int k = 31 - __clz(width);
+                    const int xs = xmin + (row_a[slot * rows_cap + lane] - lane * m.pitch), xt = xs + (width - (1 << k));
+                    const uint32_t* plane_row = pv.bits + k * pv.plane_words + static_cast<long long>(lane) * pv.wpitch;
+                    win_s = plane_row + (xs >> 5), sh_s = xs & 31;
+                    if (xt != xs) win_t = plane_row + (xt >> 5), sh_t = xt & 31;
+                  }
+                }
+              }
               if (!exact_key) {  // the hash only proposed the shape: compare the actual relative vertices
                 bool equal = true;
                 for (int v = lane; v < nv; v += 32) {
@@ -1143,7 +1172,30 @@ __global__ void __launch_bounds__(kLatThreads, LAT_MIN_BLOCKS) k_area_lattice(Ma
           const bool inside = y_base >= 0 && y_base + rows <= m.size_y && xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x;
           if constexpr (OP == OP_IS_FREE) {
             uint32_t hit_a = 0, hit_b = 0;
-            if (inside && pv.bits) lattice_rows_planes(pv, row_a + slot * rows_cap, row_m + slot * rows_cap, rows, m.pitch, xmin, y_base, lane, maxoff >= 32, oa, ob, hit_a, hit_b);
+            if (lean && inside) {
+              // lane j ORs the (up to) two power-of-two windows of scan row j; one redux per 32 offsets folds the rows
+              const long long row_off = static_cast<long long>(y_base) * pv.wpitch;
+              uint32_t r_lo = 0u, r_hi = 0u;
+              const bool third = maxoff >= 32;
+              if (win_s) {
+                const uint32_t* __restrict__ q = win_s + row_off;
+                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = third ? __ldg(q + 2) : 0u;
+                r_lo = __funnelshift_r(w0, w1, sh_s), r_hi = __funnelshift_r(w1, w2, sh_s);
+              }
+              if (win_t) {
+                const uint32_t* __restrict__ q = win_t + row_off;
+                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = third ? __ldg(q + 2) : 0u;
+                r_lo |= __funnelshift_r(w0, w1, sh_t), r_hi |= __funnelshift_r(w1, w2, sh_t);
+              }
+              r_lo = __reduce_or_sync(kFull, r_lo);
+              r_hi = third ? __reduce_or_sync(kFull, r_hi) : 0u;
+              hit_a = ((oa < 32 ? r_lo : r_hi) >> (oa & 31)) & 1u;
+              hit_b = ((ob < 32 ? r_lo : r_hi) >> (ob & 31)) & 1u;
+            } else if constexpr (LEAN) {
+              if (act_a) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
+              if (act_b) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
+              continue;
+            } else if (inside && pv.bits) lattice_rows_planes(pv, row_a + slot * rows_cap, row_m + slot * rows_cap, rows, m.pitch, xmin, y_base, lane, maxoff >= 32, oa, ob, hit_a, hit_b);
             else lattice_rows_bytes(m, row_a + slot * rows_cap, row_m + slot * rows_cap, rows, xmin, y_base, lane, oa, ob, hit_a, hit_b);
             if (act_a) {
               if (out.is_free) out.is_free[i_a] = hit_a ? 0 : 1;
@@ -2090,9 +2142,10 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_rows<OP_IS_FREE>));
   set(reinterpret_cast<const void*>(&k_area_rows<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_rows<OP_MAX>));
-  set(reinterpret_cast<const void*>(&k_area_lattice<OP_IS_FREE>));
-  set(reinterpret_cast<const void*>(&k_area_lattice<OP_ACCUMULATE>));
-  set(reinterpret_cast<const void*>(&k_area_lattice<OP_MAX>));
+  set(reinterpret_cast<const void*>(&k_area_lattice<OP_IS_FREE, false>));
+  set(reinterpret_cast<const void*>(&k_area_lattice<OP_IS_FREE, true>));
+  set(reinterpret_cast<const void*>(&k_area_lattice<OP_ACCUMULATE, false>));
+  set(reinterpret_cast<const void*>(&k_area_lattice<OP_MAX, false>));
   set(reinterpret_cast<const void*>(&k_area_expand));
   set(reinterpret_cast<const void*>(&k_outline_expand));
   set(reinterpret_cast<const void*>(&k_inflate));
@@ -2147,8 +2200,12 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
         const int rc = ensure_planes(ctx, map, row_lo, row_hi, pv);
         if (rc) return rc;
       }
-      k_area_lattice<OP><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
-                                                                   ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv);
+      if (OP == OP_IS_FREE && pv.bits && nv <= 4)
+        k_area_lattice<OP_IS_FREE, true><<<static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_LEAN_BLOCKS)), kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
+                                                                                   ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv);
+      else
+        k_area_lattice<OP, false><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
+                                                                            ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv);
     } else {
       if (ctx->old_packed_kernel) {
         const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint32_t);
