@@ -671,8 +671,9 @@ __device__ __noinline__ void lattice_rows_bytes(const MapView& m, const int* __r
 /// two overlapping power-of-two windows - two bits - instead of w bytes.
 struct PlaneView {
   const uint32_t* __restrict__ bits;  // nullptr: planes disabled, the byte walk is used
-  int wpitch;                         // words per plane row (ceil(size_x / 32) + 3 slack words)
-  long long plane_words;              // words per plane
+  int ypitch;                         // COLUMN-major planes: word (column c = x / 32, row y) lives at c * ypitch + y, so the
+                                      // lanes of a warp (= consecutive scan rows, nearly the same x) read consecutive words
+  long long plane_words;              // words per plane = (ceil(size_x / 32) + 3 slack columns) * ypitch
 };
 constexpr int kPlaneCount = 6;
 
@@ -690,17 +691,17 @@ __device__ __forceinline__ void lattice_rows_planes(const PlaneView& pv, const i
     if (width == 0) continue;
     const int k = 31 - __clz(width), tail = width - (1 << k);
     const int xs = x_base + (row_a[j] - j * pitch);
-    const uint32_t* __restrict__ rowp = pv.bits + k * pv.plane_words + static_cast<long long>(y_base + j) * pv.wpitch;
+    const uint32_t* __restrict__ rowp = pv.bits + k * pv.plane_words + (y_base + j);
     {
-      const uint32_t* __restrict__ q = rowp + (xs >> 5);
-      const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = third ? __ldg(q + 2) : 0u;
+      const uint32_t* __restrict__ q = rowp + static_cast<long long>(xs >> 5) * pv.ypitch;
+      const uint32_t w0 = __ldg(q), w1 = __ldg(q + pv.ypitch), w2 = third ? __ldg(q + 2 * pv.ypitch) : 0u;
       r_lo |= __funnelshift_r(w0, w1, xs & 31);
       r_hi |= __funnelshift_r(w1, w2, xs & 31);
     }
     if (tail) {
       const int xt = xs + tail;
-      const uint32_t* __restrict__ q = rowp + (xt >> 5);
-      const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = third ? __ldg(q + 2) : 0u;
+      const uint32_t* __restrict__ q = rowp + static_cast<long long>(xt >> 5) * pv.ypitch;
+      const uint32_t w0 = __ldg(q), w1 = __ldg(q + pv.ypitch), w2 = third ? __ldg(q + 2 * pv.ypitch) : 0u;
       r_lo |= __funnelshift_r(w0, w1, xt & 31);
       r_hi |= __funnelshift_r(w1, w2, xt & 31);
     }
@@ -714,7 +715,7 @@ __device__ __forceinline__ void lattice_rows_planes(const PlaneView& pv, const i
 /// Builds rows [row_lo, row_hi] of the lethal bit planes.  One warp per 1024-cell stretch of a row: 33 coalesced
 /// byte loads + ballots give the lethal words L[i] (lane i keeps word i, plus the first word of the next stretch),
 /// and the doubling V |= V >> 2^k on the 64-bit value L[i] | L[i+1] << 32 yields plane k + 1 in its low word.
-__global__ void __launch_bounds__(256) k_lethal_planes(MapView m, uint32_t* __restrict__ planes, int wpitch, long long plane_words, int row_lo,
+__global__ void __launch_bounds__(256) k_lethal_planes(MapView m, uint32_t* __restrict__ planes, int ypitch, long long plane_words, int row_lo,
                                                         int row_hi) {
   const int lane = threadIdx.x & 31;
   const int stretches = (m.size_x + 1023) / 1024;
@@ -731,9 +732,9 @@ __global__ void __launch_bounds__(256) k_lethal_planes(MapView m, uint32_t* __re
       if (i == lane + 1) next = word;
     }
     const int word_index = (x0 >> 5) + lane;
-    if (word_index >= wpitch) continue;
+    if (static_cast<long long>(word_index + 1) * ypitch > plane_words) continue;
     unsigned long long v = static_cast<unsigned long long>(mine) | (static_cast<unsigned long long>(next) << 32);
-    uint32_t* __restrict__ dst = planes + static_cast<long long>(y) * wpitch + word_index;
+    uint32_t* __restrict__ dst = planes + static_cast<long long>(word_index) * ypitch + y;
 #pragma unroll
     for (int k = 0; k < kPlaneCount; ++k) {
       dst[k * plane_words] = static_cast<uint32_t>(v);
@@ -1066,7 +1067,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
         int slot = -1, st = ST_OK;  // the group's shape slot: carried from row to row while the y offsets repeat
         int xb_s = 0, x1_s = 0, rows = 0, yb_s = 0;  // its bounding box relative to vertex 0
         // OP_IS_FREE over the bit planes, lane j = scan row j of the slot's shape, decoded once per slot: the two
-        // windows' word pointers for map row 0 (the lattice row only adds y_base * wpitch) and bit shifts
+        // windows' word pointers for map row 0 (the lattice row only adds y_base) and bit shifts
         const uint32_t* win_s = nullptr;
         const uint32_t* win_t = nullptr;
         int sh_s = 0, sh_t = 0;
@@ -1137,9 +1138,9 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
                   if (width > 0 && inside_x) {
                     const int k = 31 - __clz(width);
                     const int xs = xmin + (row_a[slot * rows_cap + lane] - lane * m.pitch), xt = xs + (width - (1 << k));
-                    const uint32_t* plane_row = pv.bits + k * pv.plane_words + static_cast<long long>(lane) * pv.wpitch;
-                    win_s = plane_row + (xs >> 5), sh_s = xs & 31;
-                    if (xt != xs) win_t = plane_row + (xt >> 5), sh_t = xt & 31;
+                    const uint32_t* plane_row = pv.bits + k * pv.plane_words + lane;
+                    win_s = plane_row + static_cast<long long>(xs >> 5) * pv.ypitch, sh_s = xs & 31;
+                    if (xt != xs) win_t = plane_row + static_cast<long long>(xt >> 5) * pv.ypitch, sh_t = xt & 31;
                   }
                 }
               }
@@ -1174,17 +1175,16 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
             uint32_t hit_a = 0, hit_b = 0;
             if (lean && inside) {
               // lane j ORs the (up to) two power-of-two windows of scan row j; one redux per 32 offsets folds the rows
-              const long long row_off = static_cast<long long>(y_base) * pv.wpitch;
               uint32_t r_lo = 0u, r_hi = 0u;
               const bool third = maxoff >= 32;
               if (win_s) {
-                const uint32_t* __restrict__ q = win_s + row_off;
-                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = third ? __ldg(q + 2) : 0u;
+                const uint32_t* __restrict__ q = win_s + y_base;
+                const uint32_t w0 = __ldg(q), w1 = __ldg(q + pv.ypitch), w2 = third ? __ldg(q + 2 * pv.ypitch) : 0u;
                 r_lo = __funnelshift_r(w0, w1, sh_s), r_hi = __funnelshift_r(w1, w2, sh_s);
               }
               if (win_t) {
-                const uint32_t* __restrict__ q = win_t + row_off;
-                const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = third ? __ldg(q + 2) : 0u;
+                const uint32_t* __restrict__ q = win_t + y_base;
+                const uint32_t w0 = __ldg(q), w1 = __ldg(q + pv.ypitch), w2 = third ? __ldg(q + 2 * pv.ypitch) : 0u;
                 r_lo |= __funnelshift_r(w0, w1, sh_t), r_hi |= __funnelshift_r(w1, w2, sh_t);
               }
               r_lo = __reduce_or_sync(kFull, r_lo);
@@ -1836,7 +1836,7 @@ struct cover_map {
   // invalidated by everything that changes the map
   mutable uint32_t* planes = nullptr;
   mutable int planes_lo = 0, planes_hi = -1;  // rows whose planes match the current image
-  int wpitch = 0;
+  int ypitch = 0;
   long long plane_words = 0;
 };
 
@@ -1993,11 +1993,11 @@ int ensure_planes(cover_ctx* ctx, const cover_map* map, int row_lo, int row_hi, 
   if (row_lo < map->planes_lo || row_hi > map->planes_hi) {
     const long long tasks = static_cast<long long>(row_hi - row_lo + 1) * ((map->view.size_x + 1023) / 1024);
     const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((tasks + 7) / 8, static_cast<long long>(ctx->sm_count) * 8)));
-    k_lethal_planes<<<grid, 256, 0, ctx->stream>>>(map->view, map->planes, map->wpitch, map->plane_words, row_lo, row_hi);
+    k_lethal_planes<<<grid, 256, 0, ctx->stream>>>(map->view, map->planes, map->ypitch, map->plane_words, row_lo, row_hi);
     ++ctx->launches;
     map->planes_lo = row_lo, map->planes_hi = row_hi;
   }
-  pv = PlaneView{map->planes, map->wpitch, map->plane_words};
+  pv = PlaneView{map->planes, map->ypitch, map->plane_words};
   return COVER_OK;
 }
 
@@ -2507,8 +2507,8 @@ int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double reso
   m->dev = dev;
   m->resolution = resolution;
   m->band_rows = (size_y + kMapBands - 1) / kMapBands;
-  m->wpitch = (size_x + 31) / 32 + 3;
-  m->plane_words = static_cast<long long>(m->wpitch) * size_y;
+  m->ypitch = (size_y + 31) & ~31;
+  m->plane_words = static_cast<long long>((size_x + 31) / 32 + 3) * m->ypitch;
   for (cudaEvent_t& e : m->band_done) {
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
       for (cudaEvent_t& d : m->band_done)
