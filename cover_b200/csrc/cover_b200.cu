@@ -2,7 +2,8 @@
 //
 // The costmap (<= 64 MB) lives in the 126 MB L2; HBM only sees the first touch.  Kernels:
 //   k_area_lattice<OP>   pose-lattice checks: warp = 64 x-adjacent poses, separable exact vertex profiles,
-//                        per-CTA shape cache, ballot bit windows (the headline path)
+//                        per-CTA shape cache, verdicts from precomputed lethal bit planes (k_lethal_planes), value
+//                        folds from per-row prefix / sliding-max tables (the headline path)
 //   k_area_pair<OP>      area checks, arbitrary poses, rows with <= 2 ranges: thread = pose, the warp's 32 outline
 //                        walks fused in lock-step, 64-bit pair table in shared memory
 //   k_area_slots<OP,4>   second per-thread pass over the poses k_area_pair deferred (non-convex polygons): 4 ranges/row
@@ -554,18 +555,21 @@ __global__ void __launch_bounds__(kBlock) k_area_slots(MapView m, const double* 
 //    cell offsets relative to vertex 0 only change where a coordinate sits within rounding noise of a
 //    cell boundary.
 // A persistent CTA walks a contiguous range of units; each warp owns one unit at a time (lane = two
-// columns, ix and ix+32) and, per lattice row,
-//   1. combines the exact x- and y-profiles into the key of the RELATIVE shape (the packed vertex offsets
-//      themselves for <= 4 vertices, else a 64-bit hash),
-//   2. looks the shape up in a shared-memory cache that persists across the CTA's units; the lane that
+// columns, ix and ix+32; lane r also owns lattice row r of the unit) and
+//   1. computes the exact x-profile of its columns and the y-profile of its row (key = the packed vertex
+//      offsets themselves for <= 4 vertices, else a 64-bit hash that is always verified against the actual
+//      offsets) and notes which rows repeat the previous row's offsets,
+//   2. forms column groups ONCE per unit: columns with identical x offsets at most 64 cells apart,
+//   3. per row and group looks the shape (x key, y key) up in a shared-memory cache that persists across the
+//      CTA's units - or carries the slot over from the previous row while the y offsets repeat; the lane that
 //      inserts a NEW shape rasterises it on the spot (the same run detector / packed row table as
 //      k_area_packed, so the scan-line semantics are literally the same code) and publishes it; warps that
-//      meet a shape still being rasterised wait for its status word — no CTA-wide barrier,
-//   3. (hashed keys only) verifies each pose's relative vertices against the cached canonical ones, so
-//      exactness never rests on the hash,
-//   4. tests up to 64 x-adjacent poses at once: per scan row the warp loads the row segment one byte per
-//      lane (three coalesced 32-byte pieces), ballots "lethal or outside" into a 96-cell bit window, and
-//      every pose ANDs its own sub-window.
+//      meet a shape still being rasterised wait for its status word - no CTA-wide barrier,
+//   4. tests the group's (up to 64) poses at once.  Verdicts: lane j = scan row j reads the two power-of-two
+//      windows of its row from the lethal bit planes, a redux.or folds the rows, every pose picks the bit at
+//      its own x offset.  Value folds / map border: the row segment is loaded one byte per lane (three
+//      coalesced 32-byte pieces) and turned into a per-row table (prefix sums, sliding maxima) or a ballot
+//      bit window.
 // Poses whose shape needs more than two ranges on a row, is wider than 32 cells, or finds the cache
 // full go to the todo list and are finished by the general kernels.
 // ---------------------------------------------------------------------------------------------------
