@@ -720,7 +720,7 @@ __device__ __forceinline__ void lattice_rows_planes(const PlaneView& pv, const i
 /// byte loads + ballots give the lethal words L[i] (lane i keeps word i, plus the first word of the next stretch),
 /// and the doubling V |= V >> 2^k on the 64-bit value L[i] | L[i+1] << 32 yields plane k + 1 in its low word.
 __global__ void __launch_bounds__(256) k_lethal_planes(MapView m, uint32_t* __restrict__ planes, int ypitch, long long plane_words, int row_lo,
-                                                        int row_hi) {
+                                                        int row_hi, bool inflated) {
   const int lane = threadIdx.x & 31;
   const int stretches = (m.size_x + 1023) / 1024;
   const long long n_tasks = static_cast<long long>(row_hi - row_lo + 1) * stretches;
@@ -731,7 +731,8 @@ __global__ void __launch_bounds__(256) k_lethal_planes(MapView m, uint32_t* __re
 #pragma unroll 11
     for (int i = 0; i < 33; ++i) {
       const int x = x0 + 32 * i + lane;
-      const uint32_t word = __ballot_sync(kFull, x < m.size_x && __ldg(rowp + x) == kLethal);
+      const int cost = x < m.size_x ? __ldg(rowp + x) : 0;
+      const uint32_t word = __ballot_sync(kFull, cost == kLethal || (inflated && cost == kInscribed));
       if (i == lane) mine = word;
       if (i == lane + 1) next = word;
     }
@@ -1591,7 +1592,8 @@ __global__ void __launch_bounds__(kBlock) k_cells_free(MapView m, const int4* __
     const int4 sp = __ldg(spans + j);
     const int y = sp.x + off.y, lo = sp.y + off.x, hi = sp.z + off.x;
     hit = static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) || lo < 0 || hi >= m.size_x ||
-          row_any_eq(m.data + static_cast<size_t>(y) * m.pitch, lo, hi, 0xFEFEFEFEu);
+          (m.planes ? span_any_bits(m.planes, m.ypitch, m.plane_words, y, lo, hi)
+                    : row_any_eq(m.data + static_cast<size_t>(y) * m.pitch, lo, hi, 0xFEFEFEFEu));
   }
   emit_free(out, i, !hit);
   if (out.status) out.status[i] = ST_OK;
@@ -1618,13 +1620,15 @@ __global__ void __launch_bounds__(kBlock) k_footprints(MapView m, const int4* __
     const int4 sp = __ldg(spans + j);
     const int y = sp.x + off.y, lo = sp.y + off.x, hi = sp.z + off.x;
     hit = static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) || lo < 0 || hi >= m.size_x ||
-          row_any_inflated(m.data + static_cast<size_t>(y) * m.pitch, lo, hi);
+          (m.planes_inf ? span_any_bits(m.planes_inf, m.ypitch, m.plane_words, y, lo, hi)
+                        : row_any_inflated(m.data + static_cast<size_t>(y) * m.pitch, lo, hi));
   }
   for (int j = a_rng.x; j < a_rng.y && !hit; ++j) {
     const int4 sp = __ldg(spans + j);
     const int y = sp.x + off.y, lo = sp.y + off.x, hi = sp.z + off.x;
     hit = static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) || lo < 0 || hi >= m.size_x ||
-          row_any_eq(m.data + static_cast<size_t>(y) * m.pitch, lo, hi, 0xFEFEFEFEu);
+          (m.planes ? span_any_bits(m.planes, m.ypitch, m.plane_words, y, lo, hi)
+                    : row_any_eq(m.data + static_cast<size_t>(y) * m.pitch, lo, hi, 0xFEFEFEFEu));
   }
   emit_free(out, i, !hit);
   if (out.status) out.status[i] = ST_OK;
@@ -1813,6 +1817,7 @@ struct cover_ctx {
   int64_t launches = 0;
   bool disable_lattice_kernel = false;
   bool disable_planes = false;          // COVER_B200_NO_PLANES=1: lattice verdicts walk the cost bytes (A/B measurements)
+  int64_t planes_min_batch = 32768;     // COVER_B200_PLANES_MIN_BATCH: smallest batch that triggers a bit-plane build (tests: 0)
   bool old_packed_kernel = false;       // COVER_B200_OLD_PACKED=1: first-generation per-thread kernel (A/B measurements)
   bool force_list_kernel = false;
   bool always_try_packed = true;        // COVER_B200_PACKED_ONLY_CONVEX=1 restricts the packed pass to convex polygons       // COVER_B200_FORCE_LIST_KERNEL=1: A/B measurements and tests of k_area_list  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
@@ -1838,8 +1843,10 @@ struct cover_map {
   mutable int hint_lo = 0, hint_hi = -1;  // bands the last lattice sweep needed
   // lethal bit planes for lattice verdict sweeps (PlaneView): built lazily for the map rows a sweep can touch,
   // invalidated by everything that changes the map
-  mutable uint32_t* planes = nullptr;
+  mutable uint32_t* planes = nullptr;      // LETHAL planes
+  mutable uint32_t* planes_inf = nullptr;  // INSCRIBED-or-LETHAL planes (outline cells of split footprints)
   mutable int planes_lo = 0, planes_hi = -1;  // rows whose planes match the current image
+  mutable int planes_inf_lo = 0, planes_inf_hi = -1;
   int ypitch = 0;
   long long plane_words = 0;
 };
@@ -1979,30 +1986,62 @@ bool lattice_row_range(const cover_map* map, const double* polygon_xy, int nv, c
   return true;
 }
 
-/// Lethal bit planes of rows [row_lo, row_hi] (built on ctx->stream when the current ones do not cover them).
-int ensure_planes(cover_ctx* ctx, const cover_map* map, int row_lo, int row_hi, PlaneView& pv) {
-  pv = PlaneView{nullptr, 0, 0};
+/// Bit planes of rows [row_lo, row_hi] (built on ctx->stream when the current ones do not cover them): the LETHAL
+/// set, or the INSCRIBED-or-LETHAL set.  Returns nullptr in `bits` when planes are disabled or cannot be allocated.
+int ensure_plane_set(cover_ctx* ctx, const cover_map* map, bool inflated, int row_lo, int row_hi, const uint32_t*& bits) {
+  bits = nullptr;
   if (ctx->disable_planes || row_lo > row_hi) return COVER_OK;
-  if (!map->planes) {
+  uint32_t*& store = inflated ? map->planes_inf : map->planes;
+  int& lo = inflated ? map->planes_inf_lo : map->planes_lo;
+  int& hi = inflated ? map->planes_inf_hi : map->planes_hi;
+  if (!store) {
     const size_t bytes = static_cast<size_t>(map->plane_words) * kPlaneCount * sizeof(uint32_t);
     uint32_t* p = nullptr;
     if (cudaMalloc(reinterpret_cast<void**>(&p), bytes) != cudaSuccess) {
-      cudaGetLastError();  // no memory for the acceleration structure: the byte walk still works
+      cudaGetLastError();  // no memory for the acceleration structure: the byte walks still work
       return COVER_OK;
     }
     CU(cudaMemsetAsync(p, 0, bytes, ctx->stream));
-    map->planes = p;
-    map->planes_lo = 0, map->planes_hi = -1;
+    store = p;
+    lo = 0, hi = -1;
   }
-  if (row_lo < map->planes_lo || row_hi > map->planes_hi) {
+  if (row_lo < lo || row_hi > hi) {
     const long long tasks = static_cast<long long>(row_hi - row_lo + 1) * ((map->view.size_x + 1023) / 1024);
     const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((tasks + 7) / 8, static_cast<long long>(ctx->sm_count) * 8)));
-    k_lethal_planes<<<grid, 256, 0, ctx->stream>>>(map->view, map->planes, map->ypitch, map->plane_words, row_lo, row_hi);
+    k_lethal_planes<<<grid, 256, 0, ctx->stream>>>(map->view, store, map->ypitch, map->plane_words, row_lo, row_hi, inflated);
     ++ctx->launches;
-    map->planes_lo = row_lo, map->planes_hi = row_hi;
+    lo = row_lo, hi = row_hi;
   }
-  pv = PlaneView{map->planes, map->ypitch, map->plane_words};
+  bits = store;
   return COVER_OK;
+}
+
+/// Building planes costs a pass over the map rows: worth it for big batches, or when they are there already.
+bool planes_pay_off(const cover_ctx* ctx, const cover_map* map, bool inflated, int row_lo, int row_hi, int64_t count) {
+  if (ctx->disable_planes) return false;
+  const bool ready = map->planes && row_lo >= map->planes_lo && row_hi <= map->planes_hi &&
+                     (!inflated || (map->planes_inf && row_lo >= map->planes_inf_lo && row_hi <= map->planes_inf_hi));
+  return ready || count >= ctx->planes_min_batch;
+}
+
+int ensure_planes(cover_ctx* ctx, const cover_map* map, int row_lo, int row_hi, PlaneView& pv) {
+  const uint32_t* bits = nullptr;
+  const int rc = ensure_plane_set(ctx, map, false, row_lo, row_hi, bits);
+  pv = PlaneView{bits, map->ypitch, map->plane_words};
+  return rc;
+}
+
+/// The map as the span-scanning kernels see it for a verdict: with the bit planes of rows [row_lo, row_hi] attached
+/// (`inflated`: both sets).  Only for launches whose poses cannot touch other rows of the map.
+int view_with_planes(cover_ctx* ctx, const cover_map* map, bool inflated, int row_lo, int row_hi, MapView& view) {
+  view = map->view;
+  view.ypitch = map->ypitch, view.plane_words = map->plane_words;
+  const uint32_t *lethal = nullptr, *inscribed = nullptr;
+  int rc = ensure_plane_set(ctx, map, false, row_lo, row_hi, lethal);
+  if (rc == COVER_OK && inflated) rc = ensure_plane_set(ctx, map, true, row_lo, row_hi, inscribed);
+  view.planes = lethal, view.planes_inf = inflated ? inscribed : nullptr;
+  if (inflated && !inscribed) view.planes = nullptr;  // (both sets or none: keep the two scans of a footprint consistent)
+  return rc;
 }
 
 int finish_out(cover_ctx* ctx, const OutStage& st, int64_t count) {
@@ -2171,6 +2210,12 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     return COVER_OK;
   }
   const int rows_cap = rows_bound(polygon_diameter(poly_host, nv), map->view.inv_res);
+  // verdicts scan row spans: attach the lethal bit planes of the rows this batch can touch (two loads per span)
+  MapView area_view = map->view;
+  if (OP == OP_IS_FREE && planes_pay_off(ctx, map, false, row_lo, row_hi, count)) {
+    const int rc = view_with_planes(ctx, map, false, row_lo, row_hi, area_view);
+    if (rc) return rc;
+  }
   // 1. fast pass: poses whose scan rows all have <= 2 ranges (every pose of a convex polygon, many poses of a
   //    mildly concave one) are finished by the packed / lattice kernel; the rest lands on the todo list.
   //    Polygons that are far from convex skip it (the pass would defer almost everything).
@@ -2217,7 +2262,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
                                                                           ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
       } else {
         const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint2);
-        k_area_pair<OP><<<grid_for(count), kBlock, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
+        k_area_pair<OP><<<grid_for(count), kBlock, smem, ctx->stream>>>(area_view, poly_dev, nv, src, count, out, rows_cap,
                                                                         ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
         if (!is_convex(poly_host, nv) && rows_cap <= 64) {
           // second per-thread pass over the deferred poses with four ranges per row; its own overflow list feeds the
@@ -2227,7 +2272,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
           CU(cudaMemsetAsync(ctx->todo2_count.ptr, 0, sizeof(unsigned int), ctx->stream));
           const size_t smem4 = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * 4 * sizeof(uint32_t);
           const unsigned int grid4 = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(static_cast<long long>(ctx->sm_count) * 4, (count + kBlock - 1) / kBlock)));
-          k_area_slots<OP, 4><<<grid4, kBlock, smem4, ctx->stream>>>(map->view, poly_dev, nv, src, out, rows_cap, ctx->todo.as<unsigned int>(),
+          k_area_slots<OP, 4><<<grid4, kBlock, smem4, ctx->stream>>>(area_view, poly_dev, nv, src, out, rows_cap, ctx->todo.as<unsigned int>(),
                                                                     ctx->todo_count.as<unsigned int>(), ctx->todo2.as<unsigned int>(),
                                                                     ctx->todo2_count.as<unsigned int>());
           ++ctx->launches;
@@ -2244,13 +2289,13 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   if (rows_kernel) {
     const long long blocks = small_drain ? ctx->sm_count : static_cast<long long>(ctx->sm_count) * 12;
     const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(blocks, (count + kRowsWarps - 1) / kRowsWarps)));
-    k_area_rows<OP><<<grid, kRowsWarps * 32, rows_smem(nv), ctx->stream>>>(map->view, poly_dev, nv, src, count, out, todo, todo_count);
+    k_area_rows<OP><<<grid, kRowsWarps * 32, rows_smem(nv), ctx->stream>>>(area_view, poly_dev, nv, src, count, out, todo, todo_count);
   } else {
     ListScratch scratch{};
     const unsigned int grid = list_grid(ctx, count, rows_cap, small_drain ? 1 : 4);
     const int rc = ensure_list_scratch(ctx, rows_cap, static_cast<long long>(grid) * kBlock, scratch);
     if (rc) return rc;
-    k_area_list<OP><<<grid, kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, scratch, todo, todo_count);
+    k_area_list<OP><<<grid, kBlock, poly_bytes, ctx->stream>>>(area_view, poly_dev, nv, src, count, out, scratch, todo, todo_count);
   }
   ++ctx->launches;
   return COVER_OK;
@@ -2340,7 +2385,14 @@ int cells_check(cover_ctx* ctx, const cover_map* map, const cover_cells* cells, 
   if (count) {
     const int2* off = reinterpret_cast<const int2*>(dev);
     CU(map_ready(ctx, map));
-    if (op == OP_IS_FREE) k_cells_free<<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->spans, cells->n_spans, off, count, st.dev);
+    if (op == OP_IS_FREE) {
+      MapView view = map->view;
+      if (planes_pay_off(ctx, map, false, 0, view.size_y - 1, count)) {
+        rc = view_with_planes(ctx, map, false, 0, view.size_y - 1, view);
+        if (rc) return rc;
+      }
+      k_cells_free<<<grid_for(count), kBlock, 0, ctx->stream>>>(view, cells->spans, cells->n_spans, off, count, st.dev);
+    }
     else if (op == OP_ACCUMULATE) k_cells<OP_ACCUMULATE><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->dev, cells->n, off, count, st.dev);
     else k_cells<OP_MAX><<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, cells->dev, cells->n, off, count, st.dev);
     ++ctx->launches;
@@ -2457,6 +2509,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = std::getenv("COVER_B200_NO_LATTICE_KERNEL")) ctx->disable_lattice_kernel = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_NO_PLANES")) ctx->disable_planes = e[0] == '1';
+  if (const char* e = std::getenv("COVER_B200_PLANES_MIN_BATCH")) ctx->planes_min_batch = std::atoll(e);
   if (const char* e = std::getenv("COVER_B200_PACKED_ONLY_CONVEX")) ctx->always_try_packed = e[0] != '1';
   if (const char* e = std::getenv("COVER_B200_OLD_PACKED")) ctx->old_packed_kernel = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_FORCE_LIST_KERNEL")) ctx->force_list_kernel = e[0] == '1';
@@ -2553,7 +2606,7 @@ int cover_map_upload_async(cover_map* map, const uint8_t* host_data) {
   }
   map->last_band = order[kMapBands - 1];
   map->bands_pending = true;
-  map->planes_hi = -1;  // the bit planes describe the old image
+  map->planes_hi = map->planes_inf_hi = -1;  // the bit planes describe the old image
   return COVER_OK;
 }
 
@@ -2563,7 +2616,7 @@ int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem) {
   Bind bind(ctx->device);
   const MapView& v = map->view;
   CU(map_ready(ctx, map));
-  map->planes_hi = -1;
+  map->planes_hi = map->planes_inf_hi = -1;
   CU(cudaMemcpy2DAsync(map->dev, v.pitch, data, v.size_x, v.size_x, v.size_y,
                        mem == COVER_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
   if (mem == COVER_MEM_HOST) CU(cudaStreamSynchronize(ctx->stream));
@@ -2578,7 +2631,7 @@ int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x
   if (w == 0 || h == 0) return COVER_OK;
   Bind bind(ctx->device);
   CU(map_ready(ctx, map));
-  map->planes_hi = -1;
+  map->planes_hi = map->planes_inf_hi = -1;
   CU(cudaMemcpy2DAsync(map->dev + static_cast<size_t>(y0) * v.pitch + x0, v.pitch, full_image + static_cast<size_t>(y0) * v.size_x + x0,
                        v.size_x, w, h, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -2634,7 +2687,7 @@ int cover_map_inflate(cover_map* map, int32_t radius_cells, const uint8_t* cost_
   const MapView& v = map->view;
   const size_t bytes = static_cast<size_t>(v.pitch) * v.size_y;
   CU(map_ready(ctx, map));
-  map->planes_hi = -1;
+  map->planes_hi = map->planes_inf_hi = -1;
   CU(ctx->in_a.ensure(bytes));  // snapshot of the un-inflated map: the kernel reads it and writes the map in place
   CU(cudaMemcpyAsync(ctx->in_a.ptr, map->dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   const size_t lut_bytes = static_cast<size_t>(radius_cells) * radius_cells + 1;
@@ -2657,6 +2710,7 @@ void cover_map_destroy(cover_map* map) {
   cudaStreamSynchronize(map->ctx->stream);
   for (cudaEvent_t e : map->band_done) cudaEventDestroy(e);
   cudaFree(map->planes);
+  cudaFree(map->planes_inf);
   cudaFree(map->dev);
   delete map;
 }
@@ -2890,7 +2944,12 @@ int cover_footprints_is_free(cover_ctx* ctx, const cover_map* map, const cover_f
   }
   if (count) {
     CU(map_ready(ctx, map));
-    k_footprints<<<grid_for(count), kBlock, 0, ctx->stream>>>(map->view, fps->spans, fps->ranges, fps->n, reinterpret_cast<const int2*>(off_dev),
+    MapView mview = map->view;
+    if (planes_pay_off(ctx, map, true, 0, mview.size_y - 1, count)) {  // outline spans: 253 | 254 planes, area spans: 254 planes
+      rc = view_with_planes(ctx, map, true, 0, mview.size_y - 1, mview);
+      if (rc) return rc;
+    }
+    k_footprints<<<grid_for(count), kBlock, 0, ctx->stream>>>(mview, fps->spans, fps->ranges, fps->n, reinterpret_cast<const int2*>(off_dev),
                                                              which_dev, count, st.dev);
     ++ctx->launches;
   }
@@ -2961,7 +3020,12 @@ int cover_split_is_free(cover_ctx* ctx, const cover_map* map, const cover_split*
     const int slot_rows = rows_cap <= 48 ? rows_cap : 0;  // shared-memory 4-range table: rows x 4 x 128 threads x 4 B
     const size_t smem = static_cast<size_t>(split->n_vertices) * 2 * sizeof(double) + static_cast<size_t>(slot_rows) * 4 * kBlock * sizeof(uint32_t);
     CU(map_ready(ctx, map));
-    k_split<<<grid, kBlock, smem, ctx->stream>>>(map->view, view, split->n_vertices, src, poses->count, st.dev, scratch, slot_rows);
+    MapView mview = map->view;
+    if (planes_pay_off(ctx, map, false, 0, mview.size_y - 1, poses->count)) {  // the area parts scan row spans
+      rc = view_with_planes(ctx, map, false, 0, mview.size_y - 1, mview);
+      if (rc) return rc;
+    }
+    k_split<<<grid, kBlock, smem, ctx->stream>>>(mview, view, split->n_vertices, src, poses->count, st.dev, scratch, slot_rows);
     ++ctx->launches;
   }
   return finish_out(ctx, st, poses->count);

@@ -39,6 +39,13 @@ struct MapView {
   const uint8_t* __restrict__ data;
   int size_x, size_y, pitch;
   double inv_res, origin_x, origin_y;
+  // Optional bit planes of the current image (nullptr: not built), see k_lethal_planes in cover_b200.cu: plane k,
+  // bit x of row y = "a cell of x .. x + 2^k - 1 is LETHAL" (`planes`) / "... is INSCRIBED or LETHAL" (`planes_inf`),
+  // k = 0..5, stored column-major: word (c = x / 32, y) at k * plane_words + c * ypitch + y.
+  const uint32_t* __restrict__ planes;
+  const uint32_t* __restrict__ planes_inf;
+  int ypitch;
+  long long plane_words;
 };
 
 struct Pose {
@@ -130,6 +137,26 @@ __device__ __forceinline__ uint32_t keep_mask(int w, int lo, int hi) {
   if (a > 0) k &= 0xFFFFFFFFu << (8 * a);
   if (b > 0) k &= 0xFFFFFFFFu >> (8 * b);
   return k;
+}
+
+/// true iff a cell of [lo, hi] of row y is marked in the bit planes `planes` (all cells inside the map): the OR of two
+/// overlapping power-of-two windows for spans of up to 32 cells - two loads, whatever the width - and of 32-cell
+/// windows beyond that.
+__device__ __forceinline__ bool span_any_bits(const uint32_t* __restrict__ planes, int ypitch, long long plane_words, int y, int lo, int hi) {
+  const int w = hi - lo + 1;
+  if (w <= 32) {
+    const int k = 31 - __clz(w);
+    const uint32_t* __restrict__ p = planes + k * plane_words + y;
+    const int x2 = hi - (1 << k) + 1;
+    const uint32_t a = __ldg(p + static_cast<long long>(lo >> 5) * ypitch) >> (lo & 31);
+    const uint32_t b = __ldg(p + static_cast<long long>(x2 >> 5) * ypitch) >> (x2 & 31);
+    return ((a | b) & 1u) != 0u;
+  }
+  const uint32_t* __restrict__ p = planes + 5 * plane_words + y;
+  const int x2 = hi - 31;
+  uint32_t acc = __ldg(p + static_cast<long long>(x2 >> 5) * ypitch) >> (x2 & 31);
+  for (int x = lo; x < x2; x += 32) acc |= __ldg(p + static_cast<long long>(x >> 5) * ypitch) >> (x & 31);
+  return (acc & 1u) != 0u;
 }
 
 /// true iff some cell of [lo,hi] equals the byte replicated in pat4.  The words of the span are loaded in
@@ -258,7 +285,8 @@ struct Fold<OP_IS_FREE> {  // std::none_of(is_lethal): out of the map counts as 
   }
   __device__ __forceinline__ bool span(const MapView& m, int y, int lo, int hi) {
     if (static_cast<unsigned>(y) >= static_cast<unsigned>(m.size_y) || lo < 0 || hi >= m.size_x ||
-        row_any_eq(m.data + static_cast<size_t>(y) * m.pitch, lo, hi, 0xFEFEFEFEu)) {
+        (m.planes ? span_any_bits(m.planes, m.ypitch, m.plane_words, y, lo, hi)
+                  : row_any_eq(m.data + static_cast<size_t>(y) * m.pitch, lo, hi, 0xFEFEFEFEu))) {
       hit = true;
       return false;
     }

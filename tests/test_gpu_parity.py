@@ -359,6 +359,68 @@ def test_split_footprint_pose_form(cb, ctx):
     assert 0.02 < c.is_free.mean() < 0.98
 
 
+@pytest.fixture()
+def ctx_planes(cb, monkeypatch):
+    """A context that builds the lethal / inscribed bit planes for EVERY batch (the default only does for >= 32768)."""
+    monkeypatch.setenv("COVER_B200_PLANES_MIN_BATCH", "0")
+    c = cb.Context(0)
+    yield c
+    c.close()
+
+
+def test_span_scans_over_bit_planes(cb, ctx_planes):
+    """Verdict kernels answer a row span from two words of the bit planes (span_any_bits) instead of scanning its cost
+    bytes: every span-scanning path against the oracle with the planes forced on - random-pose areas of all
+    reference footprints (narrow and > 32-cell spans, map border), cached cells, the footprint bank (253 | 254
+    planes for outline spans), the split footprint - and across map updates (the planes must follow the image)."""
+    ctx = ctx_planes
+    rng = np.random.default_rng(77)
+    data = mixed_map(rng, 700, 500, lethal=0.0015)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    omap = po.Costmap(data, 0.05)
+    poses = poses_around(rng, 6000, -1.0, 36.0)  # (poses hang over the map border on all sides)
+    for idx in range(7):
+        for scale in (1.0, 2.7):  # 2.7: spans wider than 32 cells
+            poly = FOOTPRINTS[idx] * scale
+            gpu = cmap.area_is_free(poly, poses)
+            cpu = po.polygon_batch(omap, poly, poses, po.SHAPE_AREA, po.OP_IS_FREE, threads=8)
+            assert_same(gpu, cpu, False, f"{FOOTPRINT_NAMES[idx]} x{scale}")
+    assert ctx.launch_count > 0
+    # the image changes: full upload, window upload, inflation - the verdicts must follow
+    data2 = mixed_map(rng, 700, 500, lethal=0.004)
+    cmap.upload(data2)
+    omap2 = po.Costmap(data2, 0.05)
+    assert_same(cmap.area_is_free(RECT, poses), po.polygon_batch(omap2, RECT, poses, po.SHAPE_AREA, po.OP_IS_FREE, threads=8), False, "after upload")
+    data3 = data2.copy()
+    data3[100:300, 200:450] = mixed_map(rng, 250, 200, lethal=0.02)
+    cmap.upload_window(data3, 200, 100, 250, 200)
+    omap3 = po.Costmap(data3, 0.05)
+    assert_same(cmap.area_is_free(RECT, poses), po.polygon_batch(omap3, RECT, poses, po.SHAPE_AREA, po.OP_IS_FREE, threads=8), False, "after window upload")
+    # cached cells and the footprint bank
+    cells = po.area_cells([po.outline_cells(po.to_discrete(0.05, FOOTPRINTS[5] * 1.8))])
+    offs = rng.integers(-30, 720, (30_000, 2)).astype(np.int32)
+    assert_same(cb.DiscretePolygon(ctx, cells).is_free(cmap, offs), po.cells_batch(omap3, cells, offs, po.OP_IS_FREE, threads=8), False, "cells")
+    toru = FOOTPRINTS[5]
+    outlines, areas = [toru * 0.45], [toru * 1.6, RECT * 0.4 + np.array([[0.5], [0.0]])]
+    bank = []
+    for k in range(8):
+        th = 2 * math.pi * k / 8
+        R = np.array([[math.cos(th), -math.sin(th)], [math.sin(th), math.cos(th)]])
+        bank.append(po.make_discrete_footprint(0.05, [R @ o for o in outlines], [R @ a for a in areas]))
+    which = rng.integers(0, 8, len(offs)).astype(np.int32)
+    got = cb.FootprintBank(ctx, bank).is_free(cmap, offs, which)
+    want = po.discrete_footprint_batch(omap3, bank, offs, which, threads=8)
+    np.testing.assert_array_equal(got.is_free, want.is_free)
+    assert want.is_free.any() and not want.is_free.all()
+    # split footprint (areas over the planes, outlines cell by cell)
+    sp_out = [toru * 0.4, toru * 0.2 + np.array([[0.3], [0.0]])]
+    sp_area = [toru * 1.5, FOOTPRINTS[6] * 0.8, RECT * 0.5 + np.array([[-0.2], [0.1]])]
+    g = cb.SplitFootprint(ctx, sp_out, sp_area).is_free(cmap, poses)
+    c = po.continuous_footprint_batch(omap3, sp_out, sp_area, poses, threads=8)
+    np.testing.assert_array_equal(g.status, c.status)
+    np.testing.assert_array_equal(g.is_free, c.is_free)
+
+
 def test_device_resident_inputs_and_outputs(cb, ctx):
     """Same numbers when poses/results stay on the device (the bench's `value` path)."""
     torch = pytest.importorskip("torch")
