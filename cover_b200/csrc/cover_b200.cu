@@ -909,15 +909,14 @@ __device__ __forceinline__ void lattice_rows_fold(const MapView& m, const int* _
   }
 }
 
-/// Bit-packed verdicts of one plane of a lattice row: lane l holds pose `base + l`, so the plane's 32 verdicts are
-/// one ballot word, OR-ed into at most two output words (shared with the neighbouring planes, hence atomic).
-__device__ __forceinline__ void lat_store_bits(const OutView& out, uint32_t free_mask, long long base, int lane) {
-  if (lane != 0 || free_mask == 0u) return;
-  const long long w = base >> 5;  // (arithmetic shift: base may be negative for a plane that straddles `first`)
+/// Bit-packed verdicts of one lattice row of a unit: lane l holds poses `base + l` (plane A) and `base + 32 + l`
+/// (plane B), so the 64 verdicts are two ballot words, shifted to the row's bit offset and OR-ed into three output
+/// words - by lanes 0..2, one word each (the words are shared with neighbouring units and groups, hence atomic).
+__device__ __forceinline__ void lat_store_bits(const OutView& out, uint32_t free_a, uint32_t free_b, long long base, int lane) {
   const int sh = static_cast<int>(base & 31);
-  const uint32_t lo_word = free_mask << sh, hi_word = sh ? free_mask >> (32 - sh) : 0u;
-  if (lo_word) atomicOr(out.free_bits + w, lo_word);
-  if (hi_word) atomicOr(out.free_bits + w + 1, hi_word);
+  const uint32_t word = lane == 0 ? free_a << sh : (lane == 1 ? __funnelshift_l(free_a, free_b, sh) : __funnelshift_l(free_b, 0u, sh));
+  // (arithmetic shift: base may be negative for a row that straddles `first` - its bits below pose 0 are zero)
+  if (lane < 3 && word != 0u) atomicOr(out.free_bits + (base >> 5) + lane, word);
 }
 
 /// LEAN = verdicts of a polygon with at most 4 vertices over the bit planes (the headline case): the shape key is
@@ -1211,8 +1210,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
               if (out.status) out.status[i_b] = ST_OK;
             }
             if (out.free_bits) {
-              lat_store_bits(out, __ballot_sync(kFull, act_a && hit_a == 0u), i_a - lane, lane);
-              lat_store_bits(out, __ballot_sync(kFull, act_b && hit_b == 0u), i_b - lane, lane);
+              lat_store_bits(out, __ballot_sync(kFull, act_a && hit_a == 0u), __ballot_sync(kFull, act_b && hit_b == 0u), i_a - lane, lane);
             }
           } else if (inside) {  // (discarded for OP_IS_FREE: the whole else-chain hangs off an `if constexpr`)
             Fold<OP> fa, fb;
