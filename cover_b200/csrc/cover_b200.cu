@@ -1811,6 +1811,8 @@ struct cover_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // banded costmap uploads (cover_map_upload_async) overlap the kernels of `stream`
   cudaEvent_t fence = nullptr;         // "everything queued on `stream` so far": what a banded upload has to wait for
+  cudaStream_t d2h_stream = nullptr;   // result chunks of a big lattice sweep travel back while the next chunk is computed
+  cudaEvent_t chunk_done = nullptr;
   std::string error;
   int64_t launches = 0;
   bool disable_lattice_kernel = false;
@@ -2322,13 +2324,47 @@ int polygon_check(cover_ctx* ctx, const cover_map* map, const double* polygon_xy
     CU(map_rows_ready(ctx, map, row_lo, row_hi));
   else
     CU(map_ready(ctx, map));
-  switch (op) {
-    case OP_IS_FREE: rc = launch_polygon<OP_IS_FREE>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev, row_lo, row_hi); break;
-    case OP_ACCUMULATE: rc = launch_polygon<OP_ACCUMULATE>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev, row_lo, row_hi); break;
-    default: rc = launch_polygon<OP_MAX>(ctx, map, pd, polygon_xy, nv, shape, src, poses->count, st.dev, row_lo, row_hi); break;
+  auto launch = [&](const PoseSource& s, int64_t n, const OutView& o) {
+    switch (op) {
+      case OP_IS_FREE: return launch_polygon<OP_IS_FREE>(ctx, map, pd, polygon_xy, nv, shape, s, n, o, row_lo, row_hi);
+      case OP_ACCUMULATE: return launch_polygon<OP_ACCUMULATE>(ctx, map, pd, polygon_xy, nv, shape, s, n, o, row_lo, row_hi);
+      default: return launch_polygon<OP_MAX>(ctx, map, pd, polygon_xy, nv, shape, s, n, o, row_lo, row_hi);
+    }
+  };
+  // A big lattice sweep whose results go to the host runs as a few contiguous index chunks: chunk k's results travel
+  // back on a second stream while chunk k + 1 is computed (chunk borders are multiples of 32 poses = whole bit words).
+  constexpr int64_t kPipelineMin = 16ll << 20;
+  constexpr int kPipelineChunks = 4;
+  if (!(st.host && poses->format == COVER_POSE_LATTICE && poses->count >= kPipelineMin)) {
+    rc = launch(src, poses->count, st.dev);
+    if (rc) return rc;
+    return finish_out(ctx, st, poses->count);
   }
-  if (rc) return rc;
-  return finish_out(ctx, st, poses->count);
+  const int64_t per = ((poses->count + kPipelineChunks - 1) / kPipelineChunks + 31) & ~static_cast<int64_t>(31);
+  for (int64_t off = 0; off < poses->count; off += per) {
+    const int64_t n = std::min<int64_t>(per, poses->count - off);
+    PoseSource s = src;
+    s.first = src.first + off;
+    OutView o = st.dev;
+    if (o.is_free) o.is_free += off;
+    if (o.cost) o.cost += off;
+    if (o.status) o.status += off;
+    if (o.free_bits) o.free_bits += off / 32;
+    rc = launch(s, n, o);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->chunk_done, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->d2h_stream, ctx->chunk_done, 0));
+    const size_t m = static_cast<size_t>(n);
+    if (out->is_free) CU(cudaMemcpyAsync(out->is_free + off, o.is_free, m, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (out->cost) CU(cudaMemcpyAsync(out->cost + off, o.cost, m * sizeof(double), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (out->status) CU(cudaMemcpyAsync(out->status + off, o.status, m, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (out->free_bits) CU(cudaMemcpyAsync(out->free_bits + off / 32, o.free_bits, ((m + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  }
+  if (out->not_ok) CU(cudaMemcpyAsync(out->not_ok, st.dev.not_ok, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->d2h_stream));
+  return COVER_OK;
 }
 
 /// Copies a host or device int array into a context buffer when needed; returns the device pointer.
@@ -2498,9 +2534,13 @@ int cover_ctx_create(int device, cover_ctx** out) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || configure_kernels() != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->fence, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->fence, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->chunk_done, cudaEventDisableTiming) != cudaSuccess) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->fence) cudaEventDestroy(ctx->fence);
     delete ctx;
     return COVER_E_CUDA;
   }
@@ -2524,6 +2564,8 @@ void cover_ctx_destroy(cover_ctx* ctx) {
                           &ctx->todo, &ctx->todo_count, &ctx->todo2, &ctx->todo2_count, &ctx->list_cnt, &ctx->list_rng, &ctx->list_seq})
     b->release();
   cudaEventDestroy(ctx->fence);
+  cudaEventDestroy(ctx->chunk_done);
+  cudaStreamDestroy(ctx->d2h_stream);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -2538,6 +2580,7 @@ int cover_ctx_synchronize(cover_ctx* ctx) {
   Bind bind(ctx->device);
   CU(cudaStreamSynchronize(ctx->copy_stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->d2h_stream));
   return COVER_OK;
 }
 
