@@ -1004,6 +1004,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
         }
       }
     }
+    const unsigned same_rows = __ballot_sync(kFull, my_same_prev) & 0xFFu;  // bit r: row r repeats row r - 1
     const int rows_here = min(kLatRows, g.n_rows - group * kLatRows);
     const long long i_base = (g.row_first + static_cast<long long>(group) * kLatRows) * src.nx - src.first;  // pose index of (row 0, column 0)
     const bool col_a = ix_a < src.nx, col_b = ix_b < src.nx;
@@ -1013,8 +1014,9 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
     // runs of rows with the same heading (one per unit; two where the unit crosses a heading boundary)
     for (int r0 = 0; r0 < rows_here;) {
       const int it = __shfl_sync(kFull, my_it, r0);
-      int r1 = r0 + 1;
-      while (r1 < rows_here && __shfl_sync(kFull, my_it, r1) == it) ++r1;
+      // rows r0 .. r1 - 1 share the heading
+      const unsigned it_rows = (__ballot_sync(kFull, my_it == it) & 0xFFu) >> r0;
+      const int r1 = min(rows_here, r0 + __ffs(~it_rows) - 1);
       const double2 cs = heading_cs(it);
       // x-profiles depend on the heading and the column only
       const LatProfile xa = lat_profile<true>(poly, nv, cs.x, cs.y, column_tx(ix_a), m, exact_key);
@@ -1092,7 +1094,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
             }
           }
           const int vy0 = __shfl_sync(kFull, my_y.c0, r);
-          if (!(r > r0 && slot >= 0 && __shfl_sync(kFull, static_cast<int>(my_same_prev), r) != 0)) {
+          if (!(r > r0 && slot >= 0 && ((same_rows >> r) & 1u) != 0u)) {
             // ---- shape cache: find, or insert + rasterise ----------------------------------------------
             const unsigned long long ykey = __shfl_sync(kFull, my_y.key, r);
             const unsigned long long kl = exact_key ? ((1ull << 63) | (kx << 24) | ykey) : ((lat_mix(kx, static_cast<int>(ykey)) ^ (ykey >> 32)) | 1ull);
