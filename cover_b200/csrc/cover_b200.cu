@@ -1136,9 +1136,9 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
               xb_s = meta[slot].xb, x1_s = meta[slot].x1, rows = meta[slot].rows, yb_s = meta[slot].yb;
               if constexpr (OP == OP_IS_FREE) {
                 lean = pv.bits != nullptr && rows <= 32 && st == ST_OK;
+                // every cell any pose of the group needs lies in x: [xmin + xb, xmin + maxoff + x1]
+                inside_x = xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x;
                 if (lean) {
-                  // every cell any pose of the group needs lies in x: [xmin + xb, xmin + maxoff + x1]
-                  inside_x = xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x;
                   const int width = lane < rows ? __popc(row_m[slot * rows_cap + lane]) : 0;
                   win_s = win_t = nullptr;
                   if (width > 0 && inside_x) {
@@ -1176,7 +1176,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
           // ---- up to 64 x-adjacent poses per 96-cell bit window ----------------------------------------
           const int y_base = vy0 + yb_s;
           // every cell any pose of the group needs lies in x: [xmin + xb, xmin + maxoff + x1]
-          const bool inside = y_base >= 0 && y_base + rows <= m.size_y && xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x;
+          const bool inside = y_base >= 0 && y_base + rows <= m.size_y && (LEAN ? inside_x : (xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x));
           if constexpr (OP == OP_IS_FREE) {
             uint32_t hit_a = 0, hit_b = 0;
             if (lean && inside) {
