@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(kBlock) k_area_slots(MapView m, const double* 
 #ifndef LAT_LEAN_BLOCKS
 #define LAT_LEAN_BLOCKS 3
 #endif
-constexpr int kLatSegX = 64, kLatRows = 8, kLatWarps = 8, kLatThreads = kLatWarps * 32, kLatSlots = 64;
+constexpr int kLatSegX = 64, kLatWarps = 8, kLatThreads = kLatWarps * 32, kLatSlots = 64;
 constexpr int kLatMaxVertices = 64;
 constexpr int kLatMaxWidth = 32;   // widest scan row (cells): 64 pose offsets + 32 cells = one 96-cell window
 constexpr int kLatPending = -2;    // shape inserted, not rasterised yet
@@ -593,7 +593,8 @@ struct LatShape {
 struct LatGeom {
   long long row_first;  // first lattice row (it*ny + iy) touched by this batch
   int n_rows, segs;     // lattice rows touched; 64-column segments per row
-  long long n_units;    // segs * ceil(n_rows / 8)
+  long long n_units;    // segs * ceil(n_rows / rows_per_unit)
+  int rows_per_unit;    // 8, 16 or 32 lattice rows per unit (lane r owns row r): as many as still fill the grid
 };
 
 __device__ __forceinline__ unsigned long long lat_mix(unsigned long long h, int v) {
@@ -944,6 +945,8 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* rowbuf = rowbufs + warp * 800;
   const bool exact_key = LEAN || nv <= 4;  // 2 x 3 offsets of 8 bits: the key IS the shape, no verification pass
+  const int kLatRows = g.rows_per_unit;
+  const unsigned kLatRowMask = kLatRows >= 32 ? 0xFFFFFFFFu : (1u << kLatRows) - 1u;
   const long long chunk = (g.n_units + gridDim.x - 1) / gridDim.x;
   const long long unit_begin = blockIdx.x * chunk, unit_end = min(g.n_units, unit_begin + chunk);
   int cached_heading = -1;
@@ -1004,7 +1007,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
         }
       }
     }
-    const unsigned same_rows = __ballot_sync(kFull, my_same_prev) & 0xFFu;  // bit r: row r repeats row r - 1
+    const unsigned same_rows = __ballot_sync(kFull, my_same_prev) & kLatRowMask;  // bit r: row r repeats row r - 1
     const int rows_here = min(kLatRows, g.n_rows - group * kLatRows);
     const long long i_base = (g.row_first + static_cast<long long>(group) * kLatRows) * src.nx - src.first;  // pose index of (row 0, column 0)
     const bool col_a = ix_a < src.nx, col_b = ix_b < src.nx;
@@ -1015,15 +1018,16 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
     for (int r0 = 0; r0 < rows_here;) {
       const int it = __shfl_sync(kFull, my_it, r0);
       // rows r0 .. r1 - 1 share the heading
-      const unsigned it_rows = (__ballot_sync(kFull, my_it == it) & 0xFFu) >> r0;
-      const int r1 = min(rows_here, r0 + __ffs(~it_rows) - 1);
+      const unsigned it_rows = (__ballot_sync(kFull, my_it == it) & kLatRowMask) >> r0;
+      const int run = __ffs(~it_rows);  // (0: every row up to bit 31 shares the heading)
+      const int r1 = min(rows_here, r0 + (run ? run - 1 : 32));
       const double2 cs = heading_cs(it);
       // x-profiles depend on the heading and the column only
       const LatProfile xa = lat_profile<true>(poly, nv, cs.x, cs.y, column_tx(ix_a), m, exact_key);
       const LatProfile xb = lat_profile<true>(poly, nv, cs.x, cs.y, column_tx(ix_b), m, exact_key);
       const bool good_a = col_a && xa.ok && xa.packable, good_b = col_b && xb.ok && xb.packable;
       const bool row_good = my_valid && my_y.ok && my_y.packable;  // (lane r: row r)
-      const unsigned bad_rows = __ballot_sync(kFull, my_valid && !row_good) & 0xFFu;
+      const unsigned bad_rows = __ballot_sync(kFull, my_valid && !row_good) & kLatRowMask;
 
       // ---- rare: coordinates out of range (status), offsets that do not fit the packed key (general kernel) ----
       if (bad_rows != 0u || __any_sync(kFull, (col_a && !good_a) || (col_b && !good_b))) {
@@ -2241,7 +2245,10 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       const long long row_last = (src.first + count - 1) / src.nx;
       g.n_rows = static_cast<int>(row_last - g.row_first + 1);
       g.segs = (src.nx + kLatSegX - 1) / kLatSegX;
-      g.n_units = static_cast<long long>((g.n_rows + kLatRows - 1) / kLatRows) * g.segs;
+      g.rows_per_unit = 32;  // more rows per unit amortise the per-unit column work; fewer keep a small batch parallel
+      const long long want_units = 4ll * ctx->sm_count * LAT_MIN_BLOCKS * kLatWarps;
+      while (g.rows_per_unit > 8 && static_cast<long long>((g.n_rows + g.rows_per_unit - 1) / g.rows_per_unit) * g.segs < want_units) g.rows_per_unit /= 2;
+      g.n_units = static_cast<long long>((g.n_rows + g.rows_per_unit - 1) / g.rows_per_unit) * g.segs;
       const size_t smem = poly_bytes + kLatSlots * (sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) +
                                                      static_cast<size_t>(rows_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape)) +
                           (OP == OP_IS_FREE ? 0 : kLatWarps * 800);  // the value folds' per-warp query tables
