@@ -1177,6 +1177,50 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
             if (act_b) store_failure(out, i_b, st);
             continue;
           }
+          if constexpr (LEAN) {
+            // ---- the usual case, as a tight loop over the rows that keep this slot: whole unit inside the batch, rows
+            //      that repeat the shape, every needed cell inside the map
+            if (lean && whole_unit && inside_x) {
+              const unsigned chain = r < 31 ? (same_rows & ~bad_rows) >> (r + 1) : 0u;  // bit q: row r + 1 + q continues with this slot
+              const int stop = __ffs(~chain);
+              const int r2 = min(r1, r + (stop ? stop : 32));
+              const bool third = maxoff >= 32;
+              const bool store_free = out.is_free != nullptr, store_status = out.status != nullptr, store_bits = out.free_bits != nullptr;
+              int q = r;
+              for (; q < r2; ++q, i_a += src.nx) {
+                const int y_base = __shfl_sync(kFull, my_y.c0, q) + yb_s;
+                if (y_base < 0 || y_base + rows > m.size_y) break;  // map border: back to the general path for this row
+                // lane j ORs the (up to) two power-of-two windows of scan row j; one redux per 32 offsets folds the rows
+                uint32_t r_lo = 0u, r_hi = 0u;
+                if (win_s) {
+                  const uint32_t* __restrict__ p = win_s + y_base;
+                  const uint32_t w0 = __ldg(p), w1 = __ldg(p + pv.ypitch), w2 = third ? __ldg(p + 2 * pv.ypitch) : 0u;
+                  r_lo = __funnelshift_r(w0, w1, sh_s), r_hi = __funnelshift_r(w1, w2, sh_s);
+                }
+                if (win_t) {
+                  const uint32_t* __restrict__ p = win_t + y_base;
+                  const uint32_t w0 = __ldg(p), w1 = __ldg(p + pv.ypitch), w2 = third ? __ldg(p + 2 * pv.ypitch) : 0u;
+                  r_lo |= __funnelshift_r(w0, w1, sh_t), r_hi |= __funnelshift_r(w1, w2, sh_t);
+                }
+                r_lo = __reduce_or_sync(kFull, r_lo);
+                r_hi = third ? __reduce_or_sync(kFull, r_hi) : 0u;
+                const uint32_t hit_a = ((oa < 32 ? r_lo : r_hi) >> (oa & 31)) & 1u, hit_b = ((ob < 32 ? r_lo : r_hi) >> (ob & 31)) & 1u;
+                if (fits_a) {
+                  if (store_free) out.is_free[i_a] = static_cast<uint8_t>(hit_a ^ 1u);
+                  if (store_status) out.status[i_a] = ST_OK;
+                }
+                if (fits_b) {
+                  if (store_free) out.is_free[i_a + 32] = static_cast<uint8_t>(hit_b ^ 1u);
+                  if (store_status) out.status[i_a + 32] = ST_OK;
+                }
+                if (store_bits) lat_store_bits(out, __ballot_sync(kFull, fits_a && hit_a == 0u), __ballot_sync(kFull, fits_b && hit_b == 0u), i_a - lane, lane);
+              }
+              if (q > r) {  // rows r .. q - 1 are done; the for loop's increment moves on to row q
+                r = q - 1, i_a -= src.nx;
+                continue;
+              }
+            }
+          }
           // ---- up to 64 x-adjacent poses per 96-cell bit window ----------------------------------------
           const int y_base = vy0 + yb_s;
           // every cell any pose of the group needs lies in x: [xmin + xb, xmin + maxoff + x1]
