@@ -2384,10 +2384,12 @@ int polygon_check(cover_ctx* ctx, const cover_map* map, const double* polygon_xy
       default: return launch_polygon<OP_MAX>(ctx, map, pd, polygon_xy, nv, shape, s, n, o, row_lo, row_hi);
     }
   };
-  // A big lattice sweep whose results go to the host runs as a few contiguous index chunks: chunk k's results travel
+  // A big lattice sweep whose results go to the host runs as 2..4 contiguous index chunks: chunk k's results travel
   // back on a second stream while chunk k + 1 is computed (chunk borders are multiples of 32 poses = whole bit words).
   constexpr int64_t kPipelineMin = 16ll << 20;
-  constexpr int kPipelineChunks = 4;
+  // (two chunks up to ~1.5e8 poses: every chunk costs ~50 us of launch overhead and kernel tail, a chunk's download ~0.1 ms)
+  int kPipelineChunks = static_cast<int>(std::min<int64_t>(4, std::max<int64_t>(2, poses->count / (48ll << 20))));
+  if (const char* e = std::getenv("COVER_B200_CHUNKS")) kPipelineChunks = std::max(1, std::atoi(e));  // (measurements)
   if (!(st.host && poses->format == COVER_POSE_LATTICE && poses->count >= kPipelineMin)) {
     rc = launch(src, poses->count, st.dev);
     if (rc) return rc;
