@@ -1135,6 +1135,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
             lean = false;
             if (slot >= 0) {  // wait for a shape another warp is still rasterising
               while ((st = *reinterpret_cast<volatile int*>(&meta[slot].status)) == kLatPending) {
+                __nanosleep(100);  // (leave the issue slots to the lane that is rasterising the shape)
               }
               __threadfence_block();
               xb_s = meta[slot].xb, x1_s = meta[slot].x1, rows = meta[slot].rows, yb_s = meta[slot].yb;
@@ -1205,13 +1206,15 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
                 r_lo = __reduce_or_sync(kFull, r_lo);
                 r_hi = third ? __reduce_or_sync(kFull, r_hi) : 0u;
                 const uint32_t hit_a = ((oa < 32 ? r_lo : r_hi) >> (oa & 31)) & 1u, hit_b = ((ob < 32 ? r_lo : r_hi) >> (ob & 31)) & 1u;
-                if (fits_a) {
-                  if (store_free) out.is_free[i_a] = static_cast<uint8_t>(hit_a ^ 1u);
-                  if (store_status) out.status[i_a] = ST_OK;
+                if (store_free) {
+                  uint8_t* __restrict__ pf = out.is_free + i_a;
+                  if (fits_a) pf[0] = static_cast<uint8_t>(hit_a ^ 1u);
+                  if (fits_b) pf[32] = static_cast<uint8_t>(hit_b ^ 1u);
                 }
-                if (fits_b) {
-                  if (store_free) out.is_free[i_a + 32] = static_cast<uint8_t>(hit_b ^ 1u);
-                  if (store_status) out.status[i_a + 32] = ST_OK;
+                if (store_status) {
+                  uint8_t* __restrict__ ps = out.status + i_a;
+                  if (fits_a) ps[0] = ST_OK;
+                  if (fits_b) ps[32] = ST_OK;
                 }
                 if (store_bits) lat_store_bits(out, __ballot_sync(kFull, fits_a && hit_a == 0u), __ballot_sync(kFull, fits_b && hit_b == 0u), i_a - lane, lane);
               }
