@@ -1178,7 +1178,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
             if (act_b) store_failure(out, i_b, st);
             continue;
           }
-          if constexpr (LEAN) {
+          if constexpr (OP == OP_IS_FREE) {
             // ---- the usual case, as a tight loop over the rows that keep this slot: whole unit inside the batch, rows
             //      that repeat the shape, every needed cell inside the map
             if (lean && whole_unit && inside_x) {

@@ -15,16 +15,25 @@ lat = cover_b200.Lattice(**desc)
 n = lat.count
 out = cover_b200.Result(torch.empty(n, dtype=torch.uint8, device="cuda"), torch.empty(n, dtype=torch.float64, device="cuda"), torch.empty(n, dtype=torch.uint8, device="cuda"))
 stream = torch.cuda.ExternalStream(ctx.stream)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+poly_name = os.environ.get("POLY", "rect")
+if poly_name == "rect":
+    POLY = wl.RECT
+elif poly_name == "potato":
+    POLY = wl.scaled(wl.potato(16), 0.6)   # 16 vertices, ~0.7 m across: hashed shape keys
+else:
+    from fixtures import FOOTPRINTS, FOOTPRINT_NAMES
+    POLY = FOOTPRINTS[FOOTPRINT_NAMES.index(poly_name)]
 for name in ("area_is_free", "area_accumulate_cost", "area_max_cost", "outline_is_free", "outline_accumulate_cost"):
     fn = getattr(cmap, name)
     for _ in range(2):
-        fn(wl.RECT, lat, out=out)
+        fn(POLY, lat, out=out)
     ctx.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record(stream)
     for _ in range(3):
-        fn(wl.RECT, lat, out=out)
+        fn(POLY, lat, out=out)
     e.record(stream)
     ctx.synchronize()
     ms = s.elapsed_time(e) / 3
-    print(json.dumps({"op": name, "poses": n, "ms": ms, "checks_per_s": n / ms * 1e3}), flush=True)
+    print(json.dumps({"polygon": poly_name, "op": name, "poses": n, "ms": ms, "checks_per_s": n / ms * 1e3}), flush=True)
