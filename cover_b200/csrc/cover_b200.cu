@@ -588,6 +588,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 
 struct LatShape {
   int xb, x1, yb, rows, status;  // bbox of the relative vertices (x: [xb, x1], y: [yb, yb+rows-1])
+  int n_spans;                   // entries of the span table (one per merged range pair, in generator order)
 };
 
 struct LatGeom {
@@ -643,20 +644,27 @@ __device__ __forceinline__ LatProfile lat_profile(const double* __restrict__ pol
   return p;
 }
 
+/// Span table of a cached shape: entry k = one merged range pair of the area, in generator order (rows ascending,
+/// x ascending): `span_a[k]` = dy * pitch + (first cell, relative to vertex 0) - the byte offset from (vertex 0's
+/// cell, first row of the shape) - and `span_m[k]` = width | dy << 8 (width <= 32).
+__device__ __forceinline__ int span_width(uint32_t m) { return static_cast<int>(m & 0xFFu); }
+__device__ __forceinline__ int span_dy(uint32_t m) { return static_cast<int>(m >> 8); }
+
 /// Byte walk of one group with per-cell bounds tests (a pose of the group touches the map border, or the bit planes
-/// are unavailable).  `row_a[r]` = r * pitch + (first cell of row r's range, relative to vertex 0), `row_m[r]` =
-/// width mask.  Each lane loads one byte of each of three coalesced 32-cell pieces, `__ballot_sync` turns "lethal or
-/// outside the map" into a 96-cell bit window and every pose ANDs its own sub-window.
-__device__ __noinline__ void lattice_rows_bytes(const MapView& m, const int* __restrict__ row_a, const uint32_t* __restrict__ row_m, int rows,
+/// are unavailable).  Each lane loads one byte of each of three coalesced 32-cell pieces per span, `__ballot_sync`
+/// turns "lethal or outside the map" into a 96-cell bit window and every pose ANDs its own sub-window.
+__device__ __noinline__ void lattice_rows_bytes(const MapView& m, const int* __restrict__ span_a, const uint32_t* __restrict__ span_m, int n_spans,
                                                 int x_base, int y_base, int lane, int off_a, int off_b, uint32_t& hit_a, uint32_t& hit_b) {
   // lane constants: which two of the three 32-cell pieces a pose's window starts in, and its shift
   const bool hi_a = off_a >= 32, hi_b = off_b >= 32;
   const int sh_a = off_a & 31, sh_b = off_b & 31;
-  for (int r = 0; r < rows; ++r) {
-    const int y = y_base + r;
+  for (int r = 0; r < n_spans; ++r) {
+    const uint32_t sm = span_m[r];
+    const int dy = span_dy(sm), width = span_width(sm);
+    const int y = y_base + dy;
     const bool y_in = static_cast<unsigned>(y) < static_cast<unsigned>(m.size_y);
     const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y_in ? y : 0) * m.pitch;
-    const int lo = row_a[r] - r * m.pitch;
+    const int lo = span_a[r] - dy * m.pitch;
     uint32_t piece[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -665,7 +673,7 @@ __device__ __noinline__ void lattice_rows_bytes(const MapView& m, const int* __r
       if (y_in && static_cast<unsigned>(x) < static_cast<unsigned>(m.size_x)) lethal = __ldg(rowp + x) == kLethal;
       piece[j] = __ballot_sync(kFull, lethal);
     }
-    const uint32_t wm = row_m[r];
+    const uint32_t wm = width >= 32 ? 0xFFFFFFFFu : ((1u << width) - 1u);
     hit_a |= __funnelshift_r(hi_a ? piece[1] : piece[0], hi_a ? piece[2] : piece[1], sh_a) & wm;
     hit_b |= __funnelshift_r(hi_b ? piece[1] : piece[0], hi_b ? piece[2] : piece[1], sh_b) & wm;
   }
@@ -682,21 +690,22 @@ struct PlaneView {
 };
 constexpr int kPlaneCount = 6;
 
-/// is_free walk of one group over the bit planes (every needed cell inside the map): LANE j owns scan row j of the
+/// is_free walk of one group over the bit planes (every needed cell inside the map): LANE j owns span j of the
 /// shape.  For the group's 64 candidate x offsets it fetches the 64-bit window of plane log2(p) that starts at the
 /// row's first cell, and the one that starts `width - p` cells later (p = largest power of two <= width); OR-ing the
 /// lanes' results (one `redux.or` per half) leaves bit `off` = "the pose at offset `off` hits a lethal cell", which
 /// every pose then reads at its own offset.  ~30 warp instructions per 64 poses, whatever the number of rows.
-__device__ __forceinline__ void lattice_rows_planes(const PlaneView& pv, const int* __restrict__ row_a, const uint32_t* __restrict__ row_m, int rows,
+__device__ __forceinline__ void lattice_rows_planes(const PlaneView& pv, const int* __restrict__ span_a, const uint32_t* __restrict__ span_m, int n_spans,
                                                     int pitch, int x_base, int y_base, int lane, bool third, int off_a, int off_b, uint32_t& hit_a,
                                                     uint32_t& hit_b) {
   uint32_t r_lo = 0u, r_hi = 0u;
-  for (int j = lane; j < rows; j += 32) {
-    const int width = __popc(row_m[j]);
+  for (int j = lane; j < n_spans; j += 32) {
+    const uint32_t sm = span_m[j];
+    const int width = span_width(sm), dy = span_dy(sm);
     if (width == 0) continue;
     const int k = 31 - __clz(width), tail = width - (1 << k);
-    const int xs = x_base + (row_a[j] - j * pitch);
-    const uint32_t* __restrict__ rowp = pv.bits + k * pv.plane_words + (y_base + j);
+    const int xs = x_base + (span_a[j] - dy * pitch);
+    const uint32_t* __restrict__ rowp = pv.bits + k * pv.plane_words + (y_base + dy);
     {
       const uint32_t* __restrict__ q = rowp + static_cast<long long>(xs >> 5) * pv.ypitch;
       const uint32_t w0 = __ldg(q), w1 = __ldg(q + pv.ypitch), w2 = third ? __ldg(q + 2 * pv.ypitch) : 0u;
@@ -749,35 +758,122 @@ __global__ void __launch_bounds__(256) k_lethal_planes(MapView m, uint32_t* __re
   }
 }
 
-/// Rasterises the relative shape `verts` into (row_a = first cell of the merged range, relative to vertex
-/// 0; row_m = width mask) and returns its descriptor.  Runs in ONE lane.
-__device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ verts, int nv, int rows_cap, int pitch, int* __restrict__ ra,
-                                                   uint32_t* __restrict__ rm) {
+/// Sink that feeds outline cells into a SlotWalker (single-lane walk).
+struct LatSlotSink {
+  SlotWalker<4>& w;
+  __device__ __forceinline__ bool cell(int x, int y) {
+    w.visit(x, y);
+    return true;
+  }
+};
+
+/// Rasterises the relative shape `verts` into the slot's span table `tbl` (span_a = tbl[0 .. cap), span_m =
+/// tbl[cap .. 2 cap)) and returns its descriptor.  Runs in ONE lane.  First attempt: at most two ranges per scan row
+/// (every convex shape), packed one word per row.  Second attempt (cap >= 2 * rows_cap, i.e. the polygon is not
+/// convex): up to four ranges per row = two merged pairs, with the slot's whole table as the [row][4] scratch.
+__device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ verts, int nv, int rows_cap, int cap, int pitch, int* __restrict__ tbl) {
+  int* __restrict__ sa = tbl;
+  uint32_t* __restrict__ sm = reinterpret_cast<uint32_t*>(tbl + cap);
   int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, x1 = -0x7FFFFFFF - 1, y1 = -0x7FFFFFFF - 1;
   for (int v = 0; v < nv; ++v) {
     x0 = min(x0, verts[v].x), x1 = max(x1, verts[v].x);
     y0 = min(y0, verts[v].y), y1 = max(y1, verts[v].y);
   }
-  LatShape sh{x0, x1, y0, y1 - y0 + 1, ST_OK};
-  if (sh.rows > rows_cap || (x1 - x0) > kPackedMaxWidth || x0 < -30000 || x1 > 30000) {
+  LatShape sh{x0, x1, y0, y1 - y0 + 1, ST_OK, 0};
+  if (sh.rows > rows_cap || (x1 - x0) > 4000 || x0 < -30000 || x1 > 30000) {
     sh.status = kLatUnfit;
     return sh;
   }
-  PackedStore store{rm, 1, x0, y0};  // the packed table is built in place in row_m, then converted
-  store.clear(sh.rows);
-  RunDetector<PackedStore> runs(store, 0, x0, x1);
-  walk_outline_cells(verts, nv, runs);
-  runs.finish();
-  if (store.overflow) sh.status = kLatUnfit;
-  for (int r = 0; r < sh.rows && sh.status != kLatUnfit; ++r) {
-    const uint32_t w = rm[r];
-    const uint32_t cnt = w >> 30;
-    if (cnt == 1u) sh.status = ST_LOGIC_ERROR;  // odd number of ranges: std::logic_error upstream
-    const int width = cnt == 2u ? static_cast<int>(((w >> 15) & 0x7FFFu) - (w & 0x7FFFu)) + 1 : 0;
-    if (width > kLatMaxWidth) sh.status = kLatUnfit;
-    ra[r] = r * pitch + x0 + static_cast<int>(w & 0x7FFFu);  // byte offset of the row's first cell from (vertex 0, row yb)
-    rm[r] = width >= 32 ? 0xFFFFFFFFu : ((1u << width) - 1u);
+  {
+    PackedStore store{sm, 1, x0, y0};  // the packed table is built in place in span_m, then converted
+    store.clear(sh.rows);
+    RunDetector<PackedStore> runs(store, 0, x0, x1);
+    walk_outline_cells(verts, nv, runs);
+    runs.finish();
+    if (!store.overflow) {
+      for (int r = 0; r < sh.rows && sh.status != kLatUnfit; ++r) {
+        const uint32_t w = sm[r];
+        const uint32_t cnt = w >> 30;
+        if (cnt == 1u) sh.status = ST_LOGIC_ERROR;  // odd number of ranges: std::logic_error upstream
+        const int width = cnt == 2u ? static_cast<int>(((w >> 15) & 0x7FFFu) - (w & 0x7FFFu)) + 1 : 0;
+        if (width > kLatMaxWidth) sh.status = kLatUnfit;
+        sa[r] = r * pitch + x0 + static_cast<int>(w & 0x7FFFu);  // byte offset of the span's first cell from (vertex 0, row yb)
+        sm[r] = static_cast<uint32_t>(width) | (static_cast<uint32_t>(r) << 8);
+      }
+      sh.n_spans = sh.rows;
+      return sh;
+    }
   }
+  if (cap < 2 * rows_cap) {
+    sh.status = kLatUnfit;
+    return sh;
+  }
+  // ---- four ranges per row
+  uint32_t* __restrict__ t4 = reinterpret_cast<uint32_t*>(tbl);
+  SlotWalker<4> w;
+  w.tab = t4, w.stride = 1, w.xb = x0, w.yb = y0;
+  for (int r = 0; r < sh.rows; ++r)
+    for (int q = 0; q < 4; ++q) w.slot(r, q) = kPairEmpty;
+  const int2 f = verts[0];
+  w.y_run = w.y0 = f.y, w.x_first = w.x0 = w.x_prev = f.x, w.y_before = f.y;
+  w.in_first = true, w.overflow = false, w.f_xlast = f.x, w.f_ynext = f.y;
+  LatSlotSink sink{w};
+  walk_outline_cells(verts, nv, sink);
+  if (w.in_first) {  // every cell on one row: ranges (min,min),(max,max) (generators.cpp:197-204)
+    const uint32_t wd = static_cast<uint32_t>(x1 - x0);
+    w.slot(w.y0 - y0, 0) = 0u;
+    w.slot(w.y0 - y0, 1) = wd | (wd << 16);
+  } else if (w.y_run == w.y0) {  // the tail run continues into cell 0
+    w.prepend(w.y0, w.x_first, w.f_xlast, w.y_before, w.f_ynext);
+  } else {
+    w.append(w.y_run, w.x_first, w.x_prev, w.y_before, w.y0);
+    w.prepend(w.y0, w.x0, w.f_xlast, w.y_run, w.f_ynext);
+  }
+  if (w.overflow) {  // more than four ranges on a row: the general kernel's sorted lists
+    sh.status = kLatUnfit;
+    return sh;
+  }
+  // pass 1: the merged pairs, one packed word each (lo 12 bits | width 8 | row 8), written over rows already read
+  int n = 0;
+  for (int r = 0; r < sh.rows; ++r) {
+    uint32_t e[4];
+    for (int q = 0; q < 4; ++q) e[q] = w.slot(r, q);
+    const int cnt = (e[0] != kPairEmpty) + (e[1] != kPairEmpty) + (e[2] != kPairEmpty) + (e[3] != kPairEmpty);
+    if (cnt & 1) {
+      sh.status = ST_LOGIC_ERROR;  // std::logic_error("Even number of line-pairs expected")
+      return sh;
+    }
+    int lo[2], hi[2], pairs = 0;
+    if (cnt == 4) {  // stable insertion sort by `min` (low 16 bits), then [r0.min, r1.max], [r2.min, r3.max]
+      for (int a2 = 1; a2 < 4; ++a2)
+        for (int b2 = a2; b2 > 0; --b2)
+          if ((e[b2] & 0xFFFFu) < (e[b2 - 1] & 0xFFFFu)) {
+            const uint32_t t = e[b2];
+            e[b2] = e[b2 - 1], e[b2 - 1] = t;
+          }
+      lo[0] = e[0] & 0xFFFFu, hi[0] = e[1] >> 16, lo[1] = e[2] & 0xFFFFu, hi[1] = e[3] >> 16, pairs = 2;
+    } else if (cnt == 2) {
+      const int lo1 = e[0] & 0xFFFFu, hi1 = e[0] >> 16, lo2 = e[1] & 0xFFFFu, hi2 = e[1] >> 16;
+      lo[0] = min(lo1, lo2), hi[0] = lo2 < lo1 ? hi1 : hi2, pairs = 1;  // stable sort by min, then [first.min, second.max]
+    }
+    for (int q = 0; q < pairs; ++q) {
+      const int width = hi[q] - lo[q] + 1;
+      if (width > kLatMaxWidth) {
+        sh.status = kLatUnfit;
+        return sh;
+      }
+      // (an empty pair - max < min - is kept with width 0: it reads nothing, like the reference's empty inner loop)
+      t4[n++] = static_cast<uint32_t>(lo[q]) | (static_cast<uint32_t>(max(width, 0)) << 12) | (static_cast<uint32_t>(r) << 20);
+    }
+  }
+  // pass 2: expand downwards into span_a / span_m (n <= 2 rows <= cap, so span_m[k] never lands on an unread word)
+  for (int k = n - 1; k >= 0; --k) {
+    const uint32_t pk = t4[k];
+    const int lo = pk & 0xFFFu, width = (pk >> 12) & 0xFFu, r = pk >> 20;
+    sm[k] = static_cast<uint32_t>(width) | (static_cast<uint32_t>(r) << 8);
+    sa[k] = r * pitch + x0 + lo;
+  }
+  sh.n_spans = n;
   return sh;
 }
 
@@ -811,7 +907,7 @@ __device__ __forceinline__ void lattice_rows_fold(const MapView& m, const int* _
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const bool live = r + u < rows;
-        width[u] = live ? __popc(row_m[r + u]) : 0;
+        width[u] = live ? span_width(row_m[r + u]) : 0;
         const uint8_t* __restrict__ q = p3 + (live ? row_a[r + u] : 0);
         v0[u] = v1[u] = v2[u] = 0;
         if (live && 3 * lane < n_cells) v0[u] = __ldg(q), v1[u] = __ldg(q + 1), v2[u] = __ldg(q + 2);  // 64 = 3 * 21 + 1: lane 21 reads two cells more, still inside the segment
@@ -871,7 +967,7 @@ __device__ __forceinline__ void lattice_rows_fold(const MapView& m, const int* _
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const bool live = r + u < rows;
-        width[u] = live ? __popc(row_m[r + u]) : 0;
+        width[u] = live ? span_width(row_m[r + u]) : 0;
         k[u] = 31 - __clz(width[u] | 1);  // 2^k <= width
         const uint8_t* __restrict__ q = p + (live ? row_a[r + u] : 0);
         l0[u] = __ldg(q), l1[u] = __ldg(q + 32), l2[u] = third ? __ldg(q + 64) : 0u;
@@ -925,16 +1021,15 @@ __device__ __forceinline__ void lat_store_bits(const OutView& out, uint32_t free
 /// to the todo list - no hashed keys, no byte walk, no out-of-line calls on the hot path.
 template <int OP, bool LEAN>
 __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_BLOCKS) k_area_lattice(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
-                                                                     long long count, OutView out, int rows_cap,
+                                                                     long long count, OutView out, int rows_cap, int span_cap,
                                                                      unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count,
                                                                      LatGeom g, PlaneView pv) {
   extern __shared__ double smem_d[];
   const double* poly = stage_polygon(poly_g, nv, smem_d);
   unsigned long long* slot_key = reinterpret_cast<unsigned long long*>(smem_d + 2 * nv);  // 0 = empty
   int2* canon = reinterpret_cast<int2*>(slot_key + kLatSlots);                          // [slot][vertex] relative cells
-  int* row_a = reinterpret_cast<int*>(canon + kLatSlots * nv);                          // [slot][row] first cell of the range
-  uint32_t* row_m = reinterpret_cast<uint32_t*>(row_a + kLatSlots * rows_cap);          // [slot][row] width mask (0 = no range)
-  LatShape* meta = reinterpret_cast<LatShape*>(row_m + kLatSlots * rows_cap);           // [slot]
+  int* span_tbl = reinterpret_cast<int*>(canon + kLatSlots * nv);                       // [slot][2 * span_cap]: span_a, then span_m
+  LatShape* meta = reinterpret_cast<LatShape*>(span_tbl + kLatSlots * 2 * span_cap);    // [slot]
   uint8_t* rowbufs = reinterpret_cast<uint8_t*>(meta + kLatSlots);                      // [warp][800]: per-row query tables of the value folds
   if (threadIdx.x < kLatSlots) {
     slot_key[threadIdx.x] = 0ull;
@@ -1075,7 +1170,9 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
         pend_b &= ~grp_b;
 
         int slot = -1, st = ST_OK;  // the group's shape slot: carried from row to row while the y offsets repeat
-        int xb_s = 0, x1_s = 0, rows = 0, yb_s = 0;  // its bounding box relative to vertex 0
+        int xb_s = 0, x1_s = 0, rows = 0, yb_s = 0, n_spans = 0;  // its bounding box relative to vertex 0, its span count
+        const int* span_a = span_tbl;
+        const uint32_t* span_m = reinterpret_cast<const uint32_t*>(span_tbl);
         // OP_IS_FREE over the bit planes, lane j = scan row j of the slot's shape, decoded once per slot: the two
         // windows' word pointers for map row 0 (the lattice row only adds y_base) and bit shifts
         const uint32_t* win_s = nullptr;
@@ -1120,8 +1217,8 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
                     if (v == 0) ax = cx, ay = cy;
                     canon[idx * nv + v] = make_int2(cx - ax, cy - ay);
                   }
-                  const LatShape sh = lattice_rasterise(canon + idx * nv, nv, rows_cap, m.pitch, row_a + idx * rows_cap, row_m + idx * rows_cap);
-                  meta[idx].xb = sh.xb, meta[idx].x1 = sh.x1, meta[idx].yb = sh.yb, meta[idx].rows = sh.rows;
+                  const LatShape sh = lattice_rasterise(canon + idx * nv, nv, rows_cap, span_cap, m.pitch, span_tbl + idx * 2 * span_cap);
+                  meta[idx].xb = sh.xb, meta[idx].x1 = sh.x1, meta[idx].yb = sh.yb, meta[idx].rows = sh.rows, meta[idx].n_spans = sh.n_spans;
                   __threadfence_block();
                   *reinterpret_cast<volatile int*>(&meta[idx].status) = sh.status;
                   sfound = idx;
@@ -1138,18 +1235,20 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
                 __nanosleep(100);  // (leave the issue slots to the lane that is rasterising the shape)
               }
               __threadfence_block();
-              xb_s = meta[slot].xb, x1_s = meta[slot].x1, rows = meta[slot].rows, yb_s = meta[slot].yb;
+              xb_s = meta[slot].xb, x1_s = meta[slot].x1, rows = meta[slot].rows, yb_s = meta[slot].yb, n_spans = meta[slot].n_spans;
+              span_a = span_tbl + slot * 2 * span_cap, span_m = reinterpret_cast<const uint32_t*>(span_a + span_cap);
               if constexpr (OP == OP_IS_FREE) {
-                lean = pv.bits != nullptr && rows <= 32 && st == ST_OK;
+                lean = pv.bits != nullptr && n_spans <= 32 && st == ST_OK;  // lane j = span j
                 // every cell any pose of the group needs lies in x: [xmin + xb, xmin + maxoff + x1]
                 inside_x = xmin + xb_s >= 0 && xmin + maxoff + x1_s < m.size_x;
                 if (lean) {
-                  const int width = lane < rows ? __popc(row_m[slot * rows_cap + lane]) : 0;
+                  const uint32_t sm = lane < n_spans ? span_m[lane] : 0u;
+                  const int width = span_width(sm), dy = span_dy(sm);
                   win_s = win_t = nullptr;
                   if (width > 0 && inside_x) {
                     const int k = 31 - __clz(width);
-                    const int xs = xmin + (row_a[slot * rows_cap + lane] - lane * m.pitch), xt = xs + (width - (1 << k));
-                    const uint32_t* plane_row = pv.bits + k * pv.plane_words + lane;
+                    const int xs = xmin + (span_a[lane] - dy * m.pitch), xt = xs + (width - (1 << k));
+                    const uint32_t* plane_row = pv.bits + k * pv.plane_words + dy;
                     win_s = plane_row + static_cast<long long>(xs >> 5) * pv.ypitch, sh_s = xs & 31;
                     if (xt != xs) win_t = plane_row + static_cast<long long>(xt >> 5) * pv.ypitch, sh_t = xt & 31;
                   }
@@ -1252,8 +1351,8 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
               if (act_a) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
               if (act_b) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
               continue;
-            } else if (inside && pv.bits) lattice_rows_planes(pv, row_a + slot * rows_cap, row_m + slot * rows_cap, rows, m.pitch, xmin, y_base, lane, maxoff >= 32, oa, ob, hit_a, hit_b);
-            else lattice_rows_bytes(m, row_a + slot * rows_cap, row_m + slot * rows_cap, rows, xmin, y_base, lane, oa, ob, hit_a, hit_b);
+            } else if (inside && pv.bits) lattice_rows_planes(pv, span_a, span_m, n_spans, m.pitch, xmin, y_base, lane, maxoff >= 32, oa, ob, hit_a, hit_b);
+            else lattice_rows_bytes(m, span_a, span_m, n_spans, xmin, y_base, lane, oa, ob, hit_a, hit_b);
             if (act_a) {
               if (out.is_free) out.is_free[i_a] = hit_a ? 0 : 1;
               if (out.status) out.status[i_a] = ST_OK;
@@ -1267,7 +1366,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
             }
           } else if (inside) {  // (discarded for OP_IS_FREE: the whole else-chain hangs off an `if constexpr`)
             Fold<OP> fa, fb;
-            lattice_rows_fold<OP>(m, row_a + slot * rows_cap, row_m + slot * rows_cap, rows, xmin, y_base, lane, maxoff >= 32, oa, ob, rowbuf, fa, fb);
+            lattice_rows_fold<OP>(m, span_a, span_m, n_spans, xmin, y_base, lane, maxoff >= 32, oa, ob, rowbuf, fa, fb);
             if (act_a) {
               fa.store(out, i_a);
               if (out.status) out.status[i_a] = ST_OK;
@@ -2296,8 +2395,11 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       const long long want_units = 4ll * ctx->sm_count * LAT_MIN_BLOCKS * kLatWarps;
       while (g.rows_per_unit > 8 && static_cast<long long>((g.n_rows + g.rows_per_unit - 1) / g.rows_per_unit) * g.segs < want_units) g.rows_per_unit /= 2;
       g.n_units = static_cast<long long>((g.n_rows + g.rows_per_unit - 1) / g.rows_per_unit) * g.segs;
+      // span table per cached shape: one span per scan row for a convex polygon, up to two (and the [row][4] scratch
+      // of the four-range rasteriser) otherwise
+      const int span_cap = is_convex(poly_host, nv) ? rows_cap : 2 * rows_cap;
       const size_t smem = poly_bytes + kLatSlots * (sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) +
-                                                     static_cast<size_t>(rows_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape)) +
+                                                     static_cast<size_t>(span_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape)) +
                           (OP == OP_IS_FREE ? 0 : kLatWarps * 800);  // the value folds' per-warp query tables
       const unsigned int grid = static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_MIN_BLOCKS));
       PlaneView pv{nullptr, 0, 0};
@@ -2306,10 +2408,10 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
         if (rc) return rc;
       }
       if (OP == OP_IS_FREE && pv.bits && nv <= 4)
-        k_area_lattice<OP_IS_FREE, true><<<static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_LEAN_BLOCKS)), kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
+        k_area_lattice<OP_IS_FREE, true><<<static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_LEAN_BLOCKS)), kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap, span_cap,
                                                                                    ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv);
       else
-        k_area_lattice<OP, false><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
+        k_area_lattice<OP, false><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap, span_cap,
                                                                             ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv);
     } else {
       if (ctx->old_packed_kernel) {

@@ -181,6 +181,32 @@ def test_lattice_other_small_footprints(cb, ctx):
                         True, f"{name} {poly.tolist()}")
 
 
+def test_lattice_non_convex_footprints(cb, ctx):
+    """Non-convex footprints on a lattice: scan rows with two merged range pairs go through the four-range rasteriser
+    of the shape cache (span table), rows with more through the general kernel - cusps, ties and all, against the
+    oracle for the three folds, on a cell-pitch and on a sub-cell-pitch lattice."""
+    from cover_b200 import workloads as wl
+    rng = np.random.default_rng(91)
+    data = mixed_map(rng, 320, 300, lethal=0.003)
+    cmap = cb.Costmap(ctx, data, 0.05, -1.0, -0.5)
+    omap = po.Costmap(data, 0.05, -1.0, -0.5)
+    th = np.concatenate([-math.pi + 2 * math.pi * np.arange(10) / 10, [0.0, math.pi / 2]])
+    cs = np.stack([np.cos(th), np.sin(th)], 1)
+    notch = np.array([[-0.5, 0.5, 0.5, 0.15, 0.15, -0.15, -0.15, -0.5], [-0.4, -0.4, 0.4, 0.4, -0.1, -0.1, 0.4, 0.4]])  # a U
+    star = np.stack([np.where(np.arange(16) % 2 == 0, 0.6, 0.22) * np.cos(2 * math.pi * np.arange(16) / 16),
+                     np.where(np.arange(16) % 2 == 0, 0.6, 0.22) * np.sin(2 * math.pi * np.arange(16) / 16)])  # > 4 ranges on some rows
+    polys = {"potato": wl.scaled(wl.potato(16), 0.6), "U": notch, "star": star, "L": FOOTPRINTS[6], "S x0.25": FOOTPRINTS[0] * 0.25,
+             "TORU": FOOTPRINTS[5]}
+    for pitch in (0.05, 0.0173):
+        desc = dict(x0=-0.4, dx=pitch, nx=150, y0=0.2, dy=pitch, ny=60, cs=cs)
+        for name, poly in polys.items():
+            for op_name, op, has_cost in OPS:
+                gpu = getattr(cmap, f"area_{op_name}")(poly, cb.Lattice(**desc))
+                cpu = po.polygon_batch(omap, poly, po.Lattice(**desc), op=op, threads=8)
+                assert_same(gpu, cpu, has_cost, f"{name} {op_name} pitch {pitch}")
+            assert cpu.is_free.any() or name == "star"
+
+
 @pytest.mark.parametrize("idx", range(7))
 @pytest.mark.parametrize("shape,prefix", [(po.SHAPE_AREA, "area"), (po.SHAPE_OUTLINE, "outline")])
 def test_reference_footprints_all_ops(cb, ctx, idx, shape, prefix):
