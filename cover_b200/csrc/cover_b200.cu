@@ -579,9 +579,10 @@ __global__ void __launch_bounds__(kBlock) k_area_slots(MapView m, const double* 
 #ifndef LAT_LEAN_BLOCKS
 #define LAT_LEAN_BLOCKS 3
 #endif
-constexpr int kLatSegX = 64, kLatWarps = 8, kLatThreads = kLatWarps * 32, kLatSlots = 64;
+constexpr int kLatSegX = 64, kLatWarps = 8, kLatThreads = kLatWarps * 32, kLatSlotsMax = 64;
 constexpr int kLatMaxVertices = 64;
-constexpr int kLatMaxWidth = 32;   // widest scan row (cells): 64 pose offsets + 32 cells = one 96-cell window
+constexpr int kLatMaxWidth = 32;   // widest span (cells): 64 pose offsets + 32 cells = one 96-cell window; wider pairs are split
+constexpr int kLatMaxRowsCap = 72; // tallest footprint (scan rows, incl. the 3 rows of slack of rows_bound) the shape cache takes
 constexpr int kLatPending = -2;    // shape inserted, not rasterised yet
 constexpr int kLatUnfit = -1;      // shape not representable by this kernel
 constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -596,6 +597,7 @@ struct LatGeom {
   int n_rows, segs;     // lattice rows touched; 64-column segments per row
   long long n_units;    // segs * ceil(n_rows / rows_per_unit)
   int rows_per_unit;    // 8, 16 or 32 lattice rows per unit (lane r owns row r): as many as still fill the grid
+  int n_slots;          // shape-cache slots per CTA (power of two <= 64: fewer when a shape's span table is big)
 };
 
 __device__ __forceinline__ unsigned long long lat_mix(unsigned long long h, int v) {
@@ -784,23 +786,47 @@ __device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ vert
     sh.status = kLatUnfit;
     return sh;
   }
+  uint32_t* __restrict__ t4 = reinterpret_cast<uint32_t*>(tbl);
+  // A merged pair [lo, hi] of row r becomes ceil(width / 32) spans, packed one word each (lo 12 bits | width 8 | row 8)
+  // at t4[n++]; false when the table is full (`limit`: first index that must not be written yet).
+  auto emit_pair = [&](int& n, int limit, int r, int lo, int hi) {
+    for (int x = lo; x <= hi; x += kLatMaxWidth) {
+      if (n >= limit) return false;
+      t4[n++] = static_cast<uint32_t>(x) | (static_cast<uint32_t>(min(kLatMaxWidth, hi - x + 1)) << 12) | (static_cast<uint32_t>(r) << 20);
+    }
+    return true;
+  };
+  // Expands the n packed words downwards into span_a / span_m (n <= cap, so span_m[k] never lands on an unread word).
+  auto expand = [&](int n) {
+    for (int k = n - 1; k >= 0; --k) {
+      const uint32_t pk = t4[k];
+      const int lo = pk & 0xFFFu, width = (pk >> 12) & 0xFFu, r = pk >> 20;
+      sm[k] = static_cast<uint32_t>(width) | (static_cast<uint32_t>(r) << 8);
+      sa[k] = r * pitch + x0 + lo;  // byte offset of the span's first cell from (vertex 0, row yb)
+    }
+    sh.n_spans = n;
+  };
   {
-    PackedStore store{sm, 1, x0, y0};  // the packed table is built in place in span_m, then converted
+    PackedStore store{sm, 1, x0, y0};  // two ranges per row, merged on arrival: one packed word per row in span_m's half
     store.clear(sh.rows);
     RunDetector<PackedStore> runs(store, 0, x0, x1);
     walk_outline_cells(verts, nv, runs);
     runs.finish();
     if (!store.overflow) {
-      for (int r = 0; r < sh.rows && sh.status != kLatUnfit; ++r) {
+      int n = 0;
+      for (int r = 0; r < sh.rows; ++r) {
         const uint32_t w = sm[r];
         const uint32_t cnt = w >> 30;
-        if (cnt == 1u) sh.status = ST_LOGIC_ERROR;  // odd number of ranges: std::logic_error upstream
-        const int width = cnt == 2u ? static_cast<int>(((w >> 15) & 0x7FFFu) - (w & 0x7FFFu)) + 1 : 0;
-        if (width > kLatMaxWidth) sh.status = kLatUnfit;
-        sa[r] = r * pitch + x0 + static_cast<int>(w & 0x7FFFu);  // byte offset of the span's first cell from (vertex 0, row yb)
-        sm[r] = static_cast<uint32_t>(width) | (static_cast<uint32_t>(r) << 8);
+        if (cnt == 1u) {  // odd number of ranges: std::logic_error upstream
+          sh.status = ST_LOGIC_ERROR;
+          return sh;
+        }
+        if (cnt == 2u && !emit_pair(n, cap, r, static_cast<int>(w & 0x7FFFu), static_cast<int>((w >> 15) & 0x7FFFu))) {
+          sh.status = kLatUnfit;
+          return sh;
+        }
       }
-      sh.n_spans = sh.rows;
+      expand(n);
       return sh;
     }
   }
@@ -809,7 +835,6 @@ __device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ vert
     return sh;
   }
   // ---- four ranges per row
-  uint32_t* __restrict__ t4 = reinterpret_cast<uint32_t*>(tbl);
   SlotWalker<4> w;
   w.tab = t4, w.stride = 1, w.xb = x0, w.yb = y0;
   for (int r = 0; r < sh.rows; ++r)
@@ -833,7 +858,7 @@ __device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ vert
     sh.status = kLatUnfit;
     return sh;
   }
-  // pass 1: the merged pairs, one packed word each (lo 12 bits | width 8 | row 8), written over rows already read
+  // pass 1: the merged pairs as packed spans, written over the scratch of rows already read (never past row r's own)
   int n = 0;
   for (int r = 0; r < sh.rows; ++r) {
     uint32_t e[4];
@@ -856,24 +881,13 @@ __device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ vert
       const int lo1 = e[0] & 0xFFFFu, hi1 = e[0] >> 16, lo2 = e[1] & 0xFFFFu, hi2 = e[1] >> 16;
       lo[0] = min(lo1, lo2), hi[0] = lo2 < lo1 ? hi1 : hi2, pairs = 1;  // stable sort by min, then [first.min, second.max]
     }
-    for (int q = 0; q < pairs; ++q) {
-      const int width = hi[q] - lo[q] + 1;
-      if (width > kLatMaxWidth) {
+    for (int q = 0; q < pairs; ++q)
+      if (!emit_pair(n, min(cap, 4 * (r + 1)), r, lo[q], hi[q])) {
         sh.status = kLatUnfit;
         return sh;
       }
-      // (an empty pair - max < min - is kept with width 0: it reads nothing, like the reference's empty inner loop)
-      t4[n++] = static_cast<uint32_t>(lo[q]) | (static_cast<uint32_t>(max(width, 0)) << 12) | (static_cast<uint32_t>(r) << 20);
-    }
   }
-  // pass 2: expand downwards into span_a / span_m (n <= 2 rows <= cap, so span_m[k] never lands on an unread word)
-  for (int k = n - 1; k >= 0; --k) {
-    const uint32_t pk = t4[k];
-    const int lo = pk & 0xFFFu, width = (pk >> 12) & 0xFFu, r = pk >> 20;
-    sm[k] = static_cast<uint32_t>(width) | (static_cast<uint32_t>(r) << 8);
-    sa[k] = r * pitch + x0 + lo;
-  }
-  sh.n_spans = n;
+  expand(n);
   return sh;
 }
 
@@ -1027,6 +1041,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
   extern __shared__ double smem_d[];
   const double* poly = stage_polygon(poly_g, nv, smem_d);
   unsigned long long* slot_key = reinterpret_cast<unsigned long long*>(smem_d + 2 * nv);  // 0 = empty
+  const int kLatSlots = LEAN ? kLatSlotsMax : g.n_slots;  // (lean shapes are small: always 64 slots, a compile-time constant)
   int2* canon = reinterpret_cast<int2*>(slot_key + kLatSlots);                          // [slot][vertex] relative cells
   int* span_tbl = reinterpret_cast<int*>(canon + kLatSlots * nv);                       // [slot][2 * span_cap]: span_a, then span_m
   LatShape* meta = reinterpret_cast<LatShape*>(span_tbl + kLatSlots * 2 * span_cap);    // [slot]
@@ -1203,7 +1218,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
             const double ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(iy), src.dy));
             int sfound = -1;
             if (lane == leader) {
-              const int home = static_cast<int>((kl * 0x9E3779B97F4A7C15ull) >> 58);
+              const int home = static_cast<int>((kl * 0x9E3779B97F4A7C15ull) >> 58) & (kLatSlots - 1);
               for (int j = 0; j < kLatSlots && sfound < 0; ++j) {
                 const int idx = (home + j) & (kLatSlots - 1);
                 unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(&slot_key[idx]);
@@ -2380,7 +2395,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   bool second_list = false;
   // Lattice batches of small footprints: shape-deduplicating warp-cooperative kernel.
   const bool lattice = fast && src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices &&
-                       rows_cap - 3 <= kLatMaxWidth && !ctx->disable_lattice_kernel;
+                       rows_cap <= kLatMaxRowsCap && !ctx->disable_lattice_kernel;
   if (fast) {
     CU(ctx->todo.ensure(static_cast<size_t>(count) * sizeof(unsigned int)));
     CU(ctx->todo_count.ensure(sizeof(unsigned int)));
@@ -2397,9 +2412,11 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       g.n_units = static_cast<long long>((g.n_rows + g.rows_per_unit - 1) / g.rows_per_unit) * g.segs;
       // span table per cached shape: one span per scan row for a convex polygon, up to two (and the [row][4] scratch
       // of the four-range rasteriser) otherwise
-      const int span_cap = is_convex(poly_host, nv) ? rows_cap : 2 * rows_cap;
-      const size_t smem = poly_bytes + kLatSlots * (sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) +
-                                                     static_cast<size_t>(span_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape)) +
+      const int span_cap = (is_convex(poly_host, nv) && rows_cap - 3 <= kLatMaxWidth) ? rows_cap : 2 * rows_cap;
+      const size_t per_slot = sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) + static_cast<size_t>(span_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape);
+      g.n_slots = kLatSlotsMax;  // (a heading has a handful of distinct shapes: 16 slots are plenty for the big ones)
+      while (g.n_slots > 16 && g.n_slots * per_slot > (28u << 10)) g.n_slots /= 2;
+      const size_t smem = poly_bytes + g.n_slots * per_slot +
                           (OP == OP_IS_FREE ? 0 : kLatWarps * 800);  // the value folds' per-warp query tables
       const unsigned int grid = static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_MIN_BLOCKS));
       PlaneView pv{nullptr, 0, 0};
@@ -2407,7 +2424,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
         const int rc = ensure_planes(ctx, map, row_lo, row_hi, pv);
         if (rc) return rc;
       }
-      if (OP == OP_IS_FREE && pv.bits && nv <= 4)
+      if (OP == OP_IS_FREE && pv.bits && nv <= 4 && span_cap <= 32)  // (the lean kernel defers shapes with more than 32 spans)
         k_area_lattice<OP_IS_FREE, true><<<static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_LEAN_BLOCKS)), kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap, span_cap,
                                                                                    ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv);
       else

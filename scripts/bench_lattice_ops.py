@@ -19,6 +19,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 poly_name = os.environ.get("POLY", "rect")
 if poly_name == "rect":
     POLY = wl.RECT
+elif poly_name == "rect2":
+    POLY = 2.0 * wl.RECT                   # 2.0 x 1.2 m: 40 x 24 cells, pairs wider than 32 cells are split
 elif poly_name == "potato":
     POLY = wl.scaled(wl.potato(16), 0.6)   # 16 vertices, ~0.7 m across: hashed shape keys
 else:

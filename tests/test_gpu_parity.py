@@ -207,6 +207,28 @@ def test_lattice_non_convex_footprints(cb, ctx):
             assert cpu.is_free.any() or name == "star"
 
 
+def test_lattice_big_footprints(cb, ctx):
+    """Footprints up to ~70 scan rows on a lattice: pairs wider than 32 cells are split into several spans of the
+    shape's span table (the 1.0 x 0.6 m rectangle on a 2 cm map, a 2.6 x 1.5 m rectangle, SOTO, a fat U at 5 cm);
+    the W footprint is taller than the cache takes and goes through the general kernels as before."""
+    rng = np.random.default_rng(92)
+    th = np.concatenate([-math.pi + 2 * math.pi * np.arange(7) / 7, [0.0, math.pi / 2]])
+    cs = np.stack([np.cos(th), np.sin(th)], 1)
+    fat_u = 2.2 * np.array([[-0.5, 0.5, 0.5, 0.15, 0.15, -0.15, -0.15, -0.5], [-0.4, -0.4, 0.4, 0.4, -0.1, -0.1, 0.4, 0.4]])
+    cases = [(0.02, RECT, "rect @ 2 cm"), (0.05, 2.6 * RECT, "2.6 x rect"), (0.05, FOOTPRINTS[4], "SOTO"), (0.05, fat_u, "fat U"),
+             (0.05, FOOTPRINTS[1], "W")]
+    for res, poly, name in cases:
+        data = mixed_map(rng, 420, 380, lethal=0.0015)
+        cmap = cb.Costmap(ctx, data, res, -1.0 * res / 0.05, -0.5 * res / 0.05)
+        omap = po.Costmap(data, res, -1.0 * res / 0.05, -0.5 * res / 0.05)
+        for pitch in (res, 0.37 * res):
+            desc = dict(x0=-0.5 * res / 0.05, dx=pitch, nx=140, y0=0.3 * res / 0.05, dy=pitch, ny=40, cs=cs)
+            for op_name, op, has_cost in OPS:
+                gpu = getattr(cmap, f"area_{op_name}")(poly, cb.Lattice(**desc))
+                cpu = po.polygon_batch(omap, poly, po.Lattice(**desc), op=op, threads=8)
+                assert_same(gpu, cpu, has_cost, f"{name} {op_name} pitch {pitch}")
+
+
 @pytest.mark.parametrize("idx", range(7))
 @pytest.mark.parametrize("shape,prefix", [(po.SHAPE_AREA, "area"), (po.SHAPE_OUTLINE, "outline")])
 def test_reference_footprints_all_ops(cb, ctx, idx, shape, prefix):
