@@ -205,10 +205,19 @@ def run_gpu(args) -> None:
         raise SystemExit("bench.py: no CUDA device — cover_b200 has no CPU path to time (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # one process per GPU on a shared host: give every rank its own cores and keep torch's CPU pools out of the
+        # way - a 0.5 ms step is short enough for the launching thread's scheduling jitter to show in the device time
+        torch.set_num_threads(1)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]) or set(cores))
+        except (AttributeError, OSError):
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     data = make_map()
-    desc = lattice_for_rank(rank)
+    desc = lattice_for_rank(int(os.environ.get("COVER_BENCH_WINDOW", rank)))  # (override: time another rank's window on one GPU)
     n_poses = desc["nx"] * desc["ny"] * desc["cs"].shape[0]
 
     ctx = cover_b200.Context(local)
