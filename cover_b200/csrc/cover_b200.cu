@@ -598,7 +598,22 @@ struct LatGeom {
   long long n_units;    // segs * ceil(n_rows / rows_per_unit)
   int rows_per_unit;    // 8, 16 or 32 lattice rows per unit (lane r owns row r): as many as still fill the grid
   int n_slots;          // shape-cache slots per CTA (power of two <= 64: fewer when a shape's span table is big)
+  int static_rounds;    // longest stretch of consecutive rounds a CTA draws at once (guided hand-out)
+  long long tickets_a, tickets_b;  // draws of `static_rounds` rounds, then of half that, then single rounds
 };
+
+/// Second level of the shape cache, shared by all CTAs of a launch (global memory, L2-resident): the CTA that meets a
+/// shape first rasterises it and publishes the result here, every other CTA copies it into its shared-memory cache
+/// instead of rasterising it again (a single-lane walk of ~20 us).  This is what lets the units be handed out
+/// dynamically, one round at a time, whatever heading they belong to.
+struct LatGlobal {
+  unsigned long long* key;   // [capacity] 0 = empty
+  int* status;               // [capacity] 0 = pending, else shape status + 16
+  int* data;                 // [capacity][entry_words]: LatShape (6 ints), canon (2 nv ints), span table (2 span_cap ints)
+  int entry_words, capacity; // capacity is a power of two
+  unsigned long long* next_round;  // dynamic work distribution: the next unit index to hand out
+};
+constexpr int kLatGlobalProbes = 16;
 
 __device__ __forceinline__ unsigned long long lat_mix(unsigned long long h, int v) {
   return (h ^ static_cast<unsigned int>(v)) * 0x100000001B3ull;  // FNV-1a step
@@ -1037,8 +1052,10 @@ template <int OP, bool LEAN>
 __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_BLOCKS) k_area_lattice(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
                                                                      long long count, OutView out, int rows_cap, int span_cap,
                                                                      unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count,
-                                                                     LatGeom g, PlaneView pv) {
+                                                                     LatGeom g, PlaneView pv, LatGlobal gl) {
   extern __shared__ double smem_d[];
+  __shared__ unsigned long long s_round;
+  __shared__ int s_used;  // occupied slots of the shared-memory cache
   const double* poly = stage_polygon(poly_g, nv, smem_d);
   unsigned long long* slot_key = reinterpret_cast<unsigned long long*>(smem_d + 2 * nv);  // 0 = empty
   const int kLatSlots = LEAN ? kLatSlotsMax : g.n_slots;  // (lean shapes are small: always 64 slots, a compile-time constant)
@@ -1050,6 +1067,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
     slot_key[threadIdx.x] = 0ull;
     meta[threadIdx.x].status = kLatPending;
   }
+  if (threadIdx.x == 0) s_used = 0;
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1057,26 +1075,45 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
   const bool exact_key = LEAN || nv <= 4;  // 2 x 3 offsets of 8 bits: the key IS the shape, no verification pass
   const int kLatRows = g.rows_per_unit;
   const unsigned kLatRowMask = kLatRows >= 32 ? 0xFFFFFFFFu : (1u << kLatRows) - 1u;
-  const long long chunk = (g.n_units + gridDim.x - 1) / gridDim.x;
-  const long long unit_begin = blockIdx.x * chunk, unit_end = min(g.n_units, unit_begin + chunk);
-  int cached_heading = -1;
+  const long long unit_end = g.n_units;
+  int chunk_left = 0;  // (thread 0) rounds left in the stretch drawn last
 
-  for (long long round = unit_begin; round < unit_end; round += kLatWarps) {
-    {  // new heading at the start of this round: start the shape cache over (depends on `round` only: CTA-uniform)
-      const long long row0 = g.row_first + (round / g.segs) * kLatRows;
-      const int it0 = static_cast<int>(row0 / src.ny);
-      if (it0 != cached_heading) {
-        if (cached_heading >= 0) {
-          __syncthreads();
-          if (threadIdx.x < kLatSlots) {
-            slot_key[threadIdx.x] = 0ull;
-            meta[threadIdx.x].status = kLatPending;
-          }
-          __syncthreads();
-        }
-        cached_heading = it0;
+  // Rounds (one unit per warp) are handed out dynamically: CTAs that draw expensive units - axis-aligned headings,
+  // where rounding noise splits a unit into several column groups - simply draw fewer of them.
+  for (;;) {
+    __syncthreads();  // everybody is done with the previous round (s_round, and the cache if it is cleared below)
+    const bool start_over = s_used > (kLatSlots * 3) / 4;  // the shape cache is nearly full (CTA-uniform)
+    if (threadIdx.x == 0) {
+      // Guided hand-out: a CTA draws a stretch of consecutive rounds (same heading: the shapes stay in its cache, the
+      // planes in its L1) whose length shrinks from `static_rounds` to one as the batch runs out, which evens out the
+      // finish however uneven the units are.
+      if (chunk_left == 0) {
+        // ticket t -> stretch: the first tickets_a tickets are stretches of `static_rounds` rounds, the next tickets_b
+        // of half that, the rest single rounds (one atomicAdd per draw: a compare-and-swap loop on one counter
+        // serialises 444 CTAs)
+        const long long t = static_cast<long long>(atomicAdd(gl.next_round, 1ull));
+        const long long la = g.static_rounds, lb = max(1, g.static_rounds / 2);
+        long long first_round, len;
+        if (t < g.tickets_a) first_round = t * la, len = la;
+        else if (t < g.tickets_a + g.tickets_b) first_round = g.tickets_a * la + (t - g.tickets_a) * lb, len = lb;
+        else first_round = g.tickets_a * la + g.tickets_b * lb + (t - g.tickets_a - g.tickets_b), len = 1;
+        s_round = static_cast<unsigned long long>(first_round) * kLatWarps, chunk_left = static_cast<int>(len);
+      } else {
+        s_round += kLatWarps;
       }
+      --chunk_left;
     }
+    if (start_over) {
+      __syncthreads();
+      if (threadIdx.x < kLatSlots) {
+        slot_key[threadIdx.x] = 0ull;
+        meta[threadIdx.x].status = kLatPending;
+      }
+      if (threadIdx.x == 0) s_used = 0;
+    }
+    __syncthreads();
+    const long long round = static_cast<long long>(s_round);
+    if (round >= unit_end) break;
     const long long unit = round + warp;
     if (unit >= unit_end) continue;
     const int group = static_cast<int>(unit / g.segs), seg = static_cast<int>(unit - static_cast<long long>(group) * g.segs);
@@ -1216,33 +1253,84 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
             const unsigned long long kl = exact_key ? ((1ull << 63) | (kx << 24) | ykey) : ((lat_mix(kx, static_cast<int>(ykey)) ^ (ykey >> 32)) | 1ull);
             const int iy = __shfl_sync(kFull, my_iy, r);
             const double ty = __dadd_rn(src.y0, __dmul_rn(static_cast<double>(iy), src.dy));
-            int sfound = -1;
+            int sfound = -1, fill = 0, gidx = -1;  // fill: 0 = nothing to do, 1 = rasterise (and publish at gidx), 2 = copy from gidx
             if (lane == leader) {
-              const int home = static_cast<int>((kl * 0x9E3779B97F4A7C15ull) >> 58) & (kLatSlots - 1);
+              const unsigned long long hash = kl * 0x9E3779B97F4A7C15ull;
+              const int home = static_cast<int>(hash >> 58) & (kLatSlots - 1);
               for (int j = 0; j < kLatSlots && sfound < 0; ++j) {
                 const int idx = (home + j) & (kLatSlots - 1);
                 unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(&slot_key[idx]);
                 if (old == 0ull) old = atomicCAS(&slot_key[idx], 0ull, kl);
-                if (old == 0ull) {  // we own the slot: publish the canonical relative vertices and the row table
+                if (old == 0ull) {  // we own the slot: fill it from the launch-wide table, or rasterise
+                  sfound = idx, fill = 1;
+                  atomicAdd(&s_used, 1);
+                  const int ghome = static_cast<int>(hash >> 32);
+                  for (int q = 0; q < kLatGlobalProbes; ++q) {
+                    const int gi = (ghome + q) & (gl.capacity - 1);
+                    unsigned long long gold = *reinterpret_cast<volatile unsigned long long*>(&gl.key[gi]);
+                    if (gold == 0ull) gold = atomicCAS(&gl.key[gi], 0ull, kl);
+                    if (gold == 0ull) {  // first CTA to meet this shape: rasterise and publish
+                      gidx = gi;
+                      break;
+                    }
+                    if (gold == kl) {  // somebody has it (or is making it): copy
+                      gidx = gi, fill = 2;
+                      break;
+                    }
+                  }
+                } else if (old == kl) {
+                  sfound = idx;
+                }
+              }
+            }
+            sfound = __shfl_sync(kFull, sfound, leader);
+            fill = __shfl_sync(kFull, fill, leader);
+            gidx = __shfl_sync(kFull, gidx, leader);
+            if (fill != 0) {
+              int* const s_tbl = span_tbl + sfound * 2 * span_cap;
+              int* const g_entry = gidx >= 0 ? gl.data + static_cast<long long>(gidx) * gl.entry_words : nullptr;
+              int shape_status = ST_OK;
+              if (fill == 2) {  // wait for the publisher, then copy entry -> slot with the whole warp
+                int gs = 0;
+                if (lane == 0) {
+                  while ((gs = *reinterpret_cast<volatile int*>(&gl.status[gidx])) == 0) __nanosleep(200);
+                }
+                gs = __shfl_sync(kFull, gs, 0);
+                __threadfence();
+                shape_status = gs - 16;
+                if (lane < 6 && lane != 4) reinterpret_cast<int*>(&meta[sfound])[lane] = __ldcg(g_entry + lane);  // (4 = status: published last)
+                for (int w = lane; w < 2 * nv; w += 32) reinterpret_cast<int*>(canon + sfound * nv)[w] = __ldcg(g_entry + 6 + w);
+                for (int w = lane; w < 2 * span_cap; w += 32) s_tbl[w] = __ldcg(g_entry + 6 + 2 * nv + w);
+              } else {
+                if (lane == leader) {
                   int ax = 0, ay = 0;
                   for (int v = 0; v < nv; ++v) {
                     int cx, cy;
                     lat_cell_x(cs.x, cs.y, tx_lead, poly[2 * v], poly[2 * v + 1], m, cx);
                     lat_cell_y(cs.x, cs.y, ty, poly[2 * v], poly[2 * v + 1], m, cy);
                     if (v == 0) ax = cx, ay = cy;
-                    canon[idx * nv + v] = make_int2(cx - ax, cy - ay);
+                    canon[sfound * nv + v] = make_int2(cx - ax, cy - ay);
                   }
-                  const LatShape sh = lattice_rasterise(canon + idx * nv, nv, rows_cap, span_cap, m.pitch, span_tbl + idx * 2 * span_cap);
-                  meta[idx].xb = sh.xb, meta[idx].x1 = sh.x1, meta[idx].yb = sh.yb, meta[idx].rows = sh.rows, meta[idx].n_spans = sh.n_spans;
-                  __threadfence_block();
-                  *reinterpret_cast<volatile int*>(&meta[idx].status) = sh.status;
-                  sfound = idx;
-                } else if (old == kl) {
-                  sfound = idx;
+                  const LatShape sh = lattice_rasterise(canon + sfound * nv, nv, rows_cap, span_cap, m.pitch, s_tbl);
+                  meta[sfound].xb = sh.xb, meta[sfound].x1 = sh.x1, meta[sfound].yb = sh.yb, meta[sfound].rows = sh.rows, meta[sfound].n_spans = sh.n_spans;
+                  shape_status = sh.status;
+                }
+                shape_status = __shfl_sync(kFull, shape_status, leader);
+                __syncwarp();
+                if (g_entry) {  // publish: slot -> entry with the whole warp
+                  if (lane < 6) g_entry[lane] = lane == 4 ? shape_status : reinterpret_cast<const int*>(&meta[sfound])[lane];
+                  for (int w = lane; w < 2 * nv; w += 32) g_entry[6 + w] = reinterpret_cast<const int*>(canon + sfound * nv)[w];
+                  for (int w = lane; w < 2 * span_cap; w += 32) g_entry[6 + 2 * nv + w] = s_tbl[w];
+                  __threadfence();
+                  __syncwarp();
+                  if (lane == 0) *reinterpret_cast<volatile int*>(&gl.status[gidx]) = shape_status + 16;
                 }
               }
+              __threadfence_block();
+              __syncwarp();
+              if (lane == 0) *reinterpret_cast<volatile int*>(&meta[sfound].status) = shape_status;
             }
-            slot = __shfl_sync(kFull, sfound, leader);
+            slot = sfound;
             st = ST_OK;
             lean = false;
             if (slot >= 0) {  // wait for a shape another warp is still rasterising
@@ -1988,7 +2076,7 @@ struct cover_ctx {
   bool old_packed_kernel = false;       // COVER_B200_OLD_PACKED=1: first-generation per-thread kernel (A/B measurements)
   bool force_list_kernel = false;
   bool always_try_packed = true;        // COVER_B200_PACKED_ONLY_CONVEX=1 restricts the packed pass to convex polygons       // COVER_B200_FORCE_LIST_KERNEL=1: A/B measurements and tests of k_area_list  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
-  DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, todo2, todo2_count, list_cnt, list_rng, list_seq;
+  DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, todo2, todo2_count, list_cnt, list_rng, list_seq, lat_global;
 };
 
 constexpr int kMapBands = 32;
@@ -2419,17 +2507,36 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       const size_t smem = poly_bytes + g.n_slots * per_slot +
                           (OP == OP_IS_FREE ? 0 : kLatWarps * 800);  // the value folds' per-warp query tables
       const unsigned int grid = static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_MIN_BLOCKS));
+      // launch-wide shape table + the round counter of the dynamic hand-out: [counter | keys | statuses | entries]
+      constexpr int kGlobalShapes = 2048;
+      LatGlobal gl{};
+      gl.capacity = kGlobalShapes, gl.entry_words = 6 + 2 * nv + 2 * span_cap;
+      const size_t head_bytes = 16 + static_cast<size_t>(kGlobalShapes) * (sizeof(unsigned long long) + sizeof(int));
+      CU(ctx->lat_global.ensure(head_bytes + static_cast<size_t>(kGlobalShapes) * gl.entry_words * sizeof(int)));
+      CU(cudaMemsetAsync(ctx->lat_global.ptr, 0, head_bytes, ctx->stream));
+      gl.next_round = ctx->lat_global.as<unsigned long long>();
+      gl.key = gl.next_round + 2;
+      gl.status = reinterpret_cast<int*>(gl.key + kGlobalShapes);
+      gl.data = gl.status + kGlobalShapes;
+      {
+        const long long total_rounds = (g.n_units + kLatWarps - 1) / kLatWarps;
+        int max_stretch = 4;
+        if (const char* e = std::getenv("COVER_B200_MAX_STRETCH")) max_stretch = std::max(1, std::atoi(e));  // (measurements)
+        g.static_rounds = static_cast<int>(std::max<long long>(1, std::min<long long>(max_stretch, total_rounds / (2ll * grid))));
+        g.tickets_a = total_rounds / 2 / g.static_rounds;                                   // half of the batch in long stretches,
+        g.tickets_b = total_rounds / 4 / std::max(1, g.static_rounds / 2);                  // a quarter in half-length ones
+      }
       PlaneView pv{nullptr, 0, 0};
       if (OP == OP_IS_FREE) {  // verdicts read the lethal bit planes of the rows under the window (built on first use)
         const int rc = ensure_planes(ctx, map, row_lo, row_hi, pv);
         if (rc) return rc;
       }
       if (OP == OP_IS_FREE && pv.bits && nv <= 4 && span_cap <= 32)  // (the lean kernel defers shapes with more than 32 spans)
-        k_area_lattice<OP_IS_FREE, true><<<static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_LEAN_BLOCKS)), kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap, span_cap,
-                                                                                   ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv);
+        k_area_lattice<OP_IS_FREE, true><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap, span_cap,
+                                                                                   ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv, gl);
       else
         k_area_lattice<OP, false><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap, span_cap,
-                                                                            ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv);
+                                                                            ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv, gl);
     } else {
       if (ctx->old_packed_kernel) {
         const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint32_t);
@@ -2738,7 +2845,7 @@ void cover_ctx_destroy(cover_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   cudaStreamSynchronize(ctx->stream);
   for (DeviceBuffer* b : {&ctx->poses, &ctx->theta, &ctx->poly, &ctx->in_a, &ctx->in_b, &ctx->out_free, &ctx->out_cost, &ctx->out_status, &ctx->out_bits, &ctx->out_not_ok,
-                          &ctx->todo, &ctx->todo_count, &ctx->todo2, &ctx->todo2_count, &ctx->list_cnt, &ctx->list_rng, &ctx->list_seq})
+                          &ctx->todo, &ctx->todo_count, &ctx->todo2, &ctx->todo2_count, &ctx->list_cnt, &ctx->list_rng, &ctx->list_seq, &ctx->lat_global})
     b->release();
   cudaEventDestroy(ctx->fence);
   cudaEventDestroy(ctx->chunk_done);
