@@ -2073,6 +2073,8 @@ struct cover_ctx {
   bool disable_lattice_kernel = false;
   bool disable_planes = false;          // COVER_B200_NO_PLANES=1: lattice verdicts walk the cost bytes (A/B measurements)
   int64_t planes_min_batch = 32768;     // COVER_B200_PLANES_MIN_BATCH: smallest batch that triggers a bit-plane build (tests: 0)
+  int max_stretch = 4;                  // COVER_B200_MAX_STRETCH: longest run of consecutive rounds a lattice CTA draws at once
+  int pipeline_chunks = 0;              // COVER_B200_CHUNKS: download chunks of a big lattice sweep (0 = by size)
   bool old_packed_kernel = false;       // COVER_B200_OLD_PACKED=1: first-generation per-thread kernel (A/B measurements)
   bool force_list_kernel = false;
   bool always_try_packed = true;        // COVER_B200_PACKED_ONLY_CONVEX=1 restricts the packed pass to convex polygons       // COVER_B200_FORCE_LIST_KERNEL=1: A/B measurements and tests of k_area_list  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
@@ -2520,9 +2522,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       gl.data = gl.status + kGlobalShapes;
       {
         const long long total_rounds = (g.n_units + kLatWarps - 1) / kLatWarps;
-        int max_stretch = 4;
-        if (const char* e = std::getenv("COVER_B200_MAX_STRETCH")) max_stretch = std::max(1, std::atoi(e));  // (measurements)
-        g.static_rounds = static_cast<int>(std::max<long long>(1, std::min<long long>(max_stretch, total_rounds / (2ll * grid))));
+        g.static_rounds = static_cast<int>(std::max<long long>(1, std::min<long long>(ctx->max_stretch, total_rounds / (2ll * grid))));
         g.tickets_a = total_rounds / 2 / g.static_rounds;                                   // half of the batch in long stretches,
         g.tickets_b = total_rounds / 4 / std::max(1, g.static_rounds / 2);                  // a quarter in half-length ones
       }
@@ -2618,7 +2618,7 @@ int polygon_check(cover_ctx* ctx, const cover_map* map, const double* polygon_xy
   constexpr int64_t kPipelineMin = 16ll << 20;
   // (two chunks up to ~1.5e8 poses: every chunk costs ~50 us of launch overhead and kernel tail, a chunk's download ~0.1 ms)
   int kPipelineChunks = static_cast<int>(std::min<int64_t>(4, std::max<int64_t>(2, poses->count / (48ll << 20))));
-  if (const char* e = std::getenv("COVER_B200_CHUNKS")) kPipelineChunks = std::max(1, std::atoi(e));  // (measurements)
+  if (ctx->pipeline_chunks > 0) kPipelineChunks = ctx->pipeline_chunks;  // (measurements)
   if (!(st.host && poses->format == COVER_POSE_LATTICE && poses->count >= kPipelineMin)) {
     rc = launch(src, poses->count, st.dev);
     if (rc) return rc;
@@ -2832,6 +2832,8 @@ int cover_ctx_create(int device, cover_ctx** out) {
   if (const char* e = std::getenv("COVER_B200_NO_LATTICE_KERNEL")) ctx->disable_lattice_kernel = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_NO_PLANES")) ctx->disable_planes = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_PLANES_MIN_BATCH")) ctx->planes_min_batch = std::atoll(e);
+  if (const char* e = std::getenv("COVER_B200_MAX_STRETCH")) ctx->max_stretch = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("COVER_B200_CHUNKS")) ctx->pipeline_chunks = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("COVER_B200_PACKED_ONLY_CONVEX")) ctx->always_try_packed = e[0] != '1';
   if (const char* e = std::getenv("COVER_B200_OLD_PACKED")) ctx->old_packed_kernel = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_FORCE_LIST_KERNEL")) ctx->force_list_kernel = e[0] == '1';
