@@ -61,12 +61,8 @@ struct CellSink {
 };
 
 template <int OP>
-__global__ void __launch_bounds__(kBlock) k_outline(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
-                                                   long long count, OutView out) {
-  extern __shared__ double smem_d[];
-  const double* poly = stage_polygon(poly_g, nv, smem_d);
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+__device__ __forceinline__ void outline_pose(const MapView& m, const double* __restrict__ poly, int nv, const PoseSource& src, long long i,
+                                             const OutView& out) {
   const Pose T = load_pose(src, i);
   int x0, y0, x1, y1;
   bool ok;
@@ -84,6 +80,27 @@ __global__ void __launch_bounds__(kBlock) k_outline(MapView m, const double* __r
   }
   sink.fold.store(out, i);
   if (out.status) out.status[i] = ST_OK;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kBlock) k_outline(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src,
+                                                   long long count, OutView out) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv, smem_d);
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < count) outline_pose<OP>(m, poly, nv, src, i, out);
+}
+
+/// The same over the poses an outline sweep of the lattice kernel deferred (persistent grid over the todo list).
+template <int OP>
+__global__ void __launch_bounds__(kBlock) k_outline_drain(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src, long long /*count*/,
+                                                         OutView out, const unsigned int* __restrict__ todo,
+                                                         const unsigned int* __restrict__ todo_count) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv, smem_d);
+  const long long n = static_cast<long long>(*todo_count), stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride)
+    outline_pose<OP>(m, poly, nv, src, static_cast<long long>(todo[j]), out);
 }
 
 template <int OP>
@@ -600,6 +617,7 @@ struct LatGeom {
   int n_slots;          // shape-cache slots per CTA (power of two <= 64: fewer when a shape's span table is big)
   int static_rounds;    // longest stretch of consecutive rounds a CTA draws at once (guided hand-out)
   long long tickets_a, tickets_b;  // draws of `static_rounds` rounds, then of half that, then single rounds
+  int outline;          // 1: the shapes are outlines (outline_generator cells), not areas
 };
 
 /// Second level of the shape cache, shared by all CTAs of a launch (global memory, L2-resident): the CTA that meets a
@@ -784,11 +802,41 @@ struct LatSlotSink {
   }
 };
 
+/// Sink of the OUTLINE rasteriser: maximal runs of outline cells that stay on one row become spans [min x, max x]
+/// (Bresenham cells are 8-connected, so a same-row run is contiguous in x).  A verdict / maximum over the outline is
+/// an any-reduction: order and duplicates do not matter.
+struct OutlineSpanSink {
+  uint32_t* t4;
+  int cap, x0, y0;  // table capacity (spans), bounding-box origin
+  int n = 0, y_run = 0, lo = 0, hi = 0;
+  bool open = false, overflow = false;
+  __device__ __forceinline__ void close() {
+    if (!open) return;
+    for (int x = lo; x <= hi; x += kLatMaxWidth) {
+      if (n >= cap) {
+        overflow = true;
+        return;
+      }
+      t4[n++] = static_cast<uint32_t>(x - x0) | (static_cast<uint32_t>(min(kLatMaxWidth, hi - x + 1)) << 12) | (static_cast<uint32_t>(y_run - y0) << 20);
+    }
+  }
+  __device__ __forceinline__ bool cell(int x, int y) {
+    if (open && y == y_run) {
+      lo = min(lo, x), hi = max(hi, x);
+    } else {
+      close();
+      open = true, y_run = y, lo = hi = x;
+    }
+    return true;
+  }
+};
+
 /// Rasterises the relative shape `verts` into the slot's span table `tbl` (span_a = tbl[0 .. cap), span_m =
 /// tbl[cap .. 2 cap)) and returns its descriptor.  Runs in ONE lane.  First attempt: at most two ranges per scan row
 /// (every convex shape), packed one word per row.  Second attempt (cap >= 2 * rows_cap, i.e. the polygon is not
 /// convex): up to four ranges per row = two merged pairs, with the slot's whole table as the [row][4] scratch.
-__device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ verts, int nv, int rows_cap, int cap, int pitch, int* __restrict__ tbl) {
+__device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ verts, int nv, int rows_cap, int cap, int pitch, int* __restrict__ tbl,
+                                                   bool outline) {
   int* __restrict__ sa = tbl;
   uint32_t* __restrict__ sm = reinterpret_cast<uint32_t*>(tbl + cap);
   int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, x1 = -0x7FFFFFFF - 1, y1 = -0x7FFFFFFF - 1;
@@ -821,6 +869,17 @@ __device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ vert
     }
     sh.n_spans = n;
   };
+  if (outline) {  // outline_generator cells (generators.cpp:54-93) as same-row runs
+    OutlineSpanSink sink{t4, cap, x0, y0};
+    walk_outline_cells(verts, nv, sink);
+    sink.close();
+    if (sink.overflow) {
+      sh.status = kLatUnfit;
+      return sh;
+    }
+    expand(sink.n);
+    return sh;
+  }
   {
     PackedStore store{sm, 1, x0, y0};  // two ranges per row, merged on arrival: one packed word per row in span_m's half
     store.clear(sh.rows);
@@ -1311,7 +1370,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
                     if (v == 0) ax = cx, ay = cy;
                     canon[sfound * nv + v] = make_int2(cx - ax, cy - ay);
                   }
-                  const LatShape sh = lattice_rasterise(canon + sfound * nv, nv, rows_cap, span_cap, m.pitch, s_tbl);
+                  const LatShape sh = lattice_rasterise(canon + sfound * nv, nv, rows_cap, span_cap, m.pitch, s_tbl, g.outline != 0);
                   meta[sfound].xb = sh.xb, meta[sfound].x1 = sh.x1, meta[sfound].yb = sh.yb, meta[sfound].rows = sh.rows, meta[sfound].n_spans = sh.n_spans;
                   shape_status = sh.status;
                 }
@@ -2461,12 +2520,17 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
                    const PoseSource& src, int64_t count, const OutView& out, int row_lo, int row_hi) {
   const size_t poly_bytes = static_cast<size_t>(nv) * 2 * sizeof(double);
   if (count == 0) return COVER_OK;
-  if (shape == SHAPE_OUTLINE) {
+  const int rows_cap = rows_bound(polygon_diameter(poly_host, nv), map->view.inv_res);
+  // Outlines over a pose lattice: a verdict or a maximum is an any-reduction over the outline's cell set, so the
+  // shape-cache kernel handles them with the outline's same-row runs as spans (accumulate_cost depends on the
+  // traversal order and on cells visited twice: per-pose kernel).
+  const bool outline_lattice = shape == SHAPE_OUTLINE && OP != OP_ACCUMULATE && src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices &&
+                               rows_cap <= kLatMaxRowsCap && !ctx->disable_lattice_kernel && count >= 4096;
+  if (shape == SHAPE_OUTLINE && !outline_lattice) {
     k_outline<OP><<<grid_for(count), kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out);
     ++ctx->launches;
     return COVER_OK;
   }
-  const int rows_cap = rows_bound(polygon_diameter(poly_host, nv), map->view.inv_res);
   // verdicts scan row spans: attach the lethal bit planes of the rows this batch can touch (two loads per span)
   MapView area_view = map->view;
   if (OP == OP_IS_FREE && planes_pay_off(ctx, map, false, row_lo, row_hi, count)) {
@@ -2476,7 +2540,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   // 1. fast pass: poses whose scan rows all have <= 2 ranges (every pose of a convex polygon, many poses of a
   //    mildly concave one) are finished by the packed / lattice kernel; the rest lands on the todo list.
   //    Polygons that are far from convex skip it (the pass would defer almost everything).
-  const bool fast = rows_cap <= kPackedMaxRows && (is_convex(poly_host, nv) || ctx->always_try_packed);
+  const bool fast = outline_lattice || (rows_cap <= kPackedMaxRows && (is_convex(poly_host, nv) || ctx->always_try_packed));
   // 2. general pass over everything (or the todo list): one warp per pose when the outline has few rays
   //    relative to its rows, else one thread per pose with per-row lists in global scratch.
   const bool rows_kernel = nv <= kRowsMaxVertices && rows_cap <= 30000 && !ctx->force_list_kernel && (nv <= 16 || rows_cap > 48);
@@ -2502,7 +2566,8 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       g.n_units = static_cast<long long>((g.n_rows + g.rows_per_unit - 1) / g.rows_per_unit) * g.segs;
       // span table per cached shape: one span per scan row for a convex polygon, up to two (and the [row][4] scratch
       // of the four-range rasteriser) otherwise
-      const int span_cap = (is_convex(poly_host, nv) && rows_cap - 3 <= kLatMaxWidth) ? rows_cap : 2 * rows_cap;
+      const int span_cap = outline_lattice ? 2 * rows_cap + 8 : ((is_convex(poly_host, nv) && rows_cap - 3 <= kLatMaxWidth) ? rows_cap : 2 * rows_cap);
+      g.outline = outline_lattice ? 1 : 0;
       const size_t per_slot = sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) + static_cast<size_t>(span_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape);
       g.n_slots = kLatSlotsMax;  // (a heading has a handful of distinct shapes: 16 slots are plenty for the big ones)
       while (g.n_slots > 16 && g.n_slots * per_slot > (28u << 10)) g.n_slots /= 2;
@@ -2565,6 +2630,12 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     ++ctx->launches;
     todo = second_list ? ctx->todo2.as<unsigned int>() : ctx->todo.as<unsigned int>();
     todo_count = second_list ? ctx->todo2_count.as<unsigned int>() : ctx->todo_count.as<unsigned int>();
+  }
+  if (outline_lattice) {  // drain: one thread per deferred pose (map border for max_cost, shapes the cache cannot hold)
+    const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(static_cast<long long>(ctx->sm_count) * 8, (count + kBlock - 1) / kBlock)));
+    k_outline_drain<OP><<<grid, kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, todo, todo_count);
+    ++ctx->launches;
+    return COVER_OK;
   }
   // A convex polygon defers (almost) nothing: a small persistent grid is enough to drain the list.
   const bool small_drain = fast && is_convex(poly_host, nv);

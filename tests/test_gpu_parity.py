@@ -207,6 +207,33 @@ def test_lattice_non_convex_footprints(cb, ctx):
             assert cpu.is_free.any() or name == "star"
 
 
+def test_lattice_outlines(cb, ctx):
+    """outline_generator checks over a lattice: verdict and maximum go through the shape cache with the outline's
+    same-row runs as spans (any-reductions), accumulate_cost through the per-pose kernel; map border included."""
+    from cover_b200 import workloads as wl
+    rng = np.random.default_rng(93)
+    data = mixed_map(rng, 300, 260, lethal=0.004)
+    cmap = cb.Costmap(ctx, data, 0.05, 0.5, 0.25)
+    omap = po.Costmap(data, 0.05, 0.5, 0.25)
+    th = np.concatenate([-math.pi + 2 * math.pi * np.arange(9) / 9, [0.0, -math.pi / 2]])
+    cs = np.stack([np.cos(th), np.sin(th)], 1)
+    spike = np.array([[0.0, 0.5, 0.0, -0.02], [0.0, 0.0, 0.02, 0.6]])  # thin spikes: runs that turn around on a row
+    polys = {"rect": RECT, "L": FOOTPRINTS[6], "TORU": FOOTPRINTS[5], "potato": wl.scaled(wl.potato(16), 0.6), "2 x rect": 2.0 * RECT,
+             "spike": spike, "point": np.array([[0.01], [0.01]]), "segment": np.array([[0.0, 0.3], [0.0, 0.45]])}
+    for pitch in (0.05, 0.0211):
+        desc = dict(x0=0.2, dx=pitch, nx=170, y0=0.0, dy=pitch, ny=70, cs=cs)  # (the first rows / columns hang over the map border)
+        for name, poly in polys.items():
+            for op_name, op, has_cost in OPS:
+                gpu = getattr(cmap, f"outline_{op_name}")(poly, cb.Lattice(**desc))
+                cpu = po.polygon_batch(omap, poly, po.Lattice(**desc), shape=po.SHAPE_OUTLINE, op=op, threads=8)
+                assert_same(gpu, cpu, has_cost, f"outline {name} {op_name} pitch {pitch}")
+    # a sub-range that starts and ends inside a row
+    desc = dict(x0=1.0, dx=0.05, nx=170, y0=1.0, dy=0.05, ny=70, cs=cs)
+    gpu = cmap.outline_is_free(RECT, cb.Lattice(**desc), first=12_345, count=77_777)
+    cpu = po.polygon_batch(omap, RECT, po.Lattice(**desc), shape=po.SHAPE_OUTLINE, first=12_345, count=77_777, threads=8)
+    assert_same(gpu, cpu, False, "outline sub-range")
+
+
 def test_lattice_big_footprints(cb, ctx):
     """Footprints up to ~70 scan rows on a lattice: pairs wider than 32 cells are split into several spans of the
     shape's span table (the 1.0 x 0.6 m rectangle on a 2 cm map, a 2.6 x 1.5 m rectangle, SOTO, a fat U at 5 cm);
