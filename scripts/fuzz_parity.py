@@ -65,13 +65,14 @@ for case in range(n_rand):
     total = nx * ny * n_th
     first = int(rng.integers(0, total)) if rng.random() < 0.4 else 0
     count = int(rng.integers(1, total - first + 1)) if rng.random() < 0.4 else total - first
-    for oname, op in ops:
-        g = getattr(cmap, f"area_{oname}")(poly, cb.Lattice(**desc), first=first, count=count)
-        c = po.polygon_batch(omap, poly, po.Lattice(**desc), op=op, threads=threads, first=first, count=count)
-        ok = np.array_equal(g.is_free, c.is_free) and np.array_equal(g.status, c.status) and (op == po.OP_IS_FREE or np.array_equal(g.cost, c.cost, equal_nan=True))
-        bad += not ok
-        if not ok or oname == "is_free":
-            print(f"random lattice {case:3d} nv={nv:2d} r={radius:4.2f} {nx:3d}x{ny:2d}x{n_th} [{first}, +{count}) {oname:15s} "
-                  f"free={c.is_free.mean():.3f} ok_status={np.mean(c.status == 0):.2f} {'OK' if ok else 'MISMATCH'}", flush=True)
+    for shape, prefix in ((po.SHAPE_AREA, "area"), (po.SHAPE_OUTLINE, "outline")):
+        for oname, op in ops:
+            g = getattr(cmap, f"{prefix}_{oname}")(poly, cb.Lattice(**desc), first=first, count=count)
+            c = po.polygon_batch(omap, poly, po.Lattice(**desc), shape=shape, op=op, threads=threads, first=first, count=count)
+            ok = np.array_equal(g.is_free, c.is_free) and np.array_equal(g.status, c.status) and (op == po.OP_IS_FREE or np.array_equal(g.cost, c.cost, equal_nan=True))
+            bad += not ok
+            if not ok or oname == "is_free":
+                print(f"random lattice {case:3d} nv={nv:2d} r={radius:4.2f} {nx:3d}x{ny:2d}x{n_th} [{first}, +{count}) {prefix:7s} {oname:15s} "
+                      f"free={c.is_free.mean():.3f} ok_status={np.mean(c.status == 0):.2f} {'OK' if ok else 'MISMATCH'}", flush=True)
 print(f"done in {time.time() - t0:.0f} s, mismatching cases: {bad}")
 sys.exit(1 if bad else 0)
