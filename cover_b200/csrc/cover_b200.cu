@@ -722,8 +722,76 @@ struct PlaneView {
   int ypitch;                         // COLUMN-major planes: word (column c = x / 32, row y) lives at c * ypitch + y, so the
                                       // lanes of a warp (= consecutive scan rows, nearly the same x) read consecutive words
   long long plane_words;              // words per plane = (ceil(size_x / 32) + 3 slack columns) * ypitch
+  // accumulate_cost sweeps: per-row exclusive prefix sums of the cost bytes (k_cost_prefix), row-major, ppitch words
+  // per row: word x = (number of cells >= 254 before x, mod 1024) << 22 | (sum of the costs before x, mod 2^22).
+  // A window of up to 32 cells is two loads; both fields are exact as differences.  nullptr: not built.
+  const uint32_t* __restrict__ prefix;
+  int ppitch;
 };
 constexpr int kPlaneCount = 6;
+
+/// accumulate_cost of one group over the prefix rows (every needed cell inside the map): the spans are walked in
+/// generator order (rows ascending, x ascending); a pose's window [off, off + width) of a span costs two loads -
+/// consecutive poses read consecutive words.  A window that holds a LETHAL / NO_INFORMATION cell is walked byte by
+/// byte for the first one (the reference's "first negative value in generator order", impl/costmap.hpp:50-63).
+__device__ __forceinline__ void lattice_spans_accumulate(const MapView& m, const PlaneView& pv, const int* __restrict__ span_a,
+                                                         const uint32_t* __restrict__ span_m, int n_spans, int x_base, int y_base, int off_a,
+                                                         int off_b, Fold<OP_ACCUMULATE>& fa, Fold<OP_ACCUMULATE>& fb) {
+  uint32_t sum_a = 0u, sum_b = 0u;
+  bool more_a = true, more_b = true;
+  for (int k = 0; k < n_spans; ++k) {
+    const uint32_t sm = span_m[k];
+    const int width = span_width(sm), dy = span_dy(sm);
+    const int xs = x_base + (span_a[k] - dy * m.pitch);
+    const uint32_t* __restrict__ row = pv.prefix + static_cast<long long>(y_base + dy) * pv.ppitch + xs;
+    const uint32_t a0 = __ldg(row + off_a), a1 = __ldg(row + off_a + width);
+    const uint32_t b0 = __ldg(row + off_b), b1 = __ldg(row + off_b + width);
+    const uint32_t cnt_a = ((a1 >> 22) - (a0 >> 22)) & 1023u, cnt_b = ((b1 >> 22) - (b0 >> 22)) & 1023u;
+    sum_a += (a1 - a0) & 0x3FFFFFu;  // (meaningless once a sentinel was met: `early` decides then)
+    sum_b += (b1 - b0) & 0x3FFFFFu;
+    if ((cnt_a != 0u && more_a) || (cnt_b != 0u && more_b)) {
+      const uint8_t* __restrict__ cells = m.data + static_cast<size_t>(y_base + dy) * m.pitch + xs;
+#pragma unroll
+      for (int plane = 0; plane < 2; ++plane) {
+        const bool hit = plane ? (cnt_b != 0u && more_b) : (cnt_a != 0u && more_a);
+        if (!hit) continue;
+        const int off = plane ? off_b : off_a;
+        int early = 0;
+        for (int x = off; x < off + width && early == 0; ++x) {
+          const int c = __ldg(cells + x);
+          if (c >= kLethal) early = c == kLethal ? -1 : -2;
+        }
+        if (plane) fb.early = early, more_b = false;
+        else fa.early = early, more_a = false;
+      }
+    }
+  }
+  fa.sum += sum_a, fb.sum += sum_b;
+}
+
+/// Builds rows [row_lo, row_hi] of the prefix rows: one warp per row, 32 cells per step, the running total carried in
+/// the warp.
+__global__ void __launch_bounds__(256) k_cost_prefix(MapView m, uint32_t* __restrict__ prefix, int ppitch, int row_lo, int row_hi) {
+  const int lane = threadIdx.x & 31;
+  const int y = row_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (y > row_hi) return;
+  const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y) * m.pitch;
+  uint32_t* __restrict__ dst = prefix + static_cast<long long>(y) * ppitch;
+  uint32_t carry_sum = 0u, carry_cnt = 0u;
+  for (int x0 = 0; x0 <= m.size_x; x0 += 32) {  // (<=: the entry at x = size_x closes the last window)
+    const int x = x0 + lane;
+    const uint32_t c = x < m.size_x ? __ldg(rowp + x) : 0u;
+    uint32_t s = c, n = c >= static_cast<uint32_t>(kLethal) ? 1u : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t us = __shfl_up_sync(kFull, s, d), un = __shfl_up_sync(kFull, n, d);
+      if (lane >= d) s += us, n += un;
+    }
+    const uint32_t ex_s = carry_sum + s - c, ex_n = carry_cnt + n - (c >= static_cast<uint32_t>(kLethal) ? 1u : 0u);  // exclusive
+    if (x <= m.size_x) dst[x] = ((ex_n & 1023u) << 22) | (ex_s & 0x3FFFFFu);
+    carry_sum += __shfl_sync(kFull, s, 31), carry_cnt += __shfl_sync(kFull, n, 31);
+  }
+}
 
 /// is_free walk of one group over the bit planes (every needed cell inside the map): LANE j owns span j of the
 /// shape.  For the group's 64 candidate x offsets it fetches the 64-bit window of plane log2(p) that starts at the
@@ -1528,7 +1596,12 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
             }
           } else if (inside) {  // (discarded for OP_IS_FREE: the whole else-chain hangs off an `if constexpr`)
             Fold<OP> fa, fb;
-            lattice_rows_fold<OP>(m, span_a, span_m, n_spans, xmin, y_base, lane, maxoff >= 32, oa, ob, rowbuf, fa, fb);
+            if constexpr (OP == OP_ACCUMULATE) {
+              if (pv.prefix) lattice_spans_accumulate(m, pv, span_a, span_m, n_spans, xmin, y_base, oa, ob, fa, fb);
+              else lattice_rows_fold<OP>(m, span_a, span_m, n_spans, xmin, y_base, lane, maxoff >= 32, oa, ob, rowbuf, fa, fb);
+            } else {
+              lattice_rows_fold<OP>(m, span_a, span_m, n_spans, xmin, y_base, lane, maxoff >= 32, oa, ob, rowbuf, fa, fb);
+            }
             if (act_a) {
               fa.store(out, i_a);
               if (out.status) out.status[i_a] = ST_OK;
@@ -2163,6 +2236,9 @@ struct cover_map {
   mutable uint32_t* planes_inf = nullptr;  // INSCRIBED-or-LETHAL planes (outline cells of split footprints)
   mutable int planes_lo = 0, planes_hi = -1;  // rows whose planes match the current image
   mutable int planes_inf_lo = 0, planes_inf_hi = -1;
+  mutable uint32_t* prefix = nullptr;  // per-row prefix sums of the costs (accumulate_cost lattice sweeps)
+  mutable int prefix_lo = 0, prefix_hi = -1;
+  int ppitch = 0;
   int ypitch = 0;
   long long plane_words = 0;
 };
@@ -2343,8 +2419,32 @@ bool planes_pay_off(const cover_ctx* ctx, const cover_map* map, bool inflated, i
 int ensure_planes(cover_ctx* ctx, const cover_map* map, int row_lo, int row_hi, PlaneView& pv) {
   const uint32_t* bits = nullptr;
   const int rc = ensure_plane_set(ctx, map, false, row_lo, row_hi, bits);
-  pv = PlaneView{bits, map->ypitch, map->plane_words};
+  pv = PlaneView{bits, map->ypitch, map->plane_words, nullptr, 0};
   return rc;
+}
+
+/// Prefix rows [row_lo, row_hi] for accumulate_cost lattice sweeps (built on ctx->stream when the current ones do not
+/// cover them); nullptr when disabled or out of memory (4 bytes per cell).
+int ensure_prefix(cover_ctx* ctx, const cover_map* map, int row_lo, int row_hi, const uint32_t*& prefix) {
+  prefix = nullptr;
+  if (ctx->disable_planes || row_lo > row_hi) return COVER_OK;
+  if (!map->prefix) {
+    uint32_t* p = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&p), static_cast<size_t>(map->ppitch) * map->view.size_y * sizeof(uint32_t)) != cudaSuccess) {
+      cudaGetLastError();
+      return COVER_OK;
+    }
+    map->prefix = p;
+    map->prefix_lo = 0, map->prefix_hi = -1;
+  }
+  if (row_lo < map->prefix_lo || row_hi > map->prefix_hi) {
+    const int rows = row_hi - row_lo + 1;
+    k_cost_prefix<<<(rows + 7) / 8, 256, 0, ctx->stream>>>(map->view, map->prefix, map->ppitch, row_lo, row_hi);
+    ++ctx->launches;
+    map->prefix_lo = row_lo, map->prefix_hi = row_hi;
+  }
+  prefix = map->prefix;
+  return COVER_OK;
 }
 
 /// The map as the span-scanning kernels see it for a verdict: with the bit planes of rows [row_lo, row_hi] attached
@@ -2595,6 +2695,11 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       if (OP == OP_IS_FREE) {  // verdicts read the lethal bit planes of the rows under the window (built on first use)
         const int rc = ensure_planes(ctx, map, row_lo, row_hi, pv);
         if (rc) return rc;
+      } else if (OP == OP_ACCUMULATE && count >= ctx->planes_min_batch) {  // sums read the prefix rows
+        const uint32_t* prefix = nullptr;
+        const int rc = ensure_prefix(ctx, map, row_lo, row_hi, prefix);
+        if (rc) return rc;
+        pv.prefix = prefix, pv.ppitch = map->ppitch;
       }
       if (OP == OP_IS_FREE && pv.bits && nv <= 4 && span_cap <= 32)  // (the lean kernel defers shapes with more than 32 spans)
         k_area_lattice<OP_IS_FREE, true><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap, span_cap,
@@ -2963,6 +3068,7 @@ int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double reso
   m->resolution = resolution;
   m->band_rows = (size_y + kMapBands - 1) / kMapBands;
   m->ypitch = (size_y + 31) & ~31;
+  m->ppitch = (size_x + 1 + 31) & ~31;
   m->plane_words = static_cast<long long>((size_x + 31) / 32 + 3) * m->ypitch;
   for (cudaEvent_t& e : m->band_done) {
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
@@ -3004,7 +3110,7 @@ int cover_map_upload_async(cover_map* map, const uint8_t* host_data) {
   }
   map->last_band = order[kMapBands - 1];
   map->bands_pending = true;
-  map->planes_hi = map->planes_inf_hi = -1;  // the bit planes describe the old image
+  map->planes_hi = map->planes_inf_hi = map->prefix_hi = -1;  // the bit planes describe the old image
   return COVER_OK;
 }
 
@@ -3014,7 +3120,7 @@ int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem) {
   Bind bind(ctx->device);
   const MapView& v = map->view;
   CU(map_ready(ctx, map));
-  map->planes_hi = map->planes_inf_hi = -1;
+  map->planes_hi = map->planes_inf_hi = map->prefix_hi = -1;
   CU(cudaMemcpy2DAsync(map->dev, v.pitch, data, v.size_x, v.size_x, v.size_y,
                        mem == COVER_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
   if (mem == COVER_MEM_HOST) CU(cudaStreamSynchronize(ctx->stream));
@@ -3029,7 +3135,7 @@ int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x
   if (w == 0 || h == 0) return COVER_OK;
   Bind bind(ctx->device);
   CU(map_ready(ctx, map));
-  map->planes_hi = map->planes_inf_hi = -1;
+  map->planes_hi = map->planes_inf_hi = map->prefix_hi = -1;
   CU(cudaMemcpy2DAsync(map->dev + static_cast<size_t>(y0) * v.pitch + x0, v.pitch, full_image + static_cast<size_t>(y0) * v.size_x + x0,
                        v.size_x, w, h, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -3085,7 +3191,7 @@ int cover_map_inflate(cover_map* map, int32_t radius_cells, const uint8_t* cost_
   const MapView& v = map->view;
   const size_t bytes = static_cast<size_t>(v.pitch) * v.size_y;
   CU(map_ready(ctx, map));
-  map->planes_hi = map->planes_inf_hi = -1;
+  map->planes_hi = map->planes_inf_hi = map->prefix_hi = -1;
   CU(ctx->in_a.ensure(bytes));  // snapshot of the un-inflated map: the kernel reads it and writes the map in place
   CU(cudaMemcpyAsync(ctx->in_a.ptr, map->dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   const size_t lut_bytes = static_cast<size_t>(radius_cells) * radius_cells + 1;
@@ -3109,6 +3215,7 @@ void cover_map_destroy(cover_map* map) {
   for (cudaEvent_t e : map->band_done) cudaEventDestroy(e);
   cudaFree(map->planes);
   cudaFree(map->planes_inf);
+  cudaFree(map->prefix);
   cudaFree(map->dev);
   delete map;
 }
