@@ -2691,7 +2691,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
         g.tickets_a = total_rounds / 2 / g.static_rounds;                                   // half of the batch in long stretches,
         g.tickets_b = total_rounds / 4 / std::max(1, g.static_rounds / 2);                  // a quarter in half-length ones
       }
-      PlaneView pv{nullptr, 0, 0};
+      PlaneView pv{nullptr, 0, 0, nullptr, 0};
       if (OP == OP_IS_FREE) {  // verdicts read the lethal bit planes of the rows under the window (built on first use)
         const int rc = ensure_planes(ctx, map, row_lo, row_hi, pv);
         if (rc) return rc;
@@ -3079,7 +3079,7 @@ int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double reso
       return fail(ctx, COVER_E_CUDA, "cudaEventCreate failed");
     }
   }
-  m->view = MapView{dev, size_x, size_y, pitch, 1. / resolution, origin_x, origin_y};  // base.hpp:56: x * (1./res)
+  m->view = MapView{dev, size_x, size_y, pitch, 1. / resolution, origin_x, origin_y, nullptr, nullptr, 0, 0};  // base.hpp:56: x * (1./res)
   *out = m;
   return COVER_OK;
 }
