@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(kBlock) k_area_slots(MapView m, const double* 
 #define LAT_MIN_BLOCKS 3
 #endif
 #ifndef LAT_LEAN_BLOCKS
-#define LAT_LEAN_BLOCKS 3
+#define LAT_LEAN_BLOCKS 4
 #endif
 constexpr int kLatSegX = 64, kLatWarps = 8, kLatThreads = kLatWarps * 32, kLatSlotsMax = 64;
 constexpr int kLatMaxVertices = 64;
@@ -2673,7 +2673,10 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       while (g.n_slots > 16 && g.n_slots * per_slot > (28u << 10)) g.n_slots /= 2;
       const size_t smem = poly_bytes + g.n_slots * per_slot +
                           (OP == OP_IS_FREE ? 0 : kLatWarps * 800);  // the value folds' per-warp query tables
-      const unsigned int grid = static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps, static_cast<long long>(ctx->sm_count) * LAT_MIN_BLOCKS));
+      // (the lean verdict kernel - at most 4 vertices, planes on, at most 32 spans per shape - runs more CTAs per SM)
+      const bool lean_kernel = OP == OP_IS_FREE && !ctx->disable_planes && nv <= 4 && span_cap <= 32;
+      const unsigned int grid = static_cast<unsigned int>(std::min<long long>((g.n_units + kLatWarps - 1) / kLatWarps,
+                                                                              static_cast<long long>(ctx->sm_count) * (lean_kernel ? LAT_LEAN_BLOCKS : LAT_MIN_BLOCKS)));
       // launch-wide shape table + the round counter of the dynamic hand-out: [counter | keys | statuses | entries]
       constexpr int kGlobalShapes = 2048;
       LatGlobal gl{};
@@ -2701,7 +2704,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
         if (rc) return rc;
         pv.prefix = prefix, pv.ppitch = map->ppitch;
       }
-      if (OP == OP_IS_FREE && pv.bits && nv <= 4 && span_cap <= 32)  // (the lean kernel defers shapes with more than 32 spans)
+      if (lean_kernel && pv.bits)  // (the lean kernel defers shapes with more than 32 spans)
         k_area_lattice<OP_IS_FREE, true><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap, span_cap,
                                                                                    ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv, gl);
       else
