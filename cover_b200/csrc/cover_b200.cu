@@ -2226,7 +2226,7 @@ struct cover_map {
   // after the whole image.
   cudaEvent_t band_done[kMapBands] = {};
   int band_rows = 0;
-  int issue_pos[kMapBands] = {};  // position of each band in the copy order of the upload in flight
+  int issue_pos[kMapBands] = {};  // copy group of each band in the upload in flight = index of its event in band_done
   int last_band = kMapBands - 1;  // the band copied last
   mutable bool bands_pending = false;
   mutable int hint_lo = 0, hint_hi = -1;  // bands the last lattice sweep needed
@@ -2343,7 +2343,7 @@ int stage_out(cover_ctx* ctx, const cover_results* out, int64_t count, OutStage&
 cudaError_t map_ready(cover_ctx* ctx, const cover_map* map) {
   if (!map->bands_pending) return cudaSuccess;
   map->bands_pending = false;
-  return cudaStreamWaitEvent(ctx->stream, map->band_done[map->last_band], 0);
+  return cudaStreamWaitEvent(ctx->stream, map->band_done[map->issue_pos[map->last_band]], 0);
 }
 
 /// Same for a reader that touches map rows [row_lo, row_hi] only (rows outside the map are never read).
@@ -2356,8 +2356,8 @@ cudaError_t map_rows_ready(cover_ctx* ctx, const cover_map* map, long long row_l
   for (int b = b_lo; b <= b_hi; ++b)
     if (map->issue_pos[b] > map->issue_pos[latest]) latest = b;
   map->hint_lo = b_lo, map->hint_hi = b_hi;
-  if (latest == map->last_band) map->bands_pending = false;
-  return cudaStreamWaitEvent(ctx->stream, map->band_done[latest], 0);
+  if (map->issue_pos[latest] == map->issue_pos[map->last_band]) map->bands_pending = false;
+  return cudaStreamWaitEvent(ctx->stream, map->band_done[map->issue_pos[latest]], 0);
 }
 
 /// Map rows a polygon check over a pose lattice can read: the lattice's y-extent +- the footprint's reach,
@@ -3095,23 +3095,28 @@ int cover_map_upload_async(cover_map* map, const uint8_t* host_data) {
   // the copy may not overtake kernels already queued that still read (or an earlier call that writes) the map
   CU(cudaEventRecord(ctx->fence, ctx->stream));
   CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->fence, 0));
-  // copy order: the bands the last lattice sweep needed first (a planner sweeps the same window every cycle)
-  int order[kMapBands], n = 0;
+  // Copy order: the bands the last lattice sweep needed first, as ONE copy (a planner sweeps the same window every
+  // cycle), then the rows below and above them; without a hint four copies of eight bands.  Few calls matter: the
+  // host issues the sweep only after it has queued the whole upload.
+  int first[4], last[4], groups = 0;  // band ranges [first, last] in copy order
   const bool hinted = map->hint_lo >= 0 && map->hint_hi < kMapBands && map->hint_lo <= map->hint_hi;
-  if (hinted)
-    for (int b = map->hint_lo; b <= map->hint_hi; ++b) order[n++] = b;
-  for (int b = 0; b < kMapBands; ++b)
-    if (!hinted || b < map->hint_lo || b > map->hint_hi) order[n++] = b;
-  for (int k = 0; k < kMapBands; ++k) {
-    const int b = order[k];
-    const int y0 = std::min<long long>(v.size_y, static_cast<long long>(b) * map->band_rows), y1 = std::min(v.size_y, y0 + map->band_rows);
+  if (hinted) {
+    first[groups] = map->hint_lo, last[groups++] = map->hint_hi;
+    if (map->hint_lo > 0) first[groups] = 0, last[groups++] = map->hint_lo - 1;
+    if (map->hint_hi < kMapBands - 1) first[groups] = map->hint_hi + 1, last[groups++] = kMapBands - 1;
+  } else {
+    for (int q = 0; q < 4; ++q) first[groups] = q * (kMapBands / 4), last[groups++] = (q + 1) * (kMapBands / 4) - 1;
+  }
+  for (int k = 0; k < groups; ++k) {
+    const int y0 = static_cast<int>(std::min<long long>(v.size_y, static_cast<long long>(first[k]) * map->band_rows));
+    const int y1 = static_cast<int>(std::min<long long>(v.size_y, static_cast<long long>(last[k] + 1) * map->band_rows));
     if (y1 > y0)
       CU(cudaMemcpy2DAsync(map->dev + static_cast<size_t>(y0) * v.pitch, v.pitch, host_data + static_cast<size_t>(y0) * v.size_x, v.size_x,
                            v.size_x, y1 - y0, cudaMemcpyHostToDevice, ctx->copy_stream));
-    CU(cudaEventRecord(map->band_done[b], ctx->copy_stream));
-    map->issue_pos[b] = k;
+    CU(cudaEventRecord(map->band_done[k], ctx->copy_stream));
+    for (int bb = first[k]; bb <= last[k]; ++bb) map->issue_pos[bb] = k;  // (= index of the band's event)
   }
-  map->last_band = order[kMapBands - 1];
+  map->last_band = last[groups - 1];
   map->bands_pending = true;
   map->planes_hi = map->planes_inf_hi = map->prefix_hi = -1;  // the bit planes describe the old image
   return COVER_OK;
