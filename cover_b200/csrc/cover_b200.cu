@@ -3143,9 +3143,29 @@ int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x
   if (w == 0 || h == 0) return COVER_OK;
   Bind bind(ctx->device);
   CU(map_ready(ctx, map));
-  map->planes_hi = map->planes_inf_hi = map->prefix_hi = -1;
   CU(cudaMemcpy2DAsync(map->dev + static_cast<size_t>(y0) * v.pitch + x0, v.pitch, full_image + static_cast<size_t>(y0) * v.size_x + x0,
                        v.size_x, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  // The acceleration structures are per map row: repair the rows of the window that they currently cover instead of
+  // throwing everything away (a planner's costmap usually changes locally).
+  const int r_lo = y0, r_hi = y0 + h - 1;
+  auto repair = [&](uint32_t* planes, int lo, int hi, bool inflated) {
+    const int a = std::max(lo, r_lo), b = std::min(hi, r_hi);
+    if (!planes || a > b) return;
+    const long long tasks = static_cast<long long>(b - a + 1) * ((v.size_x + 1023) / 1024);
+    const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((tasks + 7) / 8, static_cast<long long>(ctx->sm_count) * 8)));
+    k_lethal_planes<<<grid, 256, 0, ctx->stream>>>(v, planes, map->ypitch, map->plane_words, a, b, inflated);
+    ++ctx->launches;
+  };
+  repair(map->planes, map->planes_lo, map->planes_hi, false);
+  repair(map->planes_inf, map->planes_inf_lo, map->planes_inf_hi, true);
+  {
+    const int a = std::max(map->prefix_lo, r_lo), b = std::min(map->prefix_hi, r_hi);
+    if (map->prefix && a <= b) {
+      k_cost_prefix<<<(b - a + 1 + 7) / 8, 256, 0, ctx->stream>>>(v, map->prefix, map->ppitch, a, b);
+      ++ctx->launches;
+    }
+  }
+  CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
   return COVER_OK;
 }

@@ -524,6 +524,16 @@ def test_map_window_update(cb, ctx):
     data[100:140, 120:170] = 254
     cmap.upload_window(data, 120, 100, 50, 40)
     assert_same(cmap.area_is_free(RECT, poses), po.polygon_batch(po.Costmap(data, 0.05), RECT, poses, threads=8))
+    # with the bit planes and the prefix rows built (lattice sweeps): a window update repairs their rows in place
+    th = np.array([0.3, -1.2, 2.0])
+    desc = dict(x0=1.0, dx=0.05, nx=200, y0=1.0, dy=0.05, ny=200, cs=np.stack([np.cos(th), np.sin(th)], 1))
+    for rep in range(3):
+        for name, op, has_cost in OPS[:2]:
+            assert_same(getattr(cmap, f"area_{name}")(RECT, cb.Lattice(**desc)), po.polygon_batch(po.Costmap(data, 0.05), RECT, po.Lattice(**desc), op=op, threads=8),
+                        has_cost, f"lattice {name} after {rep} window updates")
+        x0, y0 = int(rng.integers(0, 200)), int(rng.integers(0, 220))
+        data[y0:y0 + 70, x0:x0 + 90] = mixed_map(rng, 90, 70, lethal=0.01)
+        cmap.upload_window(data, x0, y0, 90, 70)
 
 
 def test_full_size_lattice_properties(cb, ctx):
