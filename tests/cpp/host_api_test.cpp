@@ -116,6 +116,13 @@ int main() {
     size_t free_count = 0;
     for (uint8_t v : b) free_count += v;
     EXPECT(free_count > 0 && free_count < b.size());
+    // a new image queued with upload_async is what the next check sees (the library orders the reader after the copy)
+    std::vector<uint8_t> cleared(data.size(), 0);
+    m.upload_async(cleared.data());
+    const cb::batch_result c = cb::is_free_nothrow(rect, lat, m);
+    for (uint8_t v : c.is_free) EXPECT(v == 1);
+    m.upload_async(data.data());
+    EXPECT(cb::is_free_nothrow(rect, lat, m).is_free == b);
   }
   std::puts("host_api_test: all checks passed");
   return 0;
