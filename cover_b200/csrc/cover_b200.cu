@@ -617,7 +617,7 @@ struct LatGeom {
   int n_slots;          // shape-cache slots per CTA (power of two <= 64: fewer when a shape's span table is big)
   int static_rounds;    // longest stretch of consecutive rounds a CTA draws at once (guided hand-out)
   long long tickets_a, tickets_b;  // draws of `static_rounds` rounds, then of half that, then single rounds
-  int outline;          // 1: the shapes are outlines (outline_generator cells), not areas
+  int outline;          // 0: areas; 1: outlines as cell sets (verdict, maximum); 2: outlines in traversal order (accumulate_cost)
 };
 
 /// Second level of the shape cache, shared by all CTAs of a launch (global memory, L2-resident): the CTA that meets a
@@ -681,8 +681,10 @@ __device__ __forceinline__ LatProfile lat_profile(const double* __restrict__ pol
 
 /// Span table of a cached shape: entry k = one merged range pair of the area, in generator order (rows ascending,
 /// x ascending): `span_a[k]` = dy * pitch + (first cell, relative to vertex 0) - the byte offset from (vertex 0's
-/// cell, first row of the shape) - and `span_m[k]` = width | dy << 8 (width <= 32).
-__device__ __forceinline__ int span_width(uint32_t m) { return static_cast<int>(m & 0xFFu); }
+/// cell, first row of the shape) - and `span_m[k]` = width | descending << 7 | dy << 8 (width <= 32).
+__device__ __forceinline__ int span_width(uint32_t m) { return static_cast<int>(m & 0x7Fu); }
+/// (outline spans of accumulate_cost only) the traversal walks the span towards smaller x
+__device__ __forceinline__ bool span_descending(uint32_t m) { return (m & 0x80u) != 0u; }
 __device__ __forceinline__ int span_dy(uint32_t m) { return static_cast<int>(m >> 8); }
 
 /// Byte walk of one group with per-cell bounds tests (a pose of the group touches the map border, or the bit planes
@@ -757,8 +759,8 @@ __device__ __forceinline__ void lattice_spans_accumulate(const MapView& m, const
         if (!hit) continue;
         const int off = plane ? off_b : off_a;
         int early = 0;
-        for (int x = off; x < off + width && early == 0; ++x) {
-          const int c = __ldg(cells + x);
+        for (int t = 0; t < width && early == 0; ++t) {  // in traversal order (areas: ascending x)
+          const int c = __ldg(cells + off + (span_descending(sm) ? width - 1 - t : t));
           if (c >= kLethal) early = c == kLethal ? -1 : -2;
         }
         if (plane) fb.early = early, more_b = false;
@@ -876,25 +878,38 @@ struct LatSlotSink {
 struct OutlineSpanSink {
   uint32_t* t4;
   int cap, x0, y0;  // table capacity (spans), bounding-box origin
-  int n = 0, y_run = 0, lo = 0, hi = 0;
+  bool ordered;     // accumulate_cost: spans are monotone pieces of the traversal, in traversal order, never merged
+  int n = 0, y_run = 0, lo = 0, hi = 0, x_prev = 0, dir = 0;
   bool open = false, overflow = false;
+  __device__ __forceinline__ void put(int a, int b, bool desc) {
+    if (n >= cap) {
+      overflow = true;
+      return;
+    }
+    t4[n++] = static_cast<uint32_t>(a - x0) | (static_cast<uint32_t>(b - a + 1) << 12) | (static_cast<uint32_t>(y_run - y0) << 20) | (desc ? 1u << 28 : 0u);
+  }
   __device__ __forceinline__ void close() {
     if (!open) return;
-    for (int x = lo; x <= hi; x += kLatMaxWidth) {
-      if (n >= cap) {
-        overflow = true;
-        return;
-      }
-      t4[n++] = static_cast<uint32_t>(x - x0) | (static_cast<uint32_t>(min(kLatMaxWidth, hi - x + 1)) << 12) | (static_cast<uint32_t>(y_run - y0) << 20);
+    if (ordered && dir < 0) {
+      for (int x = hi; x >= lo; x -= kLatMaxWidth) put(max(lo, x - kLatMaxWidth + 1), x, true);  // chunks in traversal order
+    } else {
+      for (int x = lo; x <= hi; x += kLatMaxWidth) put(x, min(hi, x + kLatMaxWidth - 1), false);
     }
   }
   __device__ __forceinline__ bool cell(int x, int y) {
-    if (open && y == y_run) {
+    bool extend = open && y == y_run;
+    if (extend && ordered) {
+      const int step = x - x_prev;
+      extend = (step == 1 && dir >= 0) || (step == -1 && dir <= 0);
+      if (extend) dir = step;
+    }
+    if (extend) {
       lo = min(lo, x), hi = max(hi, x);
     } else {
       close();
-      open = true, y_run = y, lo = hi = x;
+      open = true, y_run = y, lo = hi = x, dir = 0;
     }
+    x_prev = x;
     return true;
   }
 };
@@ -904,7 +919,7 @@ struct OutlineSpanSink {
 /// (every convex shape), packed one word per row.  Second attempt (cap >= 2 * rows_cap, i.e. the polygon is not
 /// convex): up to four ranges per row = two merged pairs, with the slot's whole table as the [row][4] scratch.
 __device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ verts, int nv, int rows_cap, int cap, int pitch, int* __restrict__ tbl,
-                                                   bool outline) {
+                                                   int outline) {
   int* __restrict__ sa = tbl;
   uint32_t* __restrict__ sm = reinterpret_cast<uint32_t*>(tbl + cap);
   int x0 = 0x7FFFFFFF, y0 = 0x7FFFFFFF, x1 = -0x7FFFFFFF - 1, y1 = -0x7FFFFFFF - 1;
@@ -931,14 +946,14 @@ __device__ __noinline__ LatShape lattice_rasterise(const int2* __restrict__ vert
   auto expand = [&](int n) {
     for (int k = n - 1; k >= 0; --k) {
       const uint32_t pk = t4[k];
-      const int lo = pk & 0xFFFu, width = (pk >> 12) & 0xFFu, r = pk >> 20;
-      sm[k] = static_cast<uint32_t>(width) | (static_cast<uint32_t>(r) << 8);
+      const int lo = pk & 0xFFFu, width = (pk >> 12) & 0xFFu, r = (pk >> 20) & 0xFFu;
+      sm[k] = static_cast<uint32_t>(width) | ((pk >> 28) << 7) | (static_cast<uint32_t>(r) << 8);
       sa[k] = r * pitch + x0 + lo;  // byte offset of the span's first cell from (vertex 0, row yb)
     }
     sh.n_spans = n;
   };
-  if (outline) {  // outline_generator cells (generators.cpp:54-93) as same-row runs
-    OutlineSpanSink sink{t4, cap, x0, y0};
+  if (outline) {  // outline_generator cells (generators.cpp:54-93) as same-row runs (2: monotone pieces in traversal order)
+    OutlineSpanSink sink{t4, cap, x0, y0, outline == 2};
     walk_outline_cells(verts, nv, sink);
     sink.close();
     if (sink.overflow) {
@@ -1102,8 +1117,9 @@ __device__ __forceinline__ void lattice_rows_fold(const MapView& m, const int* _
           sum += d;  // (meaningless once a sentinel was met: `early` decides then)
           if ((d >> 16) != 0u && more) {  // the window holds a LETHAL / NO_INFORMATION cell: the first one in x order ends the walk
             const uint8_t* __restrict__ w = m.data + static_cast<size_t>(y_base) * m.pitch + x_base + row_a[r + u];
-            for (int x = off; x < off + width[u]; ++x) {
-              const int c = __ldg(w + x);
+            const bool desc = span_descending(row_m[r + u]);
+            for (int t = 0; t < width[u]; ++t) {  // in traversal order (areas: ascending x)
+              const int c = __ldg(w + off + (desc ? width[u] - 1 - t : t));
               if (c >= kLethal) {
                 f.early = c == kLethal ? -1 : -2;
                 break;
@@ -1438,7 +1454,7 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
                     if (v == 0) ax = cx, ay = cy;
                     canon[sfound * nv + v] = make_int2(cx - ax, cy - ay);
                   }
-                  const LatShape sh = lattice_rasterise(canon + sfound * nv, nv, rows_cap, span_cap, m.pitch, s_tbl, g.outline != 0);
+                  const LatShape sh = lattice_rasterise(canon + sfound * nv, nv, rows_cap, span_cap, m.pitch, s_tbl, g.outline);
                   meta[sfound].xb = sh.xb, meta[sfound].x1 = sh.x1, meta[sfound].yb = sh.yb, meta[sfound].rows = sh.rows, meta[sfound].n_spans = sh.n_spans;
                   shape_status = sh.status;
                 }
@@ -2621,10 +2637,10 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   const size_t poly_bytes = static_cast<size_t>(nv) * 2 * sizeof(double);
   if (count == 0) return COVER_OK;
   const int rows_cap = rows_bound(polygon_diameter(poly_host, nv), map->view.inv_res);
-  // Outlines over a pose lattice: a verdict or a maximum is an any-reduction over the outline's cell set, so the
-  // shape-cache kernel handles them with the outline's same-row runs as spans (accumulate_cost depends on the
-  // traversal order and on cells visited twice: per-pose kernel).
-  const bool outline_lattice = shape == SHAPE_OUTLINE && OP != OP_ACCUMULATE && src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices &&
+  // Outlines over a pose lattice go through the shape-cache kernel with the outline's same-row runs as spans: merged
+  // runs for a verdict or a maximum (any-reductions over the cell set), monotone pieces in traversal order for
+  // accumulate_cost (first negative value in generator order, a cell counted once per visit).
+  const bool outline_lattice = shape == SHAPE_OUTLINE && src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices &&
                                rows_cap <= kLatMaxRowsCap && !ctx->disable_lattice_kernel && count >= 4096;
   if (shape == SHAPE_OUTLINE && !outline_lattice) {
     k_outline<OP><<<grid_for(count), kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out);
@@ -2667,7 +2683,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       // span table per cached shape: one span per scan row for a convex polygon, up to two (and the [row][4] scratch
       // of the four-range rasteriser) otherwise
       const int span_cap = outline_lattice ? 2 * rows_cap + 8 : ((is_convex(poly_host, nv) && rows_cap - 3 <= kLatMaxWidth) ? rows_cap : 2 * rows_cap);
-      g.outline = outline_lattice ? 1 : 0;
+      g.outline = outline_lattice ? (OP == OP_ACCUMULATE ? 2 : 1) : 0;
       const size_t per_slot = sizeof(unsigned long long) + static_cast<size_t>(nv) * sizeof(int2) + static_cast<size_t>(span_cap) * 2 * sizeof(uint32_t) + sizeof(LatShape);
       g.n_slots = kLatSlotsMax;  // (a heading has a handful of distinct shapes: 16 slots are plenty for the big ones)
       while (g.n_slots > 16 && g.n_slots * per_slot > (28u << 10)) g.n_slots /= 2;
