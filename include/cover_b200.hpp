@@ -219,6 +219,32 @@ inline batch_result is_free_nothrow(polygon_view poly, const pose_lattice& latti
   std::vector<double> cs;
   return detail::run(cover_area_is_free, poly, detail::make_poses(lattice, cs, first, count), map, false);
 }
+/// The same sweep with bit-packed verdicts (bit i & 31 of word i >> 5 = pose i is free): 8x less to bring back.
+/// `not_ok` (optional) receives the number of poses whose status is not OK.
+inline std::vector<uint32_t> is_free_bits(polygon_view poly, const pose_lattice& lattice, const costmap& map, int64_t* not_ok = nullptr,
+                                          int64_t first = 0, int64_t count = -1) {
+  std::vector<double> cs;
+  const cover_poses p = detail::make_poses(lattice, cs, first, count);
+  std::vector<uint32_t> bits(static_cast<size_t>((p.count + 31) / 32));
+  int64_t bad = 0;
+  const cover_results out{COVER_MEM_HOST, nullptr, nullptr, nullptr, bits.data(), &bad};
+  detail::check(map.ctx().get(), cover_area_is_free(map.ctx().get(), map.get(), poly.xy, poly.n, &p, &out));
+  if (not_ok) *not_ok = bad;
+  return bits;
+}
+/// accumulate_cost / outline checks over a lattice (status array instead of exceptions, like every `_nothrow`).
+inline batch_result accumulate_cost_nothrow(polygon_view poly, const pose_lattice& lattice, const costmap& map, int64_t first = 0, int64_t count = -1) {
+  std::vector<double> cs;
+  return detail::run(cover_area_accumulate_cost, poly, detail::make_poses(lattice, cs, first, count), map, true);
+}
+inline batch_result outline_is_free_nothrow(polygon_view poly, const pose_lattice& lattice, const costmap& map, int64_t first = 0, int64_t count = -1) {
+  std::vector<double> cs;
+  return detail::run(cover_outline_is_free, poly, detail::make_poses(lattice, cs, first, count), map, false);
+}
+inline batch_result outline_accumulate_cost_nothrow(polygon_view poly, const pose_lattice& lattice, const costmap& map, int64_t first = 0, int64_t count = -1) {
+  std::vector<double> cs;
+  return detail::run(cover_outline_accumulate_cost, poly, detail::make_poses(lattice, cs, first, count), map, true);
+}
 /// is_free(const polygon&, const Costmap2D&) (costmap.cpp:71-76).
 inline bool is_free(polygon_view poly, const costmap& map) {
   const batch_result r = detail::run(cover_area_is_free, poly, detail::no_pose(), map, false);

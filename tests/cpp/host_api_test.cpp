@@ -116,6 +116,16 @@ int main() {
     size_t free_count = 0;
     for (uint8_t v : b) free_count += v;
     EXPECT(free_count > 0 && free_count < b.size());
+    // the other lattice forms against explicit poses: bit-packed verdicts, accumulate_cost, outline checks
+    {
+      int64_t not_ok = -1;
+      const std::vector<uint32_t> bits = cb::is_free_bits(rect, lat, m, &not_ok);
+      EXPECT(not_ok == 0);
+      for (size_t i = 0; i < b.size(); ++i) EXPECT(((bits[i >> 5] >> (i & 31)) & 1u) == b[i]);
+      EXPECT(cb::accumulate_cost_nothrow(rect, lat, m).cost == cb::accumulate_cost(rect, explicit_poses, m));
+      EXPECT(cb::outline_is_free_nothrow(rect, lat, m).is_free == cb::outline_is_free(rect, explicit_poses, m));
+      EXPECT(cb::outline_accumulate_cost_nothrow(rect, lat, m).cost == cb::outline_accumulate_cost(rect, explicit_poses, m));
+    }
     // a new image queued with upload_async is what the next check sees (the library orders the reader after the copy)
     std::vector<uint8_t> cleared(data.size(), 0);
     m.upload_async(cleared.data());
