@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(kBlock) k_area_slots(MapView m, const double* 
 // full go to the todo list and are finished by the general kernels.
 // ---------------------------------------------------------------------------------------------------
 #ifndef LAT_MIN_BLOCKS
-#define LAT_MIN_BLOCKS 3
+#define LAT_MIN_BLOCKS 4
 #endif
 #ifndef LAT_LEAN_BLOCKS
 #define LAT_LEAN_BLOCKS 4
