@@ -161,24 +161,10 @@ __device__ __forceinline__ void build_row(const RayRec* __restrict__ rays, int n
   }
 }
 
-/// Warp-cooperative: discretises the polygon, builds the ray table in shared memory and returns the
-/// number of rays (0 for an empty polygon); `ok` = all coordinates in range; bbox in x0..y1.
-template <int XF>
-__device__ __forceinline__ int build_rays(const double* __restrict__ poly, int nv, const Pose& T, const MapView& m, int2* verts,
-                                          RayRec* rays, int lane, bool& ok, int& x0, int& y0, int& x1, int& y1) {
-  bool good = true;
-  int lx0 = 0x7FFFFFFF, ly0 = 0x7FFFFFFF, lx1 = -0x7FFFFFFF - 1, ly1 = -0x7FFFFFFF - 1;
-  for (int v = lane; v < nv; v += 32) {
-    int cx, cy;
-    good &= to_cell<XF>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
-    verts[v] = make_int2(cx, cy);
-    lx0 = min(lx0, cx), lx1 = max(lx1, cx), ly0 = min(ly0, cy), ly1 = max(ly1, cy);
-  }
-  ok = __all_sync(0xFFFFFFFFu, good);
-  x0 = __reduce_min_sync(0xFFFFFFFFu, lx0), x1 = __reduce_max_sync(0xFFFFFFFFu, lx1);
-  y0 = __reduce_min_sync(0xFFFFFFFFu, ly0), y1 = __reduce_max_sync(0xFFFFFFFFu, ly1);
-  __syncwarp();
-  if (nv == 0) return 0;
+/// Warp-cooperative: ray table (shared memory) of the outline through the discretised vertices `verts[0..nv)`:
+/// rays v_e -> v_{e+1} with degenerate ones skipped, the closing ray iff more than one ray so far, else the one-cell
+/// dummy ray holding the last point (generators.cpp:54-93).  Returns the number of rays (nv >= 1).
+__device__ __forceinline__ int build_rays_from_verts(const int2* __restrict__ verts, int nv, RayRec* rays, int lane) {
   int n = 0;
   for (int e0 = 0; e0 < nv - 1; e0 += 32) {  // rays v_e -> v_{e+1}, degenerate ones skipped, order kept
     const int e = e0 + lane;
@@ -217,6 +203,27 @@ __device__ __forceinline__ int build_rays(const double* __restrict__ poly, int n
   }
   __syncwarp();
   return n;
+}
+
+/// Warp-cooperative: discretises the polygon, builds the ray table in shared memory and returns the
+/// number of rays (0 for an empty polygon); `ok` = all coordinates in range; bbox in x0..y1.
+template <int XF>
+__device__ __forceinline__ int build_rays(const double* __restrict__ poly, int nv, const Pose& T, const MapView& m, int2* verts,
+                                          RayRec* rays, int lane, bool& ok, int& x0, int& y0, int& x1, int& y1) {
+  bool good = true;
+  int lx0 = 0x7FFFFFFF, ly0 = 0x7FFFFFFF, lx1 = -0x7FFFFFFF - 1, ly1 = -0x7FFFFFFF - 1;
+  for (int v = lane; v < nv; v += 32) {
+    int cx, cy;
+    good &= to_cell<XF>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
+    verts[v] = make_int2(cx, cy);
+    lx0 = min(lx0, cx), lx1 = max(lx1, cx), ly0 = min(ly0, cy), ly1 = max(ly1, cy);
+  }
+  ok = __all_sync(0xFFFFFFFFu, good);
+  x0 = __reduce_min_sync(0xFFFFFFFFu, lx0), x1 = __reduce_max_sync(0xFFFFFFFFu, lx1);
+  y0 = __reduce_min_sync(0xFFFFFFFFu, ly0), y1 = __reduce_max_sync(0xFFFFFFFFu, ly1);
+  __syncwarp();
+  if (nv == 0) return 0;
+  return build_rays_from_verts(verts, nv, rays, lane);
 }
 
 /// Per-pose result of the warp; valid in every lane after `finish`.

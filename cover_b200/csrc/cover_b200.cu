@@ -22,6 +22,7 @@
 #include "../../include/cover_b200.h"
 #include "area_rows.cuh"
 #include "device_core.cuh"
+#include "lattice_words.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -831,34 +832,60 @@ __device__ __forceinline__ void lattice_rows_planes(const PlaneView& pv, const i
   hit_b = ((off_b < 32 ? r_lo : r_hi) >> (off_b & 31)) & 1u;
 }
 
-/// Builds rows [row_lo, row_hi] of the lethal bit planes.  One warp per 1024-cell stretch of a row: 33 coalesced
-/// byte loads + ballots give the lethal words L[i] (lane i keeps word i, plus the first word of the next stretch),
-/// and the doubling V |= V >> 2^k on the 64-bit value L[i] | L[i+1] << 32 yields plane k + 1 in its low word.
+/// 32 cost bytes (two 16-byte vectors) -> one word of the marked-cell bitmap: bit i = byte i is LETHAL (or INSCRIBED, if
+/// `inflated`).  Per 4 cells: a per-byte compare (0xFF / 0x00), one bit of each byte picked out, a multiply gathers the four.
+__device__ __forceinline__ uint32_t mark_bits32(const uint4& a, const uint4& b, bool inflated) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t word = 0u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t mk = __vcmpeq4(w[i], 0xFEFEFEFEu);
+    if (inflated) mk |= __vcmpeq4(w[i], 0xFDFDFDFDu);
+    word |= (((mk & 0x08040201u) * 0x01010101u) >> 24) << (4 * i);
+  }
+  return word;
+}
+
+/// Builds rows [row_lo, row_hi] of the lethal bit planes.  One warp per (32 map rows, kPlaneColsPerWarp word columns):
+/// LANE = map row, so that the plane words of a column - consecutive rows - leave as one coalesced store (the planes
+/// are column-major).  Every lane reads its row 32 bytes at a time and keeps the next word in hand: the doubling
+/// V |= V >> 2^k on the 64-bit value L[c] | L[c + 1] << 32 yields plane k + 1 in its low word.
+constexpr int kPlaneColsPerWarp = 8;
 __global__ void __launch_bounds__(256) k_lethal_planes(MapView m, uint32_t* __restrict__ planes, int ypitch, long long plane_words, int row_lo,
                                                         int row_hi, bool inflated) {
   const int lane = threadIdx.x & 31;
-  const int stretches = (m.size_x + 1023) / 1024;
-  const long long n_tasks = static_cast<long long>(row_hi - row_lo + 1) * stretches;
+  const int n_cols = (m.size_x + 31) / 32;
+  const int col_groups = (n_cols + kPlaneColsPerWarp - 1) / kPlaneColsPerWarp;
+  const long long n_tasks = static_cast<long long>((row_hi - row_lo) / 32 + 1) * col_groups;
+  const int vec_per_row = m.pitch >> 4;  // 16-byte vectors per map row (the pitch is a multiple of 16)
   for (long long task = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); task < n_tasks; task += static_cast<long long>(gridDim.x) * (blockDim.x >> 5)) {
-    const int y = row_lo + static_cast<int>(task / stretches), x0 = static_cast<int>(task % stretches) * 1024;
-    const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y) * m.pitch;
-    uint32_t mine = 0u, next = 0u;
-#pragma unroll 11
-    for (int i = 0; i < 33; ++i) {
-      const int x = x0 + 32 * i + lane;
-      const int cost = x < m.size_x ? __ldg(rowp + x) : 0;
-      const uint32_t word = __ballot_sync(kFull, cost == kLethal || (inflated && cost == kInscribed));
-      if (i == lane) mine = word;
-      if (i == lane + 1) next = word;
-    }
-    const int word_index = (x0 >> 5) + lane;
-    if (static_cast<long long>(word_index + 1) * ypitch > plane_words) continue;
-    unsigned long long v = static_cast<unsigned long long>(mine) | (static_cast<unsigned long long>(next) << 32);
-    uint32_t* __restrict__ dst = planes + static_cast<long long>(word_index) * ypitch + y;
+    const int y = row_lo + static_cast<int>(task / col_groups) * 32 + lane;
+    const int c0 = static_cast<int>(task % col_groups) * kPlaneColsPerWarp;
+    const bool row_ok = y <= row_hi;
+    const uint4* __restrict__ rowv = reinterpret_cast<const uint4*>(m.data + static_cast<size_t>(row_ok ? y : row_lo) * m.pitch);
+    auto word_at = [&](int c) {  // marked cells 32 c .. 32 c + 31 of the row (cells past the map edge: 0)
+      const int v = 2 * c;
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      const uint4 a = v < vec_per_row ? __ldg(rowv + v) : zero, b = v + 1 < vec_per_row ? __ldg(rowv + v + 1) : zero;
+      uint32_t word = mark_bits32(a, b, inflated);
+      const int in_map = m.size_x - 32 * c;
+      if (in_map < 32) word &= in_map > 0 ? (1u << in_map) - 1u : 0u;
+      return word;
+    };
+    uint32_t cur = word_at(c0);
+#pragma unroll 4
+    for (int c = c0; c < min(c0 + kPlaneColsPerWarp, n_cols); ++c) {
+      const uint32_t next = word_at(c + 1);
+      unsigned long long v = static_cast<unsigned long long>(cur) | (static_cast<unsigned long long>(next) << 32);
+      uint32_t* __restrict__ dst = planes + static_cast<long long>(c) * ypitch + y;
+      if (row_ok) {
 #pragma unroll
-    for (int k = 0; k < kPlaneCount; ++k) {
-      dst[k * plane_words] = static_cast<uint32_t>(v);
-      v |= v >> (1 << k);
+        for (int k = 0; k < kPlaneCount; ++k) {
+          dst[k * plane_words] = static_cast<uint32_t>(v);
+          v |= v >> (1 << k);
+        }
+      }
+      cur = next;
     }
   }
 }
@@ -2215,10 +2242,14 @@ struct cover_ctx {
   cudaStream_t copy_stream = nullptr;  // banded costmap uploads (cover_map_upload_async) overlap the kernels of `stream`
   cudaEvent_t fence = nullptr;         // "everything queued on `stream` so far": what a banded upload has to wait for
   cudaStream_t d2h_stream = nullptr;   // result chunks of a big lattice sweep travel back while the next chunk is computed
+  cudaStream_t aux_stream = nullptr;   // k_lw_prepare (needs no map data) runs beside the plane build / the costmap upload
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr, aux_planes = nullptr, aux_done = nullptr;
   cudaEvent_t chunk_done = nullptr;
   std::string error;
   int64_t launches = 0;
   bool disable_lattice_kernel = false;
+  bool disable_words = false;           // COVER_B200_NO_WORDS=1: lattice verdicts through the shape-cache kernel (A/B measurements, its tests)
+  int words_strip = 4;                  // COVER_B200_WORDS_STRIP: 32-pose words per thread of k_lw_sweep (2, 4 or 8)
   bool disable_planes = false;          // COVER_B200_NO_PLANES=1: lattice verdicts walk the cost bytes (A/B measurements)
   int64_t planes_min_batch = 32768;     // COVER_B200_PLANES_MIN_BATCH: smallest batch that triggers a bit-plane build (tests: 0)
   int max_stretch = 4;                  // COVER_B200_MAX_STRETCH: longest run of consecutive rounds a lattice CTA draws at once
@@ -2226,7 +2257,7 @@ struct cover_ctx {
   bool old_packed_kernel = false;       // COVER_B200_OLD_PACKED=1: first-generation per-thread kernel (A/B measurements)
   bool force_list_kernel = false;
   bool always_try_packed = true;        // COVER_B200_PACKED_ONLY_CONVEX=1 restricts the packed pass to convex polygons       // COVER_B200_FORCE_LIST_KERNEL=1: A/B measurements and tests of k_area_list  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
-  DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, todo2, todo2_count, list_cnt, list_rng, list_seq, lat_global;
+  DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, todo2, todo2_count, list_cnt, list_rng, list_seq, lat_global, lw_tables;
 };
 
 constexpr int kMapBands = 32;
@@ -2394,6 +2425,12 @@ bool lattice_row_range(const cover_map* map, const double* polygon_xy, int nv, c
   return true;
 }
 
+/// Grid of k_lethal_planes for rows [row_lo, row_hi]: one warp per (32 rows, kPlaneColsPerWarp word columns).
+unsigned int planes_grid(const cover_ctx* ctx, int size_x, int row_lo, int row_hi) {
+  const long long tasks = static_cast<long long>((row_hi - row_lo) / 32 + 1) * (((size_x + 31) / 32 + kPlaneColsPerWarp - 1) / kPlaneColsPerWarp);
+  return static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((tasks + 7) / 8, static_cast<long long>(ctx->sm_count) * 16)));
+}
+
 /// Bit planes of rows [row_lo, row_hi] (built on ctx->stream when the current ones do not cover them): the LETHAL
 /// set, or the INSCRIBED-or-LETHAL set.  Returns nullptr in `bits` when planes are disabled or cannot be allocated.
 int ensure_plane_set(cover_ctx* ctx, const cover_map* map, bool inflated, int row_lo, int row_hi, const uint32_t*& bits) {
@@ -2414,9 +2451,7 @@ int ensure_plane_set(cover_ctx* ctx, const cover_map* map, bool inflated, int ro
     lo = 0, hi = -1;
   }
   if (row_lo < lo || row_hi > hi) {
-    const long long tasks = static_cast<long long>(row_hi - row_lo + 1) * ((map->view.size_x + 1023) / 1024);
-    const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((tasks + 7) / 8, static_cast<long long>(ctx->sm_count) * 8)));
-    k_lethal_planes<<<grid, 256, 0, ctx->stream>>>(map->view, store, map->ypitch, map->plane_words, row_lo, row_hi, inflated);
+    k_lethal_planes<<<planes_grid(ctx, map->view.size_x, row_lo, row_hi), 256, 0, ctx->stream>>>(map->view, store, map->ypitch, map->plane_words, row_lo, row_hi, inflated);
     ++ctx->launches;
     lo = row_lo, hi = row_hi;
   }
@@ -2628,7 +2663,106 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_IS_FREE>));
   set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_MAX>));
+  set(reinterpret_cast<const void*>(&k_lw_prepare));
   return e;
+}
+
+
+/// Dynamic shared memory of k_lw_prepare: polygon, class tables of both axes, anchors, the shape warps' ray tables.
+size_t lw_prepare_smem(int nv, int shape_warps) {
+  return static_cast<size_t>(nv) * 16 + 2 * static_cast<size_t>(kLwClasses) * nv * sizeof(int) + kLwClasses * sizeof(int) +
+         shape_warps * (static_cast<size_t>(nv + 1) * sizeof(RayRec) + static_cast<size_t>(nv) * sizeof(int2));
+}
+
+struct LwPlan {
+  LwTables t{};
+  LwGeom g{};
+};
+
+/// First half of a bit-parallel lattice sweep (lattice_words.cuh): the class tables of every heading of the batch and one
+/// rasterisation per distinct shape (k_lw_prepare).  None of it depends on the costmap's cells, so it runs on the
+/// context's auxiliary stream, beside whatever the main stream still has to do to the map (upload, plane build).
+int lw_prepare_async(cover_ctx* ctx, const cover_map* map, const double* poly_dev, int nv, bool outline, const PoseSource& src, int64_t count,
+                     const OutView& out, LwPlan& plan) {
+  const long long per_heading = static_cast<long long>(src.nx) * src.ny;
+  LwGeom& g = plan.g;
+  g.it_lo = static_cast<int>(src.first / per_heading);
+  g.n_head = static_cast<int>((src.first + count - 1) / per_heading) - g.it_lo + 1;
+  g.nb = (src.ny + 31) / 32;
+  g.nbg = (g.nb + kLwWarps - 1) / kLwWarps;
+  auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; };
+  g.aligned4 = src.nx % 4 == 0 && src.first % 4 == 0 && aligned(out.is_free) && aligned(out.status);
+  // one allocation: [counters | per-heading ints | anchors | shapes | spans | row tables | class bytes]
+  LwTables& t = plan.t;
+  t.max_shapes = std::min(4096, g.n_head * 64);
+  t.span_pool = 1 << 19;
+  const size_t nh = static_cast<size_t>(g.n_head);
+  size_t off = 0;
+  auto carve = [&off](size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) & ~static_cast<size_t>(255);
+    return at;
+  };
+  const size_t o_counters = carve(16), o_nx = carve(nh * 4), o_ny = carve(nh * 4), o_base = carve(nh * 4), o_simple = carve(nh * 4);
+  const size_t o_anchor = carve(nh * kLwClasses * 4), o_shapes = carve(static_cast<size_t>(t.max_shapes) * sizeof(LwShape));
+  const size_t o_spans = carve(static_cast<size_t>(t.span_pool) * sizeof(LwSpan));
+  const size_t o_yc0 = carve(nh * src.ny * 4), o_xcls = carve(nh * src.nx), o_ycls = carve(nh * src.ny);
+  CU(ctx->lw_tables.ensure(off));
+  char* base = ctx->lw_tables.as<char>();
+  t.counters = reinterpret_cast<unsigned int*>(base + o_counters);
+  t.n_xcls = reinterpret_cast<int*>(base + o_nx), t.n_ycls = reinterpret_cast<int*>(base + o_ny);
+  t.shape_base = reinterpret_cast<int*>(base + o_base), t.simple = reinterpret_cast<int*>(base + o_simple);
+  t.shapes = reinterpret_cast<LwShape*>(base + o_shapes), t.spans = reinterpret_cast<LwSpan*>(base + o_spans);
+  t.xanchor = reinterpret_cast<int*>(base + o_anchor), t.yc0 = reinterpret_cast<int*>(base + o_yc0);
+  t.xcls = reinterpret_cast<uint8_t*>(base + o_xcls), t.ycls = reinterpret_cast<uint8_t*>(base + o_ycls);
+  // fork: everything queued on the main stream so far (polygon / heading table uploads, the previous sweep that still
+  // reads these tables) comes first
+  CU(cudaEventRecord(ctx->aux_fork, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+  CU(cudaMemsetAsync(base + o_counters, 0, 16, ctx->aux_stream));
+  const size_t per_warp = static_cast<size_t>(nv + 1) * sizeof(RayRec) + static_cast<size_t>(nv) * sizeof(int2);
+  const int shape_warps = static_cast<int>(std::max<size_t>(1, std::min<size_t>(16, (static_cast<size_t>(kMaxDynamicSmem) - lw_prepare_smem(nv, 0)) / per_warp)));
+  k_lw_prepare<<<g.n_head, kLwPrepThreads, lw_prepare_smem(nv, shape_warps), ctx->aux_stream>>>(map->view, poly_dev, nv, src, g.it_lo, t, outline ? 1 : 0,
+                                                                                              map->plane_words, shape_warps);
+  ++ctx->launches;
+  CU(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
+  return COVER_OK;
+}
+
+template <int W>
+void launch_lw_sweeps(cover_ctx* ctx, const cover_map* map, const uint32_t* bits, const PoseSource& src, int64_t count, const OutView& out,
+                      const LwTables& t, LwGeom g, bool simple, cudaStream_t stream) {
+  g.ns = (src.nx + 32 * W - 1) / (32 * W);
+  const dim3 grid(static_cast<unsigned int>(g.nbg) * g.ns, static_cast<unsigned int>(g.n_head));
+  unsigned int* todo = ctx->todo.as<unsigned int>();
+  unsigned int* todo_count = ctx->todo_count.as<unsigned int>();
+  if (simple) k_lw_sweep<W, true><<<grid, kLwWarps * 32, 0, stream>>>(map->view, bits, map->ypitch, map->plane_words, src, count, out, t, g, todo, todo_count);
+  else k_lw_sweep<W, false><<<grid, kLwWarps * 32, 0, stream>>>(map->view, bits, map->ypitch, map->plane_words, src, count, out, t, g, todo, todo_count);
+}
+
+/// Second half: the sweep over the lethal bit planes `bits`, two launches side by side - the tasks of single-shape
+/// headings inside the map on the main stream, the rest (few tasks, several walks each: latency-bound on its own) on the
+/// auxiliary stream, where k_lw_prepare just finished.  Poses neither can finish land on ctx->todo (already reset).
+int lw_sweep(cover_ctx* ctx, const cover_map* map, const PoseSource& src, int64_t count, const OutView& out, const LwPlan& plan, const uint32_t* bits) {
+  auto launch = [&](bool simple, cudaStream_t stream) {
+    if (ctx->words_strip == 8) launch_lw_sweeps<8>(ctx, map, bits, src, count, out, plan.t, plan.g, simple, stream);
+    else if (ctx->words_strip == 2) launch_lw_sweeps<2>(ctx, map, bits, src, count, out, plan.t, plan.g, simple, stream);
+    else launch_lw_sweeps<4>(ctx, map, bits, src, count, out, plan.t, plan.g, simple, stream);
+  };
+  // the auxiliary stream needs what the main stream did so far: planes, zeroed outputs and counters
+  CU(cudaEventRecord(ctx->aux_planes, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_planes, 0));
+  launch(false, ctx->aux_stream);
+  CU(cudaEventRecord(ctx->aux_done, ctx->aux_stream));
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));  // the tables of k_lw_prepare
+  launch(true, ctx->stream);
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_done, 0));
+  ctx->launches += 2;
+  if (std::getenv("COVER_B200_DEBUG_SYNC")) {  // (bring-up: a fault surfaces here, not at the next call)
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "k_lw_sweep");
+  }
+  return COVER_OK;
 }
 
 template <int OP>
@@ -2640,8 +2774,25 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   // Outlines over a pose lattice go through the shape-cache kernel with the outline's same-row runs as spans: merged
   // runs for a verdict or a maximum (any-reductions over the cell set), monotone pieces in traversal order for
   // accumulate_cost (first negative value in generator order, a cell counted once per visit).
-  const bool outline_lattice = shape == SHAPE_OUTLINE && src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices &&
-                               rows_cap <= kLatMaxRowsCap && !ctx->disable_lattice_kernel && count >= 4096;
+  // Verdict sweeps of a lattice at cell pitch in x (any polygon up to 256 vertices, areas and outlines): the bit-parallel
+  // kernels of lattice_words.cuh, when the lethal bit planes of the rows under the window are (or are worth being) built.
+  const uint32_t* word_bits = nullptr;
+  LwPlan lw_plan;
+  if (OP == OP_IS_FREE && src.format == POSE_LATTICE && nv >= 1 && nv <= kRowsMaxVertices && !ctx->disable_lattice_kernel &&
+      !ctx->disable_words && !ctx->disable_planes && std::fabs(src.dx * map->view.inv_res - 1.0) < 1e-9 && count >= 4096 &&
+      planes_pay_off(ctx, map, false, row_lo, row_hi, count) && map->plane_words * kPlaneCount < (1ll << 31) &&
+      (src.first + count - 1) / (static_cast<long long>(src.nx) * src.ny) - src.first / (static_cast<long long>(src.nx) * src.ny) < 65535) {
+    int rc = lw_prepare_async(ctx, map, poly_dev, nv, shape == SHAPE_OUTLINE, src, count, out, lw_plan);  // (beside the plane build)
+    if (rc) return rc;
+    PlaneView pvw{nullptr, 0, 0, nullptr, 0};
+    rc = ensure_planes(ctx, map, row_lo, row_hi, pvw);
+    if (rc) return rc;
+    word_bits = pvw.bits;  // (nullptr: no memory for the planes - the other kernels walk bytes then)
+    if (!word_bits) CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
+  }
+  const bool words = word_bits != nullptr;
+  const bool outline_lattice = shape == SHAPE_OUTLINE && src.format == POSE_LATTICE && nv >= 1 && !ctx->disable_lattice_kernel && count >= 4096 &&
+                               (words || (nv <= kLatMaxVertices && rows_cap <= kLatMaxRowsCap));
   if (shape == SHAPE_OUTLINE && !outline_lattice) {
     k_outline<OP><<<grid_for(count), kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out);
     ++ctx->launches;
@@ -2656,7 +2807,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   // 1. fast pass: poses whose scan rows all have <= 2 ranges (every pose of a convex polygon, many poses of a
   //    mildly concave one) are finished by the packed / lattice kernel; the rest lands on the todo list.
   //    Polygons that are far from convex skip it (the pass would defer almost everything).
-  const bool fast = outline_lattice || (rows_cap <= kPackedMaxRows && (is_convex(poly_host, nv) || ctx->always_try_packed));
+  const bool fast = outline_lattice || words || (rows_cap <= kPackedMaxRows && (is_convex(poly_host, nv) || ctx->always_try_packed));
   // 2. general pass over everything (or the todo list): one warp per pose when the outline has few rays
   //    relative to its rows, else one thread per pose with per-row lists in global scratch.
   const bool rows_kernel = nv <= kRowsMaxVertices && rows_cap <= 30000 && !ctx->force_list_kernel && (nv <= 16 || rows_cap > 48);
@@ -2670,7 +2821,11 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     CU(ctx->todo.ensure(static_cast<size_t>(count) * sizeof(unsigned int)));
     CU(ctx->todo_count.ensure(sizeof(unsigned int)));
     CU(cudaMemsetAsync(ctx->todo_count.ptr, 0, sizeof(unsigned int), ctx->stream));
-    if (lattice) {
+    if (words) {
+      const int rc = lw_sweep(ctx, map, src, count, out, lw_plan, word_bits);
+      if (rc) return rc;
+      --ctx->launches;  // (counted once more below)
+    } else if (lattice) {
       LatGeom g{};
       g.row_first = src.first / src.nx;
       const long long row_last = (src.first + count - 1) / src.nx;
@@ -2762,7 +2917,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     return COVER_OK;
   }
   // A convex polygon defers (almost) nothing: a small persistent grid is enough to drain the list.
-  const bool small_drain = fast && is_convex(poly_host, nv);
+  const bool small_drain = words || (fast && is_convex(poly_host, nv));  // (the word sweep defers next to nothing, whatever the polygon)
   if (rows_kernel) {
     const long long blocks = small_drain ? ctx->sm_count : static_cast<long long>(ctx->sm_count) * 12;
     const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(blocks, (count + kRowsWarps - 1) / kRowsWarps)));
@@ -3015,10 +3170,21 @@ int cover_ctx_create(int device, cover_ctx** out) {
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->fence, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->chunk_done, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->chunk_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->aux_planes, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->aux_done, cudaEventDisableTiming) != cudaSuccess) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+    if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
+    if (ctx->aux_planes) cudaEventDestroy(ctx->aux_planes);
+    if (ctx->aux_done) cudaEventDestroy(ctx->aux_done);
+    if (ctx->chunk_done) cudaEventDestroy(ctx->chunk_done);
     if (ctx->fence) cudaEventDestroy(ctx->fence);
     delete ctx;
     return COVER_E_CUDA;
@@ -3026,6 +3192,8 @@ int cover_ctx_create(int device, cover_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = std::getenv("COVER_B200_NO_LATTICE_KERNEL")) ctx->disable_lattice_kernel = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_NO_PLANES")) ctx->disable_planes = e[0] == '1';
+  if (const char* e = std::getenv("COVER_B200_NO_WORDS")) ctx->disable_words = e[0] == '1';
+  if (const char* e = std::getenv("COVER_B200_WORDS_STRIP")) ctx->words_strip = std::atoi(e);
   if (const char* e = std::getenv("COVER_B200_PLANES_MIN_BATCH")) ctx->planes_min_batch = std::atoll(e);
   if (const char* e = std::getenv("COVER_B200_MAX_STRETCH")) ctx->max_stretch = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("COVER_B200_CHUNKS")) ctx->pipeline_chunks = std::max(0, std::atoi(e));
@@ -3042,10 +3210,16 @@ void cover_ctx_destroy(cover_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   cudaStreamSynchronize(ctx->stream);
   for (DeviceBuffer* b : {&ctx->poses, &ctx->theta, &ctx->poly, &ctx->in_a, &ctx->in_b, &ctx->out_free, &ctx->out_cost, &ctx->out_status, &ctx->out_bits, &ctx->out_not_ok,
-                          &ctx->todo, &ctx->todo_count, &ctx->todo2, &ctx->todo2_count, &ctx->list_cnt, &ctx->list_rng, &ctx->list_seq, &ctx->lat_global})
+                          &ctx->todo, &ctx->todo_count, &ctx->todo2, &ctx->todo2_count, &ctx->list_cnt, &ctx->list_rng, &ctx->list_seq, &ctx->lat_global, &ctx->lw_tables})
     b->release();
   cudaEventDestroy(ctx->fence);
   cudaEventDestroy(ctx->chunk_done);
+  cudaEventDestroy(ctx->aux_fork);
+  cudaEventDestroy(ctx->aux_join);
+  cudaEventDestroy(ctx->aux_planes);
+  cudaEventDestroy(ctx->aux_done);
+  cudaStreamSynchronize(ctx->aux_stream);
+  cudaStreamDestroy(ctx->aux_stream);
   cudaStreamDestroy(ctx->d2h_stream);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
@@ -3062,6 +3236,7 @@ int cover_ctx_synchronize(cover_ctx* ctx) {
   CU(cudaStreamSynchronize(ctx->copy_stream));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->d2h_stream));
+  CU(cudaStreamSynchronize(ctx->aux_stream));
   return COVER_OK;
 }
 
@@ -3167,9 +3342,7 @@ int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x
   auto repair = [&](uint32_t* planes, int lo, int hi, bool inflated) {
     const int a = std::max(lo, r_lo), b = std::min(hi, r_hi);
     if (!planes || a > b) return;
-    const long long tasks = static_cast<long long>(b - a + 1) * ((v.size_x + 1023) / 1024);
-    const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((tasks + 7) / 8, static_cast<long long>(ctx->sm_count) * 8)));
-    k_lethal_planes<<<grid, 256, 0, ctx->stream>>>(v, planes, map->ypitch, map->plane_words, a, b, inflated);
+    k_lethal_planes<<<planes_grid(ctx, v.size_x, a, b), 256, 0, ctx->stream>>>(v, planes, map->ypitch, map->plane_words, a, b, inflated);
     ++ctx->launches;
   };
   repair(map->planes, map->planes_lo, map->planes_hi, false);

@@ -1,0 +1,595 @@
+// lattice_words.cuh — verdict sweeps over an (x, y, heading) pose lattice at cell pitch, bit-parallel in x.
+//
+// is_free(polygon, pose, map) (src/cover/costmap.cpp:78-85) and is_free(outline_generator(...), map)
+// (src/cover/impl/costmap.hpp:23-27) for every pose of a cover_lattice whose x pitch is one cell.  Three kernels:
+//
+//  k_lw_classes  one CTA per heading.  The pose transform separates - the x cells of the vertices depend on (heading,
+//                ix) only, the y cells on (heading, iy) only - so a heading needs nx + ny vertex profiles, not nx * ny
+//                transforms (the same __dmul_rn/__dadd_rn/__dsub_rn/__double2int_rz sequence as to_cell, per
+//                coordinate).  Columns are sorted into CLASSES of identical (vertex offsets relative to vertex 0,
+//                anchor = cell of vertex 0 minus ix), rows into classes of identical offsets; nearly every heading has
+//                one class per axis, the axis-aligned headings (vertices within rounding noise of a cell boundary) a
+//                handful.  The comparison is exact (no hashing).
+//  k_lw_shapes   one warp per (heading, x class, y class): the discretised polygon relative to vertex 0 is rasterised
+//                once with the closed-form scan-row construction of area_rows.cuh (runs, cusps, stable sort by `min`,
+//                pair merge - generators.cpp:189-255) into a list of spans (dx, dy, width <= 32) in a global pool.
+//  k_lw_sweep    one warp per (heading, 32 lattice rows, 32 * W columns): LANE = lattice row, and every thread keeps
+//                the verdicts of 32 * W x-adjacent poses as W words.  "Some cell of a w-cell window is lethal" is the
+//                OR of two overlapping power-of-two windows of the lethal bit planes (k_lethal_planes), and for 32
+//                x-adjacent poses those are 32 consecutive plane bits: per span W + 2 coalesced word loads (the planes
+//                are column-major, so the 32 lanes = 32 consecutive map rows read consecutive words) and 2 W funnel
+//                shifts decide 32 W poses.  Columns of another x class are masked out and walked with their own shape.
+// Nothing here waits for another warp: the sweep only ever reads finished tables.
+#pragma once
+
+#include "area_rows.cuh"
+
+#include <cstdio>
+
+namespace cvr {
+
+constexpr int kLwClasses = 32;                                   // distinct profiles per axis and heading
+constexpr int kLwBad = 0xFF, kLwOverflow = 0xFE, kLwNone = 0xFD;  // class codes: coordinates out of range / table full / no such column
+constexpr int kLwUnfit = -1;                                     // shape status besides cvr::Status: left to the general kernels
+constexpr int kLwWarps = 8;
+constexpr int kLwPrepThreads = 512;                              // k_lw_prepare: threads per CTA (up to 16 of its warps rasterise shapes)
+constexpr int kLwSpanCache = 128;                                // spans of the current shape kept in shared memory per warp
+
+/// One span of a rasterised shape, decoded for the walk: .x = first cell relative to vertex 0, .y = word offset
+/// k * plane_words + dy (k = floor(log2(width)): the plane; dy = row relative to vertex 0), .z = width - 2^k (start of
+/// the second power-of-two window), .w = (dy + 32768) | k << 16 (for the bounds-checked walk at the map border).
+typedef int4 LwSpan;
+
+struct LwShape {
+  int status, n_spans, span_first;
+  int xb, x1, yb, rows;  // bounding box of the vertices relative to vertex 0: x in [xb, x1], y in [yb, yb + rows - 1]
+  int pad;
+};
+
+struct LwTables {
+  int* n_xcls;         // [n_head]
+  int* n_ycls;         // [n_head]
+  int* shape_base;     // [n_head] shape (xc, yc) of the heading lives at shape_base + xc * n_ycls + yc; -1: pool exhausted
+  int* simple;         // [n_head] 1: one x class, one y class, every column and row in range, the shape rasterised fine
+  uint8_t* xcls;       // [n_head][nx]
+  uint8_t* ycls;       // [n_head][ny]
+  int* yc0;            // [n_head][ny] map row of vertex 0
+  int* xanchor;        // [n_head][kLwClasses] map column of vertex 0 minus ix
+  LwShape* shapes;     // [max_shapes]
+  LwSpan* spans;       // [span_pool]
+  unsigned int* counters;  // [0] shapes handed out, [1] spans handed out
+  int max_shapes, span_pool;
+};
+
+/// x cell of one vertex: the x half of to_cell<XF_PATH_A> (same operations in the same order).
+__device__ __forceinline__ bool lw_cell_x(double c, double s, double tx, double px, double py, const MapView& m, int& cx) {
+  const double q = __dsub_rn(__dadd_rn(tx, __dadd_rn(__dmul_rn(c, px), __dmul_rn(-s, py))), m.origin_x);
+  const double sc = __dmul_rn(q, m.inv_res);
+  cx = __double2int_rz(sc);
+  return fabs(sc) < kCoordLimit;
+}
+/// y cell of one vertex: the y half of to_cell<XF_PATH_A>.
+__device__ __forceinline__ bool lw_cell_y(double c, double s, double ty, double px, double py, const MapView& m, int& cy) {
+  const double q = __dsub_rn(__dadd_rn(ty, __dadd_rn(__dmul_rn(s, px), __dmul_rn(c, py))), m.origin_y);
+  const double sc = __dmul_rn(q, m.inv_res);
+  cy = __double2int_rz(sc);
+  return fabs(sc) < kCoordLimit;
+}
+
+/// Spans of scan row `y` of the shape (area: merged range pairs; outline: the rays' cells on the row), each cut into
+/// pieces of at most 32 cells: calls emit(index, x_first, width) per piece and returns their number.
+template <class Emit>
+__device__ __forceinline__ int lw_row_spans(const RayRec* __restrict__ rays, int n_rays, int y, bool outline, bool single_row, int x0, int x1,
+                                            bool& odd, bool& overflow, Emit emit) {
+  int n = 0;
+  auto piece = [&](int lo, int hi) {
+    for (int x = lo; x <= hi; x += 32) {
+      emit(n, x, min(32, hi - x + 1));
+      ++n;
+    }
+  };
+  if (outline) {
+    for (int e = 0; e < n_rays; ++e) {
+      int k_lo, k_hi, xa, xb;
+      if (ray_row_interval(rays[e], y, k_lo, k_hi, xa, xb)) piece(min(xa, xb), max(xa, xb));
+    }
+  } else if (single_row) {  // every cell on one row: ranges (min,min),(max,max) -> [min, max] (generators.cpp:197-204)
+    piece(x0, x1);
+  } else {
+    RowList L;
+    build_row(rays, n_rays, y, L);
+    odd |= (L.n & 1) != 0;
+    overflow |= L.overflow;
+    if (!(L.n & 1) && !L.overflow)
+      for (int k = 0; k + 1 < L.n; k += 2) piece(L.lo[k], L.hi[k + 1]);  // [r[2k].min, r[2k+1].max] (generators.cpp:253-254)
+  }
+  return n;
+}
+
+/// One warp: rasterises the shape with vertices `verts` (relative to vertex 0) into the span pool; returns its record.
+__device__ __forceinline__ LwShape lw_rasterise(int2* verts, int nv, RayRec* rays, int lane, int outline, long long plane_words, const LwTables& t) {
+  int lx0 = 0x7FFFFFFF, ly0 = 0x7FFFFFFF, lx1 = -0x7FFFFFFF - 1, ly1 = -0x7FFFFFFF - 1;
+  for (int v = lane; v < nv; v += 32) {
+    const int2 c = verts[v];
+    lx0 = min(lx0, c.x), lx1 = max(lx1, c.x), ly0 = min(ly0, c.y), ly1 = max(ly1, c.y);
+  }
+  const int x0 = __reduce_min_sync(0xFFFFFFFFu, lx0), x1 = __reduce_max_sync(0xFFFFFFFFu, lx1);
+  const int y0 = __reduce_min_sync(0xFFFFFFFFu, ly0), y1 = __reduce_max_sync(0xFFFFFFFFu, ly1);
+  const int n_rays = build_rays_from_verts(verts, nv, rays, lane);
+  const bool single_row = y0 == y1;
+  int status = ST_OK, n_total = 0, span_first = 0;
+  if (y1 - y0 > 30000 || x1 - x0 > 1000000) status = kLwUnfit;  // (dy travels in 16 bits)
+  for (int pass = 0; pass < 2 && status == ST_OK; ++pass) {
+    int base = 0;
+    bool odd = false, overflow = false;
+    for (int yb = y0; yb <= y1; yb += 32) {
+      const int y = yb + lane;
+      const bool live = y <= y1 && !(single_row && !outline && lane != 0);
+      int mine = 0;
+      if (live) mine = lw_row_spans(rays, n_rays, y, outline != 0, single_row, x0, x1, odd, overflow, [](int, int, int) {});
+      int incl = mine;
+      for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += up;
+      }
+      if (pass == 1 && live) {
+        LwSpan* dst = t.spans + span_first + base + incl - mine;
+        bool o2 = false, v2 = false;
+        lw_row_spans(rays, n_rays, y, outline != 0, single_row, x0, x1, o2, v2, [&](int k, int x, int width) {
+          const int lg = 31 - __clz(width);
+          dst[k] = make_int4(x, static_cast<int>(lg * plane_words) + y, width - (1 << lg), (y + 32768) | (lg << 16));
+        });
+      }
+      base += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (pass == 0) {
+      if (__any_sync(0xFFFFFFFFu, odd)) status = ST_LOGIC_ERROR;  // std::logic_error("Even number of line-pairs expected")
+      else if (__any_sync(0xFFFFFFFFu, overflow)) status = ST_ROW_COMPLEXITY;
+      n_total = base;
+      if (status == ST_OK) {
+        unsigned int first = 0;
+        if (lane == 0) first = atomicAdd(&t.counters[1], static_cast<unsigned int>(n_total));
+        first = __shfl_sync(0xFFFFFFFFu, first, 0);
+        if (first + static_cast<unsigned int>(n_total) > static_cast<unsigned int>(t.span_pool)) status = kLwUnfit;
+        span_first = static_cast<int>(first);
+      }
+    }
+  }
+  return LwShape{status, n_total, span_first, x0, x1, y0, y1 - y0 + 1, 0};
+}
+
+/// Per heading (one CTA): column and row classes, then one rasterisation per (x class, y class).
+/// Dynamic shared memory: polygon | x offsets [K][nv] | y offsets [K][nv] | anchors [K] | per shape warp: rays, vertices.
+__global__ void __launch_bounds__(kLwPrepThreads) k_lw_prepare(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src, int it_lo,
+                                                              LwTables t, int outline, long long plane_words, int shape_warps) {
+  extern __shared__ double smem_d[];
+  __shared__ int s_n[2], s_elect, s_base, s_flaw, s_bad_shape;
+  const int tid = threadIdx.x;
+  double* poly = smem_d;
+  int* xoff = reinterpret_cast<int*>(smem_d + 2 * nv);
+  int* yoff = xoff + kLwClasses * nv;
+  int* anchor_tab = yoff + kLwClasses * nv;
+  for (int i = tid; i < 2 * nv; i += blockDim.x) poly[i] = poly_g[i];
+  const int h = blockIdx.x, it = it_lo + h;
+  const double2 cs = __ldg(reinterpret_cast<const double2*>(src.theta_cs) + it);
+  if (tid == 0) s_n[0] = s_n[1] = 0, s_elect = 0x7FFFFFFF, s_flaw = 0, s_bad_shape = 0;
+  __syncthreads();
+#pragma unroll 1
+  for (int axis = 0; axis < 2; ++axis) {
+    const bool is_x = axis == 0;
+    const int n = is_x ? src.nx : src.ny;
+    int* off_tab = is_x ? xoff : yoff;
+    uint8_t* cls_out = is_x ? t.xcls + static_cast<long long>(h) * src.nx : t.ycls + static_cast<long long>(h) * src.ny;
+    for (int base = 0; base < n; base += blockDim.x) {
+      const int idx = base + tid;
+      const bool valid = idx < n;
+      // t = x0 + i * dx: multiply, then add, each rounded (the ABI's stated rule, cover_b200.h)
+      const double tr = is_x ? __dadd_rn(src.x0, __dmul_rn(static_cast<double>(idx), src.dx)) : __dadd_rn(src.y0, __dmul_rn(static_cast<double>(idx), src.dy));
+      auto cell_of = [&](int v, int& cell) {
+        return is_x ? lw_cell_x(cs.x, cs.y, tr, poly[2 * v], poly[2 * v + 1], m, cell) : lw_cell_y(cs.x, cs.y, tr, poly[2 * v], poly[2 * v + 1], m, cell);
+      };
+      int cell0 = 0;
+      bool ok = true;
+      for (int v = 0; v < nv; ++v) {
+        int c;
+        ok &= cell_of(v, c);
+        if (v == 0) cell0 = c;
+      }
+      const int anchor = is_x ? cell0 - idx : 0;
+      bool pending = valid && ok;
+      int my = valid ? (ok ? kLwOverflow : kLwBad) : kLwNone;
+      int tried = 0;
+      for (;;) {
+        const int ncur = s_n[axis];  // (only changes between the barriers below)
+        if (pending) {
+          for (int k = tried; k < ncur && pending; ++k) {
+            if (is_x && anchor_tab[k] != anchor) continue;
+            bool same = true;
+            for (int v = 1; v < nv && same; ++v) {
+              int c;
+              cell_of(v, c);
+              same = c - cell0 == off_tab[k * nv + v];
+            }
+            if (same) my = k, pending = false;
+          }
+          if (pending && ncur >= kLwClasses) pending = false;  // table full: `my` stays kLwOverflow
+        }
+        tried = ncur;
+        if (!__syncthreads_or(pending)) break;
+        if (pending) atomicMin(&s_elect, tid);
+        __syncthreads();
+        if (tid == s_elect) {  // the first unmatched column / row founds the next class
+          for (int v = 0; v < nv; ++v) {
+            int c;
+            cell_of(v, c);
+            off_tab[ncur * nv + v] = c - cell0;
+          }
+          if (is_x) {
+            anchor_tab[ncur] = anchor;
+            t.xanchor[h * kLwClasses + ncur] = anchor;
+          }
+          my = ncur, pending = false;
+          s_n[axis] = ncur + 1;
+        }
+        __syncthreads();
+        if (tid == 0) s_elect = 0x7FFFFFFF;
+        __syncthreads();
+      }
+      if (valid) {
+        cls_out[idx] = static_cast<uint8_t>(my);
+        if (!is_x) t.yc0[static_cast<long long>(h) * src.ny + idx] = cell0;
+        if (my >= kLwClasses) s_flaw = 1;  // (benign race: everybody writes 1)
+      }
+    }
+    __syncthreads();
+  }
+  // shape slots of this heading: one per (x class, y class)
+  const int nxc = s_n[0], nyc = s_n[1], n_shapes = nxc * nyc;
+  if (tid == 0) {
+    t.n_xcls[h] = nxc, t.n_ycls[h] = nyc;
+    const unsigned int b = atomicAdd(&t.counters[0], static_cast<unsigned int>(n_shapes));
+    s_base = b + static_cast<unsigned int>(n_shapes) <= static_cast<unsigned int>(t.max_shapes) ? static_cast<int>(b) : -1;
+    t.shape_base[h] = s_base;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  if (s_base >= 0 && warp < shape_warps) {
+    RayRec* rays = reinterpret_cast<RayRec*>(anchor_tab + kLwClasses) + warp * (nv + 1);
+    int2* verts = reinterpret_cast<int2*>(reinterpret_cast<RayRec*>(anchor_tab + kLwClasses) + shape_warps * (nv + 1)) + warp * nv;
+    for (int i = warp; i < n_shapes; i += shape_warps) {
+      const int xc = i / nyc, yc = i - xc * nyc;
+      __syncwarp();
+      for (int v = lane; v < nv; v += 32) verts[v] = make_int2(xoff[xc * nv + v], yoff[yc * nv + v]);
+      __syncwarp();
+      const LwShape sh = lw_rasterise(verts, nv, rays, lane, outline, plane_words, t);
+      if (lane == 0) {
+        t.shapes[s_base + i] = sh;
+        if (sh.status != ST_OK) s_bad_shape = 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) t.simple[h] = (s_base >= 0 && n_shapes == 1 && !s_flaw && !s_bad_shape) ? 1 : 0;
+}
+
+/// ORs, for the 32 * W x-adjacent poses whose vertex 0 sits at columns x_base .. x_base + 32 W - 1 of map row y_lane,
+/// "some cell of the span is lethal" over all spans of ONE shape into acc (every needed word inside the planes).
+template <int W>
+__device__ __forceinline__ void lw_walk(const uint32_t* __restrict__ bits, int ypitch, const LwSpan* __restrict__ spans, int n_spans, int x_base,
+                                        int y_lane, uint32_t (&acc)[W]) {
+  const long long col = ypitch;  // (64-bit: the column offsets j * col below are loop constants)
+#pragma unroll 2
+  for (int s = 0; s < n_spans; ++s) {
+    const LwSpan sp = spans[s];
+    const int X = x_base + sp.x;
+    const int c = X >> 5, sh = X & 31;
+    uint32_t L[W + 2];
+    const uint32_t* __restrict__ p = bits + static_cast<unsigned int>(c * ypitch + sp.y + y_lane);
+#pragma unroll
+    for (int j = 0; j < W + 2; ++j) L[j] = __ldg(p + j * col);
+    // second power-of-two window: `tail` cells later (the same window again when the width is a power of two)
+    const int sh2 = sh + sp.z;
+    if (sh2 < 32) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) acc[w] |= __funnelshift_r(L[w], L[w + 1], sh) | __funnelshift_r(L[w], L[w + 1], sh2);
+    } else {
+#pragma unroll
+      for (int w = 0; w < W; ++w) acc[w] |= __funnelshift_r(L[w], L[w + 1], sh) | __funnelshift_r(L[w + 1], L[w + 2], sh2 - 32);
+    }
+  }
+}
+
+/// The same walk where every LANE has its own shape (rows of different y classes side by side in one warp): lane-private
+/// span lists of n_sp spans (0: nothing to walk), read from global memory; n_max = the longest list of the warp.
+/// GUARD: words outside the planes read as zero, and a pose whose span leaves the map counts as hit - cells outside the
+/// map are lethal (costmap.hpp:81-91).  This is tested per SPAN, not per bounding box: the reference's ranges use the
+/// runs' end points only, so the outermost cell of a cusp may belong to no range (generators.cpp:211-232).
+template <int W, bool GUARD>
+__device__ __forceinline__ void lw_walk_lanes(const uint32_t* __restrict__ bits, int ypitch, long long plane_words, int wcols, int size_x, int size_y,
+                                              const LwSpan* __restrict__ spans, int n_sp, int n_max, int x_base, int y_lane, uint32_t (&acc)[W]) {
+  const long long col = ypitch;
+  for (int s = 0; s < n_max; ++s) {
+    const bool live = s < n_sp;
+    LwSpan sp = make_int4(0, 0, 0, 32768);
+    if (live) sp = __ldg(spans + s);
+    const int X = x_base + sp.x;
+    const int c = X >> 5, sh = X & 31;
+    uint32_t L[W + 2];
+    if (!GUARD) {
+      const uint32_t* __restrict__ p = bits + static_cast<unsigned int>(c * ypitch + sp.y + y_lane);
+#pragma unroll
+      for (int j = 0; j < W + 2; ++j) L[j] = live ? __ldg(p + j * col) : 0u;
+    } else {
+      const int y = y_lane + (sp.w & 0xFFFF) - 32768, k = sp.w >> 16;
+      const bool y_ok = static_cast<unsigned>(y) < static_cast<unsigned>(size_y);
+#pragma unroll
+      for (int j = 0; j < W + 2; ++j) {
+        const int cc = c + j;
+        L[j] = (live && y_ok && static_cast<unsigned>(cc) < static_cast<unsigned>(wcols)) ? __ldg(bits + k * plane_words + cc * col + y) : 0u;
+      }
+      if (live) {
+        const int width = (1 << k) + sp.z;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          // pose j of word w has the span's cells at columns X + 32 w + j .. + width - 1: inside iff lo_ok <= j < hi_ok
+          const int lo_ok = -(X + 32 * w), hi_ok = size_x - (width - 1) - (X + 32 * w);
+          uint32_t in = y_ok ? 0xFFFFFFFFu : 0u;
+          if (lo_ok > 0) in &= lo_ok >= 32 ? 0u : (0xFFFFFFFFu << lo_ok);
+          if (hi_ok < 32) in &= hi_ok <= 0 ? 0u : ((1u << hi_ok) - 1u);
+          acc[w] |= ~in;
+        }
+      }
+    }
+    const int sh2 = sh + sp.z;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const uint32_t second = sh2 < 32 ? __funnelshift_r(L[w], L[w + 1], sh2) : __funnelshift_r(L[w + 1], L[w + 2], sh2 - 32);
+      acc[w] |= __funnelshift_r(L[w], L[w + 1], sh) | second;
+    }
+  }
+}
+
+struct LwGeom {
+  int it_lo, n_head;
+  int nb, ns;    // 32-row blocks per heading, 32 W-column strips per row
+  int nbg;       // groups of kLwWarps row blocks: grid.x = nbg * ns, grid.y = n_head
+  int aligned4;  // pose index of (row, strip start) is a multiple of 4 for every row: verdict bytes go out as words
+};
+
+/// Results of one warp task: lane = lattice row, fr / valid = verdict and ownership bits of its 32 W poses starting at pose
+/// index i0.  `plain`: no pose of the task was failed or deferred (statuses and deferred poses are written elsewhere).
+template <int W>
+__device__ __forceinline__ void lw_store(const OutView& out, const uint32_t (&fr)[W], const uint32_t (&valid)[W], const uint32_t (&skip)[W],
+                                         long long i0, bool any_valid, unsigned live_rows, bool plain, int aligned4, int warp, int lane,
+                                         uint32_t (*s_bits)[2 * W]) {
+  if (out.free_bits && any_valid) {
+    // the row's 32 W verdicts start at bit i0 of the packed array: W + 1 words, the inner ones owned by this thread
+    const long long wi = i0 >> 5;  // (arithmetic: i0 may be negative for the batch's first row; its valid bits are not)
+    const int sh = static_cast<int>(i0 & 31);
+#pragma unroll
+    for (int j = 0; j <= W; ++j) {
+      const uint32_t lo_f = j > 0 ? fr[j - 1] : 0u, hi_f = j < W ? fr[j] : 0u;
+      const uint32_t lo_v = j > 0 ? valid[j - 1] : 0u, hi_v = j < W ? valid[j] : 0u;
+      const uint32_t word = __funnelshift_l(lo_f, hi_f, sh), owned = __funnelshift_l(lo_v, hi_v, sh);
+      if (owned == 0xFFFFFFFFu) out.free_bits[wi + j] = word;
+      else if (word != 0u) atomicOr(out.free_bits + (wi + j), word);
+    }
+  }
+  if (out.is_free || out.status) {
+    if (aligned4 && plain) {
+      // transpose through shared memory so that a warp writes one lattice row at a time: lane l owns poses 4 l .. 4 l + 3
+      __syncwarp();
+#pragma unroll
+      for (int w = 0; w < W; ++w) s_bits[lane][w] = fr[w], s_bits[lane][W + w] = valid[w];
+      __syncwarp();
+      unsigned rows_left = live_rows;
+      while (rows_left) {
+        const int r = __ffs(rows_left) - 1;
+        rows_left &= rows_left - 1u;
+        const long long ir = __shfl_sync(0xFFFFFFFFu, i0, r);
+        for (int gq = lane; gq < 8 * W; gq += 32) {
+          const int sh4 = (gq & 7) * 4;
+          const uint32_t nib = (s_bits[r][gq >> 3] >> sh4) & 0xFu, vn = (s_bits[r][W + (gq >> 3)] >> sh4) & 0xFu;
+          const long long i = ir + 4 * gq;
+          if (vn == 0xFu) {
+            if (out.is_free) *reinterpret_cast<uint32_t*>(out.is_free + i) = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+            if (out.status) *reinterpret_cast<uint32_t*>(out.status + i) = 0u;  // ST_OK
+          } else if (vn) {
+            for (int b = 0; b < 4; ++b)
+              if ((vn >> b) & 1u) {
+                if (out.is_free) out.is_free[i + b] = static_cast<uint8_t>((nib >> b) & 1u);
+                if (out.status) out.status[i + b] = ST_OK;
+              }
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        uint32_t b = valid[w] & ~skip[w];
+        while (b) {
+          const int j = __ffs(b) - 1;
+          b &= b - 1u;
+          const long long i = i0 + 32 * w + j;
+          if (out.is_free) out.is_free[i] = static_cast<uint8_t>((fr[w] >> j) & 1u);
+          if (out.status) out.status[i] = ST_OK;
+        }
+      }
+    }
+  }
+}
+
+/// SIMPLE: the tasks of headings with a single shape whose poses all lie inside the map (nearly all of them) - the walk
+/// and nothing else.  The other instantiation takes the remaining tasks: several classes per heading (masked walks),
+/// the map border (bounds-checked walk, poses outside are not free), statuses, deferrals.
+template <int W, bool SIMPLE>
+__global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep(MapView m, const uint32_t* __restrict__ bits, int ypitch, long long plane_words,
+                                                           PoseSource src, long long count, OutView out, LwTables t, LwGeom g,
+                                                           unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count) {
+  __shared__ LwSpan s_spans[kLwWarps][kLwSpanCache];
+  __shared__ uint32_t s_bits[kLwWarps][32][2 * W];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warps of a CTA sweep vertically adjacent row blocks of one strip and share their halo rows in L1
+  const int sb = blockIdx.x / g.nbg, rb = (blockIdx.x - sb * g.nbg) * kLwWarps + warp;
+  if (rb >= g.nb) return;
+  const int h = blockIdx.y, it = g.it_lo + h;
+  const int iy = rb * 32 + lane, ix0 = sb * 32 * W;
+  const bool row_ok = iy < src.ny;
+  const long long i0 = (static_cast<long long>(it) * src.ny + iy) * src.nx + ix0 - src.first;  // pose index of (iy, ix0) in this batch
+  uint32_t valid[W];
+  bool any_valid = false;
+  {
+    const bool whole = i0 >= 0 && i0 + 32 * W <= count;  // (the usual row: inside the batch)
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      uint32_t v = 0u;
+      if (row_ok) {
+        const int in_row = src.nx - (ix0 + 32 * w);  // columns of this word inside the lattice row
+        if (whole) {
+          v = in_row >= 32 ? 0xFFFFFFFFu : (in_row > 0 ? (1u << in_row) - 1u : 0u);
+        } else {  // bits j with ix0 + 32 w + j < nx and 0 <= i0 + 32 w + j < count
+          const long long lo = max(0ll, -(i0 + 32 * w)), hi = min(min(32ll, static_cast<long long>(in_row)), count - (i0 + 32 * w));
+          if (hi > lo) v = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & (0xFFFFFFFFu << lo);
+        }
+      }
+      valid[w] = v;
+      any_valid |= v != 0u;
+    }
+  }
+  const unsigned live_rows = __ballot_sync(0xFFFFFFFFu, any_valid);
+  if (live_rows == 0u) return;
+  const int y0c = row_ok ? t.yc0[static_cast<long long>(h) * src.ny + iy] : 0;
+  const int base = t.shape_base[h];
+  const int wcols = (m.size_x + 31) / 32 + 3;
+  // ---- is this a simple task?  (evaluated identically by both instantiations: exactly one of them goes on)
+  bool simple = t.simple[h] != 0;
+  int x_base = 0;
+  if (simple) {
+    const LwShape* shp = t.shapes + base;
+    x_base = ix0 + t.xanchor[h * kLwClasses];
+    const bool x_in = x_base + shp->xb >= 0 && x_base + 32 * W - 1 + shp->x1 < m.size_x;
+    const bool y_in = y0c + shp->yb >= 0 && y0c + shp->yb + shp->rows <= m.size_y;
+    simple = x_in && __all_sync(0xFFFFFFFFu, y_in || !any_valid);
+  }
+  if (simple != SIMPLE) return;
+
+  uint32_t hit[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) hit[w] = 0u;
+
+  if constexpr (SIMPLE) {
+    const LwShape* shp = t.shapes + base;
+    const int n_spans = shp->n_spans;
+    const LwSpan* spans = t.spans + shp->span_first;
+    const int y_first = __shfl_sync(0xFFFFFFFFu, y0c, __ffs(live_rows) - 1);  // (every lane takes part: never inside a conditional)
+    const int y_lane = any_valid ? y0c : y_first;  // idle lanes read where a live one reads
+    if (n_spans <= kLwSpanCache) {
+      for (int k = lane; k < n_spans; k += 32) s_spans[warp][k] = spans[k];
+      __syncwarp();
+      lw_walk<W>(bits, ypitch, s_spans[warp], n_spans, x_base, y_lane, hit);
+    } else {
+      lw_walk<W>(bits, ypitch, spans, n_spans, x_base, y_lane, hit);
+    }
+    uint32_t fr[W], none[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) fr[w] = ~hit[w] & valid[w], none[w] = 0u;
+    lw_store<W>(out, fr, valid, none, i0, any_valid, live_rows, true, g.aligned4, warp, lane, s_bits[warp]);
+    return;
+  } else {
+    const int yc = row_ok ? t.ycls[static_cast<long long>(h) * src.ny + iy] : kLwNone;
+    int cw[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int ix = ix0 + 32 * w + lane;
+      cw[w] = ix < src.nx ? t.xcls[static_cast<long long>(h) * src.nx + ix] : kLwNone;
+    }
+    const int n_x = t.n_xcls[h], n_y = t.n_ycls[h];
+    uint32_t skip[W];  // poses whose result is written elsewhere: status other than OK (stored right away), or left to the general kernel
+#pragma unroll
+    for (int w = 0; w < W; ++w) skip[w] = 0u;
+
+    auto fail_poses = [&](const uint32_t (&mask)[W], int status) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        uint32_t b = mask[w] & valid[w] & ~skip[w];
+        skip[w] |= b;
+        while (b) {
+          const int j = __ffs(b) - 1;
+          b &= b - 1u;
+          store_failure(out, i0 + 32 * w + j, status);
+        }
+      }
+    };
+    auto defer_poses = [&](const uint32_t (&mask)[W]) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        uint32_t b = mask[w] & valid[w] & ~skip[w];
+        skip[w] |= b;
+        while (b) {
+          const int j = __ffs(b) - 1;
+          b &= b - 1u;
+          todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i0 + 32 * w + j);
+        }
+      }
+    };
+
+    {  // coordinates out of range (status), class tables full (general kernel)
+      uint32_t bad[W], over[W];
+      bool any = false;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        bad[w] = __ballot_sync(0xFFFFFFFFu, cw[w] == kLwBad) | (yc == kLwBad ? 0xFFFFFFFFu : 0u);
+        over[w] = __ballot_sync(0xFFFFFFFFu, cw[w] == kLwOverflow) | ((yc == kLwOverflow || base < 0) ? 0xFFFFFFFFu : 0u);
+        any |= (bad[w] | over[w]) != 0u;
+      }
+      if (any) {
+        fail_poses(bad, ST_COORD_RANGE);
+        defer_poses(over);
+      }
+    }
+
+    if (base >= 0) {
+      const bool has = any_valid && yc < kLwClasses;  // this lane's row has a shape per x class
+      for (int q = 0; q < n_x; ++q) {
+        uint32_t M[W];
+        uint32_t any_m = 0u;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          M[w] = __ballot_sync(0xFFFFFFFFu, cw[w] == q);
+          any_m |= M[w];
+        }
+        if (any_m == 0u) continue;
+        const int xq = ix0 + t.xanchor[h * kLwClasses + q];
+        // every lane walks the shape of ITS row's y class
+        const LwShape* shp = t.shapes + base + q * n_y + (has ? yc : 0);
+        const int status = has ? shp->status : ST_OK;
+        if (has && status == kLwUnfit) defer_poses(M);
+        else if (has && status != ST_OK) fail_poses(M, status);  // open outline (std::logic_error upstream) / more than 16 ranges on a row
+        const bool walk = has && status == ST_OK;
+        const int n_sp = walk ? shp->n_spans : 0;
+        const int n_max = __reduce_max_sync(0xFFFFFFFFu, n_sp);
+        const LwSpan* spans = t.spans + (walk ? shp->span_first : 0);
+        // every needed word inside the planes?  (bounding box of the vertices: sufficient, the spans lie inside it)
+        const bool inside = !walk || (xq + shp->xb >= 0 && xq + 32 * W - 1 + shp->x1 < m.size_x && y0c + shp->yb >= 0 && y0c + shp->yb + shp->rows <= m.size_y);
+        uint32_t acc[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) acc[w] = 0u;
+        if (__all_sync(0xFFFFFFFFu, inside)) lw_walk_lanes<W, false>(bits, ypitch, plane_words, wcols, m.size_x, m.size_y, spans, n_sp, n_max, xq, y0c, acc);
+        else lw_walk_lanes<W, true>(bits, ypitch, plane_words, wcols, m.size_x, m.size_y, spans, n_sp, n_max, xq, y0c, acc);
+#pragma unroll
+        for (int w = 0; w < W; ++w) hit[w] |= acc[w] & M[w];
+      }
+    }
+    uint32_t fr[W];
+    bool special = false;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      fr[w] = ~hit[w] & valid[w] & ~skip[w];
+      special |= skip[w] != 0u;
+    }
+    const bool plain = !__any_sync(0xFFFFFFFFu, special);
+    lw_store<W>(out, fr, valid, skip, i0, any_valid, live_rows, plain, g.aligned4, warp, lane, s_bits[warp]);
+  }
+}
+
+}  // namespace cvr

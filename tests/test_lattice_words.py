@@ -1,0 +1,185 @@
+"""GPU parity of the bit-parallel lattice verdict kernels (cover_b200/csrc/lattice_words.cuh: k_lw_classes,
+k_lw_shapes, k_lw_sweep) against the CPU oracle, bit for bit: every reference footprint as area and as outline,
+axis-aligned headings (vertices on cell boundaries: several shape classes per heading), lattices that hang over
+the map border, sub-ranges that start and end inside a row, byte / bit-packed / device-resident outputs, all
+strip widths, statuses.  The shape-cache kernel it replaces on this path stays covered through COVER_B200_NO_WORDS=1.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.fixtures import FOOTPRINTS, FOOTPRINT_NAMES, RECT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import cover_b200
+    return cover_b200
+
+
+def _ctx(cb, monkeypatch, **env):
+    monkeypatch.setenv("COVER_B200_PLANES_MIN_BATCH", "0")  # small test lattices take the plane-based kernels too
+    for k, v in env.items():
+        monkeypatch.setenv(k, str(v))
+    return cb.Context(0)
+
+
+def mixed_map(rng, sx, sy, lethal=0.002):
+    data = rng.integers(0, 253, (sy, sx), dtype=np.uint8)
+    r = rng.random((sy, sx))
+    data[r < lethal] = 254
+    data[(r >= lethal) & (r < 1.5 * lethal)] = 255
+    data[(r >= 1.5 * lethal) & (r < 2.5 * lethal)] = 253
+    return data
+
+
+def headings(n, extra=(0.0, math.pi / 2, math.pi, -math.pi / 2)):
+    th = np.concatenate([-math.pi + 2 * math.pi * np.arange(n) / n, np.asarray(extra, dtype=np.float64)])
+    return np.stack([np.cos(th), np.sin(th)], 1)
+
+
+def check(cmap, omap, cb, poly, desc, shape, what, first=0, count=None):
+    fn = cmap.area_is_free if shape == po.SHAPE_AREA else cmap.outline_is_free
+    gpu = fn(poly, cb.Lattice(**desc), first=first, count=count)
+    cpu = po.polygon_batch(omap, poly, po.Lattice(**desc), shape=shape, first=first, count=count, threads=8)
+    np.testing.assert_array_equal(gpu.status, cpu.status, err_msg=f"status {what}")
+    np.testing.assert_array_equal(gpu.is_free, cpu.is_free, err_msg=f"is_free {what}")
+    return cpu
+
+
+@pytest.mark.parametrize("strip", [2, 4, 8])
+def test_rect_and_reference_footprints(cb, monkeypatch, strip):
+    """Rectangle + the reference's seven test footprints (test/cover_test_utils.hpp:17-48) at 5 cm: up to ~230 scan
+    rows and 16 ranges per row (Spiral), areas and outlines, on a lattice that hangs over the map on every side."""
+    ctx = _ctx(cb, monkeypatch, COVER_B200_WORDS_STRIP=strip)
+    launches0 = ctx.launch_count
+    rng = np.random.default_rng(501)
+    data = mixed_map(rng, 400, 360, lethal=0.0008)
+    cmap = cb.Costmap(ctx, data, 0.05, -1.0, 0.5)
+    omap = po.Costmap(data, 0.05, -1.0, 0.5)
+    cs = headings(5)
+    polys = [("rect", RECT)] + list(zip(FOOTPRINT_NAMES, FOOTPRINTS))
+    for name, poly in polys:
+        big = name in ("W", "M", "S", "Spiral")
+        desc = dict(x0=-1.6, dx=0.05, nx=70 if big else 300, y0=0.1, dy=0.05, ny=33 if big else 90, cs=cs)
+        for shape in (po.SHAPE_AREA, po.SHAPE_OUTLINE):
+            cpu = check(cmap, omap, cb, poly, desc, shape, f"{name} shape {shape} strip {strip}")
+        assert cpu.is_free.size >= 4096
+    assert ctx.launch_count > launches0
+    ctx.close()
+
+
+def test_axis_aligned_headings_many_classes(cb, monkeypatch):
+    """Vertices exactly on cell boundaries: rounding noise in x0 + ix*dx flips their cells from column to column, so a
+    heading has several x and y classes and a 32-pose word mixes shapes (masked walks)."""
+    ctx = _ctx(cb, monkeypatch)
+    rng = np.random.default_rng(502)
+    data = mixed_map(rng, 420, 380, lethal=0.002)
+    th = np.array([0.0, math.pi / 2, math.pi, -math.pi / 2, math.atan2(3, 4), 1e-9, -1e-12])
+    cs = np.stack([np.cos(th), np.sin(th)], 1)
+    for origin in ((0.0, 0.0), (-1.3, 0.65), (0.1, -0.2)):
+        for x0 in (-1.0, 0.3, 0.7000000000000001):
+            desc = dict(x0=x0 + origin[0], dx=0.05, nx=380, y0=origin[1] - 0.95, dy=0.05, ny=150, cs=cs)
+            cmap = cb.Costmap(ctx, data, 0.05, *origin)
+            omap = po.Costmap(data, 0.05, *origin)
+            cpu = check(cmap, omap, cb, RECT, desc, po.SHAPE_AREA, f"origin {origin} x0 {x0}")
+            check(cmap, omap, cb, RECT, desc, po.SHAPE_OUTLINE, f"outline origin {origin} x0 {x0}")
+            assert 0.02 < cpu.is_free.mean() < 0.98
+    ctx.close()
+
+
+def test_sub_ranges_bits_and_device_outputs(cb, monkeypatch):
+    """first / count anywhere inside rows (pose sharding), nx not a multiple of 4 (byte stores), bit-packed verdicts
+    with the not-OK counter, device-resident byte outputs at an odd address."""
+    import torch
+    ctx = _ctx(cb, monkeypatch)
+    rng = np.random.default_rng(503)
+    data = mixed_map(rng, 512, 300, lethal=0.003)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    omap = po.Costmap(data, 0.05)
+    cs = headings(7)
+    for nx in (331, 332, 64, 129):
+        desc = dict(x0=0.4, dx=0.05, nx=nx, y0=0.5, dy=0.05, ny=77, cs=cs)
+        total = nx * 77 * cs.shape[0]
+        full = po.polygon_batch(omap, RECT, po.Lattice(**desc), threads=8)
+        for first, count in ((0, total), (12_345, min(50_001, total - 12_345)), (nx * 3 + 1, 4096), (total - 5000, 5000), (32 * 400, 32 * 1000)):
+            gpu = cmap.area_is_free(RECT, cb.Lattice(**desc), first=first, count=count)
+            np.testing.assert_array_equal(gpu.is_free, full.is_free[first:first + count], err_msg=f"nx {nx} first {first} count {count}")
+            np.testing.assert_array_equal(gpu.status, full.status[first:first + count])
+            out = cb.Result(free_bits=np.zeros((count + 31) // 32, dtype=np.uint32), not_ok=np.zeros(1, dtype=np.int64))
+            cmap.area_is_free(RECT, cb.Lattice(**desc), first=first, count=count, out=out)
+            np.testing.assert_array_equal(out.unpack_bits(count), full.is_free[first:first + count], err_msg=f"bits nx {nx} first {first}")
+            assert int(out.not_ok[0]) == 0
+        # device-resident outputs, byte arrays starting at an odd address
+        buf_f = torch.full((total + 3,), 7, dtype=torch.uint8, device="cuda")
+        buf_s = torch.full((total + 3,), 7, dtype=torch.uint8, device="cuda")
+        dev = cb.Result(buf_f[1:1 + total], None, buf_s[3:3 + total])
+        cmap.area_is_free(RECT, cb.Lattice(**desc), out=dev)
+        ctx.synchronize()
+        np.testing.assert_array_equal(buf_f[1:1 + total].cpu().numpy(), full.is_free)
+        np.testing.assert_array_equal(buf_s[3:3 + total].cpu().numpy(), full.status)
+        assert int(buf_f[0]) == 7 and int(buf_f[total + 1]) == 7 and int(buf_s[2]) == 7
+    ctx.close()
+
+
+def test_statuses_on_a_lattice(cb, monkeypatch):
+    """Open outlines (std::logic_error upstream), one-cell polygons, coordinates out of range."""
+    ctx = _ctx(cb, monkeypatch)
+    rng = np.random.default_rng(504)
+    data = mixed_map(rng, 256, 256, lethal=0.004)
+    cmap = cb.Costmap(ctx, data, 0.05)
+    omap = po.Costmap(data, 0.05)
+    cs = headings(8)
+    desc = dict(x0=0.2, dx=0.05, nx=230, y0=0.3, dy=0.05, ny=100, cs=cs)
+    polys = [np.array([[0.4, -0.3, -0.3], [0.0, 0.25, -0.25]]), np.array([[0.01], [0.01]]), np.array([[0.0, 0.3], [0.0, 0.45]]),
+             np.array([[0.6, 0.6, -0.6, -0.6], [0.05, -0.05, -0.05, 0.05]]), np.array([[0.0, 0.4, 0.8], [0.0, 0.0, 0.0]])]
+    seen = set()
+    for poly in polys:
+        for shape in (po.SHAPE_AREA, po.SHAPE_OUTLINE):
+            cpu = check(cmap, omap, cb, poly, desc, shape, f"{poly.tolist()} shape {shape}")
+            seen |= set(np.unique(cpu.status).tolist())
+            out = cb.Result(free_bits=np.zeros((cpu.is_free.size + 31) // 32, dtype=np.uint32), not_ok=np.zeros(1, dtype=np.int64))
+            (cmap.area_is_free if shape == po.SHAPE_AREA else cmap.outline_is_free)(poly, cb.Lattice(**desc), out=out)
+            np.testing.assert_array_equal(out.unpack_bits(cpu.is_free.size), cpu.is_free)
+            assert int(out.not_ok[0]) == int((cpu.status != 0).sum())
+    assert cb.STATUS_LOGIC_ERROR in seen
+    far = dict(x0=2.0e5, dx=0.05, nx=128, y0=0.3, dy=0.05, ny=40, cs=cs)  # x0 / res = 4e6 < 2^22 < (x0 + 6.4) / res for some columns
+    far["x0"] = 4194304 * 0.05 - 3.0
+    cpu = check(cmap, omap, cb, RECT, far, po.SHAPE_AREA, "coordinate range")
+    assert cb.STATUS_COORD_RANGE in set(np.unique(cpu.status).tolist()) and cb.STATUS_OK in set(np.unique(cpu.status).tolist())
+    ctx.close()
+
+
+def test_non_unit_y_pitch_and_resolutions(cb, monkeypatch):
+    """The x pitch must be one cell; the y pitch is free (rows carry their own anchor).  Other resolutions."""
+    ctx = _ctx(cb, monkeypatch)
+    rng = np.random.default_rng(505)
+    cs = headings(6)
+    for res, dy in ((0.05, 0.05), (0.05, 0.0173), (0.05, 0.11), (0.05, -0.05), (0.025, 0.025), (0.1, 0.1), (0.02, 0.02)):
+        data = mixed_map(rng, 380, 330, lethal=0.002)
+        cmap = cb.Costmap(ctx, data, res, -0.2, 0.1)
+        omap = po.Costmap(data, res, -0.2, 0.1)
+        desc = dict(x0=0.3, dx=res, nx=300, y0=(0.4 if dy > 0 else 300 * res), dy=dy, ny=64, cs=cs)
+        for poly in (RECT, FOOTPRINTS[6], FOOTPRINTS[5]):
+            check(cmap, omap, cb, poly, desc, po.SHAPE_AREA, f"res {res} dy {dy}")
+    ctx.close()
+
+
+def test_shape_cache_kernel_still_exact(cb, monkeypatch):
+    """COVER_B200_NO_WORDS=1: the same sweeps through k_area_lattice (still the path of the value folds and of
+    lattices whose x pitch is not one cell)."""
+    ctx = _ctx(cb, monkeypatch, COVER_B200_NO_WORDS=1)
+    rng = np.random.default_rng(506)
+    data = mixed_map(rng, 400, 360, lethal=0.002)
+    cmap = cb.Costmap(ctx, data, 0.05, -1.0, 0.5)
+    omap = po.Costmap(data, 0.05, -1.0, 0.5)
+    cs = headings(5)
+    desc = dict(x0=-1.6, dx=0.05, nx=300, y0=0.1, dy=0.05, ny=90, cs=cs)
+    for poly in (RECT, FOOTPRINTS[6], FOOTPRINTS[4]):
+        check(cmap, omap, cb, poly, desc, po.SHAPE_AREA, "shape-cache kernel")
+        check(cmap, omap, cb, poly, desc, po.SHAPE_OUTLINE, "shape-cache kernel, outline")
+    ctx.close()
