@@ -221,7 +221,7 @@ class Backend:
 
 
     def multi_polygon_batch(self, cmap: Costmap, outlines, poses, op=OP_IS_FREE, first=0, count=None, threads=1) -> Result:
-        """area_generator(res, polygon_vec) checks (holes); restatement only (not exported by oracle/_ref)."""
+        """area_generator(res, polygon_vec) checks (holes): src/cover/generators.cpp:126-135."""
         xy, starts = pack_polygons(outlines)
         fmt, arr, lat, total, _keep = _pose_args(poses)
         n = total - first if count is None else count

@@ -150,30 +150,72 @@ int oracle_polygon_batch(const oracle_map* map, const double* poly_xy, int32_t n
   parallel_for(count, threads, [&](int64_t b, int64_t e) {
     for (int64_t i = b; i < e; ++i) {
       try {
-        // costmap.cpp:71-85 spelled out so that outline and accumulate variants share the transform.
-        const cover::polygon q = pose_format == POSE_NONE
-                                     ? cover::polygon(poly.colwise() - origin)
-                                     : cover::polygon((pose_at(pose_format, poses, lattice, first + i) * poly).colwise() - origin);
+        // costmap.cpp:71-85 spelled out for the outline and accumulate variants; the verdict over the area goes through
+        // the public entry itself (which transforms the polygon on its own: no second transform here)
+        auto transformed = [&] {
+          return pose_format == POSE_NONE ? cover::polygon(poly.colwise() - origin)
+                                          : cover::polygon((pose_at(pose_format, poses, lattice, first + i) * poly).colwise() - origin);
+        };
         bool fr = false;
         double cs = 0;
         if (shape == SHAPE_AREA) {
           if (op == OP_IS_FREE && pose_format != POSE_NONE) {
-            fr = cover::is_free(poly, pose_at(pose_format, poses, lattice, first + i), cm);  // the public entry itself
+            fr = cover::is_free(poly, pose_at(pose_format, poses, lattice, first + i), cm);  // costmap.cpp:78-85
           } else if (op == OP_IS_FREE) {
             fr = cover::is_free(poly, cm);
           } else {
-            const cover::area_generator gen(cm.getResolution(), q);
+            const cover::area_generator gen(cm.getResolution(), transformed());
             cs = cover::accumulate_cost(gen, cm);
             fr = cs >= 0;
           }
         } else {
-          const cover::outline_generator gen(cm.getResolution(), q);
+          const cover::outline_generator gen(cm.getResolution(), transformed());
           if (op == OP_IS_FREE) {
             fr = cover::is_free(gen, cm);
           } else {
             cs = cover::accumulate_cost(gen, cm);
             fr = cs >= 0;
           }
+        }
+        if (is_free) is_free[i] = fr;
+        if (cost) cost[i] = cs;
+        if (status) status[i] = ST_OK;
+      } catch (const std::logic_error&) {
+        if (is_free) is_free[i] = 0;
+        if (cost) cost[i] = std::numeric_limits<double>::quiet_NaN();
+        if (status) status[i] = ST_LOGIC_ERROR;
+      }
+    }
+  });
+  return 0;
+}
+
+/// Several outlines (holes): is_free / accumulate_cost over area_generator(resolution, polygon_vec)
+/// (src/cover/generators.cpp:133-135), every outline transformed like the single polygon of costmap.cpp:78-85.
+int oracle_multi_polygon_batch(const oracle_map* map, const double* polys_xy, const int32_t* starts, int32_t n_outlines, int32_t op,
+                               int32_t pose_format, const void* poses, const oracle_lattice* lattice, int64_t first, int64_t count,
+                               uint8_t* is_free, double* cost, uint8_t* status, int64_t* cells_read, int32_t threads) {
+  if (!map || map->resolution <= 0) return -1;
+  const Costmap2D cm = wrap(map);
+  std::vector<cover::polygon> polys;
+  for (int32_t o = 0; o < n_outlines; ++o) polys.push_back(make_poly(polys_xy + 2 * starts[o], starts[o + 1] - starts[o]));
+  const cover::point origin(cm.getOriginX(), cm.getOriginY());
+  if (cells_read) *cells_read = -1;
+  parallel_for(count, threads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i) {
+      try {
+        cover::polygon_vec moved;
+        for (const cover::polygon& p : polys)
+          moved.push_back(pose_format == POSE_NONE ? cover::polygon(p.colwise() - origin)
+                                                   : cover::polygon((pose_at(pose_format, poses, lattice, first + i) * p).colwise() - origin));
+        const cover::area_generator gen(cm.getResolution(), moved);
+        bool fr;
+        double cs = 0;
+        if (op == OP_IS_FREE) {
+          fr = cover::is_free(gen, cm);
+        } else {
+          cs = cover::accumulate_cost(gen, cm);
+          fr = cs >= 0;
         }
         if (is_free) is_free[i] = fr;
         if (cost) cost[i] = cs;

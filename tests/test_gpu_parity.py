@@ -953,6 +953,14 @@ def test_area_with_holes(cb, ctx):
             gpu = cmap.area_multi(outlines, poses, op=name)
             cpu = po.multi_polygon_batch(omap, outlines, poses, op=op, threads=8)
             assert_same(gpu, cpu, name != "is_free", f"{len(outlines)} outlines {name}")
+            ref = po.reference()
+            if ref is not None and op != po.OP_MAX and all(o.shape[1] > 0 for o in outlines):  # the reference's own constructor (generators.cpp:133-135)
+                r = ref.multi_polygon_batch(omap, outlines, poses, op=op, threads=8)
+                ok = gpu.status == 0
+                np.testing.assert_array_equal((gpu.status == cb.STATUS_LOGIC_ERROR), (r.status == po.LOGIC_ERROR))
+                np.testing.assert_array_equal(gpu.is_free[ok], r.is_free[ok], err_msg=f"vs reference: {len(outlines)} outlines {name}")
+                if name != "is_free":
+                    np.testing.assert_array_equal(gpu.cost[ok], r.cost[ok])
     # a single outline through the multi entry equals the single-polygon entry
     a = cmap.area_multi([FOOTPRINTS[3] * 0.5], poses, op="accumulate_cost")
     b = cmap.area_accumulate_cost(FOOTPRINTS[3] * 0.5, poses)

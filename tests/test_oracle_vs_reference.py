@@ -85,6 +85,27 @@ def test_area_multi_outline_holes():
         assert port.area_cells(denses).tolist() == ref.area_cells(denses).tolist()
 
 
+def test_area_multi_outline_checks_against_the_reference():
+    """is_free / accumulate_cost over area_generator(res, polygon_vec) (generators.cpp:126-135) - the reference's own
+    constructor through oracle/_ref - against the restatement: the 'head' with nested holes under random poses."""
+    rng = np.random.default_rng(77)
+    data = random_map(rng, 300, 280, lethal=0.0001)
+    cmap = po.Costmap(data, 0.05, -0.5, 0.25)
+    poses = random_poses(rng, 400, 0.0, 12.0)
+    for op in (po.OP_IS_FREE, po.OP_ACCUMULATE):
+        a = port.multi_polygon_batch(cmap, head_polygons(), poses, op=op)
+        b = ref.multi_polygon_batch(cmap, head_polygons(), poses, op=op)
+        assert a.is_free.tolist() == b.is_free.tolist()
+        assert (a.status == po.LOGIC_ERROR).tolist() == (b.status == po.LOGIC_ERROR).tolist()
+        if op == po.OP_ACCUMULATE:
+            np.testing.assert_array_equal(a.cost, b.cost)
+        else:
+            assert 0.02 < a.is_free.mean() < 0.98
+    a = port.multi_polygon_batch(cmap, head_polygons(), None)
+    b = ref.multi_polygon_batch(cmap, head_polygons(), None)
+    assert a.is_free.tolist() == b.is_free.tolist()
+
+
 @pytest.mark.parametrize("idx", range(7))
 @pytest.mark.parametrize("shape", [po.SHAPE_AREA, po.SHAPE_OUTLINE])
 def test_polygon_pose_checks(idx, shape):
