@@ -2530,6 +2530,9 @@ int finish_out(cover_ctx* ctx, const OutStage& st, int64_t count) {
   }
   if (st.user->not_ok) CU(cudaMemcpyAsync(st.user->not_ok, st.dev.not_ok, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  // cover_map_upload_async's contract: the caller may reuse its image buffer once a call has returned results to the
+  // host.  A windowed sweep only waited (on the device) for the bands under its window - let the rest land first.
+  CU(cudaStreamSynchronize(ctx->copy_stream));
   return COVER_OK;
 }
 
@@ -2946,6 +2949,7 @@ int polygon_check(cover_ctx* ctx, const cover_map* map, const double* polygon_xy
   if (!map || map->ctx != ctx) return fail(ctx, COVER_E_INVALID_ARG, "map does not belong to this context");
   if (nv < 0 || (nv > 0 && !polygon_xy)) return fail(ctx, COVER_E_INVALID_ARG, "bad polygon");
   if (nv > kMaxVertices) return fail(ctx, COVER_E_UNSUPPORTED, "polygons with more than 4096 vertices are not supported");
+  if (poses && poses->count > 0xFFFFFFFFll) return fail(ctx, COVER_E_UNSUPPORTED, "more than 2^32 - 1 poses in one call (deferred poses are indexed with 32 bits): split the batch");
   Bind bind(ctx->device);
   PoseSource src;
   int rc = stage_poses(ctx, poses, src);
@@ -3005,6 +3009,7 @@ int polygon_check(cover_ctx* ctx, const cover_map* map, const double* polygon_xy
   if (out->not_ok) CU(cudaMemcpyAsync(out->not_ok, st.dev.not_ok, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->d2h_stream));
+  CU(cudaStreamSynchronize(ctx->copy_stream));  // (see finish_out)
   return COVER_OK;
 }
 
@@ -3161,6 +3166,15 @@ void append_row_spans(std::vector<int4>& spans, const int32_t* cells, int64_t b,
 extern "C" {
 
 int cover_abi_version(void) { return COVER_B200_ABI_VERSION; }
+
+int cover_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
 
 int cover_ctx_create(int device, cover_ctx** out) {
   if (!out) return COVER_E_INVALID_ARG;

@@ -94,6 +94,8 @@ typedef struct cover_results {
 
 /* ---- context ------------------------------------------------------------------------------------ */
 int cover_abi_version(void);
+/* number of CUDA devices this process sees (0 without a driver): one cover_ctx per device for pose sharding. */
+int cover_device_count(void);
 int cover_ctx_create(int device, cover_ctx** out);
 void cover_ctx_destroy(cover_ctx* ctx);
 const char* cover_last_error(const cover_ctx* ctx);
@@ -118,7 +120,8 @@ int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem);
  * later call that reads the map is ordered after the bands it needs on the device - a lattice check of a small
  * footprint starts on the first rows of the map while the rest is still in flight (the per-planning-cycle
  * "new costmap, then sweep" sequence).  `host_data` (page-locked memory for a truly asynchronous copy) must stay
- * unchanged until a later call that returns results to the host, or cover_ctx_synchronize, has returned. */
+ * unchanged until a later call that returns results to the host, or cover_ctx_synchronize, has returned: both wait
+ * for the whole image to have landed, also when the check itself only needed a few bands of it. */
 int cover_map_upload_async(cover_map* map, const uint8_t* host_data);
 /* re-upload the window [x0,x0+w) x [y0,y0+h) from a full-size HOST image (dirty-rectangle update). */
 int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x0, int32_t y0, int32_t w, int32_t h);

@@ -31,10 +31,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <exception>
 #include <limits>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -584,5 +586,118 @@ inline trajectory_scores trajectory_reduce(const context& ctx, const std::vector
                                                    out.score.empty() ? nullptr : out.score.data()));
   return out;
 }
+
+// ---- pose sharding across the GPUs of one box ---------------------------------------------------------
+//
+// Poses are independent units: every device gets a contiguous block of the pose range and a replica of the costmap,
+// one host thread drives each device's context, and every block's results land in ITS slice of one host buffer.
+// No collective, no exchange between devices.  (The same device may be listed several times: the shards then run as
+// independent contexts = streams of that device.)
+
+class multi_gpu {
+public:
+  /// `devices` empty = every device the process sees.
+  explicit multi_gpu(std::vector<int> devices = {}) {
+    if (devices.empty())
+      for (int d = 0; d < cover_device_count(); ++d) devices.push_back(d);
+    if (devices.empty()) throw std::runtime_error("cover_b200: no usable CUDA device (there is no CPU fallback)");
+    for (int d : devices) ctxs_.emplace_back(d);
+  }
+  int size() const { return static_cast<int>(ctxs_.size()); }
+  const context& ctx(int k) const { return ctxs_[static_cast<size_t>(k)]; }
+
+  /// Replicates the costmap: one device copy per context, uploaded side by side.
+  void set_costmap(int size_x, int size_y, double resolution, double origin_x, double origin_y, const uint8_t* char_map) {
+    maps_.clear();
+    for (const context& c : ctxs_) maps_.emplace_back(c, size_x, size_y, resolution, origin_x, origin_y, nullptr);
+    upload(char_map);
+  }
+  void upload(const uint8_t* char_map) {
+    each([&](int k) { maps_[static_cast<size_t>(k)].upload(char_map); });
+  }
+  const costmap& map(int k) const { return maps_.at(static_cast<size_t>(k)); }
+
+  /// Contiguous, balanced block of [0, count) owned by shard k (the first count % size() shards get one item more);
+  /// with `granule` > 1 the block borders are multiples of it (bit-packed verdicts: whole 32-pose words).
+  std::pair<int64_t, int64_t> block(int64_t count, int k, int64_t granule = 1) const {
+    const int64_t units = (count + granule - 1) / granule, n = size();
+    const int64_t base = units / n, extra = units % n;
+    const int64_t first = (k * base + std::min<int64_t>(k, extra)) * granule;
+    const int64_t len = (base + (k < extra ? 1 : 0)) * granule;
+    return {std::min(first, count), std::min(len, std::max<int64_t>(0, count - first))};
+  }
+
+  /// is_free(polygon, pose, map) for every pose: the pose vector is split, the verdict / status arrays are shared.
+  batch_result is_free_nothrow(polygon_view poly, const std::vector<pose>& poses) const {
+    batch_result r;
+    r.is_free.resize(poses.size());
+    r.status.resize(poses.size());
+    each([&](int k) {
+      const auto b = block(static_cast<int64_t>(poses.size()), k);
+      if (b.second == 0) return;
+      cover_poses p{};
+      p.format = COVER_POSE_CS, p.mem = COVER_MEM_HOST, p.count = b.second, p.data = poses.data() + b.first;
+      const cover_results out{COVER_MEM_HOST, r.is_free.data() + b.first, nullptr, r.status.data() + b.first, nullptr, nullptr};
+      detail::check(ctxs_[static_cast<size_t>(k)].get(), cover_area_is_free(ctxs_[static_cast<size_t>(k)].get(), map(k).get(), poly.xy, poly.n, &p, &out));
+    });
+    return r;
+  }
+  /// The lattice sweep, sharded through cover_poses.first / count.
+  batch_result is_free_nothrow(polygon_view poly, const pose_lattice& lattice) const {
+    batch_result r;
+    const int64_t n = lattice.count();
+    r.is_free.resize(static_cast<size_t>(n));
+    r.status.resize(static_cast<size_t>(n));
+    each([&](int k) {
+      const auto b = block(n, k);
+      if (b.second == 0) return;
+      std::vector<double> cs;
+      const cover_poses p = detail::make_poses(lattice, cs, b.first, b.second);
+      const cover_results out{COVER_MEM_HOST, r.is_free.data() + b.first, nullptr, r.status.data() + b.first, nullptr, nullptr};
+      detail::check(ctxs_[static_cast<size_t>(k)].get(), cover_area_is_free(ctxs_[static_cast<size_t>(k)].get(), map(k).get(), poly.xy, poly.n, &p, &out));
+    });
+    return r;
+  }
+  /// The same sweep with bit-packed verdicts; `not_ok` (optional) = poses whose status is not OK, summed over the shards.
+  std::vector<uint32_t> is_free_bits(polygon_view poly, const pose_lattice& lattice, int64_t* not_ok = nullptr) const {
+    const int64_t n = lattice.count();
+    std::vector<uint32_t> bits(static_cast<size_t>((n + 31) / 32));
+    std::vector<int64_t> bad(static_cast<size_t>(size()), 0);
+    each([&](int k) {
+      const auto b = block(n, k, 32);
+      if (b.second == 0) return;
+      std::vector<double> cs;
+      const cover_poses p = detail::make_poses(lattice, cs, b.first, b.second);
+      const cover_results out{COVER_MEM_HOST, nullptr, nullptr, nullptr, bits.data() + b.first / 32, &bad[static_cast<size_t>(k)]};
+      detail::check(ctxs_[static_cast<size_t>(k)].get(), cover_area_is_free(ctxs_[static_cast<size_t>(k)].get(), map(k).get(), poly.xy, poly.n, &p, &out));
+    });
+    if (not_ok) {
+      *not_ok = 0;
+      for (int64_t v : bad) *not_ok += v;
+    }
+    return bits;
+  }
+
+private:
+  /// Runs body(k) for every shard on its own host thread; the first exception (if any) is rethrown here.
+  template <class Body>
+  void each(Body&& body) const {
+    std::vector<std::exception_ptr> errors(static_cast<size_t>(size()));
+    std::vector<std::thread> threads;
+    for (int k = 0; k < size(); ++k)
+      threads.emplace_back([&, k] {
+        try {
+          body(k);
+        } catch (...) {
+          errors[static_cast<size_t>(k)] = std::current_exception();
+        }
+      });
+    for (std::thread& t : threads) t.join();
+    for (const std::exception_ptr& e : errors)
+      if (e) std::rethrow_exception(e);
+  }
+  std::vector<context> ctxs_;
+  std::vector<costmap> maps_;
+};
 
 }  // namespace cover_b200

@@ -625,6 +625,16 @@ def test_async_banded_upload_is_ordered_before_every_reader(cb, ctx):
         np.testing.assert_array_equal(amap.outline_accumulate_cost(RECT, poses).cost, sync_map.outline_accumulate_cost(RECT, poses).cost)
         amap.upload_async(pinned[mi])
         np.testing.assert_array_equal(amap.download(), images[mi])
+    # the image buffer may be overwritten as soon as a check has returned its results to the host - also when that
+    # check only waited for the bands under its window (the rest of the copy must have landed by then)
+    scratch = torch.from_numpy(images[1].copy()).pin_memory().numpy()
+    for _ in range(5):
+        scratch[:] = images[1]
+        amap.upload_async(scratch)
+        small = amap.area_is_free(RECT, cb.Lattice(**wl.dwa_lattice(nx=200, ny=64, n_theta=4, x0=30.0, y0=6.0)))  # touches the first bands only
+        scratch[:] = 254  # the caller refills its buffer for the next cycle
+        assert small.is_free.any()
+        np.testing.assert_array_equal(amap.download(), images[1])
     # a synchronous upload right after an asynchronous one wins
     amap.upload_async(pinned[1])
     amap.upload(images[0])
