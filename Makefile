@@ -9,7 +9,7 @@ LIB := cover_b200/libcover_b200.so
 
 all: $(LIB)
 
-$(LIB): cover_b200/csrc/cover_b200.cu cover_b200/csrc/device_core.cuh cover_b200/csrc/area_rows.cuh cover_b200/csrc/lattice_words.cuh include/cover_b200.h
+$(LIB): cover_b200/csrc/cover_b200.cu cover_b200/csrc/device_core.cuh cover_b200/csrc/area_rows.cuh cover_b200/csrc/lattice_words.cuh cover_b200/csrc/polygon_split.hpp include/cover_b200.h
 	$(NVCC) $(NVCCFLAGS) -o $@ cover_b200/csrc/cover_b200.cu
 
 oracle:

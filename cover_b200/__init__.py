@@ -26,7 +26,7 @@ from . import _build
 
 __all__ = [
     "CoverError", "Context", "Costmap", "Lattice", "Result", "DiscretePolygon", "FootprintBank", "SplitFootprint",
-    "trajectory_reduce", "STATUS_OK", "STATUS_LOGIC_ERROR", "STATUS_ROW_COMPLEXITY", "STATUS_COORD_RANGE", "library_path", "build",
+    "trajectory_reduce", "get_radius", "split_polygon", "STATUS_OK", "STATUS_LOGIC_ERROR", "STATUS_ROW_COMPLEXITY", "STATUS_COORD_RANGE", "library_path", "build",
 ]
 
 STATUS_OK, STATUS_LOGIC_ERROR, STATUS_ROW_COMPLEXITY, STATUS_COORD_RANGE = 0, 1, 2, 3
@@ -249,6 +249,40 @@ def trajectory_reduce(ctx: "Context", is_free=None, cost=None, steps: int = 1):
     ctx._check(ctx._lib.cover_trajectory_reduce(ctx._h, C.c_void_p(_ptr(is_free)), C.c_void_p(_ptr(cost)), C.c_int32(_MEM_DEVICE if dev else _MEM_HOST),
                                                 C.c_int64(t), C.c_int32(steps), C.c_void_p(_ptr(first)), C.c_void_p(_ptr(score))))
     return first, score
+
+
+def get_radius(polygon) -> float:
+    """get_radius(polygon) (src/cover/footprints.cpp:55-77): min distance from the centroid to the polygon's edges."""
+    lib = _load()
+    lib.cover_get_radius.restype = C.c_double
+    xy = polygon_xy(polygon)
+    return float(lib.cover_get_radius(C.c_void_p(xy.ctypes.data), C.c_int32(xy.size // 2)))
+
+
+def split_polygon(polygon, radius: Optional[float] = None, max_vertices: int = 1 << 16, max_polygons: int = 256):
+    """continuous_footprint(radius, polygon) without boost::geometry (footprints.cpp:79-128; one-argument form:
+    radius = get_radius(polygon)): returns (outlines, areas), two lists of [2, V] polygons - the always-inscribed
+    sub-regions whose outline cells are checked for 253/254 and the remainder that is scanned for 254 - ready for
+    `SplitFootprint(ctx, outlines, areas)`.  Raises ValueError for a non-positive radius (std::invalid_argument upstream)."""
+    lib = _load()
+    xy = polygon_xy(polygon)
+    if radius is None:
+        radius = get_radius(polygon)
+    bufs = [np.empty(2 * max_vertices, dtype=np.float64) for _ in range(2)]
+    starts = [np.zeros(max_polygons + 1, dtype=np.int32) for _ in range(2)]
+    counts = [C.c_int32(0), C.c_int32(0)]
+    rc = lib.cover_split_polygon(C.c_double(radius), C.c_void_p(xy.ctypes.data), C.c_int32(xy.size // 2),
+                                 C.c_void_p(bufs[0].ctypes.data), C.c_void_p(starts[0].ctypes.data), C.byref(counts[0]),
+                                 C.c_void_p(bufs[1].ctypes.data), C.c_void_p(starts[1].ctypes.data), C.byref(counts[1]),
+                                 C.c_int32(max_vertices), C.c_int32(max_polygons))
+    if rc == -1:
+        raise ValueError("Radius must be positive")
+    if rc != 0:
+        raise CoverError(rc, "cover_split_polygon failed (more polygons / vertices than the buffers hold?)")
+    out = []
+    for b, st, n in zip(bufs, starts, counts):
+        out.append([b[2 * st[k]:2 * st[k + 1]].reshape(-1, 2).T.copy() for k in range(n.value)])
+    return out[0], out[1]
 
 
 class Costmap:

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libcover_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "cover_b200.cu")]
-DEPENDS = SOURCES + [os.path.join(HERE, "csrc", "device_core.cuh"), os.path.join(HERE, "csrc", "area_rows.cuh"), os.path.join(HERE, "csrc", "lattice_words.cuh"),
+DEPENDS = SOURCES + [os.path.join(HERE, "csrc", "device_core.cuh"), os.path.join(HERE, "csrc", "area_rows.cuh"), os.path.join(HERE, "csrc", "lattice_words.cuh"), os.path.join(HERE, "csrc", "polygon_split.hpp"),
                      os.path.join(ROOT, "include", "cover_b200.h")]
 
 NVCC_FLAGS = [

@@ -23,6 +23,7 @@
 #include "area_rows.cuh"
 #include "device_core.cuh"
 #include "lattice_words.cuh"
+#include "polygon_split.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -3537,6 +3538,40 @@ int cover_area_expand(cover_ctx* ctx, const cover_map* map, const double* xy, in
 int cover_outline_expand(cover_ctx* ctx, const cover_map* map, const double* xy, int32_t nv, const cover_poses* poses, int32_t* cells,
                          int64_t capacity, int64_t* starts, uint8_t* status, int32_t mem) {
   return expand_cells(ctx, map, xy, nv, false, poses, cells, capacity, starts, status, mem);
+}
+
+double cover_get_radius(const double* polygon_xy, int32_t n_vertices) {
+  if (n_vertices <= 0 || !polygon_xy) return 0;
+  return cvr_split::get_radius(polygon_xy, n_vertices);
+}
+
+int cover_split_polygon(double radius, const double* polygon_xy, int32_t n_vertices, double* outline_xy, int32_t* outline_starts,
+                        int32_t* n_outlines, double* area_xy, int32_t* area_starts, int32_t* n_areas, int32_t max_vertices,
+                        int32_t max_polygons) {
+  if (n_vertices < 0 || (n_vertices > 0 && !polygon_xy) || !outline_starts || !n_outlines || !area_starts || !n_areas) return COVER_E_INVALID_ARG;
+  cvr_split::Split sp;
+  try {
+    sp = cvr_split::split(radius, polygon_xy, n_vertices);
+  } catch (const std::invalid_argument&) {
+    return COVER_E_INVALID_ARG;
+  } catch (const std::bad_alloc&) {
+    return COVER_E_NOMEM;
+  }
+  auto pack = [&](const std::vector<cvr_split::Ring>& rings, double* xy, int32_t* starts, int32_t* count) {
+    size_t total = 0;
+    for (const cvr_split::Ring& r : rings) total += r.size();
+    if (rings.size() > static_cast<size_t>(max_polygons) || total > static_cast<size_t>(max_vertices) || (total && !xy)) return false;
+    starts[0] = 0;
+    int32_t at = 0;
+    for (size_t k = 0; k < rings.size(); ++k) {
+      for (const cvr_split::Pt& p : rings[k]) xy[2 * at] = p.x, xy[2 * at + 1] = p.y, ++at;
+      starts[k + 1] = at;
+    }
+    *count = static_cast<int32_t>(rings.size());
+    return true;
+  };
+  if (!pack(sp.outlines, outline_xy, outline_starts, n_outlines) || !pack(sp.areas, area_xy, area_starts, n_areas)) return COVER_E_NOMEM;
+  return COVER_OK;
 }
 
 int cover_trajectory_reduce(cover_ctx* ctx, const uint8_t* is_free, const double* cost, int32_t mem, int64_t n_trajectories, int32_t steps,

@@ -217,6 +217,21 @@ void cover_split_destroy(cover_split* split);
 int cover_split_is_free(cover_ctx* ctx, const cover_map* map, const cover_split* split, const cover_poses* poses,
                         const cover_results* out);
 
+/* ---- the split itself, on the HOST and without boost::geometry --------------------------------------
+ * get_radius(polygon) (src/cover/footprints.cpp:55-77): min distance from the centroid to the edges; 0 for no points.
+ * cover_split_polygon = continuous_footprint(radius, polygon) (footprints.cpp:79-125): the polygon eroded by
+ * radius * (1 - 1e-6) -> outlines; the polygon minus the band of width `radius` around the first eroded ring -> areas;
+ * polygons with inner rings are dropped (impl/boost_io.hpp:108-124).  Rings come back closed and clockwise, packed like
+ * the inputs of cover_split_create: polygon k = vertices [starts[k], starts[k+1]).  The caller provides room for
+ * max_vertices vertices per list and max_polygons (+ 1 start) per list; COVER_E_NOMEM if that is too little,
+ * COVER_E_INVALID_ARG for radius <= 0 (std::invalid_argument upstream; an EMPTY polygon is a no-op first).
+ * The vertex coordinates are NOT boost's (they depend on its buffer strategies and are pinned by no reference test);
+ * the construction and its safety property are (cover_b200/csrc/polygon_split.hpp). */
+double cover_get_radius(const double* polygon_xy, int32_t n_vertices);
+int cover_split_polygon(double radius, const double* polygon_xy, int32_t n_vertices, double* outline_xy, int32_t* outline_starts,
+                        int32_t* n_outlines, double* area_xy, int32_t* area_starts, int32_t* n_areas, int32_t max_vertices,
+                        int32_t max_polygons);
+
 /* ---- trajectory scoring (EXTENSION: the DWA-style caller right after the pose checks) -------
  * Poses grouped as n_trajectories x steps (pose index = trajectory * steps + step), e.g. the outputs of the
  * entries above left on the device.  first_blocked[t] = first step with verdict 0 (`steps` if none);

@@ -454,6 +454,39 @@ private:
   std::shared_ptr<cover_split> split_;
 };
 
+// ---- the split as POLYGONS: get_radius / continuous_footprint(radius, polygon) without boost::geometry --------------
+
+/// get_radius(polygon) (footprints.cpp:55-77).
+inline double get_radius(polygon_view poly) { return cover_get_radius(poly.xy, poly.n); }
+
+struct polygon_split {
+  std::vector<polygon> outlines, areas;
+};
+/// continuous_footprint(radius, polygon)'s constructor (footprints.cpp:79-125) on the host: (outlines, areas) for
+/// `continuous_footprint(ctx, outlines, areas)`.  Throws std::invalid_argument for radius <= 0, like the reference.
+inline polygon_split split_polygon(double radius, polygon_view poly) {
+  const int32_t max_vertices = 1 << 16, max_polygons = 256;
+  std::vector<double> oxy(2 * static_cast<size_t>(max_vertices)), axy(2 * static_cast<size_t>(max_vertices));
+  std::vector<int32_t> os(max_polygons + 1), as(max_polygons + 1);
+  int32_t no = 0, na = 0;
+  const int rc = cover_split_polygon(radius, poly.xy, poly.n, oxy.data(), os.data(), &no, axy.data(), as.data(), &na, max_vertices, max_polygons);
+  if (rc == COVER_E_INVALID_ARG) throw std::invalid_argument("Radius must be positive");
+  if (rc != COVER_OK) throw std::runtime_error("cover_split_polygon failed");
+  polygon_split out;
+  auto unpack = [](const std::vector<double>& xy, const std::vector<int32_t>& st, int32_t n, std::vector<polygon>& dst) {
+    for (int32_t k = 0; k < n; ++k) {
+      polygon p(st[static_cast<size_t>(k) + 1] - st[static_cast<size_t>(k)]);
+      std::copy(xy.begin() + 2 * st[static_cast<size_t>(k)], xy.begin() + 2 * st[static_cast<size_t>(k) + 1], p.v.begin());
+      dst.push_back(std::move(p));
+    }
+  };
+  unpack(oxy, os, no, out.outlines);
+  unpack(axy, as, na, out.areas);
+  return out;
+}
+/// One-argument form (footprints.cpp:127-128): radius = get_radius(polygon) ("convex only" upstream).
+inline polygon_split split_polygon(polygon_view poly) { return split_polygon(get_radius(poly), poly); }
+
 // ---- grid split: continuous_footprint(radius, polygon) without boost::geometry ---------------------------
 //
 // The reference erodes / dilates the continuous polygon with boost::geometry (footprints.cpp:79-125) and then
