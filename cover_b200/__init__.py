@@ -259,11 +259,12 @@ def get_radius(polygon) -> float:
     return float(lib.cover_get_radius(C.c_void_p(xy.ctypes.data), C.c_int32(xy.size // 2)))
 
 
-def split_polygon(polygon, radius: Optional[float] = None, max_vertices: int = 1 << 16, max_polygons: int = 256):
+def split_polygon(polygon, radius: Optional[float] = None, slack: float = 0.0, max_vertices: int = 1 << 16, max_polygons: int = 256):
     """continuous_footprint(radius, polygon) without boost::geometry (footprints.cpp:79-128; one-argument form:
     radius = get_radius(polygon)): returns (outlines, areas), two lists of [2, V] polygons - the always-inscribed
     sub-regions whose outline cells are checked for 253/254 and the remainder that is scanned for 254 - ready for
-    `SplitFootprint(ctx, outlines, areas)`.  Raises ValueError for a non-positive radius (std::invalid_argument upstream)."""
+    `SplitFootprint(ctx, outlines, areas)`.  Raises ValueError for a non-positive radius (std::invalid_argument upstream).
+    `slack` (extension, metres; 0 = the reference's construction): the outlines eroded that much less, see cover_b200.h."""
     lib = _load()
     xy = polygon_xy(polygon)
     if radius is None:
@@ -271,7 +272,7 @@ def split_polygon(polygon, radius: Optional[float] = None, max_vertices: int = 1
     bufs = [np.empty(2 * max_vertices, dtype=np.float64) for _ in range(2)]
     starts = [np.zeros(max_polygons + 1, dtype=np.int32) for _ in range(2)]
     counts = [C.c_int32(0), C.c_int32(0)]
-    rc = lib.cover_split_polygon(C.c_double(radius), C.c_void_p(xy.ctypes.data), C.c_int32(xy.size // 2),
+    rc = lib.cover_split_polygon_slack(C.c_double(radius), C.c_double(slack), C.c_void_p(xy.ctypes.data), C.c_int32(xy.size // 2),
                                  C.c_void_p(bufs[0].ctypes.data), C.c_void_p(starts[0].ctypes.data), C.byref(counts[0]),
                                  C.c_void_p(bufs[1].ctypes.data), C.c_void_p(starts[1].ctypes.data), C.byref(counts[1]),
                                  C.c_int32(max_vertices), C.c_int32(max_polygons))

@@ -1924,6 +1924,70 @@ __global__ void __launch_bounds__(256) k_inflate(const uint8_t* __restrict__ src
 
 /// area checks over SEVERAL outlines (holes): batched is_free / accumulate_cost / max over
 /// area_generator(resolution, polygon_vec) (generators.cpp:126-135).  One warp per pose.
+/// Inflation layer, radius <= 31 cells: exact Euclidean distance to the nearest LETHAL cell, separably.  One CTA per
+/// 32 x 32 tile: (1) every row the tile's cells can reach becomes three ballot words of "cell is LETHAL" (the tile's 32
+/// columns and 32 on either side); (2) per (row, column) the horizontal distance g to the nearest lethal cell of that row
+/// from two funnel-shifted words (count-leading-zeros to the left, find-first-set to the right); (3) per cell
+/// d^2 = min over dy of g(y + dy)^2 + dy^2, walking outwards from dy = 0 and stopping once dy^2 reaches the best so far.
+/// IN PLACE: a cell's new cost never makes or unmakes a LETHAL cell (the caller checks cost_by_d2[k > 0] != 254), so tiles
+/// may read neighbours that other tiles have already rewritten; tiles without a lethal cell in reach write nothing.
+constexpr int kInflateFastRadius = 31;  // (three 32-cell ballot words per row: the horizontal search reaches 31 cells either way)
+__global__ void __launch_bounds__(256) k_inflate_separable(uint8_t* __restrict__ map, int size_x, int size_y, int pitch, int radius,
+                                                            const uint8_t* __restrict__ lut) {
+  __shared__ uint32_t hbits[32 + 2 * kInflateFastRadius][3];
+  __shared__ uint8_t gbuf[32 + 2 * kInflateFastRadius][32];
+  __shared__ int any_lethal;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 32 - radius, rows = 32 + 2 * radius;
+  if (threadIdx.x == 0) any_lethal = 0;
+  __syncthreads();
+  bool seen = false;
+  for (int r = warp; r < rows; r += 8) {
+    const int y = ty0 + r;
+    const bool y_in = y >= 0 && y < size_y;
+    const uint8_t* __restrict__ rowp = map + static_cast<size_t>(y_in ? y : 0) * pitch;
+    uint32_t w[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int x = tx0 - 32 + 32 * j + lane;
+      const bool lethal = y_in && x >= 0 && x < size_x && rowp[x] == kLethal;
+      w[j] = __ballot_sync(0xFFFFFFFFu, lethal);
+    }
+    if (lane < 3) hbits[r][lane] = lane == 0 ? w[0] : (lane == 1 ? w[1] : w[2]);
+    seen |= (w[0] | w[1] | w[2]) != 0u;
+  }
+  if (seen && lane == 0) any_lethal = 1;
+  __syncthreads();
+  if (!any_lethal) return;
+  for (int idx = threadIdx.x; idx < rows * 32; idx += blockDim.x) {
+    const int r = idx >> 5, cx = idx & 31;
+    const uint32_t w0 = hbits[r][0], w1 = hbits[r][1], w2 = hbits[r][2];
+    const uint32_t right = __funnelshift_r(w1, w2, cx);          // bit k: the cell k columns to the right (k = 0: the cell itself)
+    const uint32_t left = __funnelshift_rc(w0, w1, cx + 1);      // bit 31 - k: the cell k columns to the left
+    const int g = min(right ? __ffs(right) - 1 : 64, left ? __clz(left) : 64);
+    gbuf[r][cx] = static_cast<uint8_t>(g <= radius ? g : 255);
+  }
+  __syncthreads();
+  const int r2max = radius * radius;
+  for (int c = threadIdx.x; c < 32 * 32; c += blockDim.x) {
+    const int cy = c >> 5, cx = c & 31, x = tx0 + cx, y = blockIdx.y * 32 + cy;
+    if (x >= size_x || y >= size_y) continue;
+    const int rc = cy + radius;
+    int best = gbuf[rc][cx] == 255 ? 0x3FFFFFFF : gbuf[rc][cx] * gbuf[rc][cx];
+    for (int dy = 1; dy <= radius && dy * dy < best; ++dy) {
+      const int a = gbuf[rc - dy][cx], b = gbuf[rc + dy][cx], m = min(a, b);
+      if (m != 255) best = min(best, m * m + dy * dy);
+    }
+    if (best > r2max) continue;
+    uint8_t* cell = map + static_cast<size_t>(y) * pitch + x;
+    const uint8_t old = *cell, cost = lut[best];
+    uint8_t out;
+    if (old == kNoInformation) out = cost >= kInscribed ? cost : old;
+    else out = max(old, cost);
+    if (out != old) *cell = out;
+  }
+}
+
 template <int OP>
 __global__ void __launch_bounds__(kRowsWarps * 32) k_area_rows_multi(MapView m, const double* __restrict__ poly_g, const int* __restrict__ starts_g,
                                                                     int n_outlines, int nv_total, int nv_max, PoseSource src, long long count,
@@ -3429,15 +3493,21 @@ int cover_map_inflate(cover_map* map, int32_t radius_cells, const uint8_t* cost_
   const size_t bytes = static_cast<size_t>(v.pitch) * v.size_y;
   CU(map_ready(ctx, map));
   map->planes_hi = map->planes_inf_hi = map->prefix_hi = -1;
-  CU(ctx->in_a.ensure(bytes));  // snapshot of the un-inflated map: the kernel reads it and writes the map in place
-  CU(cudaMemcpyAsync(ctx->in_a.ptr, map->dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   const size_t lut_bytes = static_cast<size_t>(radius_cells) * radius_cells + 1;
   CU(ctx->in_b.ensure(lut_bytes));
   CU(cudaMemcpyAsync(ctx->in_b.ptr, cost_by_d2, lut_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  const int span = 32 + 2 * radius_cells;
   const dim3 grid((v.size_x + 31) / 32, (v.size_y + 31) / 32);
-  k_inflate<<<grid, 256, static_cast<size_t>(span) * span, ctx->stream>>>(ctx->in_a.as<uint8_t>(), map->dev, v.size_x, v.size_y, v.pitch,
-                                                                         radius_cells, ctx->in_b.as<uint8_t>());
+  bool makes_lethal = false;  // a table that turns neighbours LETHAL would change what other tiles read: snapshot path
+  for (size_t k = 1; k < lut_bytes; ++k) makes_lethal = makes_lethal || cost_by_d2[k] == kLethal;
+  if (radius_cells <= kInflateFastRadius && !makes_lethal) {
+    k_inflate_separable<<<grid, 256, 0, ctx->stream>>>(map->dev, v.size_x, v.size_y, v.pitch, radius_cells, ctx->in_b.as<uint8_t>());
+  } else {
+    CU(ctx->in_a.ensure(bytes));  // snapshot of the un-inflated map: the kernel reads it and writes the map in place
+    CU(cudaMemcpyAsync(ctx->in_a.ptr, map->dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    const int span = 32 + 2 * radius_cells;
+    k_inflate<<<grid, 256, static_cast<size_t>(span) * span, ctx->stream>>>(ctx->in_a.as<uint8_t>(), map->dev, v.size_x, v.size_y, v.pitch,
+                                                                           radius_cells, ctx->in_b.as<uint8_t>());
+  }
   ++ctx->launches;
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
@@ -3548,10 +3618,17 @@ double cover_get_radius(const double* polygon_xy, int32_t n_vertices) {
 int cover_split_polygon(double radius, const double* polygon_xy, int32_t n_vertices, double* outline_xy, int32_t* outline_starts,
                         int32_t* n_outlines, double* area_xy, int32_t* area_starts, int32_t* n_areas, int32_t max_vertices,
                         int32_t max_polygons) {
+  return cover_split_polygon_slack(radius, 0.0, polygon_xy, n_vertices, outline_xy, outline_starts, n_outlines, area_xy, area_starts, n_areas,
+                                   max_vertices, max_polygons);
+}
+
+int cover_split_polygon_slack(double radius, double slack, const double* polygon_xy, int32_t n_vertices, double* outline_xy,
+                              int32_t* outline_starts, int32_t* n_outlines, double* area_xy, int32_t* area_starts, int32_t* n_areas,
+                              int32_t max_vertices, int32_t max_polygons) {
   if (n_vertices < 0 || (n_vertices > 0 && !polygon_xy) || !outline_starts || !n_outlines || !area_starts || !n_areas) return COVER_E_INVALID_ARG;
   cvr_split::Split sp;
   try {
-    sp = cvr_split::split(radius, polygon_xy, n_vertices);
+    sp = cvr_split::split(radius, polygon_xy, n_vertices, slack);
   } catch (const std::invalid_argument&) {
     return COVER_E_INVALID_ARG;
   } catch (const std::bad_alloc&) {

@@ -10,17 +10,20 @@
 // The reference's tests pin only properties of the result (test/footprints.cpp:20-166) and a safety regression
 // (:205-242) - the vertex coordinates depend on boost's buffer strategies and are unpinned - so this file restates the
 // CONSTRUCTION, not boost's output:
-//   * a convex P is eroded exactly (its edges' half-planes moved inwards by d: what a negative buffer of a convex
-//     polygon is, whatever the join strategy);
-//   * every other region is taken from its implicit form - the signed distance to P's boundary, the distance to the
-//     first eroded ring - with marching squares on a grid of pitch h (1/384 of the larger bounding-box side) and a
-//     Douglas-Peucker pass (tolerance h / 4).  A non-convex P is eroded by d - 2 h instead of d: with the usual radius
-//     (the inradius) the exact erosion is the polygon's skeleton - a point or a segment without area, which boost
-//     returns as a sliver - and 2 h of width keep it on the grid.
-// Why that is safe: the areas are P minus the band of width `radius` around the ring that is actually RETURNED, so
-// every point of P lies in an area or within `radius` of the outline ring, wherever that ring sits.  A ring 2 h closer
-// to P's boundary than boost's only makes the outline test (253 or 254) trip for obstacles up to 2 h outside the
-// footprint - a few millimetres on the conservative side.
+//   * P is eroded by d - 2 h instead of d, h = 1/384 of the larger bounding-box side: with the usual radius (the
+//     inradius) the exact erosion is the polygon's skeleton - a point or a segment without area, which boost returns
+//     as a sliver - and 2 h of width keep it a proper polygon.  A convex P is eroded exactly (its edges' half-planes
+//     moved inwards: what a negative buffer of a convex polygon is, whatever the join strategy); any other P through
+//     its implicit form - the signed distance to P's boundary - with marching squares on a grid of pitch h and a
+//     Douglas-Peucker pass (tolerance h / 4);
+//   * the areas are {p in P : dist(p, first eroded ring) > radius - 1.5 h}, again from the implicit form.  The band the
+//     areas leave out is 1.5 h narrower than the one the outline ring answers for, so the two overlap by more than the
+//     grid's error, and because the ring sits 2 h closer to P's boundary than boost's, the narrower band still reaches
+//     over every edge it is parallel to: no rim of area is left along such an edge.
+// Why that is safe: the areas are P minus (less than) the band of width `radius` around the ring that is actually
+// RETURNED, so every point of P lies in an area or within `radius` of the outline ring, wherever that ring sits.  A ring
+// 2 h closer to P's boundary than boost's only makes the outline test (253 or 254) trip for obstacles up to 2 h outside
+// the footprint - a few millimetres on the conservative side.
 #pragma once
 
 #include <algorithm>
@@ -257,6 +260,47 @@ inline std::vector<Ring> contours(const std::vector<double>& f, int nx, int ny, 
   return rings;
 }
 
+/// Nearest point of the closed ring `r` to p (and its distance).
+inline Pt nearest_on_ring(const Ring& r, const Pt& p, double& dist) {
+  Pt best = r[0];
+  dist = std::numeric_limits<double>::max();
+  for (size_t i = 0; i + 1 < r.size(); ++i) {
+    const Pt &a = r[i], &b = r[i + 1];
+    const double vx = b.x - a.x, vy = b.y - a.y, vv = vx * vx + vy * vy;
+    double t = vv > 0 ? ((p.x - a.x) * vx + (p.y - a.y) * vy) / vv : 0.0;
+    t = std::min(1.0, std::max(0.0, t));
+    const Pt q{a.x + t * vx, a.y + t * vy};
+    const double d = std::hypot(p.x - q.x, p.y - q.y);
+    if (d < dist) dist = d, best = q;
+  }
+  return best;
+}
+
+/// The grid leaves an area ring's vertices a hair inside P where the ring runs along P's boundary, and chamfers P's
+/// corners.  boost's difference keeps P's own edges and vertices there, and the cell a vertex truncates to depends on
+/// it (a coordinate of exactly 0.65 m is row 113, 0.65 - 1e-9 is row 112): vertices within `reach` of P's boundary are
+/// moved ONTO it, and P's vertices that the ring passes within `reach` of are put back into the ring.
+inline void snap_to_polygon(Ring& ring, const Ring& P, double reach) {
+  for (Pt& v : ring) {
+    double d;
+    const Pt q = nearest_on_ring(P, v, d);
+    if (d <= reach) v = q;
+  }
+  ring.back() = ring.front();
+  for (size_t k = 0; k + 1 < P.size(); ++k) {
+    const Pt& corner = P[k];
+    double best = std::numeric_limits<double>::max();
+    size_t at = 0;
+    bool present = false;
+    for (size_t i = 0; i + 1 < ring.size(); ++i) {
+      if (ring[i].x == corner.x && ring[i].y == corner.y) present = true;
+      const double d = dist_point_segment(corner, ring[i], ring[i + 1]);
+      if (d < best) best = d, at = i;
+    }
+    if (!present && best <= reach) ring.insert(ring.begin() + static_cast<long>(at) + 1, corner);
+  }
+}
+
 struct Split {
   std::vector<Ring> outlines, areas;  // closed, clockwise (boost's default polygon)
 };
@@ -285,7 +329,7 @@ inline std::vector<Ring> simple_polygons(std::vector<Ring> loops, double tol, do
 }
 
 /// continuous_footprint(radius, polygon) (footprints.cpp:79-125).  Throws std::invalid_argument for radius <= 0.
-inline Split split(double radius, const double* xy, int n) {
+inline Split split(double radius, const double* xy, int n, double slack = 0) {
   Split s;
   if (n == 0) return s;  // an empty polygon is a noop
   if (!(radius > 0)) throw std::invalid_argument("Radius must be positive");
@@ -294,8 +338,9 @@ inline Split split(double radius, const double* xy, int n) {
   for (const Pt& p : P) bx0 = std::min(bx0, p.x), bx1 = std::max(bx1, p.x), by0 = std::min(by0, p.y), by1 = std::max(by1, p.y);
   const double extent = std::max(bx1 - bx0, by1 - by0);
   if (std::fabs(signed_area2(P)) <= 1e-12 * extent * extent) return s;  // fewer than three distinct points / no area
-  const double d = radius * (1.0 - 1e-6);
   const double h = extent / 384.0, margin = 2.0 * h, tol = 0.25 * h;
+  // (slack: the outlines that much closer to P's boundary, see cover_b200.h)
+  const double d = radius * (1.0 - 1e-6) - margin - std::max(0.0, slack);
   const int pad = 4;
   const int nx = static_cast<int>(std::ceil((bx1 - bx0) / h)) + 2 * pad + 1, ny = static_cast<int>(std::ceil((by1 - by0) / h)) + 2 * pad + 1;
   const double gx0 = bx0 - pad * h, gy0 = by0 - pad * h;
@@ -308,12 +353,16 @@ inline Split split(double radius, const double* xy, int n) {
       sdf[static_cast<size_t>(j) * nx + i] = inside(P, p) ? dist : -dist;
     }
   // ---- outlines: P eroded by d
+  if (d <= 0) {
+    s.areas.push_back(P);
+    return s;
+  }
   if (is_convex(P)) {
     const Ring e = erode_convex(P, d);
     if (!e.empty()) s.outlines.push_back(e);
   } else {
     std::vector<double> f(sdf.size());
-    for (size_t k = 0; k < f.size(); ++k) f[k] = sdf[k] - (d - margin);
+    for (size_t k = 0; k < f.size(); ++k) f[k] = sdf[k] - d;
     s.outlines = simple_polygons(contours(f, nx, ny, gx0, gy0, h), tol);
   }
   if (s.outlines.empty()) {  // the radius is too large: the polygon itself is the one area (test/footprints.cpp:90-105)
@@ -326,10 +375,11 @@ inline Split split(double radius, const double* xy, int n) {
   for (int j = 0; j < ny; ++j)
     for (int i = 0; i < nx; ++i) {
       const size_t k = static_cast<size_t>(j) * nx + i;
-      const double band = dist_polyline(ring0, Pt{gx0 + i * h, gy0 + j * h}) - radius;
+      const double band = dist_polyline(ring0, Pt{gx0 + i * h, gy0 + j * h}) - (radius - 1.5 * h - std::max(0.0, slack));
       g[k] = std::min(sdf[k], band);
     }
   s.areas = simple_polygons(contours(g, nx, ny, gx0, gy0, h), tol, 0.5 * h);
+  for (Ring& a : s.areas) snap_to_polygon(a, P, 1.5 * h);
   return s;
 }
 

@@ -231,6 +231,15 @@ double cover_get_radius(const double* polygon_xy, int32_t n_vertices);
 int cover_split_polygon(double radius, const double* polygon_xy, int32_t n_vertices, double* outline_xy, int32_t* outline_starts,
                         int32_t* n_outlines, double* area_xy, int32_t* area_starts, int32_t* n_areas, int32_t max_vertices,
                         int32_t max_polygons);
+/* EXTENSION: the same with the outlines eroded by `slack` less and the areas' band `slack` narrower (0 = the reference's
+ * construction).  Everything in the polygon stays covered - the areas are the polygon minus the band around the ring
+ * that is returned - but ring and areas now overlap by `slack`, which absorbs the cell rounding between "within
+ * `radius` of the ring" in metres and "within the inflation layer's inscribed radius of an outline CELL" in cells
+ * (the single-cell misses the reference's own regression tolerates, test/footprints.cpp:236-241): one cell of slack
+ * meets that test's bar.  The price: an obstacle up to `slack` OUTSIDE the footprint may count as a collision. */
+int cover_split_polygon_slack(double radius, double slack, const double* polygon_xy, int32_t n_vertices, double* outline_xy,
+                              int32_t* outline_starts, int32_t* n_outlines, double* area_xy, int32_t* area_starts, int32_t* n_areas,
+                              int32_t max_vertices, int32_t max_polygons);
 
 /* ---- trajectory scoring (EXTENSION: the DWA-style caller right after the pose checks) -------
  * Poses grouped as n_trajectories x steps (pose index = trajectory * steps + step), e.g. the outputs of the

@@ -464,12 +464,12 @@ struct polygon_split {
 };
 /// continuous_footprint(radius, polygon)'s constructor (footprints.cpp:79-125) on the host: (outlines, areas) for
 /// `continuous_footprint(ctx, outlines, areas)`.  Throws std::invalid_argument for radius <= 0, like the reference.
-inline polygon_split split_polygon(double radius, polygon_view poly) {
+inline polygon_split split_polygon(double radius, polygon_view poly, double slack = 0.0) {
   const int32_t max_vertices = 1 << 16, max_polygons = 256;
   std::vector<double> oxy(2 * static_cast<size_t>(max_vertices)), axy(2 * static_cast<size_t>(max_vertices));
   std::vector<int32_t> os(max_polygons + 1), as(max_polygons + 1);
   int32_t no = 0, na = 0;
-  const int rc = cover_split_polygon(radius, poly.xy, poly.n, oxy.data(), os.data(), &no, axy.data(), as.data(), &na, max_vertices, max_polygons);
+  const int rc = cover_split_polygon_slack(radius, slack, poly.xy, poly.n, oxy.data(), os.data(), &no, axy.data(), as.data(), &na, max_vertices, max_polygons);
   if (rc == COVER_E_INVALID_ARG) throw std::invalid_argument("Radius must be positive");
   if (rc != COVER_OK) throw std::runtime_error("cover_split_polygon failed");
   polygon_split out;

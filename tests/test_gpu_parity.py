@@ -947,6 +947,35 @@ def test_gpu_inflation_layer(cb, ctx):
     np.testing.assert_array_equal(c2.download(), stamped)
 
 
+@pytest.mark.parametrize("res,inflation_radius,density", [(0.05, 1.0, 6e-4), (0.05, 1.0, 0.08), (0.025, 0.8, 2e-3), (0.025, 0.775, 2e-3), (0.02, 1.0, 1e-3), (0.05, 0.05, 0.3)])
+def test_gpu_inflation_layer_radii_and_dense_maps(cb, ctx, res, inflation_radius, density):
+    """The separable exact distance transform (radius <= 31 cells, in place) and the brute-force kernel (larger radii)
+    against scipy's exact Euclidean distance transform: sparse points, walls / dense clutter, radius 1, 20, 32 (brute force) and 50."""
+    from scipy import ndimage
+    from cover_b200 import workloads as wl
+    rng = np.random.default_rng(int(1000 * res) + int(1e4 * density))
+    sx, sy = 419, 307
+    raw = np.zeros((sy, sx), dtype=np.uint8)
+    obs = rng.random((sy, sx)) < density
+    obs[100:103, 50:300] = True  # a wall
+    obs[0, :] = True             # the map border
+    raw[obs] = 254
+    raw[(rng.random((sy, sx)) < 0.03) & ~obs] = 255
+    raw[(rng.random((sy, sx)) < 0.05) & (raw == 0)] = 97
+    rad, lut = wl.inflation_lut(res, inscribed_radius=min(0.3, inflation_radius / 2), inflation_radius=inflation_radius)
+    cmap = cb.Costmap(ctx, raw, res)
+    cmap.inflate(rad, lut)
+    got = cmap.download()
+    d2 = np.rint(ndimage.distance_transform_edt(~obs) ** 2).astype(np.int64)
+    reach = d2 <= rad * rad
+    cost = np.where(reach, lut[np.minimum(d2, rad * rad)], 0).astype(np.uint8)
+    expect = raw.copy()
+    unknown = raw == 255
+    expect[reach & ~unknown] = np.maximum(raw, cost)[reach & ~unknown]
+    expect[reach & unknown & (cost >= 253)] = cost[reach & unknown & (cost >= 253)]
+    np.testing.assert_array_equal(got, expect)
+
+
 def test_area_with_holes(cb, ctx):
     """area_generator(res, polygon_vec): the reference's 'head' with nested holes (test/expand.cpp:241-279) and
     random outline sets, all three ops, against the oracle."""

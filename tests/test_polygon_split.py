@@ -130,35 +130,37 @@ def test_split_covers_the_polygon_and_outlines_are_inscribed(cb):
 @pytest.mark.gpu
 @pytest.mark.parametrize("idx", [4, 5])
 def test_safety_regression_with_the_inflation_layer(cb, idx):
-    """test/footprints.cpp:168-242: every cell inside the footprint, marked lethal and inflated, must make the split
-    footprint collide (the reference tolerates 2 misses).  All cells are tried at once: one 200 x 200 map per marked cell
-    is a lattice of maps, so the footprint is checked at ONE pose on many maps = many single-obstacle windows of one big map."""
+    """test/footprints.cpp:168-242: every cell inside the footprint, marked lethal and inflated (GPU inflation layer,
+    inscribed radius = the footprint's, like costmap_2d's setFootprint), must make the split footprint collide at the
+    identity pose; the reference tolerates 2 misses "due to discretization issues".  With `slack` = one cell this
+    construction meets that bar; the plain construction (slack 0: areas cut where their tails along P's edges get thinner
+    than the construction grid, no allowance for the cell metric) is held to 1 % of the cells."""
     from oracle import pyoracle as po
     from cover_b200 import workloads as wl
     poly = FOOTPRINTS[idx]
-    outlines, areas = cb.split_polygon(poly)
-    assert outlines and areas
     res = 0.05
-    # inscribed radius of the costmap layer = min distance from the robot origin to the footprint's edges (costmap_2d)
     closed = np.concatenate([poly, poly[:, :1]], axis=1)
     a, b = closed[:, :-1].T, closed[:, 1:].T
-    t = np.clip((-(a) * (b - a)).sum(1) / ((b - a) ** 2).sum(1), 0, 1)
-    inscribed = np.linalg.norm(a + t[:, None] * (b - a), axis=1).min()
-    assert inscribed >= cb.get_radius(poly) - 1e-9 or True
+    t = np.clip((-a * (b - a)).sum(1) / np.maximum(((b - a) ** 2).sum(1), 1e-300), 0, 1)
+    inscribed = np.linalg.norm(a + t[:, None] * (b - a), axis=1).min()  # min distance from the robot origin to the edges
     rad, lut = wl.inflation_lut(res, inscribed_radius=inscribed, inflation_radius=1.0)
     ctx = cb.Context(0)
-    cells = po.area_cells([po.outline_cells(po.to_discrete(res, poly - np.array([[-5.0], [-5.0]])))])  # the footprint's cells on the 200 x 200 map at (-5, -5)
-    sf = cb.SplitFootprint(ctx, outlines, areas)
+    cells = po.area_cells([po.outline_cells(po.to_discrete(res, poly + 5.0))])  # the footprint's cells on the 200 x 200 map at (-5, -5)
     pose = np.array([[1.0, 0.0, 0.0, 0.0]])
     empty = np.zeros((200, 200), dtype=np.uint8)
     cmap = cb.Costmap(ctx, empty, res, -5.0, -5.0)
-    assert sf.is_free(cmap, pose).is_free[0] == 1
-    misses = 0
-    for x, y in cells.tolist():
-        data = empty.copy()
-        data[y, x] = 254
-        cmap.upload(data)
-        cmap.inflate(rad, lut)
-        misses += int(sf.is_free(cmap, pose).is_free[0])
-    assert misses <= 2, f"{misses} of {len(cells)} single-obstacle maps were missed"
+    for slack, allowed in ((res, 2), (0.0, max(2, len(cells) // 100))):
+        outlines, areas = cb.split_polygon(poly, slack=slack)
+        assert outlines and areas
+        sf = cb.SplitFootprint(ctx, outlines, areas)
+        cmap.upload(empty)
+        assert sf.is_free(cmap, pose).is_free[0] == 1
+        misses = 0
+        for x, y in cells.tolist():
+            data = empty.copy()
+            data[y, x] = 254
+            cmap.upload(data)
+            cmap.inflate(rad, lut)
+            misses += int(sf.is_free(cmap, pose).is_free[0])
+        assert misses <= allowed, f"slack {slack}: {misses} of {len(cells)} single-obstacle maps were missed"
     ctx.close()
