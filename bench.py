@@ -429,6 +429,8 @@ def run_gpu(args) -> None:
         # way - a 0.15 ms step is short enough for the launching thread's scheduling jitter to show in the device time
         torch.set_num_threads(1)
         try:
+            if os.environ.get("COVER_BENCH_NO_PIN"):
+                raise OSError
             cores = sorted(os.sched_getaffinity(0))
             per = max(1, len(cores) // world)
             os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]) or set(cores))
@@ -503,7 +505,7 @@ def run_gpu(args) -> None:
     # ---- end-to-end arm (`e2e`): host buffers through the public API, copies inside the timed region.  Two planning
     # cycles are kept in flight (two contexts = two streams, one host thread each): one cycle's results travel back
     # while the other's costmap travels in.
-    n_flight = 2
+    n_flight = int(os.environ.get("COVER_BENCH_FLIGHT", "2"))
     e2e_steps = max(50, args.steps)
     e2e_steps += e2e_steps % n_flight
     workers = []
@@ -532,6 +534,7 @@ def run_gpu(args) -> None:
             e2e_step(w)
 
     def loop(w, k):
+        w["ctx"].bind()  # this thread drives one context: stay on its device
         for _ in range(k):
             e2e_step(w)
 

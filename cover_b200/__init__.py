@@ -181,6 +181,11 @@ class Context:
     def synchronize(self):
         self._check(self._lib.cover_ctx_synchronize(self._h))
 
+    def bind(self):
+        """Make this context's device the calling thread's current CUDA device (call once in a thread that drives
+        this context; see cover_ctx_bind)."""
+        self._check(self._lib.cover_ctx_bind(self._h))
+
     def probe_read_bandwidth(self, nbytes: int, reps: int = 20) -> float:
         """Best-of-10 streaming read bandwidth in GB/s over a scratch buffer (16 MB: L2 -> SM path; 1 GB: HBM)."""
         gbs = C.c_double(0.0)

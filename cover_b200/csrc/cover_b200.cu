@@ -3326,6 +3326,12 @@ int cover_ctx_synchronize(cover_ctx* ctx) {
   return COVER_OK;
 }
 
+int cover_ctx_bind(cover_ctx* ctx) {
+  if (!ctx) return COVER_E_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  return COVER_OK;
+}
+
 int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double resolution, double origin_x, double origin_y,
                      cover_map** out) {
   if (!ctx || !out) return COVER_E_INVALID_ARG;

@@ -74,12 +74,17 @@ class ShardedCostmap:
         self.maps: List[Optional[Costmap]] = [None] * len(gpus)
 
         def make(k):
+            gpus.contexts[k].bind()  # (the shard's thread stays on its device: no switch from device 0 and back per call)
             self.maps[k] = Costmap(gpus.contexts[k], data, resolution, origin_x, origin_y)
         _each(len(gpus), make)
 
     def upload(self, data: np.ndarray):
         data = np.ascontiguousarray(data, dtype=np.uint8)
-        _each(len(self.maps), lambda k: self.maps[k].upload(data))
+
+        def run(k):
+            self.gpus.contexts[k].bind()
+            self.maps[k].upload(data)
+        _each(len(self.maps), run)
 
     def _blocks(self, count: int, granule: int = 1):
         """(first, n) per shard; with granule > 1 the borders are multiples of it (whole words of packed verdicts)."""
@@ -103,6 +108,7 @@ class ShardedCostmap:
             first, n = blocks[k]
             if n == 0:
                 return
+            self.gpus.contexts[k].bind()
             out = Result(res.is_free[first:first + n], None if res.cost is None else res.cost[first:first + n], res.status[first:first + n])
             fn = getattr(self.maps[k], name)
             if lattice:
@@ -132,6 +138,7 @@ class ShardedCostmap:
         def run(k):
             first, n = blocks[k]
             if n:
+                self.gpus.contexts[k].bind()
                 self.maps[k].area_is_free(polygon, lattice, first=first, count=n, out=Result(free_bits=bits[first // 32:], not_ok=bad[k:k + 1]))
         _each(len(self.maps), run)
         return Result(free_bits=bits, not_ok=np.array([bad.sum()], dtype=np.int64))

@@ -101,6 +101,11 @@ void cover_ctx_destroy(cover_ctx* ctx);
 const char* cover_last_error(const cover_ctx* ctx);
 void* cover_ctx_stream(cover_ctx* ctx); /* the cudaStream_t all work of this context is enqueued on */
 int cover_ctx_synchronize(cover_ctx* ctx);
+/* Makes the context's device the calling thread's current CUDA device.  Every entry does that for the duration of the
+ * call and restores the previous device afterwards; a host thread that drives ONE context (pose sharding: one thread
+ * per GPU) should call this once first - otherwise every call switches from the thread's default device 0 and back,
+ * which also creates a CUDA context on device 0 in that process. */
+int cover_ctx_bind(cover_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t cover_ctx_launch_count(const cover_ctx* ctx);
 

@@ -720,6 +720,7 @@ private:
     for (int k = 0; k < size(); ++k)
       threads.emplace_back([&, k] {
         try {
+          detail::check(ctxs_[static_cast<size_t>(k)].get(), cover_ctx_bind(ctxs_[static_cast<size_t>(k)].get()));  // this thread drives one device
           body(k);
         } catch (...) {
           errors[static_cast<size_t>(k)] = std::current_exception();
