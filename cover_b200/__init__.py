@@ -51,7 +51,7 @@ class _Lattice(C.Structure):
 
 class _Poses(C.Structure):
     _fields_ = [("format", C.c_int32), ("mem", C.c_int32), ("first", C.c_int64), ("count", C.c_int64), ("data", C.c_void_p),
-                ("lattice", _Lattice)]
+                ("lattice", _Lattice), ("cell_offset", C.c_int32 * 2)]
 
 
 class _Results(C.Structure):
@@ -83,7 +83,7 @@ def _load():
     lib.cover_ctx_launch_count.restype = C.c_int64
     for name in ("cover_ctx_destroy", "cover_map_destroy", "cover_cells_destroy", "cover_footprints_destroy", "cover_split_destroy"):
         getattr(lib, name).restype = None
-    if lib.cover_abi_version() != 1:
+    if lib.cover_abi_version() != 2:
         raise CoverError(-4, "libcover_b200.so has a different ABI version; rebuild it")
     _lib = lib
     return lib
@@ -197,9 +197,11 @@ class Context:
             raise CoverError(rc, self._lib.cover_last_error(self._h).decode())
 
     # -- argument marshalling ------------------------------------------------------------------
-    def _poses(self, poses, first: int, count: Optional[int]):
+    def _poses(self, poses, first: int, count: Optional[int], offset=None):
         keep = []
         p = _Poses()
+        if offset is not None:  # the offset overloads: added to every generated cell (impl/costmap.hpp:29-35,74-81)
+            p.cell_offset[0], p.cell_offset[1] = int(offset[0]), int(offset[1])
         if poses is None:
             p.format, p.mem, p.first, p.count, p.data = _POSE_NONE, _MEM_HOST, 0, 1, None
         elif isinstance(poses, Lattice):
@@ -361,10 +363,10 @@ class Costmap:
             pass
 
     # -- polygon x poses (path A) --------------------------------------------------------------
-    def _polygon(self, fn: str, polygon, poses, first, count, out, want_cost):
+    def _polygon(self, fn: str, polygon, poses, first, count, out, want_cost, offset=None):
         ctx = self.ctx
         xy = polygon_xy(polygon)
-        p, keep = ctx._poses(poses, first, count)
+        p, keep = ctx._poses(poses, first, count, offset)
         r, res = ctx._results(int(p.count), True, want_cost, True, out)
         ctx._check(getattr(ctx._lib, fn)(ctx._h, self._h, C.c_void_p(xy.ctypes.data), C.c_int32(xy.size // 2), C.byref(p), C.byref(r)))
         del keep
@@ -383,26 +385,26 @@ class Costmap:
         del keep
         return res
 
-    def area_is_free(self, polygon, poses, first=0, count=None, out=None) -> Result:
+    def area_is_free(self, polygon, poses, first=0, count=None, out=None, offset=None) -> Result:
         """Batched is_free(polygon, pose, map) (costmap.cpp:78-85); poses=None is is_free(polygon, map)."""
-        return self._polygon("cover_area_is_free", polygon, poses, first, count, out, False)
+        return self._polygon("cover_area_is_free", polygon, poses, first, count, out, False, offset)
 
-    def area_accumulate_cost(self, polygon, poses, first=0, count=None, out=None) -> Result:
+    def area_accumulate_cost(self, polygon, poses, first=0, count=None, out=None, offset=None) -> Result:
         """Batched accumulate_cost(area_generator(res, pose*polygon - origin), map)."""
-        return self._polygon("cover_area_accumulate_cost", polygon, poses, first, count, out, True)
+        return self._polygon("cover_area_accumulate_cost", polygon, poses, first, count, out, True, offset)
 
-    def area_max_cost(self, polygon, poses, first=0, count=None, out=None) -> Result:
-        return self._polygon("cover_area_max_cost", polygon, poses, first, count, out, True)
+    def area_max_cost(self, polygon, poses, first=0, count=None, out=None, offset=None) -> Result:
+        return self._polygon("cover_area_max_cost", polygon, poses, first, count, out, True, offset)
 
-    def outline_is_free(self, polygon, poses, first=0, count=None, out=None) -> Result:
+    def outline_is_free(self, polygon, poses, first=0, count=None, out=None, offset=None) -> Result:
         """Batched is_free(outline_generator(res, pose*polygon - origin), map)."""
-        return self._polygon("cover_outline_is_free", polygon, poses, first, count, out, False)
+        return self._polygon("cover_outline_is_free", polygon, poses, first, count, out, False, offset)
 
-    def outline_accumulate_cost(self, polygon, poses, first=0, count=None, out=None) -> Result:
-        return self._polygon("cover_outline_accumulate_cost", polygon, poses, first, count, out, True)
+    def outline_accumulate_cost(self, polygon, poses, first=0, count=None, out=None, offset=None) -> Result:
+        return self._polygon("cover_outline_accumulate_cost", polygon, poses, first, count, out, True, offset)
 
-    def outline_max_cost(self, polygon, poses, first=0, count=None, out=None) -> Result:
-        return self._polygon("cover_outline_max_cost", polygon, poses, first, count, out, True)
+    def outline_max_cost(self, polygon, poses, first=0, count=None, out=None, offset=None) -> Result:
+        return self._polygon("cover_outline_max_cost", polygon, poses, first, count, out, True, offset)
 
     # -- expand (to_outline / to_area, batched) ------------------------------------------------
     def _expand(self, fn: str, polygon, poses, first, count):

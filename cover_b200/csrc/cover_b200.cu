@@ -2488,8 +2488,8 @@ bool lattice_row_range(const cover_map* map, const double* polygon_xy, int nv, c
   for (int t = 0; t < L.ntheta; ++t) scale = std::max(scale, std::hypot(L.cs[2 * t], L.cs[2 * t + 1]));  // |(c,s)| need not be 1
   const double reach = radius * scale;
   const double ya = L.y0, yb = L.y0 + static_cast<double>(L.ny - 1) * L.dy;
-  const double lo = (std::min(ya, yb) - reach - map->view.origin_y) * map->view.inv_res - 2.0;
-  const double hi = (std::max(ya, yb) + reach - map->view.origin_y) * map->view.inv_res + 2.0;
+  const double lo = (std::min(ya, yb) - reach - map->view.origin_y) * map->view.inv_res - 2.0 + poses->cell_offset[1];  // (the offset moves every cell)
+  const double hi = (std::max(ya, yb) + reach - map->view.origin_y) * map->view.inv_res + 2.0 + poses->cell_offset[1];
   row_lo = 0, row_hi = map->view.size_y - 1;
   if (!(std::isfinite(lo) && std::isfinite(hi))) return false;
   if (lo > row_lo) row_lo = lo > row_hi ? row_hi + 1 : static_cast<int>(std::floor(lo));
@@ -2606,6 +2606,7 @@ int stage_poses(cover_ctx* ctx, const cover_poses* poses, PoseSource& src) {
   if (poses->count < 0) return fail(ctx, COVER_E_INVALID_ARG, "negative pose count");
   std::memset(&src, 0, sizeof(src));
   src.format = poses->format;
+  src.off_x = poses->cell_offset[0], src.off_y = poses->cell_offset[1];
   switch (poses->format) {
     case COVER_POSE_CS: {
       if (poses->count && !poses->data) return fail(ctx, COVER_E_INVALID_ARG, "POSE_CS needs data");
@@ -2867,7 +2868,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   }
   const bool words = word_bits != nullptr;
   const bool outline_lattice = shape == SHAPE_OUTLINE && src.format == POSE_LATTICE && nv >= 1 && !ctx->disable_lattice_kernel && count >= 4096 &&
-                               (words || (nv <= kLatMaxVertices && rows_cap <= kLatMaxRowsCap));
+                               (words || (nv <= kLatMaxVertices && rows_cap <= kLatMaxRowsCap && src.off_x == 0 && src.off_y == 0));
   if (shape == SHAPE_OUTLINE && !outline_lattice) {
     k_outline<OP><<<grid_for(count), kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out);
     ++ctx->launches;
@@ -2890,8 +2891,8 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   const unsigned int* todo_count = nullptr;
   bool second_list = false;
   // Lattice batches of small footprints: shape-deduplicating warp-cooperative kernel.
-  const bool lattice = fast && src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices &&
-                       rows_cap <= kLatMaxRowsCap && !ctx->disable_lattice_kernel;
+  const bool lattice = fast && src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices && src.off_x == 0 && src.off_y == 0 &&
+                       rows_cap <= kLatMaxRowsCap && !ctx->disable_lattice_kernel;  // (the shape-cache kernel knows no cell offset)
   if (fast) {
     CU(ctx->todo.ensure(static_cast<size_t>(count) * sizeof(unsigned int)));
     CU(ctx->todo_count.ensure(sizeof(unsigned int)));

@@ -50,6 +50,7 @@ struct MapView {
 
 struct Pose {
   double c, s, tx, ty;  // linear part [c -s; s c] (Eigen::Rotation2D::toRotationMatrix)
+  int ox, oy;           // cell offset added after discretisation (with_offset, costmap.hpp:135-155)
 };
 
 struct PoseSource {
@@ -59,6 +60,7 @@ struct PoseSource {
   const double* theta_cs;  // POSE_LATTICE: ntheta x 2 (device copy)
   double x0, dx, y0, dy;
   int nx, ny;
+  int off_x, off_y;        // cover_poses.cell_offset
 };
 
 struct OutView {
@@ -77,6 +79,7 @@ __device__ __forceinline__ void emit_free(const OutView& o, long long i, bool is
 
 __device__ __forceinline__ Pose load_pose(const PoseSource& src, long long i) {
   Pose T;
+  T.ox = src.off_x, T.oy = src.off_y;
   if (src.format == POSE_CS) {
     const double2* q = reinterpret_cast<const double2*>(src.cs) + 2 * i;
     const double2 a = __ldg(q), b = __ldg(q + 1);
@@ -118,8 +121,8 @@ __device__ __forceinline__ bool to_cell(const Pose& T, double px, double py, con
     }  // XF_PATH_B: the caller folded (-origin) into T.tx/T.ty (footprints.cpp:134-135)
   }
   const double sx = __dmul_rn(qx, m.inv_res), sy = __dmul_rn(qy, m.inv_res);
-  cx = __double2int_rz(sx);  // base.hpp:56: cast<int>() truncates toward zero
-  cy = __double2int_rz(sy);
+  cx = __double2int_rz(sx) + T.ox;  // base.hpp:56: cast<int>() truncates toward zero; then the offset (costmap.hpp:150-153)
+  cy = __double2int_rz(sy) + T.oy;
   return (fabs(sx) < kCoordLimit) && (fabs(sy) < kCoordLimit);  // false also for NaN
 }
 

@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(kLwPrepThreads) k_lw_prepare(MapView m, const 
         ok &= cell_of(v, c);
         if (v == 0) cell0 = c;
       }
+      const int raw0 = cell0;  // vertex 0's cell without the offset: what the other vertices' cells are relative to
+      cell0 += is_x ? src.off_x : src.off_y;  // the offset overloads: added after discretisation, so only vertex 0's cell moves
       const int anchor = is_x ? cell0 - idx : 0;
       bool pending = valid && ok;
       int my = valid ? (ok ? kLwOverflow : kLwBad) : kLwNone;
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(kLwPrepThreads) k_lw_prepare(MapView m, const 
             for (int v = 1; v < nv && same; ++v) {
               int c;
               cell_of(v, c);
-              same = c - cell0 == off_tab[k * nv + v];
+              same = c - raw0 == off_tab[k * nv + v];
             }
             if (same) my = k, pending = false;
           }
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(kLwPrepThreads) k_lw_prepare(MapView m, const 
           for (int v = 0; v < nv; ++v) {
             int c;
             cell_of(v, c);
-            off_tab[ncur * nv + v] = c - cell0;
+            off_tab[ncur * nv + v] = c - raw0;
           }
           if (is_x) {
             anchor_tab[ncur] = anchor;

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define COVER_B200_ABI_VERSION 1
+#define COVER_B200_ABI_VERSION 2
 
 typedef struct cover_ctx cover_ctx;
 typedef struct cover_map cover_map;
@@ -79,6 +79,9 @@ typedef struct cover_poses {
   int64_t count;         /* number of poses in this batch */
   const void* data;      /* CS: count x 4 doubles */
   cover_lattice lattice; /* LATTICE */
+  int32_t cell_offset[2]; /* added to every generated cell: the offset overloads is_free / accumulate_cost(gen, offset, map)
+                             (src/cover/impl/costmap.hpp:29-35,74-81) for the outline / area generator of the transformed
+                             polygon; {0, 0} for the plain overloads */
 } cover_poses;
 
 typedef struct cover_results {

@@ -175,9 +175,10 @@ private:
 };
 
 namespace detail {
-inline cover_poses make_poses(const std::vector<pose>& poses) {
+inline cover_poses make_poses(const std::vector<pose>& poses, int32_t off_x = 0, int32_t off_y = 0) {
   cover_poses p{};
   p.format = COVER_POSE_CS, p.mem = COVER_MEM_HOST, p.first = 0, p.count = static_cast<int64_t>(poses.size()), p.data = poses.data();
+  p.cell_offset[0] = off_x, p.cell_offset[1] = off_y;
   return p;
 }
 inline cover_poses make_poses(const pose_lattice& lat, std::vector<double>& cs, int64_t first, int64_t count) {
@@ -265,6 +266,25 @@ inline std::vector<double> accumulate_cost(polygon_view poly, const std::vector<
 /// Extension: max of detail::get_cell_cost over the area (-3 when a cell is outside the map).
 inline batch_result max_cost_nothrow(polygon_view poly, const std::vector<pose>& poses, const costmap& map) {
   return detail::run(cover_area_max_cost, poly, detail::make_poses(poses), map, true);
+}
+
+// ---- the offset overloads: is_free / accumulate_cost(generator, offset, map) (impl/costmap.hpp:29-35,74-81) --------
+// The offset (cells) is added to every cell the generator of the transformed polygon yields.
+
+struct cell_shift {
+  int32_t x, y;
+};
+inline batch_result is_free_nothrow(polygon_view poly, const std::vector<pose>& poses, cell_shift offset, const costmap& map) {
+  return detail::run(cover_area_is_free, poly, detail::make_poses(poses, offset.x, offset.y), map, false);
+}
+inline batch_result accumulate_cost_nothrow(polygon_view poly, const std::vector<pose>& poses, cell_shift offset, const costmap& map) {
+  return detail::run(cover_area_accumulate_cost, poly, detail::make_poses(poses, offset.x, offset.y), map, true);
+}
+inline batch_result outline_is_free_nothrow(polygon_view poly, const std::vector<pose>& poses, cell_shift offset, const costmap& map) {
+  return detail::run(cover_outline_is_free, poly, detail::make_poses(poses, offset.x, offset.y), map, false);
+}
+inline batch_result outline_accumulate_cost_nothrow(polygon_view poly, const std::vector<pose>& poses, cell_shift offset, const costmap& map) {
+  return detail::run(cover_outline_accumulate_cost, poly, detail::make_poses(poses, offset.x, offset.y), map, true);
 }
 
 // ---- outline generator -----------------------------------------------------------------------------

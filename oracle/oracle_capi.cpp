@@ -187,11 +187,25 @@ int64_t oracle_area_cells(const int32_t* dense, const int64_t* sizes, int32_t n_
 
 /// Path A: cells = to_discrete(res, (pose * polygon) - origin) (costmap.cpp:71-85), then
 /// outline_generator / area_generator, then is_free / accumulate_cost / max.
+int oracle_polygon_batch_offset(const oracle_map* map, const double* poly_xy, int32_t n_vertices, int32_t shape, int32_t op,
+                                int32_t pose_format, const void* poses, const oracle_lattice* lattice, int64_t first, int64_t count,
+                                const int32_t* offset, uint8_t* is_free, double* cost, uint8_t* status, int64_t* cells_read, int32_t threads);
+
 int oracle_polygon_batch(const oracle_map* map, const double* poly_xy, int32_t n_vertices, int32_t shape, int32_t op,
                          int32_t pose_format, const void* poses, const oracle_lattice* lattice, int64_t first,
                          int64_t count, uint8_t* is_free, double* cost, uint8_t* status, int64_t* cells_read,
                          int32_t threads) {
+  return oracle_polygon_batch_offset(map, poly_xy, n_vertices, shape, op, pose_format, poses, lattice, first, count, nullptr, is_free, cost, status,
+                                     cells_read, threads);
+}
+
+/// The same with a cell offset added to every generated cell: is_free / accumulate_cost(gen, offset, map)
+/// (src/cover/impl/costmap.hpp:29-35,74-81).
+int oracle_polygon_batch_offset(const oracle_map* map, const double* poly_xy, int32_t n_vertices, int32_t shape, int32_t op,
+                                int32_t pose_format, const void* poses, const oracle_lattice* lattice, int64_t first, int64_t count,
+                                const int32_t* offset, uint8_t* is_free, double* cost, uint8_t* status, int64_t* cells_read, int32_t threads) {
   if (!map || map->resolution <= 0) return -1;
+  const Cell cell_off = offset ? Cell{offset[0], offset[1]} : Cell{0, 0};
   const MapView m = view(map);
   const OutSink out{is_free, cost, status};
   std::vector<int64_t> tallies(static_cast<size_t>(std::max(threads, 1)), 0);
@@ -211,10 +225,10 @@ int oracle_polygon_batch(const oracle_map* map, const double* poly_xy, int32_t n
         if (shape == ORACLE_SHAPE_AREA) {
           const Area a = make_area({dense_outline(sparse)});
           if (a.max_ranges_per_row > 16) st = ORACLE_ROW_COMPLEXITY;
-          run_op(op, [&a](auto&& f) { return walk_area(a, f); }, Cell{0, 0}, m, out, i, &t);
+          run_op(op, [&a](auto&& f) { return walk_area(a, f); }, cell_off, m, out, i, &t);
         } else {
           const Outline o = make_outline(sparse);
-          run_op(op, [&o](auto&& f) { return walk_outline(o, f); }, Cell{0, 0}, m, out, i, &t);
+          run_op(op, [&o](auto&& f) { return walk_outline(o, f); }, cell_off, m, out, i, &t);
         }
         if (status) status[i] = static_cast<uint8_t>(st);
       } catch (const std::logic_error&) {

@@ -204,13 +204,22 @@ class Backend:
 
 
 
-    def polygon_batch(self, cmap: Costmap, poly, poses, shape=SHAPE_AREA, op=OP_IS_FREE, first=0, count=None, threads=1) -> Result:
+    def polygon_batch(self, cmap: Costmap, poly, poses, shape=SHAPE_AREA, op=OP_IS_FREE, first=0, count=None, threads=1, offset=None) -> Result:
+        """`offset` (2 ints): the offset overloads is_free / accumulate_cost(gen, offset, map), impl/costmap.hpp:29-35,74-81."""
         xy = polygon_xy(poly)
         fmt, arr, lat, total, _keep = _pose_args(poses)
         n = total - first if count is None else count
         free, cost, status = _outputs(n)
         read = C.c_int64(0)
         m = cmap.c()
+        if offset is not None:
+            off = np.ascontiguousarray(offset, dtype=np.int32).reshape(2)
+            rc = self._lib.oracle_polygon_batch_offset(C.byref(m), _p(xy), C.c_int32(xy.size // 2), C.c_int32(shape), C.c_int32(op), C.c_int32(fmt), _p(arr),
+                                                       lat, C.c_int64(first), C.c_int64(n), _p(off), _p(free), _p(cost), _p(status), C.byref(read),
+                                                       C.c_int32(threads))
+            if rc != 0:
+                raise ValueError("oracle_polygon_batch_offset failed (resolution must be positive)")
+            return Result(free, cost, status, read.value)
         rc = self._lib.oracle_polygon_batch(C.byref(m), _p(xy), C.c_int32(xy.size // 2), C.c_int32(shape), C.c_int32(op),
                                         C.c_int32(fmt), _p(arr), lat, C.c_int64(first), C.c_int64(n), _p(free), _p(cost),
                                         _p(status), C.byref(read), C.c_int32(threads))

@@ -138,6 +138,55 @@ int oracle_to_discrete(double res, const double* xy, int64_t n, int32_t* out) {
   }
 }
 
+/// is_free / accumulate_cost(gen, offset, map) (src/cover/impl/costmap.hpp:29-35,74-81) over the outline / area generator
+/// of the transformed polygon: the reference's own offset overloads.
+int oracle_polygon_batch_offset(const oracle_map* map, const double* poly_xy, int32_t n_vertices, int32_t shape, int32_t op,
+                                int32_t pose_format, const void* poses, const oracle_lattice* lattice, int64_t first, int64_t count,
+                                const int32_t* offset, uint8_t* is_free, double* cost, uint8_t* status, int64_t* cells_read, int32_t threads) {
+  if (!map || map->resolution <= 0) return -1;
+  const Costmap2D cm = wrap(map);
+  const cover::polygon poly = make_poly(poly_xy, n_vertices);
+  const cover::point origin(cm.getOriginX(), cm.getOriginY());
+  const cover::cell off(offset ? offset[0] : 0, offset ? offset[1] : 0);
+  if (cells_read) *cells_read = -1;
+  parallel_for(count, threads, [&](int64_t b, int64_t e) {
+    for (int64_t i = b; i < e; ++i) {
+      try {
+        const cover::polygon q = pose_format == POSE_NONE
+                                     ? cover::polygon(poly.colwise() - origin)
+                                     : cover::polygon((pose_at(pose_format, poses, lattice, first + i) * poly).colwise() - origin);
+        bool fr = false;
+        double cs = 0;
+        if (shape == SHAPE_AREA) {
+          const cover::area_generator gen(cm.getResolution(), q);
+          if (op == OP_IS_FREE) {
+            fr = cover::is_free(gen, off, cm);
+          } else {
+            cs = cover::accumulate_cost(gen, off, cm);
+            fr = cs >= 0;
+          }
+        } else {
+          const cover::outline_generator gen(cm.getResolution(), q);
+          if (op == OP_IS_FREE) {
+            fr = cover::is_free(gen, off, cm);
+          } else {
+            cs = cover::accumulate_cost(gen, off, cm);
+            fr = cs >= 0;
+          }
+        }
+        if (is_free) is_free[i] = fr;
+        if (cost) cost[i] = cs;
+        if (status) status[i] = ST_OK;
+      } catch (const std::logic_error&) {
+        if (is_free) is_free[i] = 0;
+        if (cost) cost[i] = std::numeric_limits<double>::quiet_NaN();
+        if (status) status[i] = ST_LOGIC_ERROR;
+      }
+    }
+  });
+  return 0;
+}
+
 int oracle_polygon_batch(const oracle_map* map, const double* poly_xy, int32_t n_vertices, int32_t shape, int32_t op,
                          int32_t pose_format, const void* poses, const oracle_lattice* lattice, int64_t first,
                          int64_t count, uint8_t* is_free, double* cost, uint8_t* status, int64_t* cells_read,

@@ -36,7 +36,7 @@ def test_header_declares_the_expected_entries():
 def test_library_exports_every_declared_symbol(lib):
     missing = [n for n in declared_functions() if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.cover_abi_version() == 1
+    assert lib.cover_abi_version() == 2
 
 
 def test_header_is_plain_c():

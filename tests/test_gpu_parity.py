@@ -976,6 +976,39 @@ def test_gpu_inflation_layer_radii_and_dense_maps(cb, ctx, res, inflation_radius
     np.testing.assert_array_equal(got, expect)
 
 
+def test_generator_offset_overloads(cb, ctx):
+    """is_free / accumulate_cost(gen, offset, map) (impl/costmap.hpp:29-35,74-81) for the outline and area generators
+    of a transformed polygon: cover_poses.cell_offset, against the reference's own offset overloads (oracle/_ref) and
+    the restatement - random poses, a lattice (bit-parallel kernels and the value folds), offsets that push cells off
+    the map."""
+    rng = np.random.default_rng(123)
+    data = mixed_map(rng, 500, 420, lethal=0.002)
+    cmap = cb.Costmap(ctx, data, 0.05, -1.0, 0.5)
+    omap = po.Costmap(data, 0.05, -1.0, 0.5)
+    poses = poses_around(rng, 60_000, -1.0, 20.0)
+    th = np.concatenate([-math.pi + 2 * math.pi * np.arange(7) / 7, [0.0, math.pi / 2]])
+    desc = dict(x0=0.0, dx=0.05, nx=300, y0=1.0, dy=0.05, ny=120, cs=np.stack([np.cos(th), np.sin(th)], 1))
+    backends = [po.default()] + ([po.reference()] if po.reference() is not None else [])
+    for offset in ((0, 0), (7, -3), (-40, 55), (120, 0)):
+        for poly in (RECT, FOOTPRINTS[6], FOOTPRINTS[5]):
+            for shape, prefix in ((po.SHAPE_AREA, "area"), (po.SHAPE_OUTLINE, "outline")):
+                for op_name, op in (("is_free", po.OP_IS_FREE), ("accumulate_cost", po.OP_ACCUMULATE)):
+                    for p_gpu, p_cpu, what in ((poses, poses, "random poses"), (cb.Lattice(**desc), po.Lattice(**desc), "lattice")):
+                        gpu = getattr(cmap, f"{prefix}_{op_name}")(poly, p_gpu, offset=offset)
+                        for be in backends:
+                            r = be.polygon_batch(omap, poly, p_cpu, shape=shape, op=op, threads=8, offset=offset)
+                            ok = (gpu.status == 0) & (r.status == 0)
+                            np.testing.assert_array_equal(gpu.status == 1, r.status == 1)
+                            np.testing.assert_array_equal(gpu.is_free[ok], r.is_free[ok], err_msg=f"{be.name} {prefix} {op_name} {what} offset {offset}")
+                            if op == po.OP_ACCUMULATE:
+                                np.testing.assert_array_equal(gpu.cost[ok], r.cost[ok], err_msg=f"{be.name} {prefix} {op_name} {what} offset {offset}")
+    # an offset is not a shifted origin: cells are truncated towards zero BEFORE the offset is added
+    near_zero = np.array([[1.0, 0.0, -0.98, 0.53]])  # vertices land in (-1, 0) map cells before the offset
+    a = cmap.area_is_free(RECT * 0.01, near_zero, offset=(3, 3))
+    b = po.polygon_batch(omap, RECT * 0.01, near_zero, offset=(3, 3))
+    np.testing.assert_array_equal(a.is_free, b.is_free)
+
+
 def test_area_with_holes(cb, ctx):
     """area_generator(res, polygon_vec): the reference's 'head' with nested holes (test/expand.cpp:241-279) and
     random outline sets, all three ops, against the oracle."""
