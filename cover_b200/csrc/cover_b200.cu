@@ -95,14 +95,15 @@ __global__ void __launch_bounds__(kBlock) k_outline(MapView m, const double* __r
 
 /// The same over the poses an outline sweep of the lattice kernel deferred (persistent grid over the todo list).
 template <int OP>
-__global__ void __launch_bounds__(kBlock) k_outline_drain(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src, long long /*count*/,
+__global__ void __launch_bounds__(kBlock) k_outline_drain(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src, long long count,
                                                          OutView out, const unsigned int* __restrict__ todo,
                                                          const unsigned int* __restrict__ todo_count) {
   extern __shared__ double smem_d[];
   const double* poly = stage_polygon(poly_g, nv, smem_d);
-  const long long n = static_cast<long long>(*todo_count), stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  bool listed;
+  const long long n = todo_items(todo_count, count, listed), stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride)
-    outline_pose<OP>(m, poly, nv, src, static_cast<long long>(todo[j]), out);
+    outline_pose<OP>(m, poly, nv, src, listed ? static_cast<long long>(todo[j]) : j, out);
 }
 
 template <int OP>
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(kBlock) k_area_packed(MapView m, const double*
     defer = store.overflow;
   }
   if (defer) {  // more than two ranges on some row: the list kernel finishes this pose
-    todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i);
+    push_todo(todo, todo_count, i);
     return;
   }
   bool odd = false;
@@ -384,7 +385,7 @@ __device__ __forceinline__ void area_pair_pose(const double* __restrict__ poly, 
   // statuses and deferrals
   bool scan = walk && !w.overflow;
   if (valid && !in_range) store_failure(out, i, ST_COORD_RANGE);
-  if (valid && in_range && (too_big || w.overflow)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i);  // > 2 ranges on a row
+  if (valid && in_range && (too_big || w.overflow)) push_todo(todo, todo_count, i);  // > 2 ranges on a row
   bool odd = false;
   for (int r = 0; r < rows_max; ++r) {
     if (scan && r < rows) {
@@ -501,7 +502,7 @@ __device__ __forceinline__ void area_slot_pose(const double* __restrict__ poly, 
   // statuses and deferrals
   bool scan = walk && !w.overflow;
   if (valid && !in_range) store_failure(out, i, ST_COORD_RANGE);
-  if (valid && in_range && (too_big || w.overflow)) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i);  // too many ranges on a row
+  if (valid && in_range && (too_big || w.overflow)) push_todo(todo, todo_count, i);  // too many ranges on a row
   bool odd = false;
   for (int r = 0; r < rows_max; ++r)
     if (scan && r < rows) odd |= (w.count(r) & 1) != 0;
@@ -543,20 +544,21 @@ __device__ __forceinline__ void area_slot_pose(const double* __restrict__ poly, 
 }
 
 template <int OP, int SLOTS>
-__global__ void __launch_bounds__(kBlock) k_area_slots(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src, OutView out,
+__global__ void __launch_bounds__(kBlock) k_area_slots(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src, long long count, OutView out,
                                                       int rows_cap, const unsigned int* __restrict__ in_list,
                                                       const unsigned int* __restrict__ in_count, unsigned int* __restrict__ todo,
                                                       unsigned int* __restrict__ todo_count) {
   extern __shared__ double smem_d[];
   const double* poly = stage_polygon(poly_g, nv, smem_d);
   uint32_t* table = reinterpret_cast<uint32_t*>(smem_d + 2 * nv);
-  const long long n_items = *in_count;
+  bool listed;
+  const long long n_items = todo_items(in_count, count, listed);
   const long long n_threads = static_cast<long long>(gridDim.x) * blockDim.x;
   // persistent grid over the deferred poses; whole warps iterate together (lock-step walk)
   for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x; base < n_items; base += n_threads) {
     const long long item = base + threadIdx.x;
     const bool valid = item < n_items;
-    const long long i = valid ? static_cast<long long>(in_list[item]) : 0;
+    const long long i = valid ? (listed ? static_cast<long long>(in_list[item]) : item) : 0;
     const Pose T = load_pose(src, i);
     if (src.format == POSE_NONE) area_slot_pose<XF_NONE, OP, SLOTS>(poly, nv, T, m, table, rows_cap, out, i, valid, todo, todo_count);
     else area_slot_pose<XF_PATH_A, OP, SLOTS>(poly, nv, T, m, table, rows_cap, out, i, valid, todo, todo_count);
@@ -1354,11 +1356,11 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
           const long long i_a = i_base + static_cast<long long>(r) * src.nx + ix_a, i_b = i_a + 32;
           if (col_a && i_a >= 0 && i_a < count && !(good_a && y_good)) {
             if (!(xa.ok && y_ok)) store_failure(out, i_a, ST_COORD_RANGE);
-            else todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
+            else push_todo(todo, todo_count, i_a);
           }
           if (col_b && i_b >= 0 && i_b < count && !(good_b && y_good)) {
             if (!(xb.ok && y_ok)) store_failure(out, i_b, ST_COORD_RANGE);
-            else todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
+            else push_todo(todo, todo_count, i_b);
           }
         }
       }
@@ -1542,8 +1544,8 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
             }
           }
           if (slot < 0 || st == kLatUnfit) {  // cache full, hash clash or a shape the packed table cannot hold
-            if (act_a) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
-            if (act_b) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
+            if (act_a) push_todo(todo, todo_count, i_a);
+            if (act_b) push_todo(todo, todo_count, i_b);
             continue;
           }
           if (st != ST_OK) {  // open outline: std::logic_error in the reference
@@ -1622,8 +1624,8 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
               hit_a = ((oa < 32 ? r_lo : r_hi) >> (oa & 31)) & 1u;
               hit_b = ((ob < 32 ? r_lo : r_hi) >> (ob & 31)) & 1u;
             } else if constexpr (LEAN) {
-              if (act_a) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
-              if (act_b) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
+              if (act_a) push_todo(todo, todo_count, i_a);
+              if (act_b) push_todo(todo, todo_count, i_b);
               continue;
             } else if (inside && pv.bits) lattice_rows_planes(pv, span_a, span_m, n_spans, m.pitch, xmin, y_base, lane, maxoff >= 32, oa, ob, hit_a, hit_b);
             else lattice_rows_bytes(m, span_a, span_m, n_spans, xmin, y_base, lane, oa, ob, hit_a, hit_b);
@@ -1655,8 +1657,8 @@ __global__ void __launch_bounds__(kLatThreads, LEAN ? LAT_LEAN_BLOCKS : LAT_MIN_
               if (out.status) out.status[i_b] = ST_OK;
             }
           } else {  // a pose of the group touches the map border: the general kernel resolves out-of-map cells in order
-            if (act_a) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_a);
-            if (act_b) todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i_b);
+            if (act_a) push_todo(todo, todo_count, i_a);
+            if (act_b) push_todo(todo, todo_count, i_b);
           }
         }
       }
@@ -1700,10 +1702,11 @@ __global__ void __launch_bounds__(kBlock) k_area_list(MapView m, const double* _
   const double* poly = stage_polygon(poly_g, nv, smem_d);
   const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long me = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long n_items = todo ? static_cast<long long>(*todo_count) : count;
+  bool listed = false;
+  const long long n_items = todo ? todo_items(todo_count, count, listed) : count;
   const bool none = src.format == POSE_NONE;
   for (long long item = me; item < n_items; item += nthreads) {
-    const long long i = todo ? static_cast<long long>(todo[item]) : item;
+    const long long i = (todo && listed) ? static_cast<long long>(todo[item]) : item;
     const Pose T = load_pose(src, i);
     int x0, y0, x1, y1;
     const bool ok = none ? polygon_bbox<XF_NONE>(poly, nv, T, m, x0, y0, x1, y1) : polygon_bbox<XF_PATH_A>(poly, nv, T, m, x0, y0, x1, y1);
@@ -1750,10 +1753,11 @@ __global__ void __launch_bounds__(kRowsWarps * 32) k_area_rows(MapView m, const 
   RayRec* rays = reinterpret_cast<RayRec*>(smem_d + 2 * nv) + warp * (nv + 1);
   int2* verts = reinterpret_cast<int2*>(reinterpret_cast<RayRec*>(smem_d + 2 * nv) + kRowsWarps * (nv + 1)) + warp * nv;
   const long long n_warps = static_cast<long long>(gridDim.x) * kRowsWarps;
-  const long long n_items = todo ? static_cast<long long>(*todo_count) : count;
+  bool listed = false;
+  const long long n_items = todo ? todo_items(todo_count, count, listed) : count;
   const bool none = src.format == POSE_NONE;
   for (long long item = static_cast<long long>(blockIdx.x) * kRowsWarps + warp; item < n_items; item += n_warps) {
-    const long long i = todo ? static_cast<long long>(todo[item]) : item;
+    const long long i = (todo && listed) ? static_cast<long long>(todo[item]) : item;
     const Pose T = load_pose(src, i);
     WarpFold<OP> wf;
     const int status = none ? area_rows_pose<OP, XF_NONE>(poly, nv, T, m, verts, rays, lane, wf)
@@ -2312,8 +2316,10 @@ struct cover_ctx {
   cudaEvent_t chunk_done = nullptr;
   std::string error;
   int64_t launches = 0;
+  unsigned int todo_header[2] = {0u, 0u}, todo2_header[2] = {0u, 0u};  // {pushed = 0, capacity} staged for the deferred-pose lists
   bool disable_lattice_kernel = false;
   bool disable_words = false;           // COVER_B200_NO_WORDS=1: lattice verdicts through the shape-cache kernel (A/B measurements, its tests)
+  int64_t todo_cap_limit = 0;           // COVER_B200_TODO_CAP: caps every deferred-pose list (tests of the overflow path)
   int words_strip = 4;                  // COVER_B200_WORDS_STRIP: 32-pose words per thread of k_lw_sweep (2, 4 or 8)
   bool disable_planes = false;          // COVER_B200_NO_PLANES=1: lattice verdicts walk the cost bytes (A/B measurements)
   int64_t planes_min_batch = 32768;     // COVER_B200_PLANES_MIN_BATCH: smallest batch that triggers a bit-plane build (tests: 0)
@@ -2894,9 +2900,15 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   const bool lattice = fast && src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices && src.off_x == 0 && src.off_y == 0 &&
                        rows_cap <= kLatMaxRowsCap && !ctx->disable_lattice_kernel;  // (the shape-cache kernel knows no cell offset)
   if (fast) {
-    CU(ctx->todo.ensure(static_cast<size_t>(count) * sizeof(unsigned int)));
-    CU(ctx->todo_count.ensure(sizeof(unsigned int)));
-    CU(cudaMemsetAsync(ctx->todo_count.ptr, 0, sizeof(unsigned int), ctx->stream));
+    // deferred-pose list: {pushed, capacity} + the entries.  A lattice sweep defers next to nothing (poses at the map
+    // border, shapes beyond the tables): a small list, and if it ever overflows the drain kernel takes every pose.  The
+    // per-pose fast passes may defer most of a batch (concave polygons): room for all of it.
+    int64_t todo_cap = (words || (src.format == POSE_LATTICE && !ctx->disable_lattice_kernel)) ? std::min<int64_t>(count, int64_t{4} << 20) : count;
+    if (ctx->todo_cap_limit > 0) todo_cap = std::min(todo_cap, ctx->todo_cap_limit);
+    CU(ctx->todo.ensure(static_cast<size_t>(todo_cap) * sizeof(unsigned int)));
+    CU(ctx->todo_count.ensure(2 * sizeof(unsigned int)));
+    ctx->todo_header[0] = 0u, ctx->todo_header[1] = static_cast<unsigned int>(todo_cap);
+    CU(cudaMemcpyAsync(ctx->todo_count.ptr, ctx->todo_header, 2 * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
     if (words) {
       const int rc = lw_sweep(ctx, map, src, count, out, lw_plan, word_bits);
       if (rc) return rc;
@@ -2969,12 +2981,13 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
         if (!is_convex(poly_host, nv) && rows_cap <= 64) {
           // second per-thread pass over the deferred poses with four ranges per row; its own overflow list feeds the
           // general kernel below
-          CU(ctx->todo2.ensure(static_cast<size_t>(count) * sizeof(unsigned int)));
-          CU(ctx->todo2_count.ensure(sizeof(unsigned int)));
-          CU(cudaMemsetAsync(ctx->todo2_count.ptr, 0, sizeof(unsigned int), ctx->stream));
+          CU(ctx->todo2.ensure(static_cast<size_t>(count) * sizeof(unsigned int)));  // (a concave polygon may defer most of the batch twice)
+          CU(ctx->todo2_count.ensure(2 * sizeof(unsigned int)));
+          ctx->todo2_header[0] = 0u, ctx->todo2_header[1] = static_cast<unsigned int>(ctx->todo_cap_limit > 0 ? std::min<int64_t>(count, ctx->todo_cap_limit) : count);
+          CU(cudaMemcpyAsync(ctx->todo2_count.ptr, ctx->todo2_header, 2 * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
           const size_t smem4 = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * 4 * sizeof(uint32_t);
           const unsigned int grid4 = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(static_cast<long long>(ctx->sm_count) * 4, (count + kBlock - 1) / kBlock)));
-          k_area_slots<OP, 4><<<grid4, kBlock, smem4, ctx->stream>>>(area_view, poly_dev, nv, src, out, rows_cap, ctx->todo.as<unsigned int>(),
+          k_area_slots<OP, 4><<<grid4, kBlock, smem4, ctx->stream>>>(area_view, poly_dev, nv, src, count, out, rows_cap, ctx->todo.as<unsigned int>(),
                                                                     ctx->todo_count.as<unsigned int>(), ctx->todo2.as<unsigned int>(),
                                                                     ctx->todo2_count.as<unsigned int>());
           ++ctx->launches;
@@ -3281,6 +3294,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
   if (const char* e = std::getenv("COVER_B200_NO_PLANES")) ctx->disable_planes = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_NO_WORDS")) ctx->disable_words = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_WORDS_STRIP")) ctx->words_strip = std::atoi(e);
+  if (const char* e = std::getenv("COVER_B200_TODO_CAP")) ctx->todo_cap_limit = std::atoll(e);
   if (const char* e = std::getenv("COVER_B200_PLANES_MIN_BATCH")) ctx->planes_min_batch = std::atoll(e);
   if (const char* e = std::getenv("COVER_B200_MAX_STRETCH")) ctx->max_stretch = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("COVER_B200_CHUNKS")) ctx->pipeline_chunks = std::max(0, std::atoi(e));

@@ -378,6 +378,20 @@ struct Fold<OP_MAX> {  // extension: max of get_cell_cost; any cell outside the 
   }
 };
 
+/// Deferred-pose list: `counter[0]` counts the poses pushed, `counter[1]` is the list's capacity.  A push beyond the
+/// capacity only counts; the kernel that drains the list then sees counter[0] > counter[1] and takes EVERY pose of the
+/// batch instead (results are exact either way - the list is an optimisation, its size a guess).
+__device__ __forceinline__ void push_todo(unsigned int* __restrict__ list, unsigned int* __restrict__ counter, long long i) {
+  const unsigned int at = atomicAdd(counter, 1u);
+  if (at < counter[1]) list[at] = static_cast<unsigned int>(i);
+}
+/// Number of items a drain kernel has to take and whether they are list entries (else: poses 0 .. count - 1).
+__device__ __forceinline__ long long todo_items(const unsigned int* __restrict__ counter, long long count, bool& listed) {
+  const unsigned int n = counter[0], cap = counter[1];
+  listed = n <= cap;
+  return listed ? static_cast<long long>(n) : count;
+}
+
 __device__ __forceinline__ void store_failure(const OutView& o, long long i, int status) {
   if (o.is_free) o.is_free[i] = 0;
   if (o.cost) o.cost[i] = __longlong_as_double(0x7FF8000000000000LL);  // quiet NaN

@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep(MapView m, const uin
         while (b) {
           const int j = __ffs(b) - 1;
           b &= b - 1u;
-          todo[atomicAdd(todo_count, 1u)] = static_cast<unsigned int>(i0 + 32 * w + j);
+          push_todo(todo, todo_count, i0 + 32 * w + j);
         }
       }
     };

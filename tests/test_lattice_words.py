@@ -183,3 +183,30 @@ def test_shape_cache_kernel_still_exact(cb, monkeypatch):
         check(cmap, omap, cb, poly, desc, po.SHAPE_AREA, "shape-cache kernel")
         check(cmap, omap, cb, poly, desc, po.SHAPE_OUTLINE, "shape-cache kernel, outline")
     ctx.close()
+
+
+@pytest.mark.parametrize("env", [{}, {"COVER_B200_NO_WORDS": 1}])
+def test_deferred_pose_list_overflow(cb, monkeypatch, env):
+    """COVER_B200_TODO_CAP=64: every deferred-pose list overflows, so the drain kernels take the whole batch - concave
+    footprints under random poses (the per-pose fast passes defer most of them, twice), a lattice over the map border
+    (the shape-cache kernel defers the border poses) and outlines on it."""
+    ctx = _ctx(cb, monkeypatch, COVER_B200_TODO_CAP=64, **env)
+    rng = np.random.default_rng(507)
+    data = mixed_map(rng, 300, 280, lethal=0.002)
+    cmap = cb.Costmap(ctx, data, 0.05, -0.5, 0.25)
+    omap = po.Costmap(data, 0.05, -0.5, 0.25)
+    th = rng.uniform(-math.pi, math.pi, 30_000)
+    poses = np.stack([np.cos(th), np.sin(th), rng.uniform(-1.0, 15.0, th.size), rng.uniform(-1.0, 14.0, th.size)], 1)
+    for poly in (RECT, FOOTPRINTS[6], FOOTPRINTS[0] * 0.3, FOOTPRINTS[2] * 0.3):
+        for name, op, cost in (("area_is_free", po.OP_IS_FREE, False), ("area_accumulate_cost", po.OP_ACCUMULATE, True)):
+            gpu = getattr(cmap, name)(poly, poses)
+            cpu = po.polygon_batch(omap, poly, poses, op=op, threads=8)
+            np.testing.assert_array_equal(gpu.status, cpu.status)
+            np.testing.assert_array_equal(gpu.is_free, cpu.is_free)
+            if cost:
+                np.testing.assert_array_equal(gpu.cost, cpu.cost)
+    desc = dict(x0=-1.2, dx=0.05, nx=330, y0=-0.6, dy=0.05, ny=150, cs=headings(5))
+    for poly in (RECT, FOOTPRINTS[6]):
+        check(cmap, omap, cb, poly, desc, po.SHAPE_AREA, f"overflowing list, area {env}")
+        check(cmap, omap, cb, poly, desc, po.SHAPE_OUTLINE, f"overflowing list, outline {env}")
+    ctx.close()
