@@ -2319,6 +2319,12 @@ struct cover_ctx {
   unsigned int todo_header[2] = {0u, 0u}, todo2_header[2] = {0u, 0u};  // {pushed = 0, capacity} staged for the deferred-pose lists
   bool disable_lattice_kernel = false;
   bool disable_words = false;           // COVER_B200_NO_WORDS=1: lattice verdicts through the shape-cache kernel (A/B measurements, its tests)
+  // class / shape tables of the last bit-parallel lattice sweep (lw_tables): they depend on the polygon, the lattice and the
+  // map's GEOMETRY only - not on its cells - and are reused while those stay the same (COVER_B200_NO_TABLE_CACHE=1: never)
+  std::string lw_key_base, lw_key;
+  cvr::LwTables lw_cached_t{};
+  cvr::LwGeom lw_cached_g{};
+  bool lw_cache_valid = false, lw_cache_disabled = false;
   int64_t todo_cap_limit = 0;           // COVER_B200_TODO_CAP: caps every deferred-pose list (tests of the overflow path)
   int words_strip = 4;                  // COVER_B200_WORDS_STRIP: 32-pose words per thread of k_lw_sweep (2, 4 or 8)
   bool disable_planes = false;          // COVER_B200_NO_PLANES=1: lattice verdicts walk the cost bytes (A/B measurements)
@@ -2774,6 +2780,16 @@ int lw_prepare_async(cover_ctx* ctx, const cover_map* map, const double* poly_de
   g.nbg = (g.nb + kLwWarps - 1) / kLwWarps;
   auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; };
   g.aligned4 = src.nx % 4 == 0 && src.first % 4 == 0 && aligned(out.is_free) && aligned(out.status);
+  // the tables of the last sweep, if they were made from the same polygon, lattice range and map geometry
+  std::string key = ctx->lw_key_base;
+  key.append(reinterpret_cast<const char*>(&g.it_lo), sizeof g.it_lo).append(reinterpret_cast<const char*>(&g.n_head), sizeof g.n_head);
+  if (!ctx->lw_cache_disabled && ctx->lw_cache_valid && !ctx->lw_key_base.empty() && key == ctx->lw_key) {
+    const int aligned4 = g.aligned4;
+    plan.t = ctx->lw_cached_t, plan.g = ctx->lw_cached_g;
+    plan.g.aligned4 = aligned4;
+    return COVER_OK;
+  }
+  ctx->lw_cache_valid = false;
   // one allocation: [counters | per-heading ints | anchors | shapes | spans | row tables | class bytes]
   LwTables& t = plan.t;
   t.max_shapes = std::min(4096, g.n_head * 64);
@@ -2808,6 +2824,7 @@ int lw_prepare_async(cover_ctx* ctx, const cover_map* map, const double* poly_de
                                                                                               map->plane_words, shape_warps);
   ++ctx->launches;
   CU(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
+  if (!ctx->lw_key_base.empty()) ctx->lw_key = key, ctx->lw_cached_t = plan.t, ctx->lw_cached_g = plan.g, ctx->lw_cache_valid = true;
   return COVER_OK;
 }
 
@@ -3040,6 +3057,18 @@ int polygon_check(cover_ctx* ctx, const cover_map* map, const double* polygon_xy
   CU(ctx->poly.ensure(std::max<size_t>(poly_bytes, 16)));
   if (poly_bytes) CU(cudaMemcpyAsync(ctx->poly.ptr, polygon_xy, poly_bytes, cudaMemcpyHostToDevice, ctx->stream));
   const double* pd = ctx->poly.as<double>();
+  ctx->lw_key_base.clear();
+  if (poses->format == COVER_POSE_LATTICE && poses->lattice.cs) {  // everything the class / shape tables of a lattice sweep depend on
+    auto put = [ctx](const void* p, size_t n) { ctx->lw_key_base.append(static_cast<const char*>(p), n); };
+    const cover_lattice& L = poses->lattice;
+    const MapView& v = map->view;
+    put(&nv, sizeof nv), put(&shape, sizeof shape), put(polygon_xy, poly_bytes);
+    put(&L.x0, sizeof L.x0), put(&L.dx, sizeof L.dx), put(&L.y0, sizeof L.y0), put(&L.dy, sizeof L.dy);
+    put(&L.nx, sizeof L.nx), put(&L.ny, sizeof L.ny), put(&L.ntheta, sizeof L.ntheta), put(L.cs, static_cast<size_t>(L.ntheta) * 2 * sizeof(double));
+    put(poses->cell_offset, sizeof poses->cell_offset);
+    put(&v.size_x, sizeof v.size_x), put(&v.size_y, sizeof v.size_y), put(&v.inv_res, sizeof v.inv_res), put(&v.origin_x, sizeof v.origin_x), put(&v.origin_y, sizeof v.origin_y);
+    put(&map->plane_words, sizeof map->plane_words);
+  }
   // costmap upload still in flight: a lattice sweep starts as soon as the rows under its window have landed
   int row_lo = 0, row_hi = map->view.size_y - 1;  // map rows the check can read
   if (poses->format == COVER_POSE_LATTICE && poses->lattice.cs && lattice_row_range(map, polygon_xy, nv, poses, row_lo, row_hi))
@@ -3295,6 +3324,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
   if (const char* e = std::getenv("COVER_B200_NO_WORDS")) ctx->disable_words = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_WORDS_STRIP")) ctx->words_strip = std::atoi(e);
   if (const char* e = std::getenv("COVER_B200_TODO_CAP")) ctx->todo_cap_limit = std::atoll(e);
+  if (const char* e = std::getenv("COVER_B200_NO_TABLE_CACHE")) ctx->lw_cache_disabled = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_PLANES_MIN_BATCH")) ctx->planes_min_batch = std::atoll(e);
   if (const char* e = std::getenv("COVER_B200_MAX_STRETCH")) ctx->max_stretch = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("COVER_B200_CHUNKS")) ctx->pipeline_chunks = std::max(0, std::atoi(e));

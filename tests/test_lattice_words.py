@@ -210,3 +210,35 @@ def test_deferred_pose_list_overflow(cb, monkeypatch, env):
         check(cmap, omap, cb, poly, desc, po.SHAPE_AREA, f"overflowing list, area {env}")
         check(cmap, omap, cb, poly, desc, po.SHAPE_OUTLINE, f"overflowing list, outline {env}")
     ctx.close()
+
+
+def test_table_cache_across_calls(cb, monkeypatch):
+    """The class / shape tables are kept from one sweep to the next while polygon, lattice range, offset and map geometry
+    stay the same - and only then: same sweep twice, a new costmap image in between (the tables do not depend on the cells),
+    another polygon / lattice / sub-range / outline / offset, then the first again."""
+    ctx = _ctx(cb, monkeypatch)
+    rng = np.random.default_rng(508)
+    images = [mixed_map(rng, 400, 360, lethal=0.002), mixed_map(rng, 400, 360, lethal=0.004)]
+    cmap = cb.Costmap(ctx, images[0], 0.05, -1.0, 0.5)
+    cs = headings(6)
+    d1 = dict(x0=-0.3, dx=0.05, nx=300, y0=0.7, dy=0.05, ny=90, cs=cs)
+    d2 = dict(x0=-0.3, dx=0.05, nx=300, y0=0.7000001, dy=0.05, ny=90, cs=cs)
+    calls = [(RECT, d1, po.SHAPE_AREA, 0, None, None), (RECT, d1, po.SHAPE_AREA, 0, None, None), (RECT, d1, po.SHAPE_OUTLINE, 0, None, None),
+             (FOOTPRINTS[6], d1, po.SHAPE_AREA, 0, None, None), (RECT, d2, po.SHAPE_AREA, 0, None, None), (RECT, d1, po.SHAPE_AREA, 27000 * 2 + 5, 60000, None),
+             (RECT, d1, po.SHAPE_AREA, 0, None, (3, -2)), (RECT, d1, po.SHAPE_AREA, 0, None, None)]
+    for rep in range(2):
+        for k, (poly, desc, shape, first, count, offset) in enumerate(calls):
+            image = images[(k + rep) % 2]
+            cmap.upload(image)
+            omap = po.Costmap(image, 0.05, -1.0, 0.5)
+            fn = cmap.area_is_free if shape == po.SHAPE_AREA else cmap.outline_is_free
+            launches = ctx.launch_count
+            gpu = fn(poly, cb.Lattice(**desc), first=first, count=count, offset=offset)
+            cpu = po.polygon_batch(omap, poly, po.Lattice(**desc), shape=shape, first=first, count=count, threads=8, offset=offset)
+            np.testing.assert_array_equal(gpu.is_free, cpu.is_free, err_msg=f"call {k} rep {rep}")
+            np.testing.assert_array_equal(gpu.status, cpu.status)
+            if rep == 0 and k == 0:
+                first_launches = ctx.launch_count - launches
+            if rep == 0 and k == 1:  # the very same sweep again: no k_lw_prepare launch
+                assert ctx.launch_count - launches == first_launches - 1
+    ctx.close()
