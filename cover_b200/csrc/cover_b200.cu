@@ -2321,6 +2321,8 @@ struct cover_ctx {
   bool disable_words = false;           // COVER_B200_NO_WORDS=1: lattice verdicts through the shape-cache kernel (A/B measurements, its tests)
   // class / shape tables of the last bit-parallel lattice sweep (lw_tables): they depend on the polygon, the lattice and the
   // map's GEOMETRY only - not on its cells - and are reused while those stay the same (COVER_B200_NO_TABLE_CACHE=1: never)
+  std::string theta_host;                // bytes of the heading table currently in `theta` (re-uploaded only when they change)
+  const void* theta_dev = nullptr;
   std::string lw_key_base, lw_key;
   cvr::LwTables lw_cached_t{};
   cvr::LwGeom lw_cached_g{};
@@ -2639,7 +2641,11 @@ int stage_poses(cover_ctx* ctx, const cover_poses* poses, PoseSource& src) {
       if (poses->first < 0 || poses->first + poses->count > total) return fail(ctx, COVER_E_INVALID_ARG, "lattice range out of bounds");
       const size_t bytes = static_cast<size_t>(L.ntheta) * 2 * sizeof(double);
       CU(ctx->theta.ensure(bytes));
-      CU(cudaMemcpyAsync(ctx->theta.ptr, L.cs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+      // (a planner sweeps the same heading table every cycle: the device copy is kept while the bytes are the same)
+      if (ctx->theta_host.size() != bytes || ctx->theta_dev != ctx->theta.ptr || std::memcmp(ctx->theta_host.data(), L.cs, bytes) != 0) {
+        CU(cudaMemcpyAsync(ctx->theta.ptr, L.cs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->theta_host.assign(reinterpret_cast<const char*>(L.cs), bytes), ctx->theta_dev = ctx->theta.ptr;
+      }
       src.theta_cs = ctx->theta.as<double>();
       src.first = poses->first;
       src.x0 = L.x0, src.dx = L.dx, src.y0 = L.y0, src.dy = L.dy;
@@ -2752,6 +2758,9 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_MAX>));
   set(reinterpret_cast<const void*>(&k_lw_prepare));
+  set(reinterpret_cast<const void*>(&k_lw_sweep_simple<2>));
+  set(reinterpret_cast<const void*>(&k_lw_sweep_simple<4>));
+  set(reinterpret_cast<const void*>(&k_lw_sweep_simple<8>));
   return e;
 }
 
@@ -2765,6 +2774,7 @@ size_t lw_prepare_smem(int nv, int shape_warps) {
 struct LwPlan {
   LwTables t{};
   LwGeom g{};
+  int nk = kPlaneCount;  // planes the simple sweep stages in shared memory: 5 while no span can be 32 cells wide, else all 6
 };
 
 /// First half of a bit-parallel lattice sweep (lattice_words.cuh): the class tables of every heading of the batch and one
@@ -2830,13 +2840,18 @@ int lw_prepare_async(cover_ctx* ctx, const cover_map* map, const double* poly_de
 
 template <int W>
 void launch_lw_sweeps(cover_ctx* ctx, const cover_map* map, const uint32_t* bits, const PoseSource& src, int64_t count, const OutView& out,
-                      const LwTables& t, LwGeom g, bool simple, cudaStream_t stream) {
+                      const LwTables& t, LwGeom g, int nk, bool simple, cudaStream_t stream) {
   g.ns = (src.nx + 32 * W - 1) / (32 * W);
-  const dim3 grid(static_cast<unsigned int>(g.nbg) * g.ns, static_cast<unsigned int>(g.n_head));
-  unsigned int* todo = ctx->todo.as<unsigned int>();
-  unsigned int* todo_count = ctx->todo_count.as<unsigned int>();
-  if (simple) k_lw_sweep<W, true><<<grid, kLwWarps * 32, 0, stream>>>(map->view, bits, map->ypitch, map->plane_words, src, count, out, t, g, todo, todo_count);
-  else k_lw_sweep<W, false><<<grid, kLwWarps * 32, 0, stream>>>(map->view, bits, map->ypitch, map->plane_words, src, count, out, t, g, todo, todo_count);
+  const dim3 grid(static_cast<unsigned int>(g.nbg), static_cast<unsigned int>(g.ns), static_cast<unsigned int>(g.n_head));
+  if (simple) {
+    // shared-memory tile of the planes (+ the transposition buffer of the byte outputs)
+    const size_t smem = static_cast<size_t>(nk) * (W + kLwTileColsExtra) * kLwTileRows * sizeof(uint32_t) +
+                        ((out.is_free || out.status) ? static_cast<size_t>(kLwWarps) * 32 * 2 * W * sizeof(uint32_t) : 0);
+    k_lw_sweep_simple<W><<<grid, kLwWarps * 32, smem, stream>>>(map->view, bits, map->ypitch, map->plane_words, src, count, out, t, g, nk);
+  } else {
+    k_lw_sweep_general<W><<<grid, kLwWarps * 32, 0, stream>>>(map->view, bits, map->ypitch, map->plane_words, src, count, out, t, g,
+                                                              ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
+  }
 }
 
 /// Second half: the sweep over the lethal bit planes `bits`, two launches side by side - the tasks of single-shape
@@ -2844,9 +2859,9 @@ void launch_lw_sweeps(cover_ctx* ctx, const cover_map* map, const uint32_t* bits
 /// auxiliary stream, where k_lw_prepare just finished.  Poses neither can finish land on ctx->todo (already reset).
 int lw_sweep(cover_ctx* ctx, const cover_map* map, const PoseSource& src, int64_t count, const OutView& out, const LwPlan& plan, const uint32_t* bits) {
   auto launch = [&](bool simple, cudaStream_t stream) {
-    if (ctx->words_strip == 8) launch_lw_sweeps<8>(ctx, map, bits, src, count, out, plan.t, plan.g, simple, stream);
-    else if (ctx->words_strip == 2) launch_lw_sweeps<2>(ctx, map, bits, src, count, out, plan.t, plan.g, simple, stream);
-    else launch_lw_sweeps<4>(ctx, map, bits, src, count, out, plan.t, plan.g, simple, stream);
+    if (ctx->words_strip == 8) launch_lw_sweeps<8>(ctx, map, bits, src, count, out, plan.t, plan.g, plan.nk, simple, stream);
+    else if (ctx->words_strip == 2) launch_lw_sweeps<2>(ctx, map, bits, src, count, out, plan.t, plan.g, plan.nk, simple, stream);
+    else launch_lw_sweeps<4>(ctx, map, bits, src, count, out, plan.t, plan.g, plan.nk, simple, stream);
   };
   // the auxiliary stream needs what the main stream did so far: planes, zeroed outputs and counters
   CU(cudaEventRecord(ctx->aux_planes, ctx->stream));
@@ -2883,6 +2898,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       (src.first + count - 1) / (static_cast<long long>(src.nx) * src.ny) - src.first / (static_cast<long long>(src.nx) * src.ny) < 65535) {
     int rc = lw_prepare_async(ctx, map, poly_dev, nv, shape == SHAPE_OUTLINE, src, count, out, lw_plan);  // (beside the plane build)
     if (rc) return rc;
+    lw_plan.nk = rows_cap - 4 < 32 ? kPlaneCount - 1 : kPlaneCount;  // (rows_cap bounds the bounding box's extent in cells, + 4)
     PlaneView pvw{nullptr, 0, 0, nullptr, 0};
     rc = ensure_planes(ctx, map, row_lo, row_hi, pvw);
     if (rc) return rc;

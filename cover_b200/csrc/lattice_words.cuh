@@ -43,7 +43,7 @@ typedef int4 LwSpan;
 struct LwShape {
   int status, n_spans, span_first;
   int xb, x1, yb, rows;  // bounding box of the vertices relative to vertex 0: x in [xb, x1], y in [yb, yb + rows - 1]
-  int pad;
+  int pad;               // the largest plane index k = floor(log2(width)) of its spans
 };
 
 struct LwTables {
@@ -117,7 +117,7 @@ __device__ __forceinline__ LwShape lw_rasterise(int2* verts, int nv, RayRec* ray
   const int y0 = __reduce_min_sync(0xFFFFFFFFu, ly0), y1 = __reduce_max_sync(0xFFFFFFFFu, ly1);
   const int n_rays = build_rays_from_verts(verts, nv, rays, lane);
   const bool single_row = y0 == y1;
-  int status = ST_OK, n_total = 0, span_first = 0;
+  int status = ST_OK, n_total = 0, span_first = 0, kmax = 0;
   if (y1 - y0 > 30000 || x1 - x0 > 1000000) status = kLwUnfit;  // (dy travels in 16 bits)
   for (int pass = 0; pass < 2 && status == ST_OK; ++pass) {
     int base = 0;
@@ -137,6 +137,7 @@ __device__ __forceinline__ LwShape lw_rasterise(int2* verts, int nv, RayRec* ray
         bool o2 = false, v2 = false;
         lw_row_spans(rays, n_rays, y, outline != 0, single_row, x0, x1, o2, v2, [&](int k, int x, int width) {
           const int lg = 31 - __clz(width);
+          kmax = max(kmax, lg);
           dst[k] = make_int4(x, static_cast<int>(lg * plane_words) + y, width - (1 << lg), (y + 32768) | (lg << 16));
         });
       }
@@ -155,7 +156,8 @@ __device__ __forceinline__ LwShape lw_rasterise(int2* verts, int nv, RayRec* ray
       }
     }
   }
-  return LwShape{status, n_total, span_first, x0, x1, y0, y1 - y0 + 1, 0};
+  kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
+  return LwShape{status, n_total, span_first, x0, x1, y0, y1 - y0 + 1, kmax};
 }
 
 /// Per heading (one CTA): column and row classes, then one rasterisation per (x class, y class).
@@ -354,7 +356,7 @@ __device__ __forceinline__ void lw_walk_lanes(const uint32_t* __restrict__ bits,
 struct LwGeom {
   int it_lo, n_head;
   int nb, ns;    // 32-row blocks per heading, 32 W-column strips per row
-  int nbg;       // groups of kLwWarps row blocks: grid.x = nbg * ns, grid.y = n_head
+  int nbg;       // groups of kLwWarps row blocks: grid = (nbg, ns, n_head)
   int aligned4;  // pose index of (row, strip start) is a multiple of 4 for every row: verdict bytes go out as words
 };
 
@@ -421,83 +423,181 @@ __device__ __forceinline__ void lw_store(const OutView& out, const uint32_t (&fr
   }
 }
 
-/// SIMPLE: the tasks of headings with a single shape whose poses all lie inside the map (nearly all of them) - the walk
-/// and nothing else.  The other instantiation takes the remaining tasks: several classes per heading (masked walks),
-/// the map border (bounds-checked walk, poses outside are not free), statuses, deferrals.
-template <int W, bool SIMPLE>
-__global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep(MapView m, const uint32_t* __restrict__ bits, int ypitch, long long plane_words,
-                                                           PoseSource src, long long count, OutView out, LwTables t, LwGeom g,
-                                                           unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count) {
-  __shared__ LwSpan s_spans[kLwWarps][kLwSpanCache];
-  __shared__ uint32_t s_bits[kLwWarps][32][2 * W];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // the warps of a CTA sweep vertically adjacent row blocks of one strip and share their halo rows in L1
-  const int sb = blockIdx.x / g.nbg, rb = (blockIdx.x - sb * g.nbg) * kLwWarps + warp;
-  if (rb >= g.nb) return;
-  const int h = blockIdx.y, it = g.it_lo + h;
-  const int iy = rb * 32 + lane, ix0 = sb * 32 * W;
-  const bool row_ok = iy < src.ny;
-  const long long i0 = (static_cast<long long>(it) * src.ny + iy) * src.nx + ix0 - src.first;  // pose index of (iy, ix0) in this batch
-  uint32_t valid[W];
-  bool any_valid = false;
-  {
-    const bool whole = i0 >= 0 && i0 + 32 * W <= count;  // (the usual row: inside the batch)
+/// One warp's task: heading h, lattice rows rb * 32 + lane, columns ix0 .. ix0 + 32 W - 1.
+template <int W>
+struct LwTask {
+  int h, it, iy, ix0, y0c;
+  bool row_ok, any_valid;
+  long long i0;          // pose index of (iy, ix0) in this batch (may lie outside [0, count) for the batch's first / last rows)
+  uint32_t valid[W];     // poses of this lane's row that belong to the batch
+  unsigned live_rows;    // lanes with at least one such pose
+};
+
+/// Fills the task of this warp; false when it has no pose of the batch (the whole warp leaves).
+template <int W>
+__device__ __forceinline__ bool lw_task_setup(const PoseSource& src, long long count, const LwTables& t, const LwGeom& g, int rb, int sb, int h,
+                                              int lane, LwTask<W>& k) {
+  k.h = h, k.it = g.it_lo + h;
+  k.iy = rb * 32 + lane, k.ix0 = sb * 32 * W;
+  k.row_ok = rb < g.nb && k.iy < src.ny;
+  k.i0 = (static_cast<long long>(k.it) * src.ny + k.iy) * src.nx + k.ix0 - src.first;
+  k.any_valid = false;
+  const bool whole = k.i0 >= 0 && k.i0 + 32 * W <= count;  // (the usual row: inside the batch)
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
-      uint32_t v = 0u;
-      if (row_ok) {
-        const int in_row = src.nx - (ix0 + 32 * w);  // columns of this word inside the lattice row
-        if (whole) {
-          v = in_row >= 32 ? 0xFFFFFFFFu : (in_row > 0 ? (1u << in_row) - 1u : 0u);
-        } else {  // bits j with ix0 + 32 w + j < nx and 0 <= i0 + 32 w + j < count
-          const long long lo = max(0ll, -(i0 + 32 * w)), hi = min(min(32ll, static_cast<long long>(in_row)), count - (i0 + 32 * w));
-          if (hi > lo) v = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & (0xFFFFFFFFu << lo);
-        }
+  for (int w = 0; w < W; ++w) {
+    uint32_t v = 0u;
+    if (k.row_ok) {
+      const int in_row = src.nx - (k.ix0 + 32 * w);  // columns of this word inside the lattice row
+      if (whole) {
+        v = in_row >= 32 ? 0xFFFFFFFFu : (in_row > 0 ? (1u << in_row) - 1u : 0u);
+      } else {  // bits j with ix0 + 32 w + j < nx and 0 <= i0 + 32 w + j < count
+        const long long lo = max(0ll, -(k.i0 + 32 * w)), hi = min(min(32ll, static_cast<long long>(in_row)), count - (k.i0 + 32 * w));
+        if (hi > lo) v = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & (0xFFFFFFFFu << lo);
       }
-      valid[w] = v;
-      any_valid |= v != 0u;
     }
+    k.valid[w] = v;
+    k.any_valid |= v != 0u;
   }
-  const unsigned live_rows = __ballot_sync(0xFFFFFFFFu, any_valid);
-  if (live_rows == 0u) return;
-  const int y0c = row_ok ? t.yc0[static_cast<long long>(h) * src.ny + iy] : 0;
-  const int base = t.shape_base[h];
-  const int wcols = (m.size_x + 31) / 32 + 3;
-  // ---- is this a simple task?  (evaluated identically by both instantiations: exactly one of them goes on)
-  bool simple = t.simple[h] != 0;
+  k.live_rows = __ballot_sync(0xFFFFFFFFu, k.any_valid);
+  k.y0c = k.row_ok ? t.yc0[static_cast<long long>(h) * src.ny + k.iy] : 0;
+  return k.live_rows != 0u;
+}
+
+/// Is this a SIMPLE task - a heading with a single shape, every pose of the task inside the map?  (Evaluated identically
+/// by both sweep kernels: exactly one of them takes the task.)  x_base = map column of vertex 0 for the task's first pose.
+template <int W>
+__device__ __forceinline__ bool lw_task_simple(const LwTask<W>& k, const MapView& m, const LwTables& t, int& x_base) {
+  x_base = 0;
+  if (t.simple[k.h] == 0) return false;
+  const LwShape* shp = t.shapes + t.shape_base[k.h];
+  x_base = k.ix0 + t.xanchor[k.h * kLwClasses];
+  const bool x_in = x_base + shp->xb >= 0 && x_base + 32 * W - 1 + shp->x1 < m.size_x;
+  const bool y_in = k.y0c + shp->yb >= 0 && k.y0c + shp->yb + shp->rows <= m.size_y;
+  return x_in && __all_sync(0xFFFFFFFFu, y_in || !k.any_valid);
+}
+
+// Shared-memory tile of the bit planes for one CTA of the simple sweep: [plane k][column][row], rows fastest, so that the
+// lanes of a warp (consecutive map rows) read consecutive words and the W + 2 words of a window are a fixed distance apart.
+constexpr int kLwTileRows = 288;                // 8 row blocks of 32 + the shape's rows + alignment slack
+constexpr int kLwTileColsExtra = 3;             // columns beyond W: the shape's x extent (< 32 cells + the window's two extra words)
+
+/// The tasks of headings with a single shape whose poses all lie inside the map (nearly all of them): the walk and nothing
+/// else.  The eight warps of a CTA sweep eight vertically adjacent row blocks of one strip; the plane words they need -
+/// (256 + shape rows) map rows x (W + 3) word columns x NK planes - are first copied into shared memory (cp.async,
+/// 16 bytes each), so that the walk's loads are LDS with immediate offsets: no address arithmetic per word, no L1 tag
+/// traffic, ~25 cycles instead of an L1 / L2 round trip.  Falls back to loading from the planes in global memory when the
+/// shape does not fit the tile (wider than 32 cells, more than `nk` planes, more than 128 spans, rows not at cell pitch).
+template <int W>
+__global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep_simple(MapView m, const uint32_t* __restrict__ bits, int ypitch, long long plane_words,
+                                                                  PoseSource src, long long count, OutView out, LwTables t, LwGeom g, int nk) {
+  extern __shared__ uint4 lw_smem[];
+  __shared__ LwSpan s_local[kLwSpanCache];
+  __shared__ int s_ymin, s_ymax, s_active;
+  constexpr int NC = W + kLwTileColsExtra, TH = kLwTileRows;
+  uint32_t* tile = reinterpret_cast<uint32_t*>(lw_smem);                  // [nk][NC][TH]
+  uint32_t(*s_bits)[2 * W] = reinterpret_cast<uint32_t(*)[2 * W]>(tile + nk * NC * TH);  // [warp * 32 + lane][2 W] (byte outputs only)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sb = blockIdx.y, rb = blockIdx.x * kLwWarps + warp;  // grid: (row block groups, strips, headings)
+  const int h = blockIdx.z;
+  if (threadIdx.x == 0) s_ymin = 0x7FFFFFFF, s_ymax = -0x7FFFFFFF - 1, s_active = 0;
+  __syncthreads();
+  LwTask<W> k;
   int x_base = 0;
-  if (simple) {
-    const LwShape* shp = t.shapes + base;
-    x_base = ix0 + t.xanchor[h * kLwClasses];
-    const bool x_in = x_base + shp->xb >= 0 && x_base + 32 * W - 1 + shp->x1 < m.size_x;
-    const bool y_in = y0c + shp->yb >= 0 && y0c + shp->yb + shp->rows <= m.size_y;
-    simple = x_in && __all_sync(0xFFFFFFFFu, y_in || !any_valid);
+  bool active = lw_task_setup<W>(src, count, t, g, rb, sb, h, lane, k);
+  if (active) active = lw_task_simple<W>(k, m, t, x_base);
+  if (active) {
+    const int lo = __reduce_min_sync(0xFFFFFFFFu, k.any_valid ? k.y0c : 0x7FFFFFFF), hi = __reduce_max_sync(0xFFFFFFFFu, k.any_valid ? k.y0c : -0x7FFFFFFF - 1);
+    if (lane == 0) atomicMin(&s_ymin, lo), atomicMax(&s_ymax, hi), s_active = 1;
   }
-  if (simple != SIMPLE) return;
+  __syncthreads();
+  if (!s_active) return;
+  // (CTA-uniform from here: the heading's one shape, the strip's x_base)
+  const LwShape* shp = t.shapes + t.shape_base[h];
+  const int n_spans = shp->n_spans, xb = shp->xb, x1 = shp->x1, yb = shp->yb, rows = shp->rows, kmax = shp->pad;
+  const LwSpan* spans = t.spans + shp->span_first;
+  const int xs_base = sb * 32 * W + t.xanchor[h * kLwClasses] + xb;  // map column of the shape's leftmost cell for the strip's first pose
+  const int c_min = xs_base >> 5, xr = xs_base & 31;
+  const int y_t0 = (s_ymin + yb) & ~3, rows_needed = s_ymax + yb + rows - y_t0;
+  const bool tile_ok = n_spans <= kLwSpanCache && kmax < nk && rows_needed <= TH && ((xr + (x1 - xb)) >> 5) + W + 2 <= NC;
+  if (tile_ok) {
+    // one (plane, column) segment = rows_needed consecutive words in global memory: a warp copies it 16 bytes per lane
+    const int chunks = (rows_needed + 3) >> 2, n_cols = ((xr + (x1 - xb)) >> 5) + W + 2;
+    for (int kk = 0; kk <= kmax; ++kk) {
+      for (int col = warp; col < n_cols; col += kLwWarps) {
+        const uint32_t* gsrc = bits + kk * plane_words + static_cast<long long>(c_min + col) * ypitch + y_t0;
+        const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(tile + (kk * NC + col) * TH));
+        for (int ch = lane; ch < chunks; ch += 32) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * ch), "l"(gsrc + 4 * ch));
+      }
+    }
+    for (int sidx = threadIdx.x; sidx < n_spans; sidx += blockDim.x) {
+      const LwSpan sp = spans[sidx];
+      const int kk = sp.w >> 16, dy = (sp.w & 0xFFFF) - 32768;
+      s_local[sidx] = make_int4(sp.x - xb, kk * NC * TH + (dy - yb), sp.z, 0);
+    }
+    asm volatile("cp.async.commit_group;" ::);
+    asm volatile("cp.async.wait_group 0;" ::);
+  }
+  __syncthreads();
+  if (!active) return;
 
   uint32_t hit[W];
 #pragma unroll
   for (int w = 0; w < W; ++w) hit[w] = 0u;
-
-  if constexpr (SIMPLE) {
-    const LwShape* shp = t.shapes + base;
-    const int n_spans = shp->n_spans;
-    const LwSpan* spans = t.spans + shp->span_first;
-    const int y_first = __shfl_sync(0xFFFFFFFFu, y0c, __ffs(live_rows) - 1);  // (every lane takes part: never inside a conditional)
-    const int y_lane = any_valid ? y0c : y_first;  // idle lanes read where a live one reads
-    if (n_spans <= kLwSpanCache) {
-      for (int k = lane; k < n_spans; k += 32) s_spans[warp][k] = spans[k];
-      __syncwarp();
-      lw_walk<W>(bits, ypitch, s_spans[warp], n_spans, x_base, y_lane, hit);
-    } else {
-      lw_walk<W>(bits, ypitch, spans, n_spans, x_base, y_lane, hit);
-    }
-    uint32_t fr[W], none[W];
+  const int y_first = __shfl_sync(0xFFFFFFFFu, k.y0c, __ffs(k.live_rows) - 1);  // (every lane takes part: never inside a conditional)
+  const int y_lane = k.any_valid ? k.y0c : y_first;  // idle lanes read where a live one reads
+  if (tile_ok) {
+    const uint32_t* __restrict__ base = tile + (y_lane + yb - y_t0);
+#pragma unroll 4
+    for (int s = 0; s < n_spans; ++s) {
+      const LwSpan sp = s_local[s];
+      const int tx = xr + sp.x;
+      const int sh = tx & 31;
+      const uint32_t* __restrict__ p = base + (tx >> 5) * TH + sp.y;
+      uint32_t L[W + 2];
 #pragma unroll
-    for (int w = 0; w < W; ++w) fr[w] = ~hit[w] & valid[w], none[w] = 0u;
-    lw_store<W>(out, fr, valid, none, i0, any_valid, live_rows, true, g.aligned4, warp, lane, s_bits[warp]);
-    return;
+      for (int j = 0; j < W + 2; ++j) L[j] = p[j * TH];
+      const int sh2 = sh + sp.z;  // second power-of-two window: `tail` cells later (the same window again for a power-of-two width)
+      if (sh2 < 32) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) hit[w] |= __funnelshift_r(L[w], L[w + 1], sh) | __funnelshift_r(L[w], L[w + 1], sh2);
+      } else {
+#pragma unroll
+        for (int w = 0; w < W; ++w) hit[w] |= __funnelshift_r(L[w], L[w + 1], sh) | __funnelshift_r(L[w + 1], L[w + 2], sh2 - 32);
+      }
+    }
   } else {
+    lw_walk<W>(bits, ypitch, spans, n_spans, x_base, y_lane, hit);
+  }
+  uint32_t fr[W], none[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) fr[w] = ~hit[w] & k.valid[w], none[w] = 0u;
+  lw_store<W>(out, fr, k.valid, none, k.i0, k.any_valid, k.live_rows, true, g.aligned4, warp, lane, s_bits + warp * 32);
+}
+
+/// The remaining tasks: several classes per heading (masked walks, every lane the shape of its own row), the map border
+/// (bounds-checked walk, a pose whose span leaves the map is not free), statuses, deferrals.
+template <int W>
+__global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep_general(MapView m, const uint32_t* __restrict__ bits, int ypitch, long long plane_words,
+                                                                   PoseSource src, long long count, OutView out, LwTables t, LwGeom g,
+                                                                   unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count) {
+  __shared__ uint32_t s_bits[kLwWarps][32][2 * W];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sb = blockIdx.y, rb = blockIdx.x * kLwWarps + warp;  // grid: (row block groups, strips, headings)
+  const int h = blockIdx.z;
+  LwTask<W> k;
+  if (!lw_task_setup<W>(src, count, t, g, rb, sb, h, lane, k)) return;
+  int x_simple;
+  if (lw_task_simple<W>(k, m, t, x_simple)) return;  // (k_lw_sweep_simple's)
+  const int iy = k.iy, ix0 = k.ix0, y0c = k.y0c;
+  const bool row_ok = k.row_ok, any_valid = k.any_valid;
+  const long long i0 = k.i0;
+  const int base = t.shape_base[h];
+  const int wcols = (m.size_x + 31) / 32 + 3;
+  uint32_t hit[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) hit[w] = 0u;
+  uint32_t (&valid)[W] = k.valid;
+  {
     const int yc = row_ok ? t.ycls[static_cast<long long>(h) * src.ny + iy] : kLwNone;
     int cw[W];
 #pragma unroll
@@ -590,7 +690,7 @@ __global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep(MapView m, const uin
       special |= skip[w] != 0u;
     }
     const bool plain = !__any_sync(0xFFFFFFFFu, special);
-    lw_store<W>(out, fr, valid, skip, i0, any_valid, live_rows, plain, g.aligned4, warp, lane, s_bits[warp]);
+    lw_store<W>(out, fr, valid, skip, i0, any_valid, k.live_rows, plain, g.aligned4, warp, lane, s_bits[warp]);
   }
 }
 
