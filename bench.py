@@ -472,7 +472,8 @@ def run_gpu(args) -> None:
     ctx.synchronize()
 
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:  # (one nvidia-smi poller per box: eight of them contend with the ranks' launch threads for the driver)
+        sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = ctx.launch_count
