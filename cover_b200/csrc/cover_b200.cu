@@ -6,7 +6,9 @@
 //                        folds from per-row prefix / sliding-max tables (the headline path)
 //   k_area_pair<OP>      area checks, arbitrary poses, rows with <= 2 ranges: thread = pose, the warp's 32 outline
 //                        walks fused in lock-step, 64-bit pair table in shared memory
-//   k_area_slots<OP,4>   second per-thread pass over the poses k_area_pair deferred (non-convex polygons): 4 ranges/row
+//   k_area_quad<OP>      the same walk for non-convex polygons up to 250 cells wide: four 8+8-bit ranges per (row, thread)
+//                        in the same 64-bit word, one pass
+//   k_area_slots<OP,4>   second per-thread pass over the poses k_area_pair deferred: 4 ranges/row (COVER_B200_NO_QUAD=1, A/B only)
 //   k_area_rows<OP>      area checks, any polygon <= 256 vertices: warp = pose, lane = scan row (area_rows.cuh);
 //                        also drains the poses the two kernels above defer;  k_area_rows_multi<OP>: holes
 //   k_area_list<OP>      area checks for > 256 vertices / many short edges: per-thread sorted lists in global scratch
@@ -563,6 +565,197 @@ __global__ void __launch_bounds__(kBlock) k_area_slots(MapView m, const double* 
     if (src.format == POSE_NONE) area_slot_pose<XF_NONE, OP, SLOTS>(poly, nv, T, m, table, rows_cap, out, i, valid, todo, todo_count);
     else area_slot_pose<XF_PATH_A, OP, SLOTS>(poly, nv, T, m, table, rows_cap, out, i, valid, todo, todo_count);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_area_quad<OP>: the per-thread pass of NON-CONVEX polygons whose bounding box is at most 250 cells wide.  Same
+// lock-step walk as k_area_pair, but a (row, thread) word of the shared-memory table holds FOUR ranges of 8+8 bits
+// (0xFFFF = empty, filled from the low end in insertion order) - an L, an S, a comb rarely puts more than four on a
+// row - so one pass finishes what k_area_pair + k_area_slots needed two for, at the pair kernel's occupancy.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kQuadMaxWidth = 250;  // relative x in 8 bits, and no entry is ever 0xFFFF
+constexpr int kQuadMaxRows = 96;    // taller polygons (four-metre combs at 5 cm) do better with a warp per pose (k_area_rows)
+
+struct QuadWalker {
+  uint2* tab;  // &table[0][threadIdx.x], stride = blockDim.x; .x = entries 0 and 1, .y = entries 2 and 3
+  int stride;
+  int xb, yb;
+  int y_run, x_first, x_prev, y_before;
+  int x0, y0, f_xlast, f_ynext;
+  bool in_first, overflow;
+
+  /// entries fill from the low end, so "entry k present" reads off two words: 0: x != ~0, 1: x < 0xFFFF0000, 2, 3: same of y
+  __device__ __forceinline__ static bool odd(uint2 v) { return (v.x != kPairEmpty && v.x >= 0xFFFF0000u) || (v.y != kPairEmpty && v.y >= 0xFFFF0000u); }
+  __device__ __forceinline__ uint32_t entry(int a, int b) const {
+    return static_cast<uint32_t>(min(a, b) - xb) | (static_cast<uint32_t>(max(a, b) - xb) << 8);
+  }
+  __device__ __forceinline__ void append(int y, int a, int b, int yp, int yn) {
+    const uint32_t e = entry(a, b);
+    uint2& w = tab[(y - yb) * stride];
+    uint2 v = w;
+    const bool f0 = v.x != kPairEmpty, f1 = v.x < 0xFFFF0000u, f2 = v.y != kPairEmpty, f3 = v.y < 0xFFFF0000u;
+    if ((yp - y) * (y - yn) < 0) {  // a cusp counts twice (generators.cpp:100-103)
+      const uint32_t ee = e | (e << 16);
+      if (!f0) {
+        v.x = ee;
+      } else if (!f1) {
+        v.x = __byte_perm(v.x, e, 0x5410), v.y = __byte_perm(v.y, e, 0x3254);
+      } else if (!f2) {
+        v.y = ee;
+      } else {
+        overflow = true;
+      }
+    } else {  // the first free 16-bit slot takes the entry
+      v.x = __byte_perm(v.x, e, !f0 ? 0x3254 : (!f1 ? 0x5410 : 0x3210));
+      v.y = __byte_perm(v.y, e, (f1 && !f2) ? 0x3254 : ((f2 && !f3) ? 0x5410 : 0x3210));
+      overflow |= f3;
+    }
+    w = v;
+  }
+  /// the run that contains outline cell 0: inserted BEFORE whatever the row already holds
+  __device__ __forceinline__ void prepend(int y, int a, int b, int yp, int yn) {
+    const uint32_t e = entry(a, b);
+    uint2& w = tab[(y - yb) * stride];
+    const uint2 v = w;
+    const bool f1 = v.x < 0xFFFF0000u, f2 = v.y != kPairEmpty, f3 = v.y < 0xFFFF0000u;
+    if ((yp - y) * (y - yn) < 0) {
+      if (f2) overflow = true;
+      else w = make_uint2(e | (e << 16), v.x);
+    } else {
+      if (f3) overflow = true;
+      else w = make_uint2((v.x << 16) | e, __byte_perm(v.x, v.y, 0x5432));
+    }
+    (void)f1;
+  }
+  __device__ __forceinline__ void row_change(int x, int y) {
+    if (in_first) {
+      f_xlast = x_prev, f_ynext = y;
+      in_first = false;
+    } else {
+      append(y_run, x_first, x_prev, y_before, y);
+    }
+    y_before = y_run;
+    y_run = y;
+    x_first = x;
+  }
+  __device__ __forceinline__ void visit(int x, int y) {
+    if (y != y_run) row_change(x, y);
+    x_prev = x;
+  }
+};
+
+template <int XF, int OP>
+__device__ __forceinline__ void area_quad_pose(const double* __restrict__ poly, int nv, const Pose& T, const MapView& m, uint2* table,
+                                               int rows_cap, const OutView& out, long long i, bool valid, unsigned int* __restrict__ todo,
+                                               unsigned int* __restrict__ todo_count) {
+  int x0, y0, x1, y1;
+  const bool in_range = polygon_bbox<XF>(poly, nv, T, m, x0, y0, x1, y1);
+  const int rows = y1 - y0 + 1;
+  const bool too_big = rows > rows_cap || (x1 - x0) > kQuadMaxWidth;
+  const bool walk = valid && in_range && !too_big;
+  QuadWalker w;
+  w.tab = table + threadIdx.x, w.stride = static_cast<int>(blockDim.x), w.xb = x0, w.yb = y0;
+  const int rows_max = __reduce_max_sync(kFullMask, walk ? rows : 0);
+  for (int r = 0; r < rows_max; ++r)
+    if (walk && r < rows) w.tab[r * w.stride] = make_uint2(kPairEmpty, kPairEmpty);
+  int fx, fy;
+  to_cell<XF>(T, poly[0], poly[1], m, fx, fy);
+  w.y_run = w.y0 = fy, w.x_first = w.x0 = w.x_prev = fx, w.y_before = fy;
+  w.in_first = true, w.overflow = false;
+  w.f_xlast = fx, w.f_ynext = fy;
+  int px = fx, py = fy, rays = 0;
+  LaneRay ray;
+  for (int v = 1; v <= nv; ++v) {  // v == nv: the closing ray, or the one-cell dummy ray of an open outline
+    int cx, cy;
+    if (v < nv) {
+      to_cell<XF>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
+    } else {
+      cx = fx, cy = fy;
+    }
+    ray.set(px, py, cx, cy);
+    if (v < nv) {
+      rays += ray.size != 0;  // degenerate rays are skipped (generators.cpp:86-93)
+    } else if (rays <= 1) {
+      ray.size = 1, ray.add = 0, ray.num = 0;  // dummy ray: the last point itself (generators.cpp:72-78)
+      ray.major_x = ray.major_y = ray.minor_x = ray.minor_y = 0;
+    }
+    if (!walk) ray.size = 0;
+    const int n_iter = __reduce_max_sync(kFullMask, ray.size);
+    for (int k = 0; k < n_iter; ++k) {
+      if (k < ray.size) {
+        w.visit(ray.x, ray.y);
+        ray.step();
+      }
+    }
+    px = cx, py = cy;
+  }
+  if (walk) {
+    if (w.in_first) {  // every cell on one row: ranges (min,min),(max,max) (generators.cpp:197-204)
+      const uint32_t wd = static_cast<uint32_t>(x1 - x0);
+      w.tab[(w.y0 - y0) * w.stride] = make_uint2((wd | (wd << 8)) << 16, kPairEmpty);
+    } else if (w.y_run == w.y0) {  // the tail run continues into cell 0
+      w.prepend(w.y0, w.x_first, w.f_xlast, w.y_before, w.f_ynext);
+    } else {
+      w.append(w.y_run, w.x_first, w.x_prev, w.y_before, w.y0);
+      w.prepend(w.y0, w.x0, w.f_xlast, w.y_run, w.f_ynext);
+    }
+  }
+  // statuses and deferrals
+  bool scan = walk && !w.overflow;
+  if (valid && !in_range) store_failure(out, i, ST_COORD_RANGE);
+  if (valid && in_range && (too_big || w.overflow)) push_todo(todo, todo_count, i);  // more than four ranges on a row
+  bool odd = false;
+  for (int r = 0; r < rows_max; ++r)
+    if (scan && r < rows) odd |= QuadWalker::odd(w.tab[r * w.stride]);
+  if (scan && odd) store_failure(out, i, ST_LOGIC_ERROR);  // std::logic_error("Even number of line-pairs expected")
+  scan = scan && !odd;
+  Fold<OP> fold;
+  bool more = scan;
+  for (int r = 0; r < rows_max; ++r) {
+    if (__all_sync(kFullMask, !more)) break;
+    if (more && r < rows) {
+      const uint2 v = w.tab[r * w.stride];
+      const uint32_t e0 = v.x & 0xFFFFu, e1 = v.x >> 16, e2 = v.y & 0xFFFFu, e3 = v.y >> 16;
+      if (e2 != 0xFFFFu) {
+        // four ranges: stable insertion sort by `min` (low byte), then [r0.min, r1.max], [r2.min, r3.max] (generators.cpp:236-255)
+        uint32_t e[4] = {e0, e1, e2, e3};
+#pragma unroll
+        for (int a = 1; a < 4; ++a) {
+#pragma unroll
+          for (int b = a; b > 0; --b) {
+            if ((e[b] & 0xFFu) < (e[b - 1] & 0xFFu)) {
+              const uint32_t t = e[b];
+              e[b] = e[b - 1], e[b - 1] = t;
+            }
+          }
+        }
+        more = fold.span(m, y0 + r, x0 + static_cast<int>(e[0] & 0xFFu), x0 + static_cast<int>(e[1] >> 8));
+        if (more) more = fold.span(m, y0 + r, x0 + static_cast<int>(e[2] & 0xFFu), x0 + static_cast<int>(e[3] >> 8));
+      } else if (e0 != 0xFFFFu) {
+        const int lo1 = e0 & 0xFF, hi1 = e0 >> 8, lo2 = e1 & 0xFF, hi2 = e1 >> 8;
+        const int lo = min(lo1, lo2), hi = lo2 < lo1 ? hi1 : hi2;  // stable sort by min, then [first.min, second.max]
+        more = fold.span(m, y0 + r, x0 + lo, x0 + hi);
+      }
+    }
+  }
+  if (scan) {
+    fold.store(out, i);
+    if (out.status) out.status[i] = ST_OK;
+  }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kBlock) k_area_quad(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src, long long count,
+                                                     OutView out, int rows_cap, unsigned int* __restrict__ todo,
+                                                     unsigned int* __restrict__ todo_count) {
+  extern __shared__ double smem_d[];
+  const double* poly = stage_polygon(poly_g, nv, smem_d);
+  uint2* table = reinterpret_cast<uint2*>(smem_d + 2 * nv);
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool valid = i < count;  // no early return: the 32 lanes of a warp walk their outlines in lock-step
+  const Pose T = load_pose(src, valid ? i : 0);
+  if (src.format == POSE_NONE) area_quad_pose<XF_NONE, OP>(poly, nv, T, m, table, rows_cap, out, i, valid, todo, todo_count);
+  else area_quad_pose<XF_PATH_A, OP>(poly, nv, T, m, table, rows_cap, out, i, valid, todo, todo_count);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -2335,6 +2528,7 @@ struct cover_ctx {
   int pipeline_chunks = 0;              // COVER_B200_CHUNKS: download chunks of a big lattice sweep (0 = by size)
   bool old_packed_kernel = false;       // COVER_B200_OLD_PACKED=1: first-generation per-thread kernel (A/B measurements)
   bool force_list_kernel = false;
+  bool disable_quad = false;            // COVER_B200_NO_QUAD=1: non-convex polygons through k_area_pair + k_area_slots (A/B measurements)
   bool always_try_packed = true;        // COVER_B200_PACKED_ONLY_CONVEX=1 restricts the packed pass to convex polygons       // COVER_B200_FORCE_LIST_KERNEL=1: A/B measurements and tests of k_area_list  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
   DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, todo2, todo2_count, list_cnt, list_rng, list_seq, lat_global, lw_tables;
 };
@@ -2721,6 +2915,20 @@ enum Shape { SHAPE_OUTLINE = 1, SHAPE_AREA = 2 };
 constexpr int kMaxVertices = 4096;                                          // 64 KB of staged polygon
 constexpr int kMaxDynamicSmem = kMaxVertices * 16 + kPackedMaxRows * kBlock * 8;  // 160 KB
 
+/// Threads per CTA of k_area_quad: the table takes rows_cap x threads x 8 B of shared memory, so a tall polygon runs in
+/// smaller CTAs to keep the warps per SM up (0: the table does not fit at all).
+int quad_block_threads(size_t poly_bytes, int rows_cap) {
+  int best = 0, best_warps = 0;
+  for (int t : {128, 64, 32}) {
+    const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * t * sizeof(unsigned long long);
+    if (smem > static_cast<size_t>(kMaxDynamicSmem)) continue;
+    const int ctas = static_cast<int>(std::min<size_t>({size_t{32}, (size_t{227} << 10) / (smem + 1024), static_cast<size_t>(1536 / t)}));
+    const int warps = ctas * t / 32;
+    if (warps * 10 > best_warps * 11) best = t, best_warps = warps;  // smaller CTAs only for > 10 % more warps
+  }
+  return best;
+}
+
 /// Opt every kernel that stages a polygon into its dynamic shared-memory budget (once per device).
 cudaError_t configure_kernels() {
   cudaError_t e = cudaSuccess;
@@ -2736,6 +2944,9 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_pair<OP_IS_FREE>));
   set(reinterpret_cast<const void*>(&k_area_pair<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_pair<OP_MAX>));
+  set(reinterpret_cast<const void*>(&k_area_quad<OP_IS_FREE>));
+  set(reinterpret_cast<const void*>(&k_area_quad<OP_ACCUMULATE>));
+  set(reinterpret_cast<const void*>(&k_area_quad<OP_MAX>));
   set(reinterpret_cast<const void*>(&k_area_slots<OP_IS_FREE, 4>));
   set(reinterpret_cast<const void*>(&k_area_slots<OP_ACCUMULATE, 4>));
   set(reinterpret_cast<const void*>(&k_area_slots<OP_MAX, 4>));
@@ -2922,7 +3133,10 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   // 1. fast pass: poses whose scan rows all have <= 2 ranges (every pose of a convex polygon, many poses of a
   //    mildly concave one) are finished by the packed / lattice kernel; the rest lands on the todo list.
   //    Polygons that are far from convex skip it (the pass would defer almost everything).
-  const bool fast = outline_lattice || words || (rows_cap <= kPackedMaxRows && (is_convex(poly_host, nv) || ctx->always_try_packed));
+  //    A non-convex polygon of moderate size goes through k_area_quad instead (four ranges per row in the same table).
+  const int quad_threads = (!outline_lattice && !words && !ctx->old_packed_kernel && !ctx->disable_quad && rows_cap <= kQuadMaxRows && !is_convex(poly_host, nv))
+                               ? quad_block_threads(poly_bytes, rows_cap) : 0;
+  const bool fast = outline_lattice || words || quad_threads > 0 || (rows_cap <= kPackedMaxRows && (is_convex(poly_host, nv) || ctx->always_try_packed));
   // 2. general pass over everything (or the todo list): one warp per pose when the outline has few rays
   //    relative to its rows, else one thread per pose with per-row lists in global scratch.
   const bool rows_kernel = nv <= kRowsMaxVertices && rows_cap <= 30000 && !ctx->force_list_kernel && (nv <= 16 || rows_cap > 48);
@@ -3003,7 +3217,12 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
         k_area_lattice<OP, false><<<grid, kLatThreads, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap, span_cap,
                                                                             ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>(), g, pv, gl);
     } else {
-      if (ctx->old_packed_kernel) {
+      if (quad_threads > 0) {
+        const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * quad_threads * sizeof(unsigned long long);
+        const unsigned int grid = static_cast<unsigned int>((count + quad_threads - 1) / quad_threads);
+        k_area_quad<OP><<<grid, quad_threads, smem, ctx->stream>>>(area_view, poly_dev, nv, src, count, out, rows_cap, ctx->todo.as<unsigned int>(),
+                                                                   ctx->todo_count.as<unsigned int>());
+      } else if (ctx->old_packed_kernel) {
         const size_t smem = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * sizeof(uint32_t);
         k_area_packed<OP><<<grid_for(count), kBlock, smem, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, rows_cap,
                                                                           ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
@@ -3345,6 +3564,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
   if (const char* e = std::getenv("COVER_B200_MAX_STRETCH")) ctx->max_stretch = std::max(1, std::atoi(e));
   if (const char* e = std::getenv("COVER_B200_CHUNKS")) ctx->pipeline_chunks = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("COVER_B200_PACKED_ONLY_CONVEX")) ctx->always_try_packed = e[0] != '1';
+  if (const char* e = std::getenv("COVER_B200_NO_QUAD")) ctx->disable_quad = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_OLD_PACKED")) ctx->old_packed_kernel = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_FORCE_LIST_KERNEL")) ctx->force_list_kernel = e[0] == '1';
   *out = ctx;

@@ -37,13 +37,14 @@ def run(fn, reps=3):
     print(f"{which}: {n} poses, {ms:.4f} ms, {n / ms / 1e6:.1f} M checks/s")
 
 
-if which in ("area_pair", "area_rows", "area_M", "area_W", "area_SOTO"):
+if which.startswith("area_"):
     big = which != "area_pair"
     size = 8000 if big else 1000
     data = wl.inflated_costmap(size, size, 0.05, seed=7) if big else wl.random_costmap(1000, 1000, seed=1, lethal_p=1e-3)
     cmap = cover_b200.Costmap(ctx, data, 0.05)
     poses = torch.from_numpy(wl.random_poses(n, seed=8, lo=8.0, hi=size * 0.05 - 8.0)).cuda()
-    poly = {"area_pair": wl.RECT, "area_rows": FOOTPRINTS[0], "area_M": FOOTPRINTS[2], "area_W": FOOTPRINTS[1], "area_SOTO": FOOTPRINTS[4]}[which]
+    poly = {"area_pair": wl.RECT, "area_rows": FOOTPRINTS[0], "area_M": FOOTPRINTS[2], "area_W": FOOTPRINTS[1], "area_SOTO": FOOTPRINTS[4],
+            "area_L": FOOTPRINTS[6], "area_TORU": FOOTPRINTS[5], "area_potato": wl.potato(64)}[which]
     run(lambda: cmap.area_is_free(poly, poses, out=out))
 elif which == "outline":
     data = wl.inflated_costmap(2000, 2000, 0.05, seed=3)
