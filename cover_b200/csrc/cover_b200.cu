@@ -2528,6 +2528,10 @@ struct cover_ctx {
   int pipeline_chunks = 0;              // COVER_B200_CHUNKS: download chunks of a big lattice sweep (0 = by size)
   bool old_packed_kernel = false;       // COVER_B200_OLD_PACKED=1: first-generation per-thread kernel (A/B measurements)
   bool force_list_kernel = false;
+  bool lazy_out = false;                // this call's launch_polygon zeroes the packed verdict words / the not-OK counter itself (or has no need to)
+  void* lazy_not_ok = nullptr;
+  bool timeline = false;                // COVER_B200_TIMELINE=1: events between the operations of a call, printed at cover_ctx_synchronize (bring-up)
+  std::vector<std::pair<const char*, cudaEvent_t>> timeline_events;
   bool disable_quad = false;            // COVER_B200_NO_QUAD=1: non-convex polygons through k_area_pair + k_area_slots (A/B measurements)
   bool always_try_packed = true;        // COVER_B200_PACKED_ONLY_CONVEX=1 restricts the packed pass to convex polygons       // COVER_B200_FORCE_LIST_KERNEL=1: A/B measurements and tests of k_area_list  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
   DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, todo2, todo2_count, list_cnt, list_rng, list_seq, lat_global, lw_tables;
@@ -2588,6 +2592,26 @@ struct cover_split {
 
 namespace {
 
+/// The auxiliary stream runs short kernels BESIDE the main stream's big one (the general half of a lattice sweep beside
+/// the simple half): at the highest priority its blocks are placed first, instead of waiting for the big grid to drain.
+cudaError_t create_priority_stream(cudaStream_t* s) {
+  int least = 0, greatest = 0;
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) {
+    cudaGetLastError();
+    return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+  }
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, greatest);
+}
+
+/// COVER_B200_TIMELINE=1: an event on the main stream, labelled (printed at the next cover_ctx_synchronize)
+void tl(cover_ctx* ctx, const char* label) {
+  if (!ctx->timeline) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, ctx->stream);
+  ctx->timeline_events.emplace_back(label, e);
+}
+
 int fail(cover_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->error = msg;
   return code;
@@ -2622,14 +2646,19 @@ struct OutStage {
   bool host = false;
 };
 
-int stage_out(cover_ctx* ctx, const cover_results* out, int64_t count, OutStage& st) {
+int stage_out(cover_ctx* ctx, const cover_results* out, int64_t count, OutStage& st, bool lazy = false) {
   st.user = out;
+  ctx->lazy_out = lazy, ctx->lazy_not_ok = nullptr;
   if (!out) return fail(ctx, COVER_E_INVALID_ARG, "results must not be NULL");
   st.host = out->mem == COVER_MEM_HOST;
   const size_t n = static_cast<size_t>(std::max<int64_t>(count, 1));
   const size_t bit_bytes = ((n + 31) / 32) * sizeof(uint32_t);
   if (!st.host) {
     st.dev = OutView{out->is_free, out->cost, out->status, out->free_bits, reinterpret_cast<unsigned long long*>(out->not_ok)};
+    if (lazy) {
+      ctx->lazy_not_ok = out->not_ok;
+      return COVER_OK;
+    }
     if (out->free_bits) CU(cudaMemsetAsync(out->free_bits, 0, bit_bytes, ctx->stream));
     if (out->not_ok) CU(cudaMemsetAsync(out->not_ok, 0, sizeof(int64_t), ctx->stream));
     return COVER_OK;
@@ -2648,12 +2677,13 @@ int stage_out(cover_ctx* ctx, const cover_results* out, int64_t count, OutStage&
   }
   if (out->free_bits) {
     CU(ctx->out_bits.ensure(bit_bytes));
-    CU(cudaMemsetAsync(ctx->out_bits.ptr, 0, bit_bytes, ctx->stream));
+    if (!lazy) CU(cudaMemsetAsync(ctx->out_bits.ptr, 0, bit_bytes, ctx->stream));
     st.dev.free_bits = ctx->out_bits.as<uint32_t>();
   }
   if (out->not_ok) {
     CU(ctx->out_not_ok.ensure(sizeof(unsigned long long)));
-    CU(cudaMemsetAsync(ctx->out_not_ok.ptr, 0, sizeof(unsigned long long), ctx->stream));
+    if (lazy) ctx->lazy_not_ok = ctx->out_not_ok.ptr;
+    else CU(cudaMemsetAsync(ctx->out_not_ok.ptr, 0, sizeof(unsigned long long), ctx->stream));
     st.dev.not_ok = ctx->out_not_ok.as<unsigned long long>();
   }
   return COVER_OK;
@@ -2749,7 +2779,9 @@ bool planes_pay_off(const cover_ctx* ctx, const cover_map* map, bool inflated, i
 
 int ensure_planes(cover_ctx* ctx, const cover_map* map, int row_lo, int row_hi, PlaneView& pv) {
   const uint32_t* bits = nullptr;
+  tl(ctx, "before planes");
   const int rc = ensure_plane_set(ctx, map, false, row_lo, row_hi, bits);
+  tl(ctx, "planes ensured");
   pv = PlaneView{bits, map->ypitch, map->plane_words, nullptr, 0};
   return rc;
 }
@@ -2982,6 +3014,15 @@ size_t lw_prepare_smem(int nv, int shape_warps) {
          shape_warps * (static_cast<size_t>(nv + 1) * sizeof(RayRec) + static_cast<size_t>(nv) * sizeof(int2));
 }
 
+/// Start of a word sweep: the deferred-pose list {pushed, capacity} is emptied and the caller's not-OK counter zeroed
+/// (one launch instead of a copy and a memset between the kernels).
+__global__ void k_call_reset(unsigned int* __restrict__ header, unsigned int capacity, unsigned long long* __restrict__ not_ok) {
+  if (threadIdx.x == 0) {
+    header[0] = 0u, header[1] = capacity;
+    if (not_ok) *not_ok = 0ull;
+  }
+}
+
 struct LwPlan {
   LwTables t{};
   LwGeom g{};
@@ -3075,13 +3116,17 @@ int lw_sweep(cover_ctx* ctx, const cover_map* map, const PoseSource& src, int64_
     else launch_lw_sweeps<4>(ctx, map, bits, src, count, out, plan.t, plan.g, plan.nk, simple, stream);
   };
   // the auxiliary stream needs what the main stream did so far: planes, zeroed outputs and counters
+  tl(ctx, "sweep: before fork");
   CU(cudaEventRecord(ctx->aux_planes, ctx->stream));
   CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_planes, 0));
   launch(false, ctx->aux_stream);
   CU(cudaEventRecord(ctx->aux_done, ctx->aux_stream));
   CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));  // the tables of k_lw_prepare
+  tl(ctx, "sweep: before simple");
   launch(true, ctx->stream);
+  tl(ctx, "sweep: after simple");
   CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_done, 0));
+  tl(ctx, "sweep: joined general");
   ctx->launches += 2;
   if (std::getenv("COVER_B200_DEBUG_SYNC")) {  // (bring-up: a fault surfaces here, not at the next call)
     const cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -3117,6 +3162,19 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     if (!word_bits) CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
   }
   const bool words = word_bits != nullptr;
+  bool reset_by_kernel = false;
+  if (ctx->lazy_out) {
+    // the word sweeps write every word of the packed verdicts they own a bit of (lw_store) - all but the unused high bits
+    // of the batch's last word; every other kernel ORs single bits into zeroed words
+    if (out.free_bits && !words) CU(cudaMemsetAsync(out.free_bits, 0, static_cast<size_t>((count + 31) / 32) * sizeof(uint32_t), ctx->stream));
+    if (out.free_bits && words && (count & 31)) CU(cudaMemsetAsync(out.free_bits + count / 32, 0, sizeof(uint32_t), ctx->stream));
+    if (words) {
+      reset_by_kernel = true;  // (one launch zeroes the counter and resets the deferred-pose list)
+    } else if (ctx->lazy_not_ok) {
+      CU(cudaMemsetAsync(ctx->lazy_not_ok, 0, sizeof(unsigned long long), ctx->stream));
+      ctx->lazy_not_ok = nullptr;
+    }
+  }
   const bool outline_lattice = shape == SHAPE_OUTLINE && src.format == POSE_LATTICE && nv >= 1 && !ctx->disable_lattice_kernel && count >= 4096 &&
                                (words || (nv <= kLatMaxVertices && rows_cap <= kLatMaxRowsCap && src.off_x == 0 && src.off_y == 0));
   if (shape == SHAPE_OUTLINE && !outline_lattice) {
@@ -3155,7 +3213,13 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     CU(ctx->todo.ensure(static_cast<size_t>(todo_cap) * sizeof(unsigned int)));
     CU(ctx->todo_count.ensure(2 * sizeof(unsigned int)));
     ctx->todo_header[0] = 0u, ctx->todo_header[1] = static_cast<unsigned int>(todo_cap);
-    CU(cudaMemcpyAsync(ctx->todo_count.ptr, ctx->todo_header, 2 * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+    if (reset_by_kernel) {
+      k_call_reset<<<1, 32, 0, ctx->stream>>>(ctx->todo_count.as<unsigned int>(), ctx->todo_header[1], static_cast<unsigned long long*>(ctx->lazy_not_ok));
+      ctx->lazy_not_ok = nullptr;
+    } else {
+      CU(cudaMemcpyAsync(ctx->todo_count.ptr, ctx->todo_header, 2 * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    tl(ctx, "todo header reset");
     if (words) {
       const int rc = lw_sweep(ctx, map, src, count, out, lw_plan, word_bits);
       if (rc) return rc;
@@ -3263,6 +3327,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     const long long blocks = small_drain ? ctx->sm_count : static_cast<long long>(ctx->sm_count) * 12;
     const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(blocks, (count + kRowsWarps - 1) / kRowsWarps)));
     k_area_rows<OP><<<grid, kRowsWarps * 32, rows_smem(nv), ctx->stream>>>(area_view, poly_dev, nv, src, count, out, todo, todo_count);
+    tl(ctx, "after drain");
   } else {
     ListScratch scratch{};
     const unsigned int grid = list_grid(ctx, count, rows_cap, small_drain ? 1 : 4);
@@ -3282,15 +3347,20 @@ int polygon_check(cover_ctx* ctx, const cover_map* map, const double* polygon_xy
   if (nv > kMaxVertices) return fail(ctx, COVER_E_UNSUPPORTED, "polygons with more than 4096 vertices are not supported");
   if (poses && poses->count > 0xFFFFFFFFll) return fail(ctx, COVER_E_UNSUPPORTED, "more than 2^32 - 1 poses in one call (deferred poses are indexed with 32 bits): split the batch");
   Bind bind(ctx->device);
+  tl(ctx, "polygon_check: entry");
   PoseSource src;
   int rc = stage_poses(ctx, poses, src);
   if (rc) return rc;
+  tl(ctx, "poses staged");
   OutStage st;
-  rc = stage_out(ctx, out, poses->count, st);
+  // (a verdict sweep of a lattice writes whole words of the packed verdicts: launch_polygon decides what needs zeroing)
+  rc = stage_out(ctx, out, poses->count, st, op == OP_IS_FREE && poses->format == COVER_POSE_LATTICE && poses->count > 0);
   if (rc) return rc;
+  tl(ctx, "outputs staged");
   const size_t poly_bytes = static_cast<size_t>(nv) * 2 * sizeof(double);
   CU(ctx->poly.ensure(std::max<size_t>(poly_bytes, 16)));
   if (poly_bytes) CU(cudaMemcpyAsync(ctx->poly.ptr, polygon_xy, poly_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  tl(ctx, "polygon uploaded");
   const double* pd = ctx->poly.as<double>();
   ctx->lw_key_base.clear();
   if (poses->format == COVER_POSE_LATTICE && poses->lattice.cs) {  // everything the class / shape tables of a lattice sweep depend on
@@ -3535,7 +3605,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
       cudaEventCreateWithFlags(&ctx->fence, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->chunk_done, cudaEventDisableTiming) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      create_priority_stream(&ctx->aux_stream) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->aux_planes, cudaEventDisableTiming) != cudaSuccess ||
@@ -3565,6 +3635,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
   if (const char* e = std::getenv("COVER_B200_CHUNKS")) ctx->pipeline_chunks = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("COVER_B200_PACKED_ONLY_CONVEX")) ctx->always_try_packed = e[0] != '1';
   if (const char* e = std::getenv("COVER_B200_NO_QUAD")) ctx->disable_quad = e[0] == '1';
+  if (const char* e = std::getenv("COVER_B200_TIMELINE")) ctx->timeline = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_OLD_PACKED")) ctx->old_packed_kernel = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_FORCE_LIST_KERNEL")) ctx->force_list_kernel = e[0] == '1';
   *out = ctx;
@@ -3604,6 +3675,15 @@ int cover_ctx_synchronize(cover_ctx* ctx) {
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->d2h_stream));
   CU(cudaStreamSynchronize(ctx->aux_stream));
+  if (ctx->timeline) {
+    for (size_t k = 1; k < ctx->timeline_events.size(); ++k) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->timeline_events[k - 1].second, ctx->timeline_events[k].second);
+      std::fprintf(stderr, "[timeline] %-28s -> %-28s %8.2f us\n", ctx->timeline_events[k - 1].first, ctx->timeline_events[k].first, ms * 1e3f);
+    }
+    for (auto& e : ctx->timeline_events) cudaEventDestroy(e.second);
+    ctx->timeline_events.clear();
+  }
   return COVER_OK;
 }
 
@@ -3692,7 +3772,9 @@ int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem) {
   const MapView& v = map->view;
   CU(map_ready(ctx, map));
   map->planes_hi = map->planes_inf_hi = map->prefix_hi = -1;
+  tl(ctx, "upload: entry");
   CU(copy_rows(map->dev, v.pitch, data, v.size_x, v.size_y, mem == COVER_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  tl(ctx, "upload: copied");
   if (mem == COVER_MEM_HOST) CU(cudaStreamSynchronize(ctx->stream));
   return COVER_OK;
 }

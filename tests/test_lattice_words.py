@@ -242,3 +242,37 @@ def test_table_cache_across_calls(cb, monkeypatch):
             if rep == 0 and k == 1:  # the very same sweep again: no k_lw_prepare launch
                 assert ctx.launch_count - launches == first_launches - 1
     ctx.close()
+
+
+@pytest.mark.parametrize("env", [{}, {"COVER_B200_NO_WORDS": 1}, {"COVER_B200_TODO_CAP": 64}])
+def test_packed_verdicts_do_not_depend_on_what_the_words_held(cb, monkeypatch, env):
+    """Device-resident packed verdicts and not-OK counter pre-filled with ones: a sweep leaves exactly the verdicts of its
+    poses (words shared by two tasks, rows that start inside a word, deferred and failed poses, the unused high bits of
+    the last word), and nothing outside its words."""
+    import torch
+    ctx = _ctx(cb, monkeypatch, **env)
+    rng = np.random.default_rng(509)
+    data = mixed_map(rng, 300, 260, lethal=0.003)
+    cmap = cb.Costmap(ctx, data, 0.05, -0.4, 0.3)
+    omap = po.Costmap(data, 0.05, -0.4, 0.3)
+    cs = headings(5)
+    for poly, shape in ((RECT, po.SHAPE_AREA), (FOOTPRINTS[1], po.SHAPE_AREA), (RECT, po.SHAPE_OUTLINE), (np.array([[0.0, 1.0], [0.0, 0.4]]), po.SHAPE_AREA)):
+        desc = dict(x0=-1.2, dx=0.05, nx=337, y0=-0.2, dy=0.05, ny=70, cs=cs)  # hangs over the map: COORD_RANGE never, deferred walks at the border
+        total = 337 * 70 * cs.shape[0]
+        full = po.polygon_batch(omap, poly, po.Lattice(**desc), shape=shape, threads=8)
+        for first, count in ((0, total), (1000, 50_001), (337 * 5 + 17, 4099)):
+            n_words = (count + 31) // 32
+            bits = torch.full((n_words + 2,), -1, dtype=torch.int32, device="cuda")
+            not_ok = torch.full((1,), 12345, dtype=torch.int64, device="cuda")
+            out = cb.Result(free_bits=bits[1:1 + n_words], not_ok=not_ok)
+            fn = cmap.area_is_free if shape == po.SHAPE_AREA else cmap.outline_is_free
+            fn(poly, cb.Lattice(**desc), first=first, count=count, out=out)
+            ctx.synchronize()
+            words = bits.cpu().numpy().view(np.uint32)
+            assert words[0] == 0xFFFFFFFF and words[-1] == 0xFFFFFFFF
+            got = np.unpackbits(words[1:1 + n_words].view(np.uint8), bitorder="little")
+            want = full.is_free[first:first + count] & (full.status[first:first + count] == 0)
+            np.testing.assert_array_equal(got[:count], want, err_msg=f"first {first} count {count} env {env}")
+            assert not got[count:].any()  # the unused bits of the last word are zero
+            assert int(not_ok.item()) == int((full.status[first:first + count] != 0).sum())
+    ctx.close()
