@@ -1047,8 +1047,20 @@ __device__ __forceinline__ uint32_t mark_bits32(const uint4& a, const uint4& b, 
 /// are column-major).  Every lane reads its row 32 bytes at a time and keeps the next word in hand: the doubling
 /// V |= V >> 2^k on the 64-bit value L[c] | L[c + 1] << 32 yields plane k + 1 in its low word.
 constexpr int kPlaneColsPerWarp = 8;
+/// Start-of-call housekeeping a kernel can do on the side: empty the deferred-pose list {pushed, capacity}, zero the
+/// caller's not-OK counter (header == nullptr: nothing to do).
+struct CallReset {
+  unsigned int* header;
+  unsigned int capacity;
+  unsigned long long* not_ok;
+};
+
 __global__ void __launch_bounds__(256) k_lethal_planes(MapView m, uint32_t* __restrict__ planes, int ypitch, long long plane_words, int row_lo,
-                                                        int row_hi, bool inflated) {
+                                                        int row_hi, bool inflated, CallReset reset) {
+  if (reset.header && blockIdx.x == 0 && threadIdx.x == 0) {  // (the sweep that reads both comes after this kernel in stream order)
+    reset.header[0] = 0u, reset.header[1] = reset.capacity;
+    if (reset.not_ok) *reset.not_ok = 0ull;
+  }
   const int lane = threadIdx.x & 31;
   const int n_cols = (m.size_x + 31) / 32;
   const int col_groups = (n_cols + kPlaneColsPerWarp - 1) / kPlaneColsPerWarp;
@@ -2528,6 +2540,7 @@ struct cover_ctx {
   int pipeline_chunks = 0;              // COVER_B200_CHUNKS: download chunks of a big lattice sweep (0 = by size)
   bool old_packed_kernel = false;       // COVER_B200_OLD_PACKED=1: first-generation per-thread kernel (A/B measurements)
   bool force_list_kernel = false;
+  CallReset pending_reset{nullptr, 0u, nullptr};  // handed to the next k_lethal_planes launch of this call (ensure_plane_set)
   bool lazy_out = false;                // this call's launch_polygon zeroes the packed verdict words / the not-OK counter itself (or has no need to)
   void* lazy_not_ok = nullptr;
   bool timeline = false;                // COVER_B200_TIMELINE=1: events between the operations of a call, printed at cover_ctx_synchronize (bring-up)
@@ -2689,9 +2702,31 @@ int stage_out(cover_ctx* ctx, const cover_results* out, int64_t count, OutStage&
   return COVER_OK;
 }
 
+__global__ void __launch_bounds__(256) k_copy16(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16, uint8_t* __restrict__ dst8,
+                                                const uint8_t* __restrict__ src8, size_t bytes) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
+    const uint4 a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride), d = __ldcs(src + i + 3 * stride);
+    dst[i] = a, dst[i + stride] = b, dst[i + 2 * stride] = c, dst[i + 3 * stride] = d;
+  }
+  for (; i < n16; i += stride) dst[i] = __ldcs(src + i);
+  if (blockIdx.x == 0 && threadIdx.x < (bytes & 15u)) dst8[(bytes & ~static_cast<size_t>(15)) + threadIdx.x] = src8[(bytes & ~static_cast<size_t>(15)) + threadIdx.x];
+}
+
 /// `rows` rows of `width` bytes, source unpadded, destination pitched: ONE linear copy when the pitch equals the width
 /// (a pitched copy of 4000-byte rows runs at about half the PCIe rate of a linear one on the B200 boxes measured).
-cudaError_t copy_rows(uint8_t* dst, size_t dpitch, const uint8_t* src, size_t width, size_t rows, cudaMemcpyKind kind, cudaStream_t stream) {
+cudaError_t copy_rows(uint8_t* dst, size_t dpitch, const uint8_t* src, size_t width, size_t rows, cudaMemcpyKind kind, cudaStream_t stream,
+                      int64_t* launches = nullptr) {
+  if (dpitch == width && kind == cudaMemcpyDeviceToDevice && width * rows >= (1u << 20) &&
+      ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
+    // a costmap that is already on the device: 16-byte loads and stores from every SM (a 16 MB image in ~7 us; the
+    // driver's device-to-device copy took 14 us on the B200 boxes measured)
+    const size_t bytes = width * rows;
+    k_copy16<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), bytes / 16, dst, src, bytes);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+  }
   if (dpitch == width) return cudaMemcpyAsync(dst, src, width * rows, kind, stream);
   return cudaMemcpy2DAsync(dst, dpitch, src, width, width, rows, kind, stream);
 }
@@ -2761,7 +2796,9 @@ int ensure_plane_set(cover_ctx* ctx, const cover_map* map, bool inflated, int ro
     lo = 0, hi = -1;
   }
   if (row_lo < lo || row_hi > hi) {
-    k_lethal_planes<<<planes_grid(ctx, map->view.size_x, row_lo, row_hi), 256, 0, ctx->stream>>>(map->view, store, map->ypitch, map->plane_words, row_lo, row_hi, inflated);
+    k_lethal_planes<<<planes_grid(ctx, map->view.size_x, row_lo, row_hi), 256, 0, ctx->stream>>>(map->view, store, map->ypitch, map->plane_words, row_lo, row_hi, inflated,
+                                                                                                 ctx->pending_reset);
+    ctx->pending_reset = CallReset{nullptr, 0u, nullptr};
     ++ctx->launches;
     lo = row_lo, hi = row_hi;
   }
@@ -3063,7 +3100,7 @@ int lw_prepare_async(cover_ctx* ctx, const cover_map* map, const double* poly_de
     off += (bytes + 255) & ~static_cast<size_t>(255);
     return at;
   };
-  const size_t o_counters = carve(16), o_nx = carve(nh * 4), o_ny = carve(nh * 4), o_base = carve(nh * 4), o_simple = carve(nh * 4);
+  const size_t o_counters = carve(16), o_nx = carve(nh * 4), o_ny = carve(nh * 4), o_base = carve(nh * 4), o_simple = carve(nh * 4), o_order = carve(nh * 4);
   const size_t o_anchor = carve(nh * kLwClasses * 4), o_shapes = carve(static_cast<size_t>(t.max_shapes) * sizeof(LwShape));
   const size_t o_spans = carve(static_cast<size_t>(t.span_pool) * sizeof(LwSpan));
   const size_t o_yc0 = carve(nh * src.ny * 4), o_xcls = carve(nh * src.nx), o_ycls = carve(nh * src.ny);
@@ -3071,7 +3108,7 @@ int lw_prepare_async(cover_ctx* ctx, const cover_map* map, const double* poly_de
   char* base = ctx->lw_tables.as<char>();
   t.counters = reinterpret_cast<unsigned int*>(base + o_counters);
   t.n_xcls = reinterpret_cast<int*>(base + o_nx), t.n_ycls = reinterpret_cast<int*>(base + o_ny);
-  t.shape_base = reinterpret_cast<int*>(base + o_base), t.simple = reinterpret_cast<int*>(base + o_simple);
+  t.shape_base = reinterpret_cast<int*>(base + o_base), t.simple = reinterpret_cast<int*>(base + o_simple), t.order = reinterpret_cast<int*>(base + o_order);
   t.shapes = reinterpret_cast<LwShape*>(base + o_shapes), t.spans = reinterpret_cast<LwSpan*>(base + o_spans);
   t.xanchor = reinterpret_cast<int*>(base + o_anchor), t.yc0 = reinterpret_cast<int*>(base + o_yc0);
   t.xcls = reinterpret_cast<uint8_t*>(base + o_xcls), t.ycls = reinterpret_cast<uint8_t*>(base + o_ycls);
@@ -3083,7 +3120,8 @@ int lw_prepare_async(cover_ctx* ctx, const cover_map* map, const double* poly_de
   const size_t per_warp = static_cast<size_t>(nv + 1) * sizeof(RayRec) + static_cast<size_t>(nv) * sizeof(int2);
   const int shape_warps = static_cast<int>(std::max<size_t>(1, std::min<size_t>(16, (static_cast<size_t>(kMaxDynamicSmem) - lw_prepare_smem(nv, 0)) / per_warp)));
   k_lw_prepare<<<g.n_head, kLwPrepThreads, lw_prepare_smem(nv, shape_warps), ctx->aux_stream>>>(map->view, poly_dev, nv, src, g.it_lo, t, outline ? 1 : 0,
-                                                                                              map->plane_words, shape_warps);
+                                                                                              map->plane_words, shape_warps,
+                                                                                              32 * (ctx->words_strip == 8 || ctx->words_strip == 2 ? ctx->words_strip : 4));
   ++ctx->launches;
   CU(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
   if (!ctx->lw_key_base.empty()) ctx->lw_key = key, ctx->lw_cached_t = plan.t, ctx->lw_cached_g = plan.g, ctx->lw_cache_valid = true;
@@ -3135,6 +3173,14 @@ int lw_sweep(cover_ctx* ctx, const cover_map* map, const PoseSource& src, int64_
   return COVER_OK;
 }
 
+/// Capacity of the deferred-pose list of a lattice sweep (it defers next to nothing: poses at the map border, shapes
+/// beyond the tables; if the list ever overflows the drain kernel takes every pose).
+int64_t words_todo_cap(const cover_ctx* ctx, int64_t count) {
+  int64_t cap = std::min<int64_t>(count, int64_t{4} << 20);
+  if (ctx->todo_cap_limit > 0) cap = std::min(cap, ctx->todo_cap_limit);
+  return cap;
+}
+
 template <int OP>
 int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev, const double* poly_host, int nv, int shape,
                    const PoseSource& src, int64_t count, const OutView& out, int row_lo, int row_hi) {
@@ -3147,6 +3193,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   // Verdict sweeps of a lattice at cell pitch in x (any polygon up to 256 vertices, areas and outlines): the bit-parallel
   // kernels of lattice_words.cuh, when the lethal bit planes of the rows under the window are (or are worth being) built.
   const uint32_t* word_bits = nullptr;
+  bool reset_done = false;
   LwPlan lw_plan;
   if (OP == OP_IS_FREE && src.format == POSE_LATTICE && nv >= 1 && nv <= kRowsMaxVertices && !ctx->disable_lattice_kernel &&
       !ctx->disable_words && !ctx->disable_planes && std::fabs(src.dx * map->view.inv_res - 1.0) < 1e-9 && count >= 4096 &&
@@ -3155,8 +3202,17 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     int rc = lw_prepare_async(ctx, map, poly_dev, nv, shape == SHAPE_OUTLINE, src, count, out, lw_plan);  // (beside the plane build)
     if (rc) return rc;
     lw_plan.nk = rows_cap - 4 < 32 ? kPlaneCount - 1 : kPlaneCount;  // (rows_cap bounds the bounding box's extent in cells, + 4)
+    if (ctx->lazy_out) {  // the plane build, if this call needs one, also resets the deferred-pose list and the not-OK counter
+      CU(ctx->todo.ensure(static_cast<size_t>(words_todo_cap(ctx, count)) * sizeof(unsigned int)));
+      CU(ctx->todo_count.ensure(2 * sizeof(unsigned int)));
+      ctx->pending_reset = CallReset{ctx->todo_count.as<unsigned int>(), static_cast<unsigned int>(words_todo_cap(ctx, count)),
+                                     static_cast<unsigned long long*>(ctx->lazy_not_ok)};
+    }
     PlaneView pvw{nullptr, 0, 0, nullptr, 0};
     rc = ensure_planes(ctx, map, row_lo, row_hi, pvw);
+    reset_done = ctx->lazy_out && ctx->pending_reset.header == nullptr;
+    ctx->pending_reset = CallReset{nullptr, 0u, nullptr};
+    if (reset_done) ctx->lazy_not_ok = nullptr;
     if (rc) return rc;
     word_bits = pvw.bits;  // (nullptr: no memory for the planes - the other kernels walk bytes then)
     if (!word_bits) CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
@@ -3208,12 +3264,14 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     // deferred-pose list: {pushed, capacity} + the entries.  A lattice sweep defers next to nothing (poses at the map
     // border, shapes beyond the tables): a small list, and if it ever overflows the drain kernel takes every pose.  The
     // per-pose fast passes may defer most of a batch (concave polygons): room for all of it.
-    int64_t todo_cap = (words || (src.format == POSE_LATTICE && !ctx->disable_lattice_kernel)) ? std::min<int64_t>(count, int64_t{4} << 20) : count;
+    int64_t todo_cap = (words || (src.format == POSE_LATTICE && !ctx->disable_lattice_kernel)) ? words_todo_cap(ctx, count) : count;
     if (ctx->todo_cap_limit > 0) todo_cap = std::min(todo_cap, ctx->todo_cap_limit);
     CU(ctx->todo.ensure(static_cast<size_t>(todo_cap) * sizeof(unsigned int)));
     CU(ctx->todo_count.ensure(2 * sizeof(unsigned int)));
     ctx->todo_header[0] = 0u, ctx->todo_header[1] = static_cast<unsigned int>(todo_cap);
-    if (reset_by_kernel) {
+    if (reset_by_kernel && reset_done) {
+      // (k_lethal_planes did it on the way)
+    } else if (reset_by_kernel) {
       k_call_reset<<<1, 32, 0, ctx->stream>>>(ctx->todo_count.as<unsigned int>(), ctx->todo_header[1], static_cast<unsigned long long*>(ctx->lazy_not_ok));
       ctx->lazy_not_ok = nullptr;
     } else {
@@ -3773,7 +3831,8 @@ int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem) {
   CU(map_ready(ctx, map));
   map->planes_hi = map->planes_inf_hi = map->prefix_hi = -1;
   tl(ctx, "upload: entry");
-  CU(copy_rows(map->dev, v.pitch, data, v.size_x, v.size_y, mem == COVER_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  CU(copy_rows(map->dev, v.pitch, data, v.size_x, v.size_y, mem == COVER_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream,
+               &ctx->launches));
   tl(ctx, "upload: copied");
   if (mem == COVER_MEM_HOST) CU(cudaStreamSynchronize(ctx->stream));
   return COVER_OK;
@@ -3795,7 +3854,7 @@ int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x
   auto repair = [&](uint32_t* planes, int lo, int hi, bool inflated) {
     const int a = std::max(lo, r_lo), b = std::min(hi, r_hi);
     if (!planes || a > b) return;
-    k_lethal_planes<<<planes_grid(ctx, v.size_x, a, b), 256, 0, ctx->stream>>>(v, planes, map->ypitch, map->plane_words, a, b, inflated);
+    k_lethal_planes<<<planes_grid(ctx, v.size_x, a, b), 256, 0, ctx->stream>>>(v, planes, map->ypitch, map->plane_words, a, b, inflated, CallReset{nullptr, 0u, nullptr});
     ++ctx->launches;
   };
   repair(map->planes, map->planes_lo, map->planes_hi, false);

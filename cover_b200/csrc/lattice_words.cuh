@@ -51,13 +51,15 @@ struct LwTables {
   int* n_ycls;         // [n_head]
   int* shape_base;     // [n_head] shape (xc, yc) of the heading lives at shape_base + xc * n_ycls + yc; -1: pool exhausted
   int* simple;         // [n_head] 1: one x class, one y class, every column and row in range, the shape rasterised fine
+  int* order;          // [n_head] the headings, those that are not simple first (the general sweep's CTAs of the few
+                       //   headings with real work start together instead of one heading after the other)
   uint8_t* xcls;       // [n_head][nx]
   uint8_t* ycls;       // [n_head][ny]
   int* yc0;            // [n_head][ny] map row of vertex 0
   int* xanchor;        // [n_head][kLwClasses] map column of vertex 0 minus ix
   LwShape* shapes;     // [max_shapes]
   LwSpan* spans;       // [span_pool]
-  unsigned int* counters;  // [0] shapes handed out, [1] spans handed out
+  unsigned int* counters;  // [0] shapes handed out, [1] spans handed out, [2] / [3] headings placed at the front / back of `order`
   int max_shapes, span_pool;
 };
 
@@ -163,9 +165,9 @@ __device__ __forceinline__ LwShape lw_rasterise(int2* verts, int nv, RayRec* ray
 /// Per heading (one CTA): column and row classes, then one rasterisation per (x class, y class).
 /// Dynamic shared memory: polygon | x offsets [K][nv] | y offsets [K][nv] | anchors [K] | per shape warp: rays, vertices.
 __global__ void __launch_bounds__(kLwPrepThreads) k_lw_prepare(MapView m, const double* __restrict__ poly_g, int nv, PoseSource src, int it_lo,
-                                                              LwTables t, int outline, long long plane_words, int shape_warps) {
+                                                              LwTables t, int outline, long long plane_words, int shape_warps, int strip_cols) {
   extern __shared__ double smem_d[];
-  __shared__ int s_n[2], s_elect, s_base, s_flaw, s_bad_shape;
+  __shared__ int s_n[2], s_elect, s_base, s_flaw, s_bad_shape, s_ymin, s_ymax;
   const int tid = threadIdx.x;
   double* poly = smem_d;
   int* xoff = reinterpret_cast<int*>(smem_d + 2 * nv);
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(kLwPrepThreads) k_lw_prepare(MapView m, const 
   for (int i = tid; i < 2 * nv; i += blockDim.x) poly[i] = poly_g[i];
   const int h = blockIdx.x, it = it_lo + h;
   const double2 cs = __ldg(reinterpret_cast<const double2*>(src.theta_cs) + it);
-  if (tid == 0) s_n[0] = s_n[1] = 0, s_elect = 0x7FFFFFFF, s_flaw = 0, s_bad_shape = 0;
+  if (tid == 0) s_n[0] = s_n[1] = 0, s_elect = 0x7FFFFFFF, s_flaw = 0, s_bad_shape = 0, s_ymin = 0x7FFFFFFF, s_ymax = -0x7FFFFFFF - 1;
   __syncthreads();
 #pragma unroll 1
   for (int axis = 0; axis < 2; ++axis) {
@@ -241,7 +243,10 @@ __global__ void __launch_bounds__(kLwPrepThreads) k_lw_prepare(MapView m, const 
       }
       if (valid) {
         cls_out[idx] = static_cast<uint8_t>(my);
-        if (!is_x) t.yc0[static_cast<long long>(h) * src.ny + idx] = cell0;
+        if (!is_x) {
+          t.yc0[static_cast<long long>(h) * src.ny + idx] = cell0;
+          atomicMin(&s_ymin, cell0), atomicMax(&s_ymax, cell0);
+        }
         if (my >= kLwClasses) s_flaw = 1;  // (benign race: everybody writes 1)
       }
     }
@@ -273,7 +278,18 @@ __global__ void __launch_bounds__(kLwPrepThreads) k_lw_prepare(MapView m, const 
     }
   }
   __syncthreads();
-  if (tid == 0) t.simple[h] = (s_base >= 0 && n_shapes == 1 && !s_flaw && !s_bad_shape) ? 1 : 0;
+  if (tid == 0) {
+    int simple = (s_base >= 0 && n_shapes == 1 && !s_flaw && !s_bad_shape) ? 1 : 0;
+    if (simple) {  // 2: and every pose of the heading's lattice keeps its shape inside the map - the general sweep has nothing to do here
+      const LwShape& sh = t.shapes[s_base];
+      const int xa = anchor_tab[0];
+      const int last_col = (src.nx + strip_cols - 1) / strip_cols * strip_cols - 1;  // (lw_task_simple tests whole strips of 32 W columns)
+      if (xa + sh.xb >= 0 && xa + last_col + sh.x1 < m.size_x && s_ymin + sh.yb >= 0 && s_ymax + sh.yb + sh.rows <= m.size_y) simple = 2;
+    }
+    t.simple[h] = simple;
+    if (simple) t.order[gridDim.x - 1u - atomicAdd(&t.counters[3], 1u)] = h;
+    else t.order[atomicAdd(&t.counters[2], 1u)] = h;
+  }
 }
 
 /// ORs, for the 32 * W x-adjacent poses whose vertex 0 sits at columns x_base .. x_base + 32 W - 1 of map row y_lane,
@@ -587,7 +603,8 @@ __global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep_general(MapView m, c
   __shared__ uint32_t s_bits[kLwWarps][32][2 * W];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sb = blockIdx.y, rb = blockIdx.x * kLwWarps + warp;  // grid: (row block groups, strips, headings)
-  const int h = blockIdx.z;
+  const int h = t.order[blockIdx.z];
+  if (t.simple[h] == 2) return;  // (every task of the heading is k_lw_sweep_simple's)
   LwTask<W> k;
   if (!lw_task_setup<W>(src, count, t, g, rb, sb, h, lane, k)) return;
   int x_simple;
