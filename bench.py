@@ -602,12 +602,12 @@ def run_gpu(args) -> None:
         rows = min(MAP_SIZE, rows_hi - rows_lo + 1)  # map rows under the lattice window +- the footprint's reach
         plane_bytes = 6 * rows * (MAP_SIZE // 8)
         moved = {"costmap_ingest_read+write": 2 * data.size, "plane_build_read": rows * MAP_SIZE, "plane_build_write": plane_bytes,
-                 "sweep_plane_read": plane_bytes, "verdict_bits_zero+write": 2 * 4 * n_words}
+                 "sweep_plane_read": plane_bytes, "verdict_bits_write": 4 * n_words}  # (no zeroing pass: the sweep writes whole words)
         moved_total = sum(moved.values())
         achieved = moved_total / (ms_per_step * 1e-3) / 1e9
         rec = recorded_counters()
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": rec.get("k_lw_sweep_dram_bytes_per_launch"), "peak_kind": peak_kind, "kernel": "k_lw_sweep<4, SIMPLE>",
+                    "traffic": rec.get("k_lw_sweep_dram_bytes_per_launch"), "peak_kind": peak_kind, "kernel": "k_lw_sweep_simple<4>",
                     "bytes_moved_per_step": moved, "sweep_only_ms": sweep_ms,
                     "note": "achieved = bytes the step must move through HBM / step time (measured in this run): the step is bound by "
                             "instruction issue and L1 wavefronts (bit-plane walk), not by HBM; `recorded` holds the ncu counters of the "
