@@ -2517,7 +2517,8 @@ struct cover_ctx {
   cudaEvent_t fence = nullptr;         // "everything queued on `stream` so far": what a banded upload has to wait for
   cudaStream_t d2h_stream = nullptr;   // result chunks of a big lattice sweep travel back while the next chunk is computed
   cudaStream_t aux_stream = nullptr;   // k_lw_prepare (needs no map data) runs beside the plane build / the costmap upload
-  cudaEvent_t aux_fork = nullptr, aux_join = nullptr, aux_planes = nullptr, aux_done = nullptr;
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr, aux_planes = nullptr, aux_done = nullptr, aux_zero = nullptr;
+  bool zero_on_aux = false;             // this call's packed verdicts are being zeroed on the auxiliary stream (aux_zero marks the end)
   cudaEvent_t chunk_done = nullptr;
   std::string error;
   int64_t launches = 0;
@@ -3160,6 +3161,7 @@ int lw_sweep(cover_ctx* ctx, const cover_map* map, const PoseSource& src, int64_
   launch(false, ctx->aux_stream);
   CU(cudaEventRecord(ctx->aux_done, ctx->aux_stream));
   CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));  // the tables of k_lw_prepare
+  if (ctx->zero_on_aux && out.free_bits) CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_zero, 0));
   tl(ctx, "sweep: before simple");
   launch(true, ctx->stream);
   tl(ctx, "sweep: after simple");
@@ -3194,6 +3196,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   // kernels of lattice_words.cuh, when the lethal bit planes of the rows under the window are (or are worth being) built.
   const uint32_t* word_bits = nullptr;
   bool reset_done = false;
+  ctx->zero_on_aux = false;
   LwPlan lw_plan;
   if (OP == OP_IS_FREE && src.format == POSE_LATTICE && nv >= 1 && nv <= kRowsMaxVertices && !ctx->disable_lattice_kernel &&
       !ctx->disable_words && !ctx->disable_planes && std::fabs(src.dx * map->view.inv_res - 1.0) < 1e-9 && count >= 4096 &&
@@ -3202,6 +3205,14 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     int rc = lw_prepare_async(ctx, map, poly_dev, nv, shape == SHAPE_OUTLINE, src, count, out, lw_plan);  // (beside the plane build)
     if (rc) return rc;
     lw_plan.nk = rows_cap - 4 < 32 ? kPlaneCount - 1 : kPlaneCount;  // (rows_cap bounds the bounding box's extent in cells, + 4)
+    if (ctx->lazy_out && out.free_bits) {
+      // the packed verdicts are zeroed on the auxiliary stream, beside the plane build (kernels OR their bits into shared words)
+      CU(cudaEventRecord(ctx->aux_fork, ctx->stream));
+      CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+      CU(cudaMemsetAsync(out.free_bits, 0, static_cast<size_t>((count + 31) / 32) * sizeof(uint32_t), ctx->aux_stream));
+      CU(cudaEventRecord(ctx->aux_zero, ctx->aux_stream));
+      ctx->zero_on_aux = true;
+    }
     if (ctx->lazy_out) {  // the plane build, if this call needs one, also resets the deferred-pose list and the not-OK counter
       CU(ctx->todo.ensure(static_cast<size_t>(words_todo_cap(ctx, count)) * sizeof(unsigned int)));
       CU(ctx->todo_count.ensure(2 * sizeof(unsigned int)));
@@ -3220,10 +3231,9 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   const bool words = word_bits != nullptr;
   bool reset_by_kernel = false;
   if (ctx->lazy_out) {
-    // the word sweeps write every word of the packed verdicts they own a bit of (lw_store) - all but the unused high bits
-    // of the batch's last word; every other kernel ORs single bits into zeroed words
-    if (out.free_bits && !words) CU(cudaMemsetAsync(out.free_bits, 0, static_cast<size_t>((count + 31) / 32) * sizeof(uint32_t), ctx->stream));
-    if (out.free_bits && words && (count & 31)) CU(cudaMemsetAsync(out.free_bits + count / 32, 0, sizeof(uint32_t), ctx->stream));
+    // every kernel ORs its bits into zeroed words of the packed verdicts (the word sweeps store the words they own entirely)
+    if (out.free_bits && ctx->zero_on_aux && !words) CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_zero, 0));  // (lw_sweep waits for it itself)
+    if (out.free_bits && !ctx->zero_on_aux) CU(cudaMemsetAsync(out.free_bits, 0, static_cast<size_t>((count + 31) / 32) * sizeof(uint32_t), ctx->stream));
     if (words) {
       reset_by_kernel = true;  // (one launch zeroes the counter and resets the deferred-pose list)
     } else if (ctx->lazy_not_ok) {
@@ -3667,7 +3677,8 @@ int cover_ctx_create(int device, cover_ctx** out) {
       cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->aux_planes, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->aux_done, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->aux_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->aux_zero, cudaEventDisableTiming) != cudaSuccess) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -3676,6 +3687,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
     if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
     if (ctx->aux_planes) cudaEventDestroy(ctx->aux_planes);
     if (ctx->aux_done) cudaEventDestroy(ctx->aux_done);
+    if (ctx->aux_zero) cudaEventDestroy(ctx->aux_zero);
     if (ctx->chunk_done) cudaEventDestroy(ctx->chunk_done);
     if (ctx->fence) cudaEventDestroy(ctx->fence);
     delete ctx;
@@ -3714,6 +3726,7 @@ void cover_ctx_destroy(cover_ctx* ctx) {
   cudaEventDestroy(ctx->aux_join);
   cudaEventDestroy(ctx->aux_planes);
   cudaEventDestroy(ctx->aux_done);
+  cudaEventDestroy(ctx->aux_zero);
   cudaStreamSynchronize(ctx->aux_stream);
   cudaStreamDestroy(ctx->aux_stream);
   cudaStreamDestroy(ctx->d2h_stream);

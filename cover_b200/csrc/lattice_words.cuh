@@ -391,12 +391,8 @@ __device__ __forceinline__ void lw_store(const OutView& out, const uint32_t (&fr
       const uint32_t lo_f = j > 0 ? fr[j - 1] : 0u, hi_f = j < W ? fr[j] : 0u;
       const uint32_t lo_v = j > 0 ? valid[j - 1] : 0u, hi_v = j < W ? valid[j] : 0u;
       const uint32_t word = __funnelshift_l(lo_f, hi_f, sh), owned = __funnelshift_l(lo_v, hi_v, sh);
-      if (owned == 0xFFFFFFFFu) {
-        out.free_bits[wi + j] = word;
-      } else if (owned != 0u) {  // a word shared with the neighbouring task: this one's bits, whatever the word held before
-        atomicAnd(out.free_bits + (wi + j), ~owned);
-        if (word != 0u) atomicOr(out.free_bits + (wi + j), word);
-      }
+      if (owned == 0xFFFFFFFFu) out.free_bits[wi + j] = word;
+      else if (word != 0u) atomicOr(out.free_bits + (wi + j), word);  // (a word shared with the neighbouring task: zeroed before the sweep)
     }
   }
   if (out.is_free || out.status) {
