@@ -3061,6 +3061,12 @@ __global__ void k_call_reset(unsigned int* __restrict__ header, unsigned int cap
   }
 }
 
+/// Before a kernel that drains a deferred-pose list: if the list overflowed, that kernel takes EVERY pose of the batch
+/// again (todo_items) - the failures the earlier passes counted would be counted twice, so the counter starts over.
+__global__ void k_overflow_recount(const unsigned int* __restrict__ header, unsigned long long* __restrict__ not_ok) {
+  if (threadIdx.x == 0 && header[0] > header[1]) *not_ok = 0ull;
+}
+
 struct LwPlan {
   LwTables t{};
   LwGeom g{};
@@ -3147,8 +3153,11 @@ void launch_lw_sweeps(cover_ctx* ctx, const cover_map* map, const uint32_t* bits
 
 /// Second half: the sweep over the lethal bit planes `bits`, two launches side by side - the tasks of single-shape
 /// headings inside the map on the main stream, the rest (few tasks, several walks each: latency-bound on its own) on the
-/// auxiliary stream, where k_lw_prepare just finished.  Poses neither can finish land on ctx->todo (already reset).
-int lw_sweep(cover_ctx* ctx, const cover_map* map, const PoseSource& src, int64_t count, const OutView& out, const LwPlan& plan, const uint32_t* bits) {
+/// auxiliary stream, where k_lw_prepare just finished.  Poses neither can finish land on ctx->todo (already reset);
+/// `drain_on(stream)` launches the kernel that takes them.
+template <class Drain>
+int lw_sweep(cover_ctx* ctx, const cover_map* map, const PoseSource& src, int64_t count, const OutView& out, const LwPlan& plan, const uint32_t* bits,
+             Drain&& drain_on) {
   auto launch = [&](bool simple, cudaStream_t stream) {
     if (ctx->words_strip == 8) launch_lw_sweeps<8>(ctx, map, bits, src, count, out, plan.t, plan.g, plan.nk, simple, stream);
     else if (ctx->words_strip == 2) launch_lw_sweeps<2>(ctx, map, bits, src, count, out, plan.t, plan.g, plan.nk, simple, stream);
@@ -3159,6 +3168,10 @@ int lw_sweep(cover_ctx* ctx, const cover_map* map, const PoseSource& src, int64_
   CU(cudaEventRecord(ctx->aux_planes, ctx->stream));
   CU(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_planes, 0));
   launch(false, ctx->aux_stream);
+  {  // only the general half defers poses: their drain follows it on the auxiliary stream, beside the simple half
+    const int rc = drain_on(ctx->aux_stream);
+    if (rc) return rc;
+  }
   CU(cudaEventRecord(ctx->aux_done, ctx->aux_stream));
   CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));  // the tables of k_lw_prepare
   if (ctx->zero_on_aux && out.free_bits) CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_zero, 0));
@@ -3270,6 +3283,35 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   // Lattice batches of small footprints: shape-deduplicating warp-cooperative kernel.
   const bool lattice = fast && src.format == POSE_LATTICE && nv >= 1 && nv <= kLatMaxVertices && src.off_x == 0 && src.off_y == 0 &&
                        rows_cap <= kLatMaxRowsCap && !ctx->disable_lattice_kernel;  // (the shape-cache kernel knows no cell offset)
+  // The kernel that takes the deferred poses (or, without a fast pass, every pose), on `stream`.
+  bool drained = false;
+  auto drain = [&](cudaStream_t stream) -> int {
+    if (todo_count && out.not_ok) {
+      k_overflow_recount<<<1, 32, 0, stream>>>(todo_count, out.not_ok);
+      ++ctx->launches;
+    }
+    if (outline_lattice) {  // one thread per deferred pose (map border for max_cost, shapes the cache cannot hold)
+      const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(static_cast<long long>(ctx->sm_count) * 8, (count + kBlock - 1) / kBlock)));
+      k_outline_drain<OP><<<grid, kBlock, poly_bytes, stream>>>(map->view, poly_dev, nv, src, count, out, todo, todo_count);
+      ++ctx->launches;
+      return COVER_OK;
+    }
+    // A convex polygon defers (almost) nothing: a small persistent grid is enough to drain the list.
+    const bool small_drain = words || (fast && is_convex(poly_host, nv));  // (the word sweep defers next to nothing, whatever the polygon)
+    if (rows_kernel) {
+      const long long blocks = small_drain ? ctx->sm_count : static_cast<long long>(ctx->sm_count) * 12;
+      const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(blocks, (count + kRowsWarps - 1) / kRowsWarps)));
+      k_area_rows<OP><<<grid, kRowsWarps * 32, rows_smem(nv), stream>>>(area_view, poly_dev, nv, src, count, out, todo, todo_count);
+    } else {
+      ListScratch scratch{};
+      const unsigned int grid = list_grid(ctx, count, rows_cap, small_drain ? 1 : 4);
+      const int rc = ensure_list_scratch(ctx, rows_cap, static_cast<long long>(grid) * kBlock, scratch);
+      if (rc) return rc;
+      k_area_list<OP><<<grid, kBlock, poly_bytes, stream>>>(area_view, poly_dev, nv, src, count, out, scratch, todo, todo_count);
+    }
+    ++ctx->launches;
+    return COVER_OK;
+  };
   if (fast) {
     // deferred-pose list: {pushed, capacity} + the entries.  A lattice sweep defers next to nothing (poses at the map
     // border, shapes beyond the tables): a small list, and if it ever overflows the drain kernel takes every pose.  The
@@ -3289,8 +3331,10 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     }
     tl(ctx, "todo header reset");
     if (words) {
-      const int rc = lw_sweep(ctx, map, src, count, out, lw_plan, word_bits);
+      todo = ctx->todo.as<unsigned int>(), todo_count = ctx->todo_count.as<unsigned int>();
+      const int rc = lw_sweep(ctx, map, src, count, out, lw_plan, word_bits, drain);
       if (rc) return rc;
+      drained = true;
       --ctx->launches;  // (counted once more below)
     } else if (lattice) {
       LatGeom g{};
@@ -3371,6 +3415,10 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
           CU(cudaMemcpyAsync(ctx->todo2_count.ptr, ctx->todo2_header, 2 * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
           const size_t smem4 = poly_bytes + static_cast<size_t>(rows_cap) * kBlock * 4 * sizeof(uint32_t);
           const unsigned int grid4 = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(static_cast<long long>(ctx->sm_count) * 4, (count + kBlock - 1) / kBlock)));
+          if (out.not_ok) {
+            k_overflow_recount<<<1, 32, 0, ctx->stream>>>(ctx->todo_count.as<unsigned int>(), out.not_ok);
+            ++ctx->launches;
+          }
           k_area_slots<OP, 4><<<grid4, kBlock, smem4, ctx->stream>>>(area_view, poly_dev, nv, src, count, out, rows_cap, ctx->todo.as<unsigned int>(),
                                                                     ctx->todo_count.as<unsigned int>(), ctx->todo2.as<unsigned int>(),
                                                                     ctx->todo2_count.as<unsigned int>());
@@ -3383,28 +3431,8 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     todo = second_list ? ctx->todo2.as<unsigned int>() : ctx->todo.as<unsigned int>();
     todo_count = second_list ? ctx->todo2_count.as<unsigned int>() : ctx->todo_count.as<unsigned int>();
   }
-  if (outline_lattice) {  // drain: one thread per deferred pose (map border for max_cost, shapes the cache cannot hold)
-    const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(static_cast<long long>(ctx->sm_count) * 8, (count + kBlock - 1) / kBlock)));
-    k_outline_drain<OP><<<grid, kBlock, poly_bytes, ctx->stream>>>(map->view, poly_dev, nv, src, count, out, todo, todo_count);
-    ++ctx->launches;
-    return COVER_OK;
-  }
-  // A convex polygon defers (almost) nothing: a small persistent grid is enough to drain the list.
-  const bool small_drain = words || (fast && is_convex(poly_host, nv));  // (the word sweep defers next to nothing, whatever the polygon)
-  if (rows_kernel) {
-    const long long blocks = small_drain ? ctx->sm_count : static_cast<long long>(ctx->sm_count) * 12;
-    const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(blocks, (count + kRowsWarps - 1) / kRowsWarps)));
-    k_area_rows<OP><<<grid, kRowsWarps * 32, rows_smem(nv), ctx->stream>>>(area_view, poly_dev, nv, src, count, out, todo, todo_count);
-    tl(ctx, "after drain");
-  } else {
-    ListScratch scratch{};
-    const unsigned int grid = list_grid(ctx, count, rows_cap, small_drain ? 1 : 4);
-    const int rc = ensure_list_scratch(ctx, rows_cap, static_cast<long long>(grid) * kBlock, scratch);
-    if (rc) return rc;
-    k_area_list<OP><<<grid, kBlock, poly_bytes, ctx->stream>>>(area_view, poly_dev, nv, src, count, out, scratch, todo, todo_count);
-  }
-  ++ctx->launches;
-  return COVER_OK;
+  if (drained) return COVER_OK;
+  return drain(ctx->stream);
 }
 
 int polygon_check(cover_ctx* ctx, const cover_map* map, const double* polygon_xy, int32_t nv, int shape, int op,

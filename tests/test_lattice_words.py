@@ -205,6 +205,15 @@ def test_deferred_pose_list_overflow(cb, monkeypatch, env):
             np.testing.assert_array_equal(gpu.is_free, cpu.is_free)
             if cost:
                 np.testing.assert_array_equal(gpu.cost, cpu.cost)
+    # the not-OK counter when the drain takes every pose: failures the fast pass already counted are not counted twice
+    far = poses.copy()
+    far[::7, 2] = 1e12  # coordinates out of range
+    for poly in (FOOTPRINTS[0] * 0.3, FOOTPRINTS[3] * 0.2):
+        out = cb.Result(free_bits=np.zeros((len(far) + 31) // 32, dtype=np.uint32), not_ok=np.zeros(1, dtype=np.int64))
+        cmap.area_is_free(poly, far, out=out)
+        cpu = po.polygon_batch(omap, poly, far, threads=8)
+        assert int(out.not_ok[0]) == int((cpu.status != 0).sum()) > 0
+        np.testing.assert_array_equal(out.unpack_bits(len(far)), cpu.is_free & (cpu.status == 0))
     desc = dict(x0=-1.2, dx=0.05, nx=330, y0=-0.6, dy=0.05, ny=150, cs=headings(5))
     for poly in (RECT, FOOTPRINTS[6]):
         check(cmap, omap, cb, poly, desc, po.SHAPE_AREA, f"overflowing list, area {env}")
