@@ -1046,7 +1046,6 @@ __device__ __forceinline__ uint32_t mark_bits32(const uint4& a, const uint4& b, 
 /// LANE = map row, so that the plane words of a column - consecutive rows - leave as one coalesced store (the planes
 /// are column-major).  Every lane reads its row 32 bytes at a time and keeps the next word in hand: the doubling
 /// V |= V >> 2^k on the 64-bit value L[c] | L[c + 1] << 32 yields plane k + 1 in its low word.
-constexpr int kPlaneColsPerWarp = 8;
 /// Start-of-call housekeeping a kernel can do on the side: empty the deferred-pose list {pushed, capacity}, zero the
 /// caller's not-OK counter (header == nullptr: nothing to do).
 struct CallReset {
@@ -1055,6 +1054,7 @@ struct CallReset {
   unsigned long long* not_ok;
 };
 
+template <int kPlaneColsPerWarp>
 __global__ void __launch_bounds__(256) k_lethal_planes(MapView m, uint32_t* __restrict__ planes, int ypitch, long long plane_words, int row_lo,
                                                         int row_hi, bool inflated, CallReset reset) {
   if (reset.header && blockIdx.x == 0 && threadIdx.x == 0) {  // (the sweep that reads both comes after this kernel in stream order)
@@ -1081,8 +1081,10 @@ __global__ void __launch_bounds__(256) k_lethal_planes(MapView m, uint32_t* __re
       return word;
     };
     uint32_t cur = word_at(c0);
-#pragma unroll 4
-    for (int c = c0; c < min(c0 + kPlaneColsPerWarp, n_cols); ++c) {
+#pragma unroll
+    for (int cc = 0; cc < kPlaneColsPerWarp; ++cc) {
+      const int c = c0 + cc;
+      if (c >= n_cols) break;
       const uint32_t next = word_at(c + 1);
       unsigned long long v = static_cast<unsigned long long>(cur) | (static_cast<unsigned long long>(next) << 32);
       uint32_t* __restrict__ dst = planes + static_cast<long long>(c) * ypitch + y;
@@ -2544,6 +2546,7 @@ struct cover_ctx {
   CallReset pending_reset{nullptr, 0u, nullptr};  // handed to the next k_lethal_planes launch of this call (ensure_plane_set)
   bool lazy_out = false;                // this call's launch_polygon zeroes the packed verdict words / the not-OK counter itself (or has no need to)
   void* lazy_not_ok = nullptr;
+  int plane_cols = 0;                   // COVER_B200_PLANE_COLS: word columns per warp of k_lethal_planes (2, 4, 8; 0 = by size)
   bool timeline = false;                // COVER_B200_TIMELINE=1: events between the operations of a call, printed at cover_ctx_synchronize (bring-up)
   std::vector<std::pair<const char*, cudaEvent_t>> timeline_events;
   bool disable_quad = false;            // COVER_B200_NO_QUAD=1: non-convex polygons through k_area_pair + k_area_slots (A/B measurements)
@@ -2771,10 +2774,23 @@ bool lattice_row_range(const cover_map* map, const double* polygon_xy, int nv, c
   return true;
 }
 
-/// Grid of k_lethal_planes for rows [row_lo, row_hi]: one warp per (32 rows, kPlaneColsPerWarp word columns).
-unsigned int planes_grid(const cover_ctx* ctx, int size_x, int row_lo, int row_hi) {
-  const long long tasks = static_cast<long long>((row_hi - row_lo) / 32 + 1) * (((size_x + 31) / 32 + kPlaneColsPerWarp - 1) / kPlaneColsPerWarp);
+/// Grid of k_lethal_planes for rows [row_lo, row_hi]: one warp per (32 rows, cols_per_warp word columns).
+unsigned int planes_grid(const cover_ctx* ctx, int size_x, int row_lo, int row_hi, int cols_per_warp) {
+  const long long tasks = static_cast<long long>((row_hi - row_lo) / 32 + 1) * (((size_x + 31) / 32 + cols_per_warp - 1) / cols_per_warp);
   return static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((tasks + 7) / 8, static_cast<long long>(ctx->sm_count) * 16)));
+}
+
+/// Launches k_lethal_planes for rows [row_lo, row_hi]: few word columns per warp when the rows are few (a lattice window:
+/// more warps in flight), eight when the whole of a big map is built.
+void launch_planes(cover_ctx* ctx, const MapView& v, uint32_t* planes, int ypitch, long long plane_words, int row_lo, int row_hi, bool inflated,
+                   const CallReset& reset) {
+  const long long warps8 = static_cast<long long>((row_hi - row_lo) / 32 + 1) * (((v.size_x + 31) / 32 + 7) / 8);
+  int cols = warps8 >= static_cast<long long>(ctx->sm_count) * 48 ? 8 : (warps8 >= static_cast<long long>(ctx->sm_count) * 24 ? 4 : 2);
+  if (ctx->plane_cols > 0) cols = ctx->plane_cols;
+  const unsigned int grid = planes_grid(ctx, v.size_x, row_lo, row_hi, cols);
+  if (cols == 8) k_lethal_planes<8><<<grid, 256, 0, ctx->stream>>>(v, planes, ypitch, plane_words, row_lo, row_hi, inflated, reset);
+  else if (cols == 4) k_lethal_planes<4><<<grid, 256, 0, ctx->stream>>>(v, planes, ypitch, plane_words, row_lo, row_hi, inflated, reset);
+  else k_lethal_planes<2><<<grid, 256, 0, ctx->stream>>>(v, planes, ypitch, plane_words, row_lo, row_hi, inflated, reset);
 }
 
 /// Bit planes of rows [row_lo, row_hi] (built on ctx->stream when the current ones do not cover them): the LETHAL
@@ -2797,8 +2813,7 @@ int ensure_plane_set(cover_ctx* ctx, const cover_map* map, bool inflated, int ro
     lo = 0, hi = -1;
   }
   if (row_lo < lo || row_hi > hi) {
-    k_lethal_planes<<<planes_grid(ctx, map->view.size_x, row_lo, row_hi), 256, 0, ctx->stream>>>(map->view, store, map->ypitch, map->plane_words, row_lo, row_hi, inflated,
-                                                                                                 ctx->pending_reset);
+    launch_planes(ctx, map->view, store, map->ypitch, map->plane_words, row_lo, row_hi, inflated, ctx->pending_reset);
     ctx->pending_reset = CallReset{nullptr, 0u, nullptr};
     ++ctx->launches;
     lo = row_lo, hi = row_hi;
@@ -3034,7 +3049,9 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_expand));
   set(reinterpret_cast<const void*>(&k_outline_expand));
   set(reinterpret_cast<const void*>(&k_inflate));
-  set(reinterpret_cast<const void*>(&k_lethal_planes));
+  set(reinterpret_cast<const void*>(&k_lethal_planes<2>));
+  set(reinterpret_cast<const void*>(&k_lethal_planes<4>));
+  set(reinterpret_cast<const void*>(&k_lethal_planes<8>));
   set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_IS_FREE>));
   set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_rows_multi<OP_MAX>));
@@ -3734,6 +3751,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
   if (const char* e = std::getenv("COVER_B200_PACKED_ONLY_CONVEX")) ctx->always_try_packed = e[0] != '1';
   if (const char* e = std::getenv("COVER_B200_NO_QUAD")) ctx->disable_quad = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_TIMELINE")) ctx->timeline = e[0] == '1';
+  if (const char* e = std::getenv("COVER_B200_PLANE_COLS")) ctx->plane_cols = std::atoi(e);
   if (const char* e = std::getenv("COVER_B200_OLD_PACKED")) ctx->old_packed_kernel = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_FORCE_LIST_KERNEL")) ctx->force_list_kernel = e[0] == '1';
   *out = ctx;
@@ -3895,7 +3913,7 @@ int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x
   auto repair = [&](uint32_t* planes, int lo, int hi, bool inflated) {
     const int a = std::max(lo, r_lo), b = std::min(hi, r_hi);
     if (!planes || a > b) return;
-    k_lethal_planes<<<planes_grid(ctx, v.size_x, a, b), 256, 0, ctx->stream>>>(v, planes, map->ypitch, map->plane_words, a, b, inflated, CallReset{nullptr, 0u, nullptr});
+    launch_planes(ctx, v, planes, map->ypitch, map->plane_words, a, b, inflated, CallReset{nullptr, 0u, nullptr});
     ++ctx->launches;
   };
   repair(map->planes, map->planes_lo, map->planes_hi, false);
