@@ -922,8 +922,8 @@ struct PlaneView {
                                       // lanes of a warp (= consecutive scan rows, nearly the same x) read consecutive words
   long long plane_words;              // words per plane = (ceil(size_x / 32) + 3 slack columns) * ypitch
   // accumulate_cost sweeps: per-row exclusive prefix sums of the cost bytes (k_cost_prefix), row-major, ppitch words
-  // per row: word x = (number of cells >= 254 before x, mod 1024) << 22 | (sum of the costs before x, mod 2^22).
-  // A window of up to 32 cells is two loads; both fields are exact as differences.  nullptr: not built.
+  // per row: word x = (NO_INFORMATION cells before x, mod 256) << 24 | (LETHAL cells before x, mod 256) << 16 | (sum of the
+  // costs before x, mod 2^16).  A window of up to 32 cells is two loads; every field is exact as a difference.  nullptr: not built.
   const uint32_t* __restrict__ prefix;
   int ppitch;
 };
@@ -945,9 +945,9 @@ __device__ __forceinline__ void lattice_spans_accumulate(const MapView& m, const
     const uint32_t* __restrict__ row = pv.prefix + static_cast<long long>(y_base + dy) * pv.ppitch + xs;
     const uint32_t a0 = __ldg(row + off_a), a1 = __ldg(row + off_a + width);
     const uint32_t b0 = __ldg(row + off_b), b1 = __ldg(row + off_b + width);
-    const uint32_t cnt_a = ((a1 >> 22) - (a0 >> 22)) & 1023u, cnt_b = ((b1 >> 22) - (b0 >> 22)) & 1023u;
-    sum_a += (a1 - a0) & 0x3FFFFFu;  // (meaningless once a sentinel was met: `early` decides then)
-    sum_b += (b1 - b0) & 0x3FFFFFu;
+    const uint32_t cnt_a = ((a1 >> 16) - (a0 >> 16)) & 0xFFFFu, cnt_b = ((b1 >> 16) - (b0 >> 16)) & 0xFFFFu;  // (both sentinel counts: zero iff none)
+    sum_a += (a1 - a0) & 0xFFFFu;  // (meaningless once a sentinel was met: `early` decides then)
+    sum_b += (b1 - b0) & 0xFFFFu;
     if ((cnt_a != 0u && more_a) || (cnt_b != 0u && more_b)) {
       const uint8_t* __restrict__ cells = m.data + static_cast<size_t>(y_base + dy) * m.pitch + xs;
 #pragma unroll
@@ -976,19 +976,21 @@ __global__ void __launch_bounds__(256) k_cost_prefix(MapView m, uint32_t* __rest
   if (y > row_hi) return;
   const uint8_t* __restrict__ rowp = m.data + static_cast<size_t>(y) * m.pitch;
   uint32_t* __restrict__ dst = prefix + static_cast<long long>(y) * ppitch;
-  uint32_t carry_sum = 0u, carry_cnt = 0u;
+  uint32_t carry_sum = 0u, carry_l = 0u, carry_n = 0u;  // running totals of the row so far (masked to their fields when stored)
   for (int x0 = 0; x0 <= m.size_x; x0 += 32) {  // (<=: the entry at x = size_x closes the last window)
     const int x = x0 + lane;
     const uint32_t c = x < m.size_x ? __ldg(rowp + x) : 0u;
-    uint32_t s = c, n = c >= static_cast<uint32_t>(kLethal) ? 1u : 0u;
+    const uint32_t is_l = c == static_cast<uint32_t>(kLethal) ? 1u : 0u, is_n = c == static_cast<uint32_t>(kNoInformation) ? 1u : 0u;
+    uint32_t s = c, v = is_l | (is_n << 8);  // (a warp holds at most 32 of either: the two 8-bit counts cannot carry into each other)
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t us = __shfl_up_sync(kFull, s, d), un = __shfl_up_sync(kFull, n, d);
-      if (lane >= d) s += us, n += un;
+      const uint32_t us = __shfl_up_sync(kFull, s, d), uv = __shfl_up_sync(kFull, v, d);
+      if (lane >= d) s += us, v += uv;
     }
-    const uint32_t ex_s = carry_sum + s - c, ex_n = carry_cnt + n - (c >= static_cast<uint32_t>(kLethal) ? 1u : 0u);  // exclusive
-    if (x <= m.size_x) dst[x] = ((ex_n & 1023u) << 22) | (ex_s & 0x3FFFFFu);
-    carry_sum += __shfl_sync(kFull, s, 31), carry_cnt += __shfl_sync(kFull, n, 31);
+    const uint32_t ex_s = carry_sum + s - c, ex_l = carry_l + (v & 0xFFu) - is_l, ex_n = carry_n + (v >> 8) - is_n;  // exclusive
+    if (x <= m.size_x) dst[x] = ((ex_n & 0xFFu) << 24) | ((ex_l & 0xFFu) << 16) | (ex_s & 0xFFFFu);
+    const uint32_t ts = __shfl_sync(kFull, s, 31), tv = __shfl_sync(kFull, v, 31);
+    carry_sum += ts, carry_l += tv & 0xFFu, carry_n += tv >> 8;
   }
 }
 
@@ -2549,6 +2551,7 @@ struct cover_ctx {
   int plane_cols = 0;                   // COVER_B200_PLANE_COLS: word columns per warp of k_lethal_planes (2, 4, 8; 0 = by size)
   bool timeline = false;                // COVER_B200_TIMELINE=1: events between the operations of a call, printed at cover_ctx_synchronize (bring-up)
   std::vector<std::pair<const char*, cudaEvent_t>> timeline_events;
+  bool disable_values = false;          // COVER_B200_NO_VALUES=1: lattice accumulate_cost / max_cost through the shape-cache kernel (A/B measurements)
   bool disable_quad = false;            // COVER_B200_NO_QUAD=1: non-convex polygons through k_area_pair + k_area_slots (A/B measurements)
   bool always_try_packed = true;        // COVER_B200_PACKED_ONLY_CONVEX=1 restricts the packed pass to convex polygons       // COVER_B200_FORCE_LIST_KERNEL=1: A/B measurements and tests of k_area_list  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
   DeviceBuffer poses, theta, poly, in_a, in_b, out_free, out_cost, out_status, out_bits, out_not_ok, todo, todo_count, todo2, todo2_count, list_cnt, list_rng, list_seq, lat_global, lw_tables;
@@ -2579,6 +2582,8 @@ struct cover_map {
   mutable int planes_inf_lo = 0, planes_inf_hi = -1;
   mutable uint32_t* prefix = nullptr;  // per-row prefix sums of the costs (accumulate_cost lattice sweeps)
   mutable int prefix_lo = 0, prefix_hi = -1;
+  mutable uint8_t* maxp = nullptr;  // sliding-maximum planes 1..5 of the costs (max_cost lattice sweeps, k_max_planes)
+  mutable int maxp_lo = 0, maxp_hi = -1;
   int ppitch = 0;
   int ypitch = 0;
   long long plane_words = 0;
@@ -2860,6 +2865,35 @@ int ensure_prefix(cover_ctx* ctx, const cover_map* map, int row_lo, int row_hi, 
     map->prefix_lo = row_lo, map->prefix_hi = row_hi;
   }
   prefix = map->prefix;
+  return COVER_OK;
+}
+
+void launch_max_planes(cover_ctx* ctx, const cover_map* map, int row_lo, int row_hi) {
+  const MapView& v = map->view;
+  const dim3 grid(static_cast<unsigned int>(((v.pitch >> 2) + 255) / 256), static_cast<unsigned int>(row_hi - row_lo + 1));
+  k_max_planes<<<grid, 256, 0, ctx->stream>>>(v, map->maxp, static_cast<long long>(v.pitch) * v.size_y, row_lo);
+  ++ctx->launches;
+}
+
+/// Sliding-maximum planes of rows [row_lo, row_hi] for max_cost lattice sweeps (built on ctx->stream when the current
+/// ones do not cover them); nullptr when disabled or out of memory (5 bytes per cell).
+int ensure_max_planes(cover_ctx* ctx, const cover_map* map, int row_lo, int row_hi, const uint8_t*& maxp) {
+  maxp = nullptr;
+  if (ctx->disable_planes || row_lo > row_hi) return COVER_OK;
+  if (!map->maxp) {
+    uint8_t* p = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&p), static_cast<size_t>(map->view.pitch) * map->view.size_y * 5 + 64) != cudaSuccess) {
+      cudaGetLastError();
+      return COVER_OK;
+    }
+    map->maxp = p;
+    map->maxp_lo = 0, map->maxp_hi = -1;
+  }
+  if (row_lo < map->maxp_lo || row_hi > map->maxp_hi) {
+    launch_max_planes(ctx, map, row_lo, row_hi);
+    map->maxp_lo = row_lo, map->maxp_hi = row_hi;
+  }
+  maxp = map->maxp;
   return COVER_OK;
 }
 
@@ -3259,6 +3293,31 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     if (!word_bits) CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
   }
   const bool words = word_bits != nullptr;
+  // accumulate_cost / max_cost of an area over such a lattice: the same class / shape tables, values from per-row prefix
+  // words / sliding-maximum planes (k_lw_values)
+  bool values = false;
+  LwValueTables value_tables{nullptr, 0, nullptr, 0};
+  if (OP != OP_IS_FREE && shape == SHAPE_AREA && src.format == POSE_LATTICE && nv >= 1 && nv <= kRowsMaxVertices && !ctx->disable_lattice_kernel &&
+      !ctx->disable_words && !ctx->disable_values && !ctx->disable_planes && std::fabs(src.dx * map->view.inv_res - 1.0) < 1e-9 &&
+      count >= std::max<int64_t>(4096, ctx->planes_min_batch) && static_cast<long long>(map->ppitch) * map->view.size_y < (1ll << 31) &&
+      (src.first + count - 1) / (static_cast<long long>(src.nx) * src.ny) - src.first / (static_cast<long long>(src.nx) * src.ny) < 65535) {
+    int rc = lw_prepare_async(ctx, map, poly_dev, nv, false, src, count, out, lw_plan);
+    if (rc) return rc;
+    if (OP == OP_ACCUMULATE) {
+      const uint32_t* prefix = nullptr;
+      rc = ensure_prefix(ctx, map, row_lo, row_hi, prefix);
+      value_tables.prefix = prefix, value_tables.ppitch = map->ppitch;
+      values = value_tables.prefix != nullptr;
+    } else {
+      const uint8_t* maxp = nullptr;
+      rc = ensure_max_planes(ctx, map, row_lo, row_hi, maxp);
+      value_tables.maxp = maxp;
+      value_tables.max_plane_bytes = static_cast<long long>(map->view.pitch) * map->view.size_y;
+      values = value_tables.maxp != nullptr;
+    }
+    if (rc) return rc;
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));  // the tables of k_lw_prepare
+  }
   bool reset_by_kernel = false;
   if (ctx->lazy_out) {
     // every kernel ORs its bits into zeroed words of the packed verdicts (the word sweeps store the words they own entirely)
@@ -3288,9 +3347,9 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   //    mildly concave one) are finished by the packed / lattice kernel; the rest lands on the todo list.
   //    Polygons that are far from convex skip it (the pass would defer almost everything).
   //    A non-convex polygon of moderate size goes through k_area_quad instead (four ranges per row in the same table).
-  const int quad_threads = (!outline_lattice && !words && !ctx->old_packed_kernel && !ctx->disable_quad && rows_cap <= kQuadMaxRows && !is_convex(poly_host, nv))
+  const int quad_threads = (!outline_lattice && !words && !values && !ctx->old_packed_kernel && !ctx->disable_quad && rows_cap <= kQuadMaxRows && !is_convex(poly_host, nv))
                                ? quad_block_threads(poly_bytes, rows_cap) : 0;
-  const bool fast = outline_lattice || words || quad_threads > 0 || (rows_cap <= kPackedMaxRows && (is_convex(poly_host, nv) || ctx->always_try_packed));
+  const bool fast = outline_lattice || words || values || quad_threads > 0 || (rows_cap <= kPackedMaxRows && (is_convex(poly_host, nv) || ctx->always_try_packed));
   // 2. general pass over everything (or the todo list): one warp per pose when the outline has few rays
   //    relative to its rows, else one thread per pose with per-row lists in global scratch.
   const bool rows_kernel = nv <= kRowsMaxVertices && rows_cap <= 30000 && !ctx->force_list_kernel && (nv <= 16 || rows_cap > 48);
@@ -3314,7 +3373,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       return COVER_OK;
     }
     // A convex polygon defers (almost) nothing: a small persistent grid is enough to drain the list.
-    const bool small_drain = words || (fast && is_convex(poly_host, nv));  // (the word sweep defers next to nothing, whatever the polygon)
+    const bool small_drain = words || values || (fast && is_convex(poly_host, nv));  // (the word sweep defers next to nothing, whatever the polygon)
     if (rows_kernel) {
       const long long blocks = small_drain ? ctx->sm_count : static_cast<long long>(ctx->sm_count) * 12;
       const unsigned int grid = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>(blocks, (count + kRowsWarps - 1) / kRowsWarps)));
@@ -3333,7 +3392,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     // deferred-pose list: {pushed, capacity} + the entries.  A lattice sweep defers next to nothing (poses at the map
     // border, shapes beyond the tables): a small list, and if it ever overflows the drain kernel takes every pose.  The
     // per-pose fast passes may defer most of a batch (concave polygons): room for all of it.
-    int64_t todo_cap = (words || (src.format == POSE_LATTICE && !ctx->disable_lattice_kernel)) ? words_todo_cap(ctx, count) : count;
+    int64_t todo_cap = (words || values || (src.format == POSE_LATTICE && !ctx->disable_lattice_kernel)) ? words_todo_cap(ctx, count) : count;
     if (ctx->todo_cap_limit > 0) todo_cap = std::min(todo_cap, ctx->todo_cap_limit);
     CU(ctx->todo.ensure(static_cast<size_t>(todo_cap) * sizeof(unsigned int)));
     CU(ctx->todo_count.ensure(2 * sizeof(unsigned int)));
@@ -3353,6 +3412,10 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
       if (rc) return rc;
       drained = true;
       --ctx->launches;  // (counted once more below)
+    } else if (values) {
+      const dim3 grid(static_cast<unsigned int>((src.ny + 7) / 8), static_cast<unsigned int>((src.nx + 63) / 64), static_cast<unsigned int>(lw_plan.g.n_head));
+      k_lw_values<OP == OP_IS_FREE ? OP_MAX : OP><<<grid, 256, 0, ctx->stream>>>(map->view, value_tables, src, count, out, lw_plan.t, lw_plan.g,
+                                                                              ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
     } else if (lattice) {
       LatGeom g{};
       g.row_first = src.first / src.nx;
@@ -3750,6 +3813,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
   if (const char* e = std::getenv("COVER_B200_CHUNKS")) ctx->pipeline_chunks = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("COVER_B200_PACKED_ONLY_CONVEX")) ctx->always_try_packed = e[0] != '1';
   if (const char* e = std::getenv("COVER_B200_NO_QUAD")) ctx->disable_quad = e[0] == '1';
+  if (const char* e = std::getenv("COVER_B200_NO_VALUES")) ctx->disable_values = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_TIMELINE")) ctx->timeline = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_PLANE_COLS")) ctx->plane_cols = std::atoi(e);
   if (const char* e = std::getenv("COVER_B200_OLD_PACKED")) ctx->old_packed_kernel = e[0] == '1';
@@ -3878,7 +3942,7 @@ int cover_map_upload_async(cover_map* map, const uint8_t* host_data) {
   }
   map->last_band = last[groups - 1];
   map->bands_pending = true;
-  map->planes_hi = map->planes_inf_hi = map->prefix_hi = -1;  // the bit planes describe the old image
+  map->planes_hi = map->planes_inf_hi = map->prefix_hi = map->maxp_hi = -1;  // the bit planes describe the old image
   return COVER_OK;
 }
 
@@ -3888,7 +3952,7 @@ int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem) {
   Bind bind(ctx->device);
   const MapView& v = map->view;
   CU(map_ready(ctx, map));
-  map->planes_hi = map->planes_inf_hi = map->prefix_hi = -1;
+  map->planes_hi = map->planes_inf_hi = map->prefix_hi = map->maxp_hi = -1;
   tl(ctx, "upload: entry");
   CU(copy_rows(map->dev, v.pitch, data, v.size_x, v.size_y, mem == COVER_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream,
                &ctx->launches));
@@ -3924,6 +3988,10 @@ int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x
       k_cost_prefix<<<(b - a + 1 + 7) / 8, 256, 0, ctx->stream>>>(v, map->prefix, map->ppitch, a, b);
       ++ctx->launches;
     }
+  }
+  {
+    const int a = std::max(map->maxp_lo, r_lo), b = std::min(map->maxp_hi, r_hi);
+    if (map->maxp && a <= b) launch_max_planes(ctx, map, a, b);
   }
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
@@ -3979,7 +4047,7 @@ int cover_map_inflate(cover_map* map, int32_t radius_cells, const uint8_t* cost_
   const MapView& v = map->view;
   const size_t bytes = static_cast<size_t>(v.pitch) * v.size_y;
   CU(map_ready(ctx, map));
-  map->planes_hi = map->planes_inf_hi = map->prefix_hi = -1;
+  map->planes_hi = map->planes_inf_hi = map->prefix_hi = map->maxp_hi = -1;
   const size_t lut_bytes = static_cast<size_t>(radius_cells) * radius_cells + 1;
   CU(ctx->in_b.ensure(lut_bytes));
   CU(cudaMemcpyAsync(ctx->in_b.ptr, cost_by_d2, lut_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -4010,6 +4078,7 @@ void cover_map_destroy(cover_map* map) {
   cudaFree(map->planes);
   cudaFree(map->planes_inf);
   cudaFree(map->prefix);
+  cudaFree(map->maxp);
   cudaFree(map->dev);
   delete map;
 }

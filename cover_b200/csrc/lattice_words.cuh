@@ -712,3 +712,180 @@ __global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep_general(MapView m, c
 }
 
 }  // namespace cvr
+
+namespace cvr {
+
+/// Tables the value folds of a lattice sweep read: accumulate_cost the per-row exclusive prefix words of k_cost_prefix
+/// (word x = NO_INFORMATION cells before x, mod 256, << 24 | LETHAL cells before x, mod 256, << 16 | sum of the costs
+/// before x, mod 2^16: a window of up to 32 cells is two loads, every field exact as a difference); max_cost the sliding-maximum byte planes of k_max_planes
+/// (plane k, byte x of row y = max of the cells x .. x + 2^k - 1; plane 0 is the costmap itself).
+struct LwValueTables {
+  const uint32_t* __restrict__ prefix;
+  int ppitch;
+  const uint8_t* __restrict__ maxp;  // planes 1..5, plane k at maxp + (k - 1) * max_plane_bytes, row pitch = the map's
+  long long max_plane_bytes;
+};
+
+/// accumulate_cost / max_cost(area_generator(res, pose * polygon - origin), map) over a lattice at cell pitch, from the
+/// class / shape tables of k_lw_prepare: WARP = 64 x-adjacent poses of one lattice row (two per lane), the spans of their
+/// shape are uniform loads, a span costs every pose two table reads - consecutive poses read consecutive words / bytes.
+/// Sums: the first window (the spans are in generator order: rows ascending, x ascending) that holds a LETHAL or a
+/// NO_INFORMATION cell decides (the reference's "first negative value in generator order", impl/costmap.hpp:50-63) - from
+/// the two counts alone unless it holds both kinds, then it is walked byte by byte for the first one.  Poses whose bounding box leaves the map, shapes beyond the tables: deferred to the per-pose kernels.
+/// -1 / -2: the first of `width` cells that is LETHAL / NO_INFORMATION (the window holds both kinds)
+__device__ __noinline__ int lw_first_sentinel(const uint8_t* __restrict__ cells, int width) {
+  for (int c = 0; c < width; ++c) {
+    const int v = __ldg(cells + c);
+    if (v >= kLethal) return v == kLethal ? -1 : -2;
+  }
+  return 0;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) k_lw_values(MapView m, LwValueTables vt, PoseSource src, long long count, OutView out, LwTables t, LwGeom g,
+                                                  unsigned int* __restrict__ todo, unsigned int* __restrict__ todo_count) {
+  constexpr unsigned kAll = 0xFFFFFFFFu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.z, it = g.it_lo + h;
+  const int iy = blockIdx.x * 8 + warp;
+  if (iy >= src.ny) return;
+  const long long row_i = (static_cast<long long>(it) * src.ny + iy) * src.nx - src.first;  // pose index of column 0 in this batch
+  const int ix_a = blockIdx.y * 64 + lane, ix_b = ix_a + 32;
+  const long long i_a = row_i + ix_a, i_b = row_i + ix_b;
+  const bool valid_a = ix_a < src.nx && i_a >= 0 && i_a < count, valid_b = ix_b < src.nx && i_b >= 0 && i_b < count;
+  if (!__any_sync(kAll, valid_a || valid_b)) return;
+  const int yc = t.ycls[static_cast<long long>(h) * src.ny + iy], y0c = t.yc0[static_cast<long long>(h) * src.ny + iy];
+  const int xc_a = valid_a ? t.xcls[static_cast<long long>(h) * src.nx + ix_a] : kLwNone;
+  const int xc_b = valid_b ? t.xcls[static_cast<long long>(h) * src.nx + ix_b] : kLwNone;
+  const int base = t.shape_base[h], n_y = t.n_ycls[h];
+  // coordinates out of range (status); class tables full or shape pool exhausted (per-pose kernels)
+  if (valid_a && (xc_a == kLwBad || yc == kLwBad)) store_failure(out, i_a, ST_COORD_RANGE);
+  else if (valid_a && (xc_a == kLwOverflow || yc == kLwOverflow || base < 0)) push_todo(todo, todo_count, i_a);
+  if (valid_b && (xc_b == kLwBad || yc == kLwBad)) store_failure(out, i_b, ST_COORD_RANGE);
+  else if (valid_b && (xc_b == kLwOverflow || yc == kLwOverflow || base < 0)) push_todo(todo, todo_count, i_b);
+  const bool live_a = valid_a && xc_a < kLwClasses && yc < kLwClasses && base >= 0;
+  const bool live_b = valid_b && xc_b < kLwClasses && yc < kLwClasses && base >= 0;
+  unsigned pend_a = __ballot_sync(kAll, live_a), pend_b = __ballot_sync(kAll, live_b);
+  while (pend_a | pend_b) {  // one pass per x class present among the 64 poses (nearly always one)
+    const int leader = pend_a ? __ffs(pend_a) - 1 : __ffs(pend_b) - 1;
+    const int qa = __shfl_sync(kAll, xc_a, leader), qb = __shfl_sync(kAll, xc_b, leader);
+    const int q = pend_a ? qa : qb;
+    const bool in_a = live_a && xc_a == q, in_b = live_b && xc_b == q;
+    pend_a &= ~__ballot_sync(kAll, in_a), pend_b &= ~__ballot_sync(kAll, in_b);
+    const LwShape* shp = t.shapes + base + q * n_y + yc;
+    const int status = shp->status;
+    if (status == kLwUnfit) {
+      if (in_a) push_todo(todo, todo_count, i_a);
+      if (in_b) push_todo(todo, todo_count, i_b);
+      continue;
+    }
+    if (status != ST_OK) {  // std::logic_error upstream / more than 16 ranges on a row
+      if (in_a) store_failure(out, i_a, status);
+      if (in_b) store_failure(out, i_b, status);
+      continue;
+    }
+    const int X_a = ix_a + t.xanchor[h * kLwClasses + q], X_b = X_a + 32;  // map column of vertex 0
+    const bool y_in = y0c + shp->yb >= 0 && y0c + shp->yb + shp->rows <= m.size_y;
+    const bool go_a = in_a && y_in && X_a + shp->xb >= 0 && X_a + shp->x1 < m.size_x;
+    const bool go_b = in_b && y_in && X_b + shp->xb >= 0 && X_b + shp->x1 < m.size_x;
+    if (in_a && !go_a) push_todo(todo, todo_count, i_a);  // at the map border: the per-pose kernels know the rules
+    if (in_b && !go_b) push_todo(todo, todo_count, i_b);
+    const LwSpan* __restrict__ spans = t.spans + shp->span_first;
+    const int n_spans = shp->n_spans;
+    // lanes without a pose in this pass read what a lane with one reads (in range; their results are dropped)
+    const unsigned ga = __ballot_sync(kAll, go_a), gb = __ballot_sync(kAll, go_b);
+    if ((ga | gb) == 0u) continue;
+    const int donor = ga ? __ffs(ga) - 1 : __ffs(gb) - 1;
+    const int donor_a = __shfl_sync(kAll, X_a, donor), donor_b = __shfl_sync(kAll, X_b, donor);
+    const int Xd = ga ? donor_a : donor_b;
+    const int Xa = go_a ? X_a : Xd, Xb = go_b ? X_b : Xd;
+    if (OP == OP_ACCUMULATE) {
+      // (32-bit indices into the tables: the host takes this path only while rows x pitch stays below 2^31)
+      uint32_t sum_a = 0u, sum_b = 0u;
+      int early_a = 0, early_b = 0;
+      for (int s = 0; s < n_spans; ++s) {
+        const LwSpan sp = __ldg(spans + s);
+        const int dy = (sp.w & 0xFFFF) - 32768, width = sp.z + (1 << (sp.w >> 16));
+        const int o = (y0c + dy) * vt.ppitch + sp.x;
+        const int oa = o + Xa, ob = o + Xb;
+        const uint32_t a0 = __ldg(vt.prefix + oa), a1 = __ldg(vt.prefix + oa + width);
+        const uint32_t b0 = __ldg(vt.prefix + ob), b1 = __ldg(vt.prefix + ob + width);
+        sum_a += (a1 - a0) & 0xFFFFu, sum_b += (b1 - b0) & 0xFFFFu;  // (meaningless once a sentinel was met: `early` decides then)
+        const uint32_t ha = ((a1 >> 16) - (a0 >> 16)) & 0xFFFFu, hb = ((b1 >> 16) - (b0 >> 16)) & 0xFFFFu;  // both sentinel counts: zero iff none
+        if ((ha != 0u && early_a == 0) || (hb != 0u && early_b == 0)) {
+          if (ha != 0u && early_a == 0 && go_a) {
+            const uint32_t n_l = ha & 0xFFu, n_n = ((a1 >> 24) - (a0 >> 24)) & 0xFFu;
+            early_a = n_n == 0u ? -1 : (n_l == 0u ? -2 : lw_first_sentinel(m.data + static_cast<size_t>(y0c + dy) * m.pitch + sp.x + X_a, width));
+          }
+          if (hb != 0u && early_b == 0 && go_b) {
+            const uint32_t n_l = hb & 0xFFu, n_n = ((b1 >> 24) - (b0 >> 24)) & 0xFFu;
+            early_b = n_n == 0u ? -1 : (n_l == 0u ? -2 : lw_first_sentinel(m.data + static_cast<size_t>(y0c + dy) * m.pitch + sp.x + X_b, width));
+          }
+        }
+      }
+      Fold<OP_ACCUMULATE> fa, fb;
+      fa.sum = sum_a, fa.early = early_a, fb.sum = sum_b, fb.early = early_b;
+      if (go_a) {
+        fa.store(out, i_a);
+        if (out.status) out.status[i_a] = ST_OK;
+      }
+      if (go_b) {
+        fb.store(out, i_b);
+        if (out.status) out.status[i_b] = ST_OK;
+      }
+    } else {
+      uint32_t best_a = 0u, best_b = 0u;
+      for (int s = 0; s < n_spans; ++s) {
+        const LwSpan sp = __ldg(spans + s);
+        const int dy = (sp.w & 0xFFFF) - 32768, lg = sp.w >> 16;
+        const uint8_t* __restrict__ pl = lg == 0 ? m.data : vt.maxp + static_cast<long long>(lg - 1) * vt.max_plane_bytes;
+        const int o = (y0c + dy) * m.pitch + sp.x;
+        const int oa = o + Xa, ob = o + Xb;
+        const uint32_t va = max(static_cast<uint32_t>(__ldg(pl + oa)), static_cast<uint32_t>(__ldg(pl + oa + sp.z)));
+        const uint32_t vb = max(static_cast<uint32_t>(__ldg(pl + ob)), static_cast<uint32_t>(__ldg(pl + ob + sp.z)));
+        best_a = max(best_a, va), best_b = max(best_b, vb);
+      }
+      Fold<OP_MAX> fa, fb;
+      fa.best4 = best_a, fb.best4 = best_b;
+      if (go_a) {
+        fa.store(out, i_a);
+        if (out.status) out.status[i_a] = ST_OK;
+      }
+      if (go_b) {
+        fb.store(out, i_b);
+        if (out.status) out.status[i_b] = ST_OK;
+      }
+    }
+  }
+}
+
+/// Sliding-maximum planes 1..5 of rows [row_lo, row_hi] (grid.y = row, one thread per 4 cells): the 4 + 32 cells after a
+/// word's first cell are doubled in registers, M_{k+1}[x] = max(M_k[x], M_k[x + 2^k]) byte-wise (__vmaxu4).
+__global__ void __launch_bounds__(256) k_max_planes(MapView m, uint8_t* __restrict__ maxp, long long plane_bytes, int row_lo) {
+  const int words = m.pitch >> 2;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= words) return;
+  const int y = row_lo + blockIdx.y;
+  const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(m.data + static_cast<size_t>(y) * m.pitch);
+  uint32_t R[10];
+#pragma unroll
+  for (int d = 0; d < 9; ++d) R[d] = j + d < words ? __ldg(row + j + d) : 0u;
+  R[9] = 0u;
+  uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(maxp + static_cast<size_t>(y) * m.pitch) + j;
+  const long long plane_words = plane_bytes >> 2;
+#pragma unroll
+  for (int d = 0; d < 9; ++d) R[d] = __vmaxu4(R[d], __funnelshift_r(R[d], R[d + 1], 8));
+  dst[0] = R[0];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) R[d] = __vmaxu4(R[d], __funnelshift_r(R[d], R[d + 1], 16));
+  dst[plane_words] = R[0];
+#pragma unroll
+  for (int d = 0; d < 7; ++d) R[d] = __vmaxu4(R[d], R[d + 1]);
+  dst[2 * plane_words] = R[0];
+#pragma unroll
+  for (int d = 0; d < 5; ++d) R[d] = __vmaxu4(R[d], R[d + 2]);
+  dst[3 * plane_words] = R[0];
+  dst[4 * plane_words] = __vmaxu4(R[0], R[4]);
+}
+
+}  // namespace cvr

@@ -285,3 +285,52 @@ def test_packed_verdicts_do_not_depend_on_what_the_words_held(cb, monkeypatch, e
             assert not got[count:].any()  # the unused bits of the last word are zero
             assert int(not_ok.item()) == int((full.status[first:first + count] != 0).sum())
     ctx.close()
+
+
+@pytest.mark.parametrize("env", [{}, {"COVER_B200_TODO_CAP": 64}])
+def test_value_folds_on_a_lattice(cb, monkeypatch, env):
+    """accumulate_cost / max_cost of areas over a lattice (k_lw_values: prefix words, sliding-maximum planes) against the
+    oracle: every reference footprint, a lattice that hangs over the map (deferred border poses), axis-aligned headings
+    (several classes per row of poses), sentinel order (LETHAL before / after NO_INFORMATION), sub-ranges, a costmap
+    update in between."""
+    ctx = _ctx(cb, monkeypatch, **env)
+    launches0 = ctx.launch_count
+    rng = np.random.default_rng(511)
+    data = mixed_map(rng, 420, 380, lethal=0.004)
+    cmap = cb.Costmap(ctx, data, 0.05, -1.0, 0.5)
+    omap = po.Costmap(data, 0.05, -1.0, 0.5)
+    cs = headings(5)
+    polys = [("rect", RECT)] + list(zip(FOOTPRINT_NAMES, FOOTPRINTS))
+    for name, poly in polys:
+        big = name in ("W", "M", "S", "Spiral")
+        desc = dict(x0=-1.6, dx=0.05, nx=75 if big else 310, y0=0.1, dy=0.05, ny=33 if big else 90, cs=cs)
+        total = desc["nx"] * desc["ny"] * cs.shape[0]
+        for op_name, op in (("area_accumulate_cost", po.OP_ACCUMULATE), ("area_max_cost", po.OP_MAX)):
+            for first, count in ((0, total), (desc["nx"] * 3 + 7, min(total - desc["nx"] * 3 - 7, 9001))):
+                gpu = getattr(cmap, op_name)(poly, cb.Lattice(**desc), first=first, count=count)
+                cpu = po.polygon_batch(omap, poly, po.Lattice(**desc), op=op, first=first, count=count, threads=8)
+                np.testing.assert_array_equal(gpu.status, cpu.status, err_msg=f"{name} {op_name} {env}")
+                np.testing.assert_array_equal(gpu.cost, cpu.cost, err_msg=f"{name} {op_name} {env}")
+                np.testing.assert_array_equal(gpu.is_free, cpu.is_free, err_msg=f"{name} {op_name} {env}")
+    # a new image: the prefix words and maximum planes are rebuilt
+    data2 = mixed_map(rng, 420, 380, lethal=0.01)
+    cmap.upload(data2)
+    omap2 = po.Costmap(data2, 0.05, -1.0, 0.5)
+    desc = dict(x0=-0.5, dx=0.05, nx=300, y0=0.6, dy=0.05, ny=120, cs=headings(3))
+    for op_name, op in (("area_accumulate_cost", po.OP_ACCUMULATE), ("area_max_cost", po.OP_MAX)):
+        gpu = getattr(cmap, op_name)(RECT, cb.Lattice(**desc))
+        cpu = po.polygon_batch(omap2, RECT, po.Lattice(**desc), op=op, threads=8)
+        np.testing.assert_array_equal(gpu.cost, cpu.cost)
+        np.testing.assert_array_equal(gpu.status, cpu.status)
+        assert (cpu.cost < 0).any() and (cpu.cost > 0).any()
+    # a window update repairs them in place
+    patch = mixed_map(rng, 64, 50, lethal=0.05)
+    data2[90:140, 100:164] = patch
+    cmap.upload_window(data2, 100, 90, 64, 50)
+    omap3 = po.Costmap(data2, 0.05, -1.0, 0.5)
+    for op_name, op in (("area_accumulate_cost", po.OP_ACCUMULATE), ("area_max_cost", po.OP_MAX)):
+        gpu = getattr(cmap, op_name)(RECT, cb.Lattice(**desc))
+        cpu = po.polygon_batch(omap3, RECT, po.Lattice(**desc), op=op, threads=8)
+        np.testing.assert_array_equal(gpu.cost, cpu.cost)
+    assert ctx.launch_count > launches0
+    ctx.close()
