@@ -1,25 +1,31 @@
-// lattice_words.cuh — verdict sweeps over an (x, y, heading) pose lattice at cell pitch, bit-parallel in x.
+// lattice_words.cuh — sweeps over an (x, y, heading) pose lattice at cell pitch: verdicts bit-parallel in x, value folds
+// from per-row tables.
 //
 // is_free(polygon, pose, map) (src/cover/costmap.cpp:78-85) and is_free(outline_generator(...), map)
-// (src/cover/impl/costmap.hpp:23-27) for every pose of a cover_lattice whose x pitch is one cell.  Three kernels:
+// (src/cover/impl/costmap.hpp:23-27) for every pose of a cover_lattice whose x pitch is one cell; accumulate_cost
+// (impl/costmap.hpp:50-63) and the max_cost extension of areas over the same lattices.  Kernels:
 //
-//  k_lw_classes  one CTA per heading.  The pose transform separates - the x cells of the vertices depend on (heading,
-//                ix) only, the y cells on (heading, iy) only - so a heading needs nx + ny vertex profiles, not nx * ny
-//                transforms (the same __dmul_rn/__dadd_rn/__dsub_rn/__double2int_rz sequence as to_cell, per
-//                coordinate).  Columns are sorted into CLASSES of identical (vertex offsets relative to vertex 0,
-//                anchor = cell of vertex 0 minus ix), rows into classes of identical offsets; nearly every heading has
-//                one class per axis, the axis-aligned headings (vertices within rounding noise of a cell boundary) a
-//                handful.  The comparison is exact (no hashing).
-//  k_lw_shapes   one warp per (heading, x class, y class): the discretised polygon relative to vertex 0 is rasterised
-//                once with the closed-form scan-row construction of area_rows.cuh (runs, cusps, stable sort by `min`,
-//                pair merge - generators.cpp:189-255) into a list of spans (dx, dy, width <= 32) in a global pool.
-//  k_lw_sweep    one warp per (heading, 32 lattice rows, 32 * W columns): LANE = lattice row, and every thread keeps
-//                the verdicts of 32 * W x-adjacent poses as W words.  "Some cell of a w-cell window is lethal" is the
-//                OR of two overlapping power-of-two windows of the lethal bit planes (k_lethal_planes), and for 32
-//                x-adjacent poses those are 32 consecutive plane bits: per span W + 2 coalesced word loads (the planes
-//                are column-major, so the 32 lanes = 32 consecutive map rows read consecutive words) and 2 W funnel
-//                shifts decide 32 W poses.  Columns of another x class are masked out and walked with their own shape.
-// Nothing here waits for another warp: the sweep only ever reads finished tables.
+//  k_lw_prepare        one CTA per heading.  The pose transform separates - the x cells of the vertices depend on
+//                      (heading, ix) only, the y cells on (heading, iy) only - so a heading needs nx + ny vertex profiles,
+//                      not nx * ny transforms (the same __dmul_rn/__dadd_rn/__dsub_rn/__double2int_rz sequence as
+//                      to_cell, per coordinate).  Columns are sorted into CLASSES of identical (vertex offsets relative to
+//                      vertex 0, anchor = cell of vertex 0 minus ix), rows into classes of identical offsets; nearly every
+//                      heading has one class per axis, the axis-aligned headings (vertices within rounding noise of a cell
+//                      boundary) a handful.  The comparison is exact (no hashing).  Then one warp per (x class, y class):
+//                      the discretised polygon relative to vertex 0 is rasterised once with the closed-form scan-row
+//                      construction of area_rows.cuh (runs, cusps, stable sort by `min`, pair merge -
+//                      generators.cpp:189-255) into a list of spans (dx, dy, width <= 32) in a global pool.
+//  k_lw_sweep_simple   one warp per (heading, 32 lattice rows, 32 * W columns) of a single-shape heading inside the map:
+//                      LANE = lattice row, every thread keeps the verdicts of 32 * W x-adjacent poses as W words.  "Some
+//                      cell of a w-cell window is lethal" is the OR of two overlapping power-of-two windows of the lethal
+//                      bit planes (k_lethal_planes), and for 32 x-adjacent poses those are 32 consecutive plane bits: per
+//                      span W + 2 word loads (from a shared-memory tile of the planes) and 2 W funnel shifts decide 32 W
+//                      poses.
+//  k_lw_sweep_general  the other tasks (several classes per heading: columns of another x class are masked out and walked
+//                      with their own shape, every lane walks the shape of its row's y class; map border; statuses).
+//  k_lw_values         accumulate_cost / max_cost: warp = 64 x-adjacent poses of one lattice row, two table reads per span
+//                      and pose (prefix words / sliding-maximum planes, k_max_planes).
+// Nothing here waits for another warp: the sweeps only ever read finished tables.
 #pragma once
 
 #include "area_rows.cuh"
