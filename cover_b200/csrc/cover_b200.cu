@@ -17,7 +17,8 @@
 //   k_rays<OP>           ray_generator checks       (a4)
 //   k_cells_free / k_cells<OP>   cached discrete_polygon x offsets (a11): row spans / ordered list
 //   k_footprints         discrete/generator footprint bank x offsets (a15/a16): host-precomputed row spans
-//   k_split              continuous_footprint::is_free (a14)
+//   k_split_lockstep     continuous_footprint::is_free (a14): thread = pose, the warp's walks fused in lock-step
+//   k_split              the same with independent per-thread walks (what the lock-step pass defers)
 //   k_area_expand, k_outline_expand   to_area / to_outline, batched
 //   k_trajectories       trajectory scoring (8f-4);  k_inflate: inflation layer (8f-3)
 // There is no CPU path in this file: without a CUDA device every entry returns COVER_E_CUDA.
@@ -644,15 +645,16 @@ struct QuadWalker {
   }
 };
 
+/// The walk of one polygon per lane, in lock-step (all 32 lanes call this together; `active` lanes have a pose whose
+/// vertices [x0, x1] x [y0, y1] are in range).  Returns 0: the area was scanned into `fold`; 1: left to the general
+/// kernels (taller / wider than the table, more than four ranges on a row); 2: an odd number of ranges on a row
+/// (std::logic_error upstream); -1: inactive lane.
 template <int XF, int OP>
-__device__ __forceinline__ void area_quad_pose(const double* __restrict__ poly, int nv, const Pose& T, const MapView& m, uint2* table,
-                                               int rows_cap, const OutView& out, long long i, bool valid, unsigned int* __restrict__ todo,
-                                               unsigned int* __restrict__ todo_count) {
-  int x0, y0, x1, y1;
-  const bool in_range = polygon_bbox<XF>(poly, nv, T, m, x0, y0, x1, y1);
+__device__ __forceinline__ int area_quad_core(const double* __restrict__ poly, int nv, const Pose& T, const MapView& m, uint2* table, int rows_cap,
+                                              bool active, int x0, int y0, int x1, int y1, Fold<OP>& fold) {
   const int rows = y1 - y0 + 1;
   const bool too_big = rows > rows_cap || (x1 - x0) > kQuadMaxWidth;
-  const bool walk = valid && in_range && !too_big;
+  const bool walk = active && !too_big;
   QuadWalker w;
   w.tab = table + threadIdx.x, w.stride = static_cast<int>(blockDim.x), w.xb = x0, w.yb = y0;
   const int rows_max = __reduce_max_sync(kFullMask, walk ? rows : 0);
@@ -700,16 +702,11 @@ __device__ __forceinline__ void area_quad_pose(const double* __restrict__ poly, 
       w.prepend(w.y0, w.x0, w.f_xlast, w.y_run, w.f_ynext);
     }
   }
-  // statuses and deferrals
   bool scan = walk && !w.overflow;
-  if (valid && !in_range) store_failure(out, i, ST_COORD_RANGE);
-  if (valid && in_range && (too_big || w.overflow)) push_todo(todo, todo_count, i);  // more than four ranges on a row
   bool odd = false;
   for (int r = 0; r < rows_max; ++r)
     if (scan && r < rows) odd |= QuadWalker::odd(w.tab[r * w.stride]);
-  if (scan && odd) store_failure(out, i, ST_LOGIC_ERROR);  // std::logic_error("Even number of line-pairs expected")
   scan = scan && !odd;
-  Fold<OP> fold;
   bool more = scan;
   for (int r = 0; r < rows_max; ++r) {
     if (__all_sync(kFullMask, !more)) break;
@@ -738,7 +735,23 @@ __device__ __forceinline__ void area_quad_pose(const double* __restrict__ poly, 
       }
     }
   }
-  if (scan) {
+  if (!active) return -1;
+  if (too_big || w.overflow) return 1;
+  return odd ? 2 : 0;
+}
+
+template <int XF, int OP>
+__device__ __forceinline__ void area_quad_pose(const double* __restrict__ poly, int nv, const Pose& T, const MapView& m, uint2* table,
+                                               int rows_cap, const OutView& out, long long i, bool valid, unsigned int* __restrict__ todo,
+                                               unsigned int* __restrict__ todo_count) {
+  int x0, y0, x1, y1;
+  const bool in_range = polygon_bbox<XF>(poly, nv, T, m, x0, y0, x1, y1);
+  Fold<OP> fold;
+  const int rc = area_quad_core<XF, OP>(poly, nv, T, m, table, rows_cap, valid && in_range, x0, y0, x1, y1, fold);
+  if (valid && !in_range) store_failure(out, i, ST_COORD_RANGE);
+  if (rc == 1) push_todo(todo, todo_count, i);
+  if (rc == 2) store_failure(out, i, ST_LOGIC_ERROR);  // std::logic_error("Even number of line-pairs expected")
+  if (rc == 0) {
     fold.store(out, i);
     if (out.status) out.status[i] = ST_OK;
   }
@@ -2369,13 +2382,17 @@ struct SlotSink {
 };
 
 __global__ void __launch_bounds__(kBlock) k_split(MapView m, SplitView fp, int n_vertices_total, PoseSource src, long long count,
-                                                 OutView out, ListScratch scratch, int slot_rows) {
+                                                 OutView out, ListScratch scratch, int slot_rows, const unsigned int* __restrict__ in_list,
+                                                 const unsigned int* __restrict__ in_count) {
   extern __shared__ double smem_d[];
   const double* xy = stage_polygon(fp.xy, n_vertices_total, smem_d);
   uint32_t* slot_table = reinterpret_cast<uint32_t*>(smem_d + 2 * n_vertices_total);  // [slot_rows][4][blockDim.x], 0 rows = disabled
   const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long me = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (long long i = me; i < count; i += nthreads) {
+  bool listed = false;  // (with a list: only the poses k_split_lockstep deferred - or all of them, if the list overflowed)
+  const long long n_items = in_count ? todo_items(in_count, count, listed) : count;
+  for (long long item = me; item < n_items; item += nthreads) {
+    const long long i = listed ? static_cast<long long>(in_list[item]) : item;
     Pose T = load_pose(src, i);
     T.tx = __dadd_rn(T.tx, -m.origin_x);  // Translation2d(-origin) * pose: translation += (-origin)
     T.ty = __dadd_rn(T.ty, -m.origin_y);
@@ -2484,6 +2501,96 @@ __global__ void __launch_bounds__(kBlock) k_split(MapView m, SplitView fp, int n
   }
 }
 
+/// continuous_footprint::is_free(pose, map) with the warp's 32 walks fused in lock-step: every pose of a batch has the
+/// same footprint, so all lanes are at the same sub-polygon and the same ray - outline cells are tested as they are
+/// generated (INSCRIBED or LETHAL, footprints.cpp:157-170), areas go through the four-ranges-per-row table of
+/// k_area_quad (area_quad_core).  Same order of decisions as k_split: coordinates of ALL sub-polygons in range, then per
+/// sub-polygon the vertex bounding box inside the map (footprints.cpp:139-155), then its cells; the first sub-polygon
+/// that is not free (or fails) ends the pose.  Poses with an area beyond the table are left to k_split (todo list).
+__global__ void __launch_bounds__(kBlock) k_split_lockstep(MapView m, SplitView fp, int n_vertices_total, PoseSource src, long long count,
+                                                          OutView out, int rows_cap, unsigned int* __restrict__ todo,
+                                                          unsigned int* __restrict__ todo_count) {
+  extern __shared__ double smem_d[];
+  const double* xy = stage_polygon(fp.xy, n_vertices_total, smem_d);
+  uint2* table = reinterpret_cast<uint2*>(smem_d + 2 * n_vertices_total);
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int n_polys = fp.n_outlines + fp.n_areas;
+  for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x; base < count; base += nthreads) {  // whole warps iterate together
+    const long long i = base + threadIdx.x;
+    const bool valid = i < count;
+    Pose T = load_pose(src, valid ? i : 0);
+    T.tx = __dadd_rn(T.tx, -m.origin_x);  // Translation2d(-origin) * pose: translation += (-origin)
+    T.ty = __dadd_rn(T.ty, -m.origin_y);
+    bool in_range = true;
+    for (int k = 0; k < n_polys; ++k) {
+      int a, b, c, d;
+      in_range &= polygon_bbox<XF_PATH_B>(xy + 2 * fp.starts[k], fp.starts[k + 1] - fp.starts[k], T, m, a, b, c, d);
+    }
+    if (valid && !in_range) store_failure(out, i, ST_COORD_RANGE);
+    bool alive = valid && in_range;  // free and OK so far
+    bool free_ = true, deferred = false;
+    int status = ST_OK;
+    for (int k = 0; k < n_polys; ++k) {
+      if (!__any_sync(kFullMask, alive)) break;
+      const double* poly = xy + 2 * fp.starts[k];
+      const int nv = fp.starts[k + 1] - fp.starts[k];
+      if (nv == 0) continue;
+      int x0, y0, x1, y1;
+      polygon_bbox<XF_PATH_B>(poly, nv, T, m, x0, y0, x1, y1);
+      if (alive && (x0 < 0 || y0 < 0 || x1 >= m.size_x || y1 >= m.size_y)) free_ = false, alive = false;  // footprints.cpp:139-155
+      if (k < fp.n_outlines) {
+        int fx, fy;
+        to_cell<XF_PATH_B>(T, poly[0], poly[1], m, fx, fy);
+        int px = fx, py = fy, rays = 0;
+        bool hit = false;
+        LaneRay ray;
+        for (int v = 1; v <= nv; ++v) {  // v == nv: the closing ray, or the one-cell dummy ray of an open outline
+          int cx, cy;
+          if (v < nv) {
+            to_cell<XF_PATH_B>(T, poly[2 * v], poly[2 * v + 1], m, cx, cy);
+          } else {
+            cx = fx, cy = fy;
+          }
+          ray.set(px, py, cx, cy);
+          if (v < nv) {
+            rays += ray.size != 0;  // degenerate rays are skipped (generators.cpp:86-93)
+          } else if (rays <= 1) {
+            ray.size = 1, ray.add = 0, ray.num = 0;  // dummy ray: the last point itself (generators.cpp:72-78)
+            ray.major_x = ray.major_y = ray.minor_x = ray.minor_y = 0;
+          }
+          if (!alive || hit) ray.size = 0;
+          const int n_iter = __reduce_max_sync(kFullMask, ray.size);
+          for (int c = 0; c < n_iter; ++c) {
+            if (c < ray.size) {
+              const int v8 = __ldg(m.data + static_cast<size_t>(ray.y) * m.pitch + ray.x);
+              if (v8 == kInscribed || v8 == kLethal) hit = true, ray.size = 0;
+              ray.step();
+            }
+          }
+          px = cx, py = cy;
+        }
+        if (alive && hit) free_ = false, alive = false;
+      } else {
+        Fold<OP_IS_FREE> fold;
+        const int rc = area_quad_core<XF_PATH_B, OP_IS_FREE>(poly, nv, T, m, table, rows_cap, alive, x0, y0, x1, y1, fold);
+        if (rc == 1) deferred = true, alive = false;
+        else if (rc == 2) status = ST_LOGIC_ERROR, alive = false;
+        else if (rc == 0 && fold.hit) free_ = false, alive = false;
+      }
+    }
+    if (valid && in_range) {
+      if (deferred) {
+        push_todo(todo, todo_count, i);
+      } else if (status != ST_OK) {
+        store_failure(out, i, status);
+      } else {
+        emit_free(out, i, free_);
+        if (out.status) out.status[i] = ST_OK;
+      }
+    }
+  }
+}
+
 // ===================================================================================================
 // Host side
 // ===================================================================================================
@@ -2551,6 +2658,7 @@ struct cover_ctx {
   int plane_cols = 0;                   // COVER_B200_PLANE_COLS: word columns per warp of k_lethal_planes (2, 4, 8; 0 = by size)
   bool timeline = false;                // COVER_B200_TIMELINE=1: events between the operations of a call, printed at cover_ctx_synchronize (bring-up)
   std::vector<std::pair<const char*, cudaEvent_t>> timeline_events;
+  bool disable_split_lockstep = false;  // COVER_B200_NO_SPLIT_LOCKSTEP=1: continuous_footprint checks through k_split alone (A/B measurements)
   bool disable_values = false;          // COVER_B200_NO_VALUES=1: lattice accumulate_cost / max_cost through the shape-cache kernel (A/B measurements)
   bool disable_quad = false;            // COVER_B200_NO_QUAD=1: non-convex polygons through k_area_pair + k_area_slots (A/B measurements)
   bool always_try_packed = true;        // COVER_B200_PACKED_ONLY_CONVEX=1 restricts the packed pass to convex polygons       // COVER_B200_FORCE_LIST_KERNEL=1: A/B measurements and tests of k_area_list  // COVER_B200_NO_LATTICE_KERNEL=1: A/B measurements only
@@ -3073,6 +3181,7 @@ cudaError_t configure_kernels() {
   set(reinterpret_cast<const void*>(&k_area_list<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_list<OP_MAX>));
   set(reinterpret_cast<const void*>(&k_split));
+  set(reinterpret_cast<const void*>(&k_split_lockstep));
   set(reinterpret_cast<const void*>(&k_area_rows<OP_IS_FREE>));
   set(reinterpret_cast<const void*>(&k_area_rows<OP_ACCUMULATE>));
   set(reinterpret_cast<const void*>(&k_area_rows<OP_MAX>));
@@ -3814,6 +3923,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
   if (const char* e = std::getenv("COVER_B200_PACKED_ONLY_CONVEX")) ctx->always_try_packed = e[0] != '1';
   if (const char* e = std::getenv("COVER_B200_NO_QUAD")) ctx->disable_quad = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_NO_VALUES")) ctx->disable_values = e[0] == '1';
+  if (const char* e = std::getenv("COVER_B200_NO_SPLIT_LOCKSTEP")) ctx->disable_split_lockstep = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_TIMELINE")) ctx->timeline = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_PLANE_COLS")) ctx->plane_cols = std::atoi(e);
   if (const char* e = std::getenv("COVER_B200_OLD_PACKED")) ctx->old_packed_kernel = e[0] == '1';
@@ -4434,7 +4544,33 @@ int cover_split_is_free(cover_ctx* ctx, const cover_map* map, const cover_split*
       rc = view_with_planes(ctx, map, false, 0, mview.size_y - 1, mview);
       if (rc) return rc;
     }
-    k_split<<<grid, kBlock, smem, ctx->stream>>>(mview, view, split->n_vertices, src, poses->count, st.dev, scratch, slot_rows);
+    // first pass in lock-step (thread = pose, the warp at the same ray); what its four-ranges-per-row table cannot hold
+    // is left to k_split over a todo list
+    const size_t poly_bytes = static_cast<size_t>(split->n_vertices) * 2 * sizeof(double);
+    const int lock_threads = (!ctx->disable_split_lockstep && rows_cap <= kQuadMaxRows) ? quad_block_threads(poly_bytes, rows_cap) : 0;
+    const unsigned int* todo = nullptr;
+    const unsigned int* todo_count = nullptr;
+    if (lock_threads > 0) {
+      int64_t todo_cap = poses->count;
+      if (ctx->todo_cap_limit > 0) todo_cap = std::min(todo_cap, ctx->todo_cap_limit);
+      CU(ctx->todo.ensure(static_cast<size_t>(todo_cap) * sizeof(unsigned int)));
+      CU(ctx->todo_count.ensure(2 * sizeof(unsigned int)));
+      ctx->todo_header[0] = 0u, ctx->todo_header[1] = static_cast<unsigned int>(todo_cap);
+      CU(cudaMemcpyAsync(ctx->todo_count.ptr, ctx->todo_header, 2 * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
+      const size_t smem_l = poly_bytes + static_cast<size_t>(rows_cap) * lock_threads * sizeof(uint2);
+      const unsigned int grid_l = static_cast<unsigned int>(std::max<long long>(1, std::min<long long>((poses->count + lock_threads - 1) / lock_threads,
+                                                                                                     static_cast<long long>(ctx->sm_count) * 32)));
+      k_split_lockstep<<<grid_l, lock_threads, smem_l, ctx->stream>>>(mview, view, split->n_vertices, src, poses->count, st.dev, rows_cap,
+                                                                      ctx->todo.as<unsigned int>(), ctx->todo_count.as<unsigned int>());
+      ++ctx->launches;
+      todo = ctx->todo.as<unsigned int>(), todo_count = ctx->todo_count.as<unsigned int>();
+      if (st.dev.not_ok) {
+        k_overflow_recount<<<1, 32, 0, ctx->stream>>>(todo_count, st.dev.not_ok);
+        ++ctx->launches;
+      }
+    }
+    k_split<<<lock_threads > 0 ? std::min<unsigned int>(grid, static_cast<unsigned int>(ctx->sm_count) * 2) : grid, kBlock, smem, ctx->stream>>>(
+        mview, view, split->n_vertices, src, poses->count, st.dev, scratch, slot_rows, todo, todo_count);
     ++ctx->launches;
   }
   return finish_out(ctx, st, poses->count);

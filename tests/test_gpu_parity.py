@@ -434,6 +434,38 @@ def test_split_footprint_pose_form(cb, ctx):
     assert 0.02 < c.is_free.mean() < 0.98
 
 
+@pytest.mark.parametrize("env", [{}, {"COVER_B200_TODO_CAP": "64"}, {"COVER_B200_NO_SPLIT_LOCKSTEP": "1"}, {"COVER_B200_PLANES_MIN_BATCH": "0"}])
+def test_split_footprint_lockstep_and_deferrals(cb, monkeypatch, env):
+    """k_split_lockstep + what it leaves to k_split: areas with more than four ranges on a row (M, Spiral), an open
+    polyline as an outline, poses over the map border and out of coordinate range, the not-OK counter, bit-packed
+    verdicts; the same with an overflowing todo list, without the lock-step pass, and with the bit planes attached."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    c = cb.Context(0)
+    rng = np.random.default_rng(52)
+    big = mixed_map(rng, 420, 400, lethal=0.001)
+    cmap, omap = cb.Costmap(c, big, 0.05, -1.0, 0.5), po.Costmap(big, 0.05, -1.0, 0.5)
+    poses = poses_around(rng, 40_000, -2.0, 22.0)
+    poses[::97, 2] = 3e9  # coordinates out of range
+    cases = [
+        ([RECT * 0.4], [FOOTPRINTS[2] * 0.3, FOOTPRINTS[3] * 0.25]),                     # M and Spiral as areas
+        ([np.array([[0.0, 0.6, 0.9], [0.0, 0.1, -0.4]]), RECT * 0.3], [FOOTPRINTS[6]]),  # an open polyline outline, L area
+        ([], [FOOTPRINTS[0] * 0.35, RECT]),
+        ([FOOTPRINTS[5] * 0.5], []),
+    ]
+    for outlines, areas in cases:
+        sf = cb.SplitFootprint(c, outlines, areas)
+        g = sf.is_free(cmap, poses)
+        r = po.continuous_footprint_batch(omap, outlines, areas, poses, threads=8)
+        np.testing.assert_array_equal(g.status, r.status, err_msg=str(env))
+        np.testing.assert_array_equal(g.is_free, r.is_free, err_msg=str(env))
+        out = cb.Result(free_bits=np.zeros((len(poses) + 31) // 32, dtype=np.uint32), not_ok=np.zeros(1, dtype=np.int64))
+        sf.is_free(cmap, poses, out=out)
+        np.testing.assert_array_equal(out.unpack_bits(len(poses)), r.is_free & (r.status == 0))
+        assert int(out.not_ok[0]) == int((r.status != 0).sum()) > 0
+    c.close()
+
+
 @pytest.fixture()
 def ctx_planes(cb, monkeypatch):
     """A context that builds the lethal / inscribed bit planes for EVERY batch (the default only does for >= 32768)."""
