@@ -2658,6 +2658,7 @@ struct cover_ctx {
   int plane_cols = 0;                   // COVER_B200_PLANE_COLS: word columns per warp of k_lethal_planes (2, 4, 8; 0 = by size)
   bool timeline = false;                // COVER_B200_TIMELINE=1: events between the operations of a call, printed at cover_ctx_synchronize (bring-up)
   std::vector<std::pair<const char*, cudaEvent_t>> timeline_events;
+  int quad_max_rows = kQuadMaxRows;     // COVER_B200_QUAD_MAX_ROWS: tallest polygon (scan rows) k_area_quad takes (measurements)
   bool disable_split_lockstep = false;  // COVER_B200_NO_SPLIT_LOCKSTEP=1: continuous_footprint checks through k_split alone (A/B measurements)
   bool disable_values = false;          // COVER_B200_NO_VALUES=1: lattice accumulate_cost / max_cost through the shape-cache kernel (A/B measurements)
   bool disable_quad = false;            // COVER_B200_NO_QUAD=1: non-convex polygons through k_area_pair + k_area_slots (A/B measurements)
@@ -3456,7 +3457,7 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
   //    mildly concave one) are finished by the packed / lattice kernel; the rest lands on the todo list.
   //    Polygons that are far from convex skip it (the pass would defer almost everything).
   //    A non-convex polygon of moderate size goes through k_area_quad instead (four ranges per row in the same table).
-  const int quad_threads = (!outline_lattice && !words && !values && !ctx->old_packed_kernel && !ctx->disable_quad && rows_cap <= kQuadMaxRows && !is_convex(poly_host, nv))
+  const int quad_threads = (!outline_lattice && !words && !values && !ctx->old_packed_kernel && !ctx->disable_quad && rows_cap <= ctx->quad_max_rows && !is_convex(poly_host, nv))
                                ? quad_block_threads(poly_bytes, rows_cap) : 0;
   const bool fast = outline_lattice || words || values || quad_threads > 0 || (rows_cap <= kPackedMaxRows && (is_convex(poly_host, nv) || ctx->always_try_packed));
   // 2. general pass over everything (or the todo list): one warp per pose when the outline has few rays
@@ -3923,6 +3924,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
   if (const char* e = std::getenv("COVER_B200_PACKED_ONLY_CONVEX")) ctx->always_try_packed = e[0] != '1';
   if (const char* e = std::getenv("COVER_B200_NO_QUAD")) ctx->disable_quad = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_NO_VALUES")) ctx->disable_values = e[0] == '1';
+  if (const char* e = std::getenv("COVER_B200_QUAD_MAX_ROWS")) ctx->quad_max_rows = std::min(250, std::max(1, std::atoi(e)));
   if (const char* e = std::getenv("COVER_B200_NO_SPLIT_LOCKSTEP")) ctx->disable_split_lockstep = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_TIMELINE")) ctx->timeline = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_PLANE_COLS")) ctx->plane_cols = std::atoi(e);
