@@ -514,14 +514,14 @@ __global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep_simple(MapView m, co
                                                                   PoseSource src, long long count, OutView out, LwTables t, LwGeom g, int nk) {
   extern __shared__ uint4 lw_smem[];
   __shared__ LwSpan s_local[kLwSpanCache];
-  __shared__ int s_ymin, s_ymax, s_active;
+  __shared__ int s_ymin, s_ymax, s_active, s_n_near, s_n_far;
   constexpr int NC = W + kLwTileColsExtra, TH = kLwTileRows;
   uint32_t* tile = reinterpret_cast<uint32_t*>(lw_smem);                  // [nk][NC][TH]
   uint32_t(*s_bits)[2 * W] = reinterpret_cast<uint32_t(*)[2 * W]>(tile + nk * NC * TH);  // [warp * 32 + lane][2 W] (byte outputs only)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sb = blockIdx.y, rb = blockIdx.x * kLwWarps + warp;  // grid: (row block groups, strips, headings)
   const int h = blockIdx.z;
-  if (threadIdx.x == 0) s_ymin = 0x7FFFFFFF, s_ymax = -0x7FFFFFFF - 1, s_active = 0;
+  if (threadIdx.x == 0) s_ymin = 0x7FFFFFFF, s_ymax = -0x7FFFFFFF - 1, s_active = 0, s_n_near = 0, s_n_far = 0;
   __syncthreads();
   LwTask<W> k;
   int x_base = 0;
@@ -551,10 +551,18 @@ __global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep_simple(MapView m, co
         for (int ch = lane; ch < chunks; ch += 32) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * ch), "l"(gsrc + 4 * ch));
       }
     }
+    // the spans, decoded for this strip (everything but the lane's row is CTA-uniform): word offset into the tile, bit
+    // offset of the first window, bit offset of the second.  Spans whose second window starts in the same word as the
+    // first ("near") go to the front of the list, the others ("far": it starts in the next word) to the back, so that
+    // each kind gets a loop without a branch (the verdict is an OR: the order of the spans does not matter).
     for (int sidx = threadIdx.x; sidx < n_spans; sidx += blockDim.x) {
       const LwSpan sp = spans[sidx];
       const int kk = sp.w >> 16, dy = (sp.w & 0xFFFF) - 32768;
-      s_local[sidx] = make_int4(sp.x - xb, kk * NC * TH + (dy - yb), sp.z, 0);
+      const int tx = xr + sp.x - xb, sh = tx & 31, sh2 = sh + sp.z;
+      const int off = (kk * NC + (tx >> 5)) * TH + (dy - yb);
+      const bool near = sh2 < 32;
+      const int pos = near ? atomicAdd(&s_n_near, 1) : n_spans - 1 - atomicAdd(&s_n_far, 1);
+      s_local[pos] = make_int4(off, sh, near ? sh2 : sh2 - 32, 0);
     }
     asm volatile("cp.async.commit_group;" ::);
     asm volatile("cp.async.wait_group 0;" ::);
@@ -569,23 +577,26 @@ __global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep_simple(MapView m, co
   const int y_lane = k.any_valid ? k.y0c : y_first;  // idle lanes read where a live one reads
   if (tile_ok) {
     const uint32_t* __restrict__ base = tile + (y_lane + yb - y_t0);
+    const int n_near = s_n_near;
 #pragma unroll 4
-    for (int s = 0; s < n_spans; ++s) {
+    for (int s = 0; s < n_near; ++s) {  // both windows start in the same plane word: W + 1 words
       const LwSpan sp = s_local[s];
-      const int tx = xr + sp.x;
-      const int sh = tx & 31;
-      const uint32_t* __restrict__ p = base + (tx >> 5) * TH + sp.y;
+      const uint32_t* __restrict__ p = base + sp.x;
+      uint32_t L[W + 1];
+#pragma unroll
+      for (int j = 0; j < W + 1; ++j) L[j] = p[j * TH];
+#pragma unroll
+      for (int w = 0; w < W; ++w) hit[w] |= __funnelshift_r(L[w], L[w + 1], sp.y) | __funnelshift_r(L[w], L[w + 1], sp.z);
+    }
+#pragma unroll 4
+    for (int s = n_near; s < n_spans; ++s) {  // the second power-of-two window starts in the next word: W + 2 words
+      const LwSpan sp = s_local[s];
+      const uint32_t* __restrict__ p = base + sp.x;
       uint32_t L[W + 2];
 #pragma unroll
       for (int j = 0; j < W + 2; ++j) L[j] = p[j * TH];
-      const int sh2 = sh + sp.z;  // second power-of-two window: `tail` cells later (the same window again for a power-of-two width)
-      if (sh2 < 32) {
 #pragma unroll
-        for (int w = 0; w < W; ++w) hit[w] |= __funnelshift_r(L[w], L[w + 1], sh) | __funnelshift_r(L[w], L[w + 1], sh2);
-      } else {
-#pragma unroll
-        for (int w = 0; w < W; ++w) hit[w] |= __funnelshift_r(L[w], L[w + 1], sh) | __funnelshift_r(L[w + 1], L[w + 2], sh2 - 32);
-      }
+      for (int w = 0; w < W; ++w) hit[w] |= __funnelshift_r(L[w], L[w + 1], sp.y) | __funnelshift_r(L[w + 1], L[w + 2], sp.z);
     }
   } else {
     lw_walk<W>(bits, ypitch, spans, n_spans, x_base, y_lane, hit);
