@@ -3268,7 +3268,7 @@ int lw_prepare_async(cover_ctx* ctx, const cover_map* map, const double* poly_de
     off += (bytes + 255) & ~static_cast<size_t>(255);
     return at;
   };
-  const size_t o_counters = carve(16), o_nx = carve(nh * 4), o_ny = carve(nh * 4), o_base = carve(nh * 4), o_simple = carve(nh * 4), o_order = carve(nh * 4);
+  const size_t o_counters = carve(16), o_nx = carve(nh * 4), o_ny = carve(nh * 4), o_base = carve(nh * 4), o_simple = carve(nh * 4), o_order = carve(nh * 4), o_heads = carve(nh * sizeof(LwHead));
   const size_t o_anchor = carve(nh * kLwClasses * 4), o_shapes = carve(static_cast<size_t>(t.max_shapes) * sizeof(LwShape));
   const size_t o_spans = carve(static_cast<size_t>(t.span_pool) * sizeof(LwSpan));
   const size_t o_yc0 = carve(nh * src.ny * 4), o_xcls = carve(nh * src.nx), o_ycls = carve(nh * src.ny);
@@ -3276,7 +3276,7 @@ int lw_prepare_async(cover_ctx* ctx, const cover_map* map, const double* poly_de
   char* base = ctx->lw_tables.as<char>();
   t.counters = reinterpret_cast<unsigned int*>(base + o_counters);
   t.n_xcls = reinterpret_cast<int*>(base + o_nx), t.n_ycls = reinterpret_cast<int*>(base + o_ny);
-  t.shape_base = reinterpret_cast<int*>(base + o_base), t.simple = reinterpret_cast<int*>(base + o_simple), t.order = reinterpret_cast<int*>(base + o_order);
+  t.shape_base = reinterpret_cast<int*>(base + o_base), t.simple = reinterpret_cast<int*>(base + o_simple), t.order = reinterpret_cast<int*>(base + o_order), t.heads = reinterpret_cast<LwHead*>(base + o_heads);
   t.shapes = reinterpret_cast<LwShape*>(base + o_shapes), t.spans = reinterpret_cast<LwSpan*>(base + o_spans);
   t.xanchor = reinterpret_cast<int*>(base + o_anchor), t.yc0 = reinterpret_cast<int*>(base + o_yc0);
   t.xcls = reinterpret_cast<uint8_t*>(base + o_xcls), t.ycls = reinterpret_cast<uint8_t*>(base + o_ycls);

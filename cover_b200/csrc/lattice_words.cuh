@@ -52,11 +52,20 @@ struct LwShape {
   int pad;               // the largest plane index k = floor(log2(width)) of its spans
 };
 
+/// Everything k_lw_sweep_simple needs to know about a heading, in one record (one load instead of a chain of three):
+/// `simple` as in LwTables::simple, the anchor of x class 0 and the heading's one shape.
+struct LwHead {
+  int simple, anchor0, span_first, n_spans;
+  int xb, x1, yb, rows;
+  int kmax, pad0, pad1, pad2;
+};
+
 struct LwTables {
   int* n_xcls;         // [n_head]
   int* n_ycls;         // [n_head]
   int* shape_base;     // [n_head] shape (xc, yc) of the heading lives at shape_base + xc * n_ycls + yc; -1: pool exhausted
   int* simple;         // [n_head] 1: one x class, one y class, every column and row in range, the shape rasterised fine
+  LwHead* heads;       // [n_head]
   int* order;          // [n_head] the headings, those that are not simple first (the general sweep's CTAs of the few
                        //   headings with real work start together instead of one heading after the other)
   uint8_t* xcls;       // [n_head][nx]
@@ -293,6 +302,12 @@ __global__ void __launch_bounds__(kLwPrepThreads) k_lw_prepare(MapView m, const 
       if (xa + sh.xb >= 0 && xa + last_col + sh.x1 < m.size_x && s_ymin + sh.yb >= 0 && s_ymax + sh.yb + sh.rows <= m.size_y) simple = 2;
     }
     t.simple[h] = simple;
+    LwHead hd{simple, anchor_tab[0], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (simple) {
+      const LwShape& sh = t.shapes[s_base];
+      hd.span_first = sh.span_first, hd.n_spans = sh.n_spans, hd.xb = sh.xb, hd.x1 = sh.x1, hd.yb = sh.yb, hd.rows = sh.rows, hd.kmax = sh.pad;
+    }
+    t.heads[h] = hd;
     if (simple) t.order[gridDim.x - 1u - atomicAdd(&t.counters[3], 1u)] = h;
     else t.order[atomicAdd(&t.counters[2], 1u)] = h;
   }
@@ -523,10 +538,16 @@ __global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep_simple(MapView m, co
   const int h = blockIdx.z;
   if (threadIdx.x == 0) s_ymin = 0x7FFFFFFF, s_ymax = -0x7FFFFFFF - 1, s_active = 0, s_n_near = 0, s_n_far = 0;
   __syncthreads();
+  const LwHead hd = t.heads[h];  // (CTA-uniform)
+  if (hd.simple == 0) return;
   LwTask<W> k;
-  int x_base = 0;
   bool active = lw_task_setup<W>(src, count, t, g, rb, sb, h, lane, k);
-  if (active) active = lw_task_simple<W>(k, m, t, x_base);
+  const int x_base = k.ix0 + hd.anchor0;
+  if (active && hd.simple != 2) {  // the same test as lw_task_simple (2: the heading's whole lattice passes it)
+    const bool x_in = x_base + hd.xb >= 0 && x_base + 32 * W - 1 + hd.x1 < m.size_x;
+    const bool y_in = k.y0c + hd.yb >= 0 && k.y0c + hd.yb + hd.rows <= m.size_y;
+    active = x_in && __all_sync(0xFFFFFFFFu, y_in || !k.any_valid);
+  }
   if (active) {
     const int lo = __reduce_min_sync(0xFFFFFFFFu, k.any_valid ? k.y0c : 0x7FFFFFFF), hi = __reduce_max_sync(0xFFFFFFFFu, k.any_valid ? k.y0c : -0x7FFFFFFF - 1);
     if (lane == 0) atomicMin(&s_ymin, lo), atomicMax(&s_ymax, hi), s_active = 1;
@@ -534,10 +555,9 @@ __global__ void __launch_bounds__(kLwWarps * 32) k_lw_sweep_simple(MapView m, co
   __syncthreads();
   if (!s_active) return;
   // (CTA-uniform from here: the heading's one shape, the strip's x_base)
-  const LwShape* shp = t.shapes + t.shape_base[h];
-  const int n_spans = shp->n_spans, xb = shp->xb, x1 = shp->x1, yb = shp->yb, rows = shp->rows, kmax = shp->pad;
-  const LwSpan* spans = t.spans + shp->span_first;
-  const int xs_base = sb * 32 * W + t.xanchor[h * kLwClasses] + xb;  // map column of the shape's leftmost cell for the strip's first pose
+  const int n_spans = hd.n_spans, xb = hd.xb, x1 = hd.x1, yb = hd.yb, rows = hd.rows, kmax = hd.kmax;
+  const LwSpan* spans = t.spans + hd.span_first;
+  const int xs_base = sb * 32 * W + hd.anchor0 + xb;  // map column of the shape's leftmost cell for the strip's first pose
   const int c_min = xs_base >> 5, xr = xs_base & 31;
   const int y_t0 = (s_ymin + yb) & ~3, rows_needed = s_ymax + yb + rows - y_t0;
   const bool tile_ok = n_spans <= kLwSpanCache && kmax < nk && rows_needed <= TH && ((xr + (x1 - xb)) >> 5) + W + 2 <= NC;
