@@ -3510,7 +3510,9 @@ int launch_polygon(cover_ctx* ctx, const cover_map* map, const double* poly_dev,
     if (reset_by_kernel && reset_done) {
       // (k_lethal_planes did it on the way)
     } else if (reset_by_kernel) {
-      k_call_reset<<<1, 32, 0, ctx->stream>>>(ctx->todo_count.as<unsigned int>(), ctx->todo_header[1], static_cast<unsigned long long*>(ctx->lazy_not_ok));
+      // on the auxiliary stream, in front of the general half and the drain - the only kernels of a word sweep that push
+      // poses or count failures (the simple half on the main stream does neither), and off the main stream's critical path
+      k_call_reset<<<1, 32, 0, ctx->aux_stream>>>(ctx->todo_count.as<unsigned int>(), ctx->todo_header[1], static_cast<unsigned long long*>(ctx->lazy_not_ok));
       ctx->lazy_not_ok = nullptr;
     } else {
       CU(cudaMemcpyAsync(ctx->todo_count.ptr, ctx->todo_header, 2 * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));

@@ -334,3 +334,26 @@ def test_value_folds_on_a_lattice(cb, monkeypatch, env):
         np.testing.assert_array_equal(gpu.cost, cpu.cost)
     assert ctx.launch_count > launches0
     ctx.close()
+
+
+@pytest.mark.parametrize("size", [(400, 360), (413, 300), (1040, 200)])
+def test_device_resident_images(cb, monkeypatch, size):
+    """cover_map_upload from DEVICE memory (k_copy16 for big 16-byte-aligned images, a driver copy otherwise) invalidates
+    the planes: sweeps after such uploads - over the same rows, over other rows, after a second new image -
+    agree with the oracle on the image they were given."""
+    import torch
+    ctx = _ctx(cb, monkeypatch)
+    rng = np.random.default_rng(520)
+    sx, sy = size
+    images = [mixed_map(rng, sx, sy, lethal=l) for l in (0.002, 0.006, 0.0005)]
+    cmap = cb.Costmap(ctx, images[0], 0.05)
+    cs = headings(3)
+    windows = [dict(x0=1.0, dx=0.05, nx=min(300, sx - 60), y0=2.0, dy=0.05, ny=100, cs=cs),
+               dict(x0=0.4, dx=0.05, nx=min(300, sx - 60), y0=6.0, dy=0.05, ny=120, cs=cs)]
+    check(cmap, po.Costmap(images[0], 0.05), cb, RECT, windows[0], po.SHAPE_AREA, "first image")
+    for k, (img, win) in enumerate(((images[1], windows[0]), (images[2], windows[1]), (images[0], windows[1]), (images[1], windows[0]))):
+        dev = torch.from_numpy(img).cuda()  # (kept alive until the checks below have returned their results)
+        cmap.upload(dev)
+        check(cmap, po.Costmap(img, 0.05), cb, RECT, win, po.SHAPE_AREA, f"device image {k}")
+        check(cmap, po.Costmap(img, 0.05), cb, FOOTPRINTS[6], win, po.SHAPE_OUTLINE, f"device image {k}, outline")
+    ctx.close()
