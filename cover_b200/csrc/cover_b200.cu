@@ -2649,6 +2649,7 @@ struct cover_ctx {
   bool disable_planes = false;          // COVER_B200_NO_PLANES=1: lattice verdicts walk the cost bytes (A/B measurements)
   int64_t planes_min_batch = 32768;     // COVER_B200_PLANES_MIN_BATCH: smallest batch that triggers a bit-plane build (tests: 0)
   int max_stretch = 4;                  // COVER_B200_MAX_STRETCH: longest run of consecutive rounds a lattice CTA draws at once
+  int64_t pipeline_min = 0;             // COVER_B200_PIPELINE_MIN: smallest lattice sweep that is downloaded in chunks (tests; default 2^28 poses)
   int pipeline_chunks = 0;              // COVER_B200_CHUNKS: download chunks of a big lattice sweep (0 = by size)
   bool old_packed_kernel = false;       // COVER_B200_OLD_PACKED=1: first-generation per-thread kernel (A/B measurements)
   bool force_list_kernel = false;
@@ -3677,7 +3678,8 @@ int polygon_check(cover_ctx* ctx, const cover_map* map, const double* polygon_xy
   };
   // A big lattice sweep whose results go to the host runs as 2..4 contiguous index chunks: chunk k's results travel
   // back on a second stream while chunk k + 1 is computed (chunk borders are multiples of 32 poses = whole bit words).
-  constexpr int64_t kPipelineMin = 256ll << 20;  // (a 1e8-pose verdict sweep computes in ~0.1 ms, its 12.5 MB of bits travel 0.22 ms: nothing to hide behind)
+  // (a 1e8-pose verdict sweep computes in ~0.1 ms, its 12.5 MB of bits travel 0.22 ms: nothing to hide behind)
+  const int64_t kPipelineMin = ctx->pipeline_min > 0 ? ctx->pipeline_min : (256ll << 20);
   // (two chunks up to ~1.5e8 poses: every chunk costs ~50 us of launch overhead and kernel tail, a chunk's download ~0.1 ms)
   int kPipelineChunks = static_cast<int>(std::min<int64_t>(4, std::max<int64_t>(2, poses->count / (48ll << 20))));
   if (ctx->pipeline_chunks > 0) kPipelineChunks = ctx->pipeline_chunks;  // (measurements)
@@ -3922,6 +3924,7 @@ int cover_ctx_create(int device, cover_ctx** out) {
   if (const char* e = std::getenv("COVER_B200_NO_TABLE_CACHE")) ctx->lw_cache_disabled = e[0] == '1';
   if (const char* e = std::getenv("COVER_B200_PLANES_MIN_BATCH")) ctx->planes_min_batch = std::atoll(e);
   if (const char* e = std::getenv("COVER_B200_MAX_STRETCH")) ctx->max_stretch = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("COVER_B200_PIPELINE_MIN")) ctx->pipeline_min = std::max<long long>(0, std::atoll(e));
   if (const char* e = std::getenv("COVER_B200_CHUNKS")) ctx->pipeline_chunks = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("COVER_B200_PACKED_ONLY_CONVEX")) ctx->always_try_packed = e[0] != '1';
   if (const char* e = std::getenv("COVER_B200_NO_QUAD")) ctx->disable_quad = e[0] == '1';

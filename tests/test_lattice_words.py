@@ -357,3 +357,33 @@ def test_device_resident_images(cb, monkeypatch, size):
         check(cmap, po.Costmap(img, 0.05), cb, RECT, win, po.SHAPE_AREA, f"device image {k}")
         check(cmap, po.Costmap(img, 0.05), cb, FOOTPRINTS[6], win, po.SHAPE_OUTLINE, f"device image {k}, outline")
     ctx.close()
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 4])
+def test_chunked_download_of_a_lattice_sweep(cb, monkeypatch, chunks):
+    """The pipelined path of big lattice sweeps with host results (chunk k's results travel back while chunk k + 1 is
+    computed; default from 2^28 poses) forced onto a small lattice: byte, bit-packed and status outputs and the not-OK
+    counter across chunk borders, for verdicts and for a value fold."""
+    ctx = _ctx(cb, monkeypatch, COVER_B200_PIPELINE_MIN=20000, COVER_B200_CHUNKS=chunks)
+    rng = np.random.default_rng(530 + chunks)
+    data = mixed_map(rng, 400, 300, lethal=0.003)
+    cmap, omap = cb.Costmap(ctx, data, 0.05, -0.5, 0.2), po.Costmap(data, 0.05, -0.5, 0.2)
+    desc = dict(x0=-1.0, dx=0.05, nx=333, y0=-0.3, dy=0.05, ny=97, cs=headings(4))
+    total = 333 * 97 * 8
+    for poly, shape in ((RECT, po.SHAPE_AREA), (np.array([[0.0, 1.0], [0.0, 0.4]]), po.SHAPE_AREA), (FOOTPRINTS[6], po.SHAPE_OUTLINE)):
+        cpu = po.polygon_batch(omap, poly, po.Lattice(**desc), shape=shape, threads=8)
+        fn = cmap.area_is_free if shape == po.SHAPE_AREA else cmap.outline_is_free
+        gpu = fn(poly, cb.Lattice(**desc))
+        np.testing.assert_array_equal(gpu.status, cpu.status)
+        np.testing.assert_array_equal(gpu.is_free, cpu.is_free)
+        out = cb.Result(free_bits=np.zeros((total + 31) // 32, dtype=np.uint32), not_ok=np.zeros(1, dtype=np.int64))
+        fn(poly, cb.Lattice(**desc), out=out)
+        np.testing.assert_array_equal(out.unpack_bits(total), cpu.is_free & (cpu.status == 0))
+        assert int(out.not_ok[0]) == int((cpu.status != 0).sum())
+        first, count = 333 * 5 + 11, 150_001  # a sub-range whose chunks start inside rows
+        sub = fn(poly, cb.Lattice(**desc), first=first, count=count)
+        np.testing.assert_array_equal(sub.is_free, cpu.is_free[first:first + count])
+    acc = cmap.area_accumulate_cost(RECT, cb.Lattice(**desc))
+    cpu = po.polygon_batch(omap, RECT, po.Lattice(**desc), op=po.OP_ACCUMULATE, threads=8)
+    np.testing.assert_array_equal(acc.cost, cpu.cost)
+    ctx.close()
