@@ -2692,7 +2692,7 @@ struct cover_map {
   mutable int planes_inf_lo = 0, planes_inf_hi = -1;
   mutable uint32_t* prefix = nullptr;  // per-row prefix sums of the costs (accumulate_cost lattice sweeps)
   mutable int prefix_lo = 0, prefix_hi = -1;
-  mutable uint8_t* maxp = nullptr;  // sliding-maximum planes 1..5 of the costs (max_cost lattice sweeps, k_max_planes)
+  mutable uint8_t* maxp = nullptr;  // sliding-maximum planes 0..5 of the costs (max_cost lattice sweeps, k_max_planes)
   mutable int maxp_lo = 0, maxp_hi = -1;
   int ppitch = 0;
   int ypitch = 0;
@@ -2986,13 +2986,14 @@ void launch_max_planes(cover_ctx* ctx, const cover_map* map, int row_lo, int row
 }
 
 /// Sliding-maximum planes of rows [row_lo, row_hi] for max_cost lattice sweeps (built on ctx->stream when the current
-/// ones do not cover them); nullptr when disabled or out of memory (5 bytes per cell).
+/// ones do not cover them); nullptr when disabled, out of memory (6 bytes per cell) or beyond 32-bit offsets.
 int ensure_max_planes(cover_ctx* ctx, const cover_map* map, int row_lo, int row_hi, const uint8_t*& maxp) {
   maxp = nullptr;
   if (ctx->disable_planes || row_lo > row_hi) return COVER_OK;
+  if (static_cast<long long>(map->view.pitch) * map->view.size_y * 6 >= (1ll << 31)) return COVER_OK;  // (k_lw_values indexes the planes with 32 bits)
   if (!map->maxp) {
     uint8_t* p = nullptr;
-    if (cudaMalloc(reinterpret_cast<void**>(&p), static_cast<size_t>(map->view.pitch) * map->view.size_y * 5 + 64) != cudaSuccess) {
+    if (cudaMalloc(reinterpret_cast<void**>(&p), static_cast<size_t>(map->view.pitch) * map->view.size_y * 6 + 64) != cudaSuccess) {
       cudaGetLastError();
       return COVER_OK;
     }

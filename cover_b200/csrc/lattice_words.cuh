@@ -755,11 +755,12 @@ namespace cvr {
 /// Tables the value folds of a lattice sweep read: accumulate_cost the per-row exclusive prefix words of k_cost_prefix
 /// (word x = NO_INFORMATION cells before x, mod 256, << 24 | LETHAL cells before x, mod 256, << 16 | sum of the costs
 /// before x, mod 2^16: a window of up to 32 cells is two loads, every field exact as a difference); max_cost the sliding-maximum byte planes of k_max_planes
-/// (plane k, byte x of row y = max of the cells x .. x + 2^k - 1; plane 0 is the costmap itself).
+/// (plane k, byte x of row y = max of the cells x .. x + 2^k - 1; plane 0 is a copy of the costmap's rows, so that a span's
+/// plane is an offset, not a choice of pointers).
 struct LwValueTables {
   const uint32_t* __restrict__ prefix;
   int ppitch;
-  const uint8_t* __restrict__ maxp;  // planes 1..5, plane k at maxp + (k - 1) * max_plane_bytes, row pitch = the map's
+  const uint8_t* __restrict__ maxp;  // planes 0..5, plane k at maxp + k * max_plane_bytes, row pitch = the map's (plane 0: a copy of the rows)
   long long max_plane_bytes;
 };
 
@@ -848,14 +849,15 @@ __global__ void __launch_bounds__(256) k_lw_values(MapView m, LwValueTables vt, 
         const uint32_t a0 = __ldg(vt.prefix + oa), a1 = __ldg(vt.prefix + oa + width);
         const uint32_t b0 = __ldg(vt.prefix + ob), b1 = __ldg(vt.prefix + ob + width);
         sum_a += (a1 - a0) & 0xFFFFu, sum_b += (b1 - b0) & 0xFFFFu;  // (meaningless once a sentinel was met: `early` decides then)
-        const uint32_t ha = ((a1 >> 16) - (a0 >> 16)) & 0xFFFFu, hb = ((b1 >> 16) - (b0 >> 16)) & 0xFFFFu;  // both sentinel counts: zero iff none
-        if ((ha != 0u && early_a == 0) || (hb != 0u && early_b == 0)) {
-          if (ha != 0u && early_a == 0 && go_a) {
-            const uint32_t n_l = ha & 0xFFu, n_n = ((a1 >> 24) - (a0 >> 24)) & 0xFFu;
+        // (the two sentinel counts live in the upper halves: a window of <= 32 cells holds a sentinel iff they differ)
+        const bool sa = ((a1 ^ a0) >> 16) != 0u && early_a == 0 && go_a, sb = ((b1 ^ b0) >> 16) != 0u && early_b == 0 && go_b;
+        if (sa || sb) {
+          if (sa) {
+            const uint32_t n_l = ((a1 >> 16) - (a0 >> 16)) & 0xFFu, n_n = ((a1 >> 24) - (a0 >> 24)) & 0xFFu;
             early_a = n_n == 0u ? -1 : (n_l == 0u ? -2 : lw_first_sentinel(m.data + static_cast<size_t>(y0c + dy) * m.pitch + sp.x + X_a, width));
           }
-          if (hb != 0u && early_b == 0 && go_b) {
-            const uint32_t n_l = hb & 0xFFu, n_n = ((b1 >> 24) - (b0 >> 24)) & 0xFFu;
+          if (sb) {
+            const uint32_t n_l = ((b1 >> 16) - (b0 >> 16)) & 0xFFu, n_n = ((b1 >> 24) - (b0 >> 24)) & 0xFFu;
             early_b = n_n == 0u ? -1 : (n_l == 0u ? -2 : lw_first_sentinel(m.data + static_cast<size_t>(y0c + dy) * m.pitch + sp.x + X_b, width));
           }
         }
@@ -872,14 +874,14 @@ __global__ void __launch_bounds__(256) k_lw_values(MapView m, LwValueTables vt, 
       }
     } else {
       uint32_t best_a = 0u, best_b = 0u;
+      const int plane_bytes = static_cast<int>(vt.max_plane_bytes);
       for (int s = 0; s < n_spans; ++s) {
         const LwSpan sp = __ldg(spans + s);
         const int dy = (sp.w & 0xFFFF) - 32768, lg = sp.w >> 16;
-        const uint8_t* __restrict__ pl = lg == 0 ? m.data : vt.maxp + static_cast<long long>(lg - 1) * vt.max_plane_bytes;
-        const int o = (y0c + dy) * m.pitch + sp.x;
+        const int o = lg * plane_bytes + (y0c + dy) * m.pitch + sp.x;  // (32-bit: the host takes this path while 6 planes stay below 2^31 bytes)
         const int oa = o + Xa, ob = o + Xb;
-        const uint32_t va = max(static_cast<uint32_t>(__ldg(pl + oa)), static_cast<uint32_t>(__ldg(pl + oa + sp.z)));
-        const uint32_t vb = max(static_cast<uint32_t>(__ldg(pl + ob)), static_cast<uint32_t>(__ldg(pl + ob + sp.z)));
+        const uint32_t va = max(static_cast<uint32_t>(__ldg(vt.maxp + oa)), static_cast<uint32_t>(__ldg(vt.maxp + oa + sp.z)));
+        const uint32_t vb = max(static_cast<uint32_t>(__ldg(vt.maxp + ob)), static_cast<uint32_t>(__ldg(vt.maxp + ob + sp.z)));
         best_a = max(best_a, va), best_b = max(best_b, vb);
       }
       Fold<OP_MAX> fa, fb;
@@ -896,7 +898,7 @@ __global__ void __launch_bounds__(256) k_lw_values(MapView m, LwValueTables vt, 
   }
 }
 
-/// Sliding-maximum planes 1..5 of rows [row_lo, row_hi] (grid.y = row, one thread per 4 cells): the 4 + 32 cells after a
+/// Sliding-maximum planes 0..5 of rows [row_lo, row_hi] (grid.y = row, one thread per 4 cells): the 4 + 32 cells after a
 /// word's first cell are doubled in registers, M_{k+1}[x] = max(M_k[x], M_k[x + 2^k]) byte-wise (__vmaxu4).
 __global__ void __launch_bounds__(256) k_max_planes(MapView m, uint8_t* __restrict__ maxp, long long plane_bytes, int row_lo) {
   const int words = m.pitch >> 2;
@@ -910,19 +912,20 @@ __global__ void __launch_bounds__(256) k_max_planes(MapView m, uint8_t* __restri
   R[9] = 0u;
   uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(maxp + static_cast<size_t>(y) * m.pitch) + j;
   const long long plane_words = plane_bytes >> 2;
-#pragma unroll
-  for (int d = 0; d < 9; ++d) R[d] = __vmaxu4(R[d], __funnelshift_r(R[d], R[d + 1], 8));
   dst[0] = R[0];
 #pragma unroll
-  for (int d = 0; d < 8; ++d) R[d] = __vmaxu4(R[d], __funnelshift_r(R[d], R[d + 1], 16));
+  for (int d = 0; d < 9; ++d) R[d] = __vmaxu4(R[d], __funnelshift_r(R[d], R[d + 1], 8));
   dst[plane_words] = R[0];
 #pragma unroll
-  for (int d = 0; d < 7; ++d) R[d] = __vmaxu4(R[d], R[d + 1]);
+  for (int d = 0; d < 8; ++d) R[d] = __vmaxu4(R[d], __funnelshift_r(R[d], R[d + 1], 16));
   dst[2 * plane_words] = R[0];
 #pragma unroll
-  for (int d = 0; d < 5; ++d) R[d] = __vmaxu4(R[d], R[d + 2]);
+  for (int d = 0; d < 7; ++d) R[d] = __vmaxu4(R[d], R[d + 1]);
   dst[3 * plane_words] = R[0];
-  dst[4 * plane_words] = __vmaxu4(R[0], R[4]);
+#pragma unroll
+  for (int d = 0; d < 5; ++d) R[d] = __vmaxu4(R[d], R[d + 2]);
+  dst[4 * plane_words] = R[0];
+  dst[5 * plane_words] = __vmaxu4(R[0], R[4]);
 }
 
 }  // namespace cvr
