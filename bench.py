@@ -539,15 +539,69 @@ def run_gpu(args) -> None:
         for _ in range(k):
             e2e_step(w)
 
-    barrier()
-    t0 = time.perf_counter()
-    threads_ = [threading.Thread(target=loop, args=(w, e2e_steps // n_flight)) for w in workers]
-    for th in threads_:
-        th.start()
-    for th in threads_:
-        th.join()
-    barrier()
-    e2e_dt = time.perf_counter() - t0
+    # N > 1 (COVER_BENCH_BCAST=0 switches it off: every rank then uploads its own copy, as at N = 1): the planning cycle's
+    # costmap reaches the host ONCE - rank 0 uploads it and fans it out
+    # over NVLink (NCCL broadcast), every rank ingests it from device memory, sweeps its own window and downloads its own
+    # verdicts.  One issuing thread per rank (collectives in the same order everywhere), two cycles in flight on the two
+    # contexts' streams; a slot is reused when its results have landed in pinned host memory.
+    use_bcast = world > 1 and os.environ.get("COVER_BENCH_BCAST", "1") == "1"
+    if use_bcast:
+        empty_pinned = torch.from_numpy(empty_map)
+        for w in workers:
+            # torch's own stream carries the copies and the collective (its allocators track the streams their tensors were
+            # used on, and the library's stream dies with its context); events order it with the library's stream
+            w["torch_stream"] = torch.cuda.Stream(device=local)
+            w["lib_stream"] = torch.cuda.ExternalStream(w["ctx"].stream, device=local)
+            w["img_dev"] = torch.empty((MAP_SIZE, MAP_SIZE), dtype=torch.uint8, device="cuda")
+            w["bits_dev"] = torch.zeros(n_words, dtype=torch.int32, device="cuda")
+            w["nok_dev"] = torch.zeros(1, dtype=torch.int64, device="cuda")
+            w["out_dev"] = cover_b200.Result(free_bits=w["bits_dev"], not_ok=w["nok_dev"])
+            w["done"] = torch.cuda.Event()
+        torch.cuda.synchronize()
+
+        def bcast_step(w, image_pinned):
+            ts, ls = w["torch_stream"], w["lib_stream"]
+            with torch.cuda.stream(ts):
+                if rank == 0:
+                    w["img_dev"].copy_(image_pinned, non_blocking=True)  # H2D: 16 MB, on rank 0 only
+                dist.broadcast(w["img_dev"], src=0)
+                arrived = ts.record_event()
+            ls.wait_event(arrived)
+            w["map"].upload(w["img_dev"])  # (device to device, then the sweep: both on the library's stream)
+            w["map"].area_is_free(wl.RECT, lat, out=w["out_dev"])
+            swept = ls.record_event()
+            ts.wait_event(swept)
+            with torch.cuda.stream(ts):
+                w["bits"].copy_(w["bits_dev"], non_blocking=True)  # D2H: 12.5 MB of verdict bits + the counter
+                w["not_ok"].copy_(w["nok_dev"], non_blocking=True)
+                w["done"].record(ts)
+
+        for w in workers:
+            bcast_step(w, empty_pinned)
+            w["done"].synchronize()
+            assert bool(w["out"].unpack_bits(n_poses).all()), "e2e: the sweep did not see the broadcast (empty) costmap"
+            bcast_step(w, w["pinned"])
+            w["done"].synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            w = workers[k % n_flight]
+            w["done"].synchronize()
+            bcast_step(w, w["pinned"])
+        for w in workers:
+            w["done"].synchronize()
+        barrier()
+        e2e_dt = time.perf_counter() - t0
+    else:
+        barrier()
+        t0 = time.perf_counter()
+        threads_ = [threading.Thread(target=loop, args=(w, e2e_steps // n_flight)) for w in workers]
+        for th in threads_:
+            th.start()
+        for th in threads_:
+            th.join()
+        barrier()
+        e2e_dt = time.perf_counter() - t0
     te = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -627,7 +681,8 @@ def run_gpu(args) -> None:
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": workload_config(world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "cycles_in_flight": n_flight},
+                    "cycles_in_flight": n_flight,
+                    **({"costmap_fanout": "rank 0 uploads the 16 MB image (h2d_bytes_per_step is rank 0's), NCCL broadcast to the other ranks"} if use_bcast else {})},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "free_fraction": free_fraction, "wall_s_timed_region": wall, "step_ms": step_ms,
         }
