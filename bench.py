@@ -10,7 +10,13 @@ costmap at 5 cm (sparse obstacles inflated like costmap_2d's InflationLayer), 1.
 
 N > 1 is launched by torchrun (one rank per GPU): poses are sharded, the costmap is replicated, no data-path collective
 (weak scaling on C4: every rank sweeps its own full lattice window; the 8-shape C5 sweep is additionally timed with its
-poses split across the ranks = strong scaling).  Prints ONE JSON line (rank 0).  DESIGN.md §6 says how each field is obtained.
+poses split across the ranks = strong scaling).  The end-to-end arm replicates the costmap the cheap way at N > 1: rank 0
+uploads it from pinned host memory, an NCCL broadcast fans it out over NVLink.  Prints ONE JSON line (rank 0).
+DESIGN.md §6 says how each field is obtained.
+
+Environment: COVER_BENCH_FLIGHT (planning cycles in flight in the e2e arm, default 2), COVER_BENCH_BCAST=0 (N > 1: every
+rank uploads its own copy of the costmap instead of the broadcast), COVER_BENCH_WINDOW (time another rank's lattice window
+on one GPU), COVER_BENCH_NO_PIN (no CPU pinning of the ranks).
 """
 from __future__ import annotations
 
@@ -47,7 +53,7 @@ def workload_config(n_gpus: int) -> dict:
         "map": [MAP_SIZE, MAP_SIZE], "resolution_m": RESOLUTION, "footprint": "rect 1.0x0.6 m",
         "poses_per_gpu": 1180 * 1180 * 72, "pose_format": "lattice", "op": "area_is_free",
         "outputs": "bit-packed verdicts (12.5 MB) + not-OK counter",
-        "parallelism": f"pose-sharded x{n_gpus}, costmap replicated, no collective",
+        "parallelism": f"pose-sharded x{n_gpus}, costmap replicated, no collective on the data path",
         "l2_flush_between_steps": True,
     }
 
