@@ -123,6 +123,11 @@ int cover_probe_read_bandwidth(cover_ctx* ctx, int64_t bytes, int32_t reps, doub
  * cover_map_create fails with COVER_E_INVALID_ARG for resolution <= 0 (base.hpp:54-55). */
 int cover_map_create(cover_ctx* ctx, int32_t size_x, int32_t size_y, double resolution, double origin_x, double origin_y,
                      cover_map** out);
+/* A new image (size_y x size_x bytes, row-major, unpadded).  mem = COVER_MEM_HOST: returns when the copy is done.
+ * mem = COVER_MEM_DEVICE: the copy is queued on the context's stream (cover_ctx_stream) and the call returns at once -
+ * `data` must stay valid and unchanged until that stream has passed it (cover_ctx_synchronize, a later call that
+ * returns results to the host, or an event of the caller's on that stream).  Everything derived from the old image
+ * (bit planes, prefix words, maximum planes) is invalidated and rebuilt by the next call that needs it. */
 int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem);
 /* Same image, HOST source, without waiting for the copy: it is queued as row bands on a second stream and every
  * later call that reads the map is ordered after the bands it needs on the device - a lattice check of a small
