@@ -14,7 +14,8 @@ poses split across the ranks = strong scaling).  The end-to-end arm replicates t
 uploads it from pinned host memory, an NCCL broadcast fans it out over NVLink.  Prints ONE JSON line (rank 0).
 DESIGN.md §6 says how each field is obtained.
 
-Environment: COVER_BENCH_FLIGHT (planning cycles in flight in the e2e arm, default 2), COVER_BENCH_BCAST=0 (N > 1: every
+Environment: COVER_BENCH_FLIGHT (planning cycles in flight in the e2e arm, default 2), COVER_BENCH_THREADS=1 (N = 1 e2e
+arm with one host thread per cycle and blocking calls instead of one thread and COVER_MEM_HOST_ASYNC results), COVER_BENCH_BCAST=0 (N > 1: every
 rank uploads its own copy of the costmap instead of the broadcast), COVER_BENCH_WINDOW (time another rank's lattice window
 on one GPU), COVER_BENCH_NO_PIN (no CPU pinning of the ranks).
 """
@@ -598,7 +599,8 @@ def run_gpu(args) -> None:
             w["done"].synchronize()
         barrier()
         e2e_dt = time.perf_counter() - t0
-    else:
+    elif os.environ.get("COVER_BENCH_THREADS", "0") == "1":
+        # one host thread per cycle in flight, every call returning when its results are on the host
         barrier()
         t0 = time.perf_counter()
         threads_ = [threading.Thread(target=loop, args=(w, e2e_steps // n_flight)) for w in workers]
@@ -606,6 +608,22 @@ def run_gpu(args) -> None:
             th.start()
         for th in threads_:
             th.join()
+        barrier()
+        e2e_dt = time.perf_counter() - t0
+    else:
+        # ONE host thread keeps the cycles in flight: results go to pinned host memory without waiting
+        # (COVER_MEM_HOST_ASYNC); a slot is reused when cover_ctx_synchronize says its previous cycle has landed
+        for w in workers:
+            w["out_async"] = cover_b200.Result(free_bits=w["out"].free_bits, not_ok=w["out"].not_ok, host_async=True)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            w = workers[k % n_flight]
+            w["ctx"].synchronize()
+            w["map"].upload_async(w["image"])
+            w["map"].area_is_free(wl.RECT, lat, out=w["out_async"])
+        for w in workers:
+            w["ctx"].synchronize()
         barrier()
         e2e_dt = time.perf_counter() - t0
     te = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")

@@ -30,7 +30,7 @@ __all__ = [
 ]
 
 STATUS_OK, STATUS_LOGIC_ERROR, STATUS_ROW_COMPLEXITY, STATUS_COORD_RANGE = 0, 1, 2, 3
-_MEM_HOST, _MEM_DEVICE = 0, 1
+_MEM_HOST, _MEM_DEVICE, _MEM_HOST_ASYNC = 0, 1, 2
 _POSE_CS, _POSE_LATTICE, _POSE_NONE = 0, 1, 2
 _ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "out of memory", -4: "unsupported"}
 
@@ -139,6 +139,7 @@ class Result:
     status: Optional[object] = None
     free_bits: Optional[object] = None
     not_ok: Optional[object] = None
+    host_async: bool = False  # host arrays (page-locked) filled without waiting: valid after Context.synchronize()
 
     def unpack_bits(self, count: int) -> np.ndarray:
         """free_bits -> uint8 verdicts [count] (host arrays only)."""
@@ -227,7 +228,7 @@ class Context:
             dev = any(_is_device(a) for a in arrays)
             if dev and not all(_is_device(a) for a in arrays):
                 raise ValueError("result arrays must all be host or all be device memory")
-            r = _Results(_MEM_DEVICE if dev else _MEM_HOST, _ptr(out.is_free), _ptr(out.cost), _ptr(out.status),
+            r = _Results(_MEM_DEVICE if dev else (_MEM_HOST_ASYNC if out.host_async else _MEM_HOST), _ptr(out.is_free), _ptr(out.cost), _ptr(out.status),
                          _ptr(out.free_bits), _ptr(out.not_ok))
             return r, out
         res = Result(np.empty(n, dtype=np.uint8) if want_free else None, np.empty(n, dtype=np.float64) if want_cost else None,

@@ -2776,13 +2776,15 @@ struct OutStage {
   OutView dev{nullptr, nullptr, nullptr, nullptr, nullptr};
   const cover_results* user = nullptr;
   bool host = false;
+  bool async = false;  // COVER_MEM_HOST_ASYNC: the downloads are queued, the call does not wait for them
 };
 
 int stage_out(cover_ctx* ctx, const cover_results* out, int64_t count, OutStage& st, bool lazy = false) {
   st.user = out;
   ctx->lazy_out = lazy, ctx->lazy_not_ok = nullptr;
   if (!out) return fail(ctx, COVER_E_INVALID_ARG, "results must not be NULL");
-  st.host = out->mem == COVER_MEM_HOST;
+  st.host = out->mem == COVER_MEM_HOST || out->mem == COVER_MEM_HOST_ASYNC;
+  st.async = out->mem == COVER_MEM_HOST_ASYNC;
   const size_t n = static_cast<size_t>(std::max<int64_t>(count, 1));
   const size_t bit_bytes = ((n + 31) / 32) * sizeof(uint32_t);
   if (!st.host) {
@@ -3032,6 +3034,7 @@ int finish_out(cover_ctx* ctx, const OutStage& st, int64_t count) {
     if (st.user->free_bits) CU(cudaMemcpyAsync(st.user->free_bits, st.dev.free_bits, ((n + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (st.user->not_ok) CU(cudaMemcpyAsync(st.user->not_ok, st.dev.not_ok, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (st.async) return COVER_OK;  // (the caller waits with cover_ctx_synchronize, which also lets a banded upload land)
   CU(cudaStreamSynchronize(ctx->stream));
   // cover_map_upload_async's contract: the caller may reuse its image buffer once a call has returned results to the
   // host.  A windowed sweep only waited (on the device) for the bands under its window - let the rest land first.

@@ -62,7 +62,11 @@ typedef enum cover_status {
   COVER_STATUS_COORD_RANGE = 3     /* |cell coordinate| >= 2^22: outside any costmap (int cast UB upstream) */
 } cover_status;
 
-typedef enum cover_mem { COVER_MEM_HOST = 0, COVER_MEM_DEVICE = 1 } cover_mem;
+/* COVER_MEM_HOST_ASYNC (cover_results only): host arrays - page-locked, or the copies are not asynchronous - that the
+ * call fills WITHOUT waiting: it returns once kernels and downloads are queued on the context's stream, the results (and
+ * the staging buffers they pass through) are valid after cover_ctx_synchronize(ctx) and until the context's next call.
+ * One host thread can so keep several contexts (= several planning cycles) in flight. */
+typedef enum cover_mem { COVER_MEM_HOST = 0, COVER_MEM_DEVICE = 1, COVER_MEM_HOST_ASYNC = 2 } cover_mem;
 typedef enum cover_pose_format { COVER_POSE_CS = 0, COVER_POSE_LATTICE = 1, COVER_POSE_NONE = 2 } cover_pose_format;
 
 typedef struct cover_lattice {
@@ -133,8 +137,9 @@ int cover_map_upload(cover_map* map, const uint8_t* data, int32_t mem);
  * later call that reads the map is ordered after the bands it needs on the device - a lattice check of a small
  * footprint starts on the first rows of the map while the rest is still in flight (the per-planning-cycle
  * "new costmap, then sweep" sequence).  `host_data` (page-locked memory for a truly asynchronous copy) must stay
- * unchanged until a later call that returns results to the host, or cover_ctx_synchronize, has returned: both wait
- * for the whole image to have landed, also when the check itself only needed a few bands of it. */
+ * unchanged until a later call that returns results to the host (COVER_MEM_HOST, not ..._ASYNC), or
+ * cover_ctx_synchronize, has returned: both wait for the whole image to have landed, also when the check itself only
+ * needed a few bands of it. */
 int cover_map_upload_async(cover_map* map, const uint8_t* host_data);
 /* re-upload the window [x0,x0+w) x [y0,y0+h) from a full-size HOST image (dirty-rectangle update). */
 int cover_map_upload_window(cover_map* map, const uint8_t* full_image, int32_t x0, int32_t y0, int32_t w, int32_t h);

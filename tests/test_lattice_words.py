@@ -387,3 +387,42 @@ def test_chunked_download_of_a_lattice_sweep(cb, monkeypatch, chunks):
     cpu = po.polygon_batch(omap, RECT, po.Lattice(**desc), op=po.OP_ACCUMULATE, threads=8)
     np.testing.assert_array_equal(acc.cost, cpu.cost)
     ctx.close()
+
+
+def test_async_host_results(cb, monkeypatch):
+    """COVER_MEM_HOST_ASYNC: results into page-locked host arrays without waiting - two contexts kept in flight by one
+    thread (banded upload + sweep each), valid after Context.synchronize(); verdict bits, byte outputs and the counter."""
+    import torch
+    rng = np.random.default_rng(540)
+    data = [mixed_map(rng, 500, 400, lethal=l) for l in (0.002, 0.005)]
+    desc = dict(x0=0.5, dx=0.05, nx=410, y0=0.7, dy=0.05, ny=130, cs=headings(4))
+    total = 410 * 130 * 8
+    n_words = (total + 31) // 32
+    slots = []
+    for img in data:
+        ctx = _ctx(cb, monkeypatch)
+        pinned_img = torch.from_numpy(img).pin_memory()
+        bits = torch.full((n_words,), -1, dtype=torch.int32).pin_memory()
+        nok = torch.full((1,), 77, dtype=torch.int64).pin_memory()
+        free = torch.full((total,), 9, dtype=torch.uint8).pin_memory()
+        status = torch.full((total,), 9, dtype=torch.uint8).pin_memory()
+        slots.append(dict(ctx=ctx, cmap=cb.Costmap(ctx, np.zeros_like(img), 0.05), img=pinned_img, bits=bits, nok=nok, free=free, status=status))
+    for rep in range(3):
+        for s in slots:  # queue both cycles, then wait
+            s["cmap"].upload_async(s["img"].numpy())
+            s["cmap"].area_is_free(RECT, cb.Lattice(**desc), out=cb.Result(free_bits=s["bits"].numpy().view(np.uint32), not_ok=s["nok"].numpy(), host_async=True))
+        for s in slots:
+            s["ctx"].synchronize()
+    for s in slots:
+        s["cmap"].outline_is_free(FOOTPRINTS[6], cb.Lattice(**desc), out=cb.Result(s["free"].numpy(), None, s["status"].numpy(), host_async=True))
+    for s, img in zip(slots, data):
+        s["ctx"].synchronize()
+        omap = po.Costmap(img, 0.05)
+        cpu = po.polygon_batch(omap, RECT, po.Lattice(**desc), threads=8)
+        got = np.unpackbits(s["bits"].numpy().view(np.uint8), bitorder="little")[:total]
+        np.testing.assert_array_equal(got, cpu.is_free)
+        assert int(s["nok"][0]) == 0
+        cpu_o = po.polygon_batch(omap, FOOTPRINTS[6], po.Lattice(**desc), shape=po.SHAPE_OUTLINE, threads=8)
+        np.testing.assert_array_equal(s["free"].numpy(), cpu_o.is_free)
+        np.testing.assert_array_equal(s["status"].numpy(), cpu_o.status)
+        s["ctx"].close()
